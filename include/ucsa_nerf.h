@@ -1,0 +1,189 @@
+/*
+ * ucsa_nerf.h -- C ABI of libucsa_nerf.so, the B200-native (sm_100a) Semantic-NeRF hot path.
+ *
+ * Drop-in boundary for the native layer of ethz-asl/ucsa_neural_rendering (nr4seg/nerf):
+ *   - replaces the pybind11 module `_raymarching`
+ *       (nr4seg/nerf/raymarching/src/bindings.cpp:5-18, raymarching.h:7-18), and
+ *   - replaces the tiny-cuda-nn modules the network calls
+ *       (nr4seg/nerf/network_tcnn_semantics.py:36-100: HashGrid, SphericalHarmonics, FullyFusedMLP), and
+ *   - provides the fused kernels behind SemanticNeRFRenderer.run()
+ *       (nr4seg/nerf/renderer_semantics.py:123-299) that the reference executes as eager torch ops.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller owns all memory; nothing is allocated, freed or synchronised inside;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and is CUDA-graph capturable;
+ *   - return value 0 = success, negative = error (UCSA_ERR_*); ucsa_last_error_string() describes it;
+ *   - fp16 buffers are IEEE binary16 (`__half`), passed as void*;
+ *   - "cat order" of a ray's samples: slot k in [0,Tc) is coarse sample k, slot Tc+j is fine sample j
+ *     (the order of torch.cat at renderer_semantics.py:221); "sorted order" is after the sort at :222.
+ */
+#ifndef UCSA_NERF_H
+#define UCSA_NERF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(UCSA_BUILDING_LIBRARY)
+#define UCSA_API __attribute__((visibility("default")))
+#else
+#define UCSA_API
+#endif
+
+#define UCSA_OK 0
+#define UCSA_ERR_INVALID_ARGUMENT (-1)
+#define UCSA_ERR_CUDA (-2)
+#define UCSA_ERR_UNSUPPORTED (-3)
+
+#define UCSA_ABI_VERSION 1
+#define UCSA_GRID_LEVELS 16
+#define UCSA_SIGMA_PARAMS 3072  /* 32->64->16            network_tcnn_semantics.py:48-58  */
+#define UCSA_COLOR_PARAMS 7168  /* 32->64->64->16        network_tcnn_semantics.py:74-84  */
+#define UCSA_MAX_CLASSES 48     /* semantics 16->64->pad16(C)  network_tcnn_semantics.py:90-100 */
+
+/* Multiresolution hash grid geometry (tcnn HashGrid config at network_tcnn_semantics.py:36-46).
+ * Filled by ucsa_grid_desc_init() on the host and passed BY VALUE to kernels. */
+typedef struct ucsa_grid_desc {
+  float scale[UCSA_GRID_LEVELS];     /* exp2f(l*log2f(pls))*base - 1                     */
+  uint32_t res[UCSA_GRID_LEVELS];    /* ceil(scale)+1                                    */
+  uint32_t entries[UCSA_GRID_LEVELS];/* min(round_up(res^3,8), 2^log2_hashmap)           */
+  uint32_t offset[UCSA_GRID_LEVELS]; /* first entry of the level (in entries of 2 feats) */
+  uint32_t hashed[UCSA_GRID_LEVELS]; /* 1 = prime-xor hash, 0 = dense x+y*res+z*res^2    */
+  uint32_t total_entries;            /* sum(entries); the table holds 2*total fp16/fp32   */
+} ucsa_grid_desc;
+
+UCSA_API int ucsa_abi_version(void);
+UCSA_API const char* ucsa_last_error_string(void);
+
+/* Host helper: geometry for `bound` (per_level_scale = 2^(log2(2048*bound/16)/15), network_tcnn_semantics.py:34). */
+UCSA_API int ucsa_grid_desc_init(float per_level_scale, uint32_t base_resolution, uint32_t log2_hashmap_size,
+                        ucsa_grid_desc* out_host);
+
+/* ---- a2. near/far.  Replaces near_far_from_aabb (raymarching.h:7, raymarching.cu:62-126). */
+UCSA_API int ucsa_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb6, uint32_t n_rays,
+                            float min_near, float* nears, float* fars, void* stream);
+
+/* ---- a3. coarse sampling (renderer_semantics.py:154-168).  Writes slots [0,Tc) of z_cat [N,T].
+ * lin[Tc] is torch.linspace(0,1,Tc).  perturb: stratified jitter; the uniform numbers come from t_rand [N,Tc]
+ * when non-null, else from the counter-based generator keyed by (seed, ray_base+n, k). */
+UCSA_API int ucsa_sample_coarse(const float* nears, const float* fars, const float* lin, const float* t_rand,
+                       uint64_t seed, uint32_t ray_base, int perturb, uint32_t n_rays, uint32_t tc, uint32_t t,
+                       float* z_cat, void* stream);
+
+/* ---- a4/a5/a6/a8. density = hash-grid encode + sigma MLP + trunc_exp (network_tcnn_semantics.py:130-144).
+ * Sample positions are either xyz [S,3] (then rays_*, z_cat are ignored and a "ray" has T=1 slot), or
+ * o + d*z clipped to aabb6 (renderer_semantics.py:171-173) for slots [k0,k1) of every ray.
+ * table_h: fp16 [2*total_entries]; w_sigma_h: fp16 [3072], layer-major, each layer [out][in] row-major.
+ * Outputs, indexed n*T+k: sigma f32; h fp16 [.,16] (h[0] = log-density, h[1:16] = geo_feat);
+ * enc fp16 [.,32] and hid fp16 [.,64] are saved for the backward pass when non-null. */
+UCSA_API int ucsa_density_fwd(const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,
+                     const float* z_cat, uint32_t n_rays, uint32_t t, uint32_t k0, uint32_t k1, float bound,
+                     const void* table_h, const ucsa_grid_desc* grid_host, const void* w_sigma_h,
+                     float* sigma, void* h, void* enc, void* hid, void* stream);
+
+/* Backward of ucsa_density_fwd for slots [k0,k1).  d_sigma f32 [N,T] (cat order); dh fp16 [N,T,16] whose
+ * elements 1..15 hold loss_scale * dL/dgeo_feat for samples with use_geo[n*T+k] != 0 (element 0 is ignored);
+ * trunc_exp backward (activation.py:16-19) is applied here.  Accumulates (atomicAdd, fp32) into
+ * grad_table [2*total] and grad_w_sigma [3072]; both already divided by loss_scale. */
+UCSA_API int ucsa_density_bwd(const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,
+                     const float* z_cat, uint32_t n_rays, uint32_t t, uint32_t k0, uint32_t k1, float bound,
+                     const ucsa_grid_desc* grid_host, const void* w_sigma_h, const void* h, const void* enc,
+                     const void* hid, const float* d_sigma, const void* dh, const uint8_t* use_geo,
+                     float loss_scale, float* grad_table, float* grad_w_sigma, void* stream);
+
+/* ---- a9/a10. importance resampling + merge (renderer_semantics.py:182-222, sample_pdf :10-46).
+ * Reads coarse z / sigma (slots [0,Tc)), writes fine z into slots [Tc,Tc+Tf) and order [N,T]
+ * (sorted position -> cat slot, the z_index of :222).  u [N,Tf] when non-null, else generated (seed). */
+UCSA_API int ucsa_resample_merge(const float* sigma, float* z_cat, const float* u, uint64_t seed, uint32_t ray_base,
+                        uint32_t n_rays, uint32_t tc, uint32_t tf, float density_scale, int32_t* order,
+                        void* stream);
+
+/* ---- a11. weights, masks, depth (renderer_semantics.py:238-250,270-277).  order may be null (identity).
+ * Writes w_sorted [N,T] (un-masked weights), depth [N] (sum of masked w*z / direction_norm),
+ * ray_count [N] (#samples with w > 1e-4) and use_geo [N,T] (cat order, 1 where masked-in). */
+UCSA_API int ucsa_weights_fwd(const float* z_cat, const float* sigma, const int32_t* order, const float* direction_norms,
+                     uint32_t n_rays, uint32_t t, float density_scale, float* w_sorted, float* depth,
+                     int32_t* ray_count, uint8_t* use_geo, void* stream);
+
+/* exclusive scan of ray_count -> ray_off [N+1] (ray_off[N] = K, the number of masked-in samples). */
+UCSA_API int ucsa_scan_counts(const int32_t* ray_count, uint32_t n_rays, int32_t* ray_off, void* stream);
+
+/* compaction: sel [K] = n*T + cat slot, w_sel [K], z_sel [K] in (ray, sorted position) order. */
+UCSA_API int ucsa_compact_masked(const float* w_sorted, const float* z_cat, const int32_t* order, const int32_t* ray_off,
+                        uint32_t n_rays, uint32_t t, int32_t* sel, float* w_sel, float* z_sel, void* stream);
+
+/* ---- a7/a12/a13. colour + semantic heads on the K masked-in rows (network_tcnn_semantics.py:147-207).
+ * K is read on the device from ray_off[n_rays]; k_max bounds the launch.  rgb [K,3] f32 (fp16 sigmoid
+ * values), logits fp16 [K,48]; hc1,hc2,hs fp16 [K,64] saved for backward when non-null. */
+UCSA_API int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32_t n_rays, uint32_t t, uint32_t k_max,
+                   const float* rays_d, const void* h, const void* w_color_h, const void* w_sem_h,
+                   uint32_t n_classes, float* rgb, void* logits, void* hc1, void* hc2, void* hs, void* stream);
+
+/* Backward of ucsa_heads_fwd.  d_rgb [K,3] f32 (w.r.t. the sigmoid output), d_logits f32 [K,48]
+ * (w.r.t. the pre-softmax logits).  Writes dh[sel][1..15] = loss_scale * dL/dgeo_feat (fp16) and
+ * accumulates grad_w_color [7168], grad_w_sem [64*16+pad16(C)*64] (fp32, unscaled). */
+UCSA_API int ucsa_heads_bwd(const int32_t* sel, const int32_t* ray_off, uint32_t n_rays, uint32_t t, uint32_t k_max,
+                   const float* rays_d, const void* h, const void* w_color_h, const void* w_sem_h,
+                   uint32_t n_classes, const float* rgb, const void* hc1, const void* hc2, const void* hs,
+                   const float* d_rgb, const float* d_logits, float loss_scale, void* dh, float* grad_w_color,
+                   float* grad_w_sem, void* stream);
+
+/* ---- a14. compositing over the compact rows (renderer_semantics.py:279-285): image = sum w*rgb,
+ * semantics = sum w*softmax(logits).  One pass, fp32. */
+UCSA_API int ucsa_composite_fwd(const int32_t* ray_off, const float* w_sel, const float* rgb, const void* logits,
+                       uint32_t n_rays, uint32_t n_classes, float* image, float* semantics, void* stream);
+
+/* Backward of composite+weights: from g_image [N,3], g_depth [N], g_semantics [N,C] produce
+ * d_rgb [K,3], d_logits f32 [K,48] (softmax backward; semantic weights are detached, :270),
+ * and d_sigma [N,T] in cat order (through weights, masked like :271). */
+UCSA_API int ucsa_composite_bwd(const int32_t* ray_off, const int32_t* sel, const float* w_sel, const float* z_sel,
+                       const float* rgb, const void* logits, const float* g_image, const float* g_depth,
+                       const float* g_semantics, const float* direction_norms, uint32_t n_rays,
+                       uint32_t n_classes, float* d_rgb, float* d_logits, float* d_w_sel, void* stream);
+UCSA_API int ucsa_weights_bwd(const float* z_cat, const float* sigma, const int32_t* order, const float* w_sorted,
+                     const int32_t* ray_off, const float* d_w_sel, uint32_t n_rays, uint32_t t,
+                     float density_scale, float* d_sigma, void* stream);
+
+/* ---- a14 (dense form, BASELINE.json configs[0]).  Everything per sample is given:
+ * sigma [N,T], z [N,T] (sorted), rgb [N,T,3], prob [N,T,C] f32.  Computes weights, the w>1e-4 masks and
+ * the three composites exactly like renderer_semantics.py:238-285. */
+UCSA_API int ucsa_composite_dense_fwd(const float* sigma, const float* z, const float* rgb, const float* prob,
+                             const float* direction_norms, uint32_t n_rays, uint32_t t, uint32_t n_classes,
+                             float density_scale, float* weights, float* depth, float* image, float* semantics,
+                             void* stream);
+UCSA_API int ucsa_composite_dense_bwd(const float* sigma, const float* z, const float* rgb, const float* weights,
+                             const float* direction_norms, const float* g_depth, const float* g_image,
+                             const float* g_semantics, uint32_t n_rays, uint32_t t, uint32_t n_classes,
+                             float density_scale, float* d_sigma, float* d_rgb, float* d_prob, void* stream);
+
+/* ---- stand-alone encoders / MLP, the module-level API the reference network exposes
+ * (self.encoder, self.encoder_dir, tcnn.Network; network_tcnn_semantics.py:108,117,121,125). */
+UCSA_API int ucsa_hashgrid_fwd(const float* x01, uint32_t n, const void* table_h, const ucsa_grid_desc* grid_host,
+                      void* enc, void* stream);
+UCSA_API int ucsa_hashgrid_bwd(const float* x01, uint32_t n, const ucsa_grid_desc* grid_host, const void* d_enc,
+                      float inv_loss_scale, float* grad_table, void* stream);
+UCSA_API int ucsa_hashgrid_indices(const float* x01, uint32_t n, const ucsa_grid_desc* grid_host, uint32_t* idx,
+                          void* stream); /* [n,16,8] global entry indices, the bit-exact contract */
+UCSA_API int ucsa_sh4_fwd(const float* d01, uint32_t n, void* out_h, void* stream);
+/* dims: n_layers+1 widths, each a multiple of 16 and <= 64; x fp16 [n,dims[0]] -> y fp16 [n,dims[L]];
+ * acts fp16 [n, sum(dims[1..L-1])] saved when non-null. */
+UCSA_API int ucsa_mlp_fwd(const void* x_h, uint32_t n, const void* w_h, const uint32_t* dims_host, uint32_t n_layers,
+                 void* y_h, void* acts_h, void* stream);
+UCSA_API int ucsa_mlp_bwd(const void* x_h, uint32_t n, const void* w_h, const uint32_t* dims_host, uint32_t n_layers,
+                 const void* acts_h, const void* dy_h, float inv_loss_scale, void* dx_h, float* grad_w,
+                 void* stream);
+
+/* ---- parameter plumbing: fp32 master -> fp16 working copy; fused Adam (row f1:
+ * joint_train_lightning_net.py:897-919: lr, betas (0.9,0.99), eps 1e-15, weight_decay on the MLPs). */
+UCSA_API int ucsa_cast_f32_to_f16(const float* src, uint64_t n, void* dst_h, void* stream);
+UCSA_API int ucsa_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_h,
+                   uint64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   float grad_scale_inv, const float* found_inf, uint32_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UCSA_NERF_H */

@@ -13,7 +13,7 @@ the published tcnn / Instant-NGP algorithm, anchored on the reference's call sit
 
 Spec decisions frozen here (DESIGN.md section "tcnn arithmetic spec"):
 
-* level scale   s_l = exp2f(l * log2f(pls)) * 16 - 1 in float32, res_l = ceil(s_l)+1,
+* level scale   s_l = float32(exp2(l * log2f(pls)) * 16 - 1) (exp2 in double, one rounding), res_l = ceil(s_l)+1,
                 entries_l = min(round_up(res_l^3, 8), 2^19); dense index
                 x + y*res + z*res^2 (mod entries_l) when res^3 <= entries_l, otherwise
                 (x*1) ^ (y*2654435761) ^ (z*805459861) (uint32) mod entries_l.
@@ -54,8 +54,7 @@ def level_table(bound: float):
     scales, res, entries, offsets, hashed = [], [], [], [], []
     off = 0
     for lvl in range(N_LEVELS):
-        s = np.float32(np.exp2(np.float32(lvl) * log2_pls)) * np.float32(BASE_RES) - np.float32(1.0)
-        s = np.float32(s)
+        s = np.float32(np.exp2(np.float64(lvl) * np.float64(log2_pls)) * np.float64(BASE_RES) - np.float64(1.0))
         r = int(math.ceil(float(s))) + 1
         n = min(((r ** 3 + 7) // 8) * 8, 1 << LOG2_HASHMAP)
         scales.append(s)

@@ -1,0 +1,217 @@
+"""End-to-end parity of the drop-in SemanticNeRFNetwork.render() (fused CUDA pipeline, called through the
+reference's own API) against the golden fixtures frozen from the reference modules and against the oracle.
+GPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import live_path
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _load(golden_dir, name):
+    return {k: v for k, v in np.load(os.path.join(golden_dir, name + ".npz")).items()}
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _net_from_oracle(heads, classes=40):
+    from ucsa_neural_rendering_b200 import build
+    from ucsa_neural_rendering_b200.nerf import SemanticNeRFNetwork
+
+    build.build_library()
+    net = SemanticNeRFNetwork(encoding="hashgrid", bound=4, cuda_ray=False, density_scale=1,
+                              num_semantic_classes=classes)
+    with torch.no_grad():
+        net.encoder.params.copy_(heads.encoder)
+        net.sigma_net.params.copy_(heads.sigma_net)
+        net.color_net.params.copy_(heads.color_net)
+        net.semantics_net.params.copy_(heads.semantics_net)
+    return net.to(DEV)
+
+
+def _oracle_heads(g):
+    return live_path.OracleHeads(bound=4, num_semantic_classes=int(g["cfg"][7]), seed=int(g["cfg"][8]),
+                                 hash_amp=float(g["hash_amp"]))
+
+
+def _close(name, got, ref, rtol, atol_rel):
+    ref = np.asarray(ref)
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol_rel * max(np.abs(ref).max(), 1e-12), err_msg=name)
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_train_small_golden(golden_dir, generic):
+    """Forward + backward of one training-mode render against the reference's own outputs / gradients."""
+    g = _load(golden_dir, "train_small")
+    n, steps, up = [int(v) for v in g["cfg"][:3]]
+    net = _net_from_oracle(_oracle_heads(g))
+    net.train()
+    kw = dict(generic=True) if generic else {}
+    out = net.render(_t(g["rays_o"]).to(DEV), _t(g["rays_d"]).to(DEV), direction_norms=_t(g["direction_norms"]).to(DEV),
+                     staged=False, bg_color=None, perturb=True, num_steps=steps, upsample_steps=up,
+                     t_rand=_t(g["t_rand"]).to(DEV), u=_t(g["u"]).to(DEV), **kw)
+    assert out["image"].dtype == torch.float32 and out["image"].shape == (1, n, 3)
+    assert out["depth"].shape == (1, n) and out["semantics"].shape == (1, n, 40)
+    # fp16 encoding / MLP chain => 2e-3
+    for k in ("depth", "image", "semantics"):
+        _close(k, out[k].detach().cpu().numpy(), g[k], rtol=4e-3, atol_rel=2e-3)
+    loss = (out["image"] * _t(g["g_image"]).to(DEV)).sum() + (out["depth"] * _t(g["g_depth"]).to(DEV)).sum() \
+        + (out["semantics"] * _t(g["g_semantics"]).to(DEV)).sum()
+    loss.backward()
+    for name, mod in (("sigma_net", net.sigma_net), ("color_net", net.color_net),
+                      ("semantics_net", net.semantics_net)):
+        _close("grad_" + name, mod.params.grad.cpu().numpy(), g["grad_" + name], rtol=3e-2, atol_rel=1e-2)
+    gh = net.encoder.params.grad.cpu()
+    _close("grad_hash", gh[_t(g["grad_hash_idx"])].numpy(), g["grad_hash_val"], rtol=3e-2, atol_rel=1e-2)
+    assert abs(float(gh.double().abs().sum()) - float(g["grad_hash_abs"])) < 2e-2 * float(g["grad_hash_abs"])
+
+
+def test_infer_staged_golden(golden_dir):
+    """staged=True chunk loop (ragged tail, rays that miss the box) in eval mode."""
+    g = _load(golden_dir, "infer_staged")
+    n, steps, up = [int(v) for v in g["cfg"][:3]]
+    net = _net_from_oracle(_oracle_heads(g))
+    net.eval()
+    with torch.no_grad():
+        out = net.render(_t(g["rays_o"]).to(DEV), _t(g["rays_d"]).to(DEV),
+                         direction_norms=_t(g["direction_norms"]).to(DEV), staged=True,
+                         max_ray_batch=int(g["cfg"][6]), bg_color=1, perturb=False, num_steps=steps,
+                         upsample_steps=up, u=_t(g["u"]).to(DEV))
+    for k in ("depth", "image", "semantics"):
+        _close(k, out[k].cpu().numpy(), g[k], rtol=4e-3, atol_rel=2e-3)
+
+
+def test_fused_equals_generic_path_at_reference_sizes():
+    """256 + 256 samples (the reference defaults): the fused pipeline and the method-by-method path agree."""
+    heads = live_path.OracleHeads(bound=4, num_semantic_classes=40, seed=5, hash_amp=0.3)
+    net = _net_from_oracle(heads)
+    net.train()
+    n = 512
+    g = torch.Generator().manual_seed(17)
+    o = ((torch.rand(1, n, 3, generator=g) - 0.5) * 2).to(DEV)
+    d = torch.nn.functional.normalize(torch.randn(1, n, 3, generator=g), dim=-1).to(DEV)
+    dn = (1 + 0.2 * torch.rand(1, n, 1, generator=g)).to(DEV)
+    t_rand = torch.rand(n, 256, generator=g).to(DEV)
+    u = torch.rand(n, 256, generator=g).to(DEV)
+    outs = []
+    grads = []
+    for generic in (False, True):
+        net.zero_grad(set_to_none=True)
+        kw = dict(generic=True) if generic else {}
+        out = net.render(o, d, direction_norms=dn, staged=False, perturb=True, t_rand=t_rand, u=u, **kw)
+        (out["image"].sum() + out["depth"].sum() + (out["semantics"] ** 2).sum()).backward()
+        outs.append({k: v.detach() for k, v in out.items()})
+        grads.append([p.grad.clone() for p in net.parameters()])
+    for k in outs[0]:
+        torch.testing.assert_close(outs[0][k], outs[1][k], rtol=2e-3, atol=2e-3)
+    for a, b in zip(*grads):
+        scale = float(b.abs().max())
+        torch.testing.assert_close(a, b, rtol=3e-2, atol=1e-2 * scale)
+
+
+def test_oracle_on_fresh_inputs():
+    """A second, larger seeded case straight against the CPU oracle (no fixture)."""
+    heads = live_path.OracleHeads(bound=4, num_semantic_classes=40, seed=77, hash_amp=0.4)
+    net = _net_from_oracle(heads)
+    net.train()
+    n, steps, up = 200, 64, 64
+    g = torch.Generator().manual_seed(4)
+    o = (torch.rand(1, n, 3, generator=g) - 0.5) * 3
+    d = torch.nn.functional.normalize(torch.randn(1, n, 3, generator=g), dim=-1)
+    dn = 1 + 0.3 * torch.rand(1, n, 1, generator=g)
+    t_rand = torch.rand(n, steps, generator=g)
+    u = torch.rand(n, up, generator=g)
+    ref = live_path.run(heads, o, d, dn, num_steps=steps, upsample_steps=up, perturb=True, t_rand=t_rand, u=u)
+    out = net.render(o.to(DEV), d.to(DEV), direction_norms=dn.to(DEV), perturb=True, num_steps=steps,
+                     upsample_steps=up, t_rand=t_rand.to(DEV), u=u.to(DEV))
+    for k in ("depth", "image", "semantics"):
+        _close(k, out[k].detach().cpu().numpy(), ref[k].detach().numpy(), rtol=4e-3, atol_rel=2e-3)
+    gi = torch.randn(1, n, 3, generator=g)
+    gs = torch.randn(1, n, 40, generator=g)
+    ((ref["image"] * gi).sum() + (ref["semantics"] * gs).sum() + ref["depth"].sum()).backward()
+    ((out["image"] * gi.to(DEV)).sum() + (out["semantics"] * gs.to(DEV)).sum() + out["depth"].sum()).backward()
+    for name, p_ref, mod in (("sigma", heads.sigma_net, net.sigma_net), ("color", heads.color_net, net.color_net),
+                             ("sem", heads.semantics_net, net.semantics_net), ("hash", heads.encoder, net.encoder)):
+        _close("grad_" + name, mod.params.grad.cpu().numpy(), p_ref.grad.numpy(), rtol=3e-2, atol_rel=1e-2)
+
+
+def test_module_level_api_matches_reference_contract():
+    """density()/color()/semantics()/forward(): shapes, dtypes and masked semantics of the reference network."""
+    heads = live_path.OracleHeads(bound=4, num_semantic_classes=40, seed=3, hash_amp=0.4)
+    net = _net_from_oracle(heads)
+    g = torch.Generator().manual_seed(2)
+    x = (torch.rand(777, 3, generator=g) - 0.5) * 8
+    d = torch.nn.functional.normalize(torch.randn(777, 3, generator=g), dim=-1)
+    mask = torch.rand(777, generator=g) > 0.5
+    dens = net.density(x.to(DEV))
+    ref = heads.density(x)
+    assert dens["sigma"].dtype == torch.float32 and dens["geo_feat"].dtype == torch.float16
+    _close("sigma", dens["sigma"].detach().cpu().numpy(), ref["sigma"].detach().numpy(), 4e-3, 2e-3)
+    _close("geo", dens["geo_feat"].float().detach().cpu().numpy(), ref["geo_feat"].detach().numpy(), 4e-3, 2e-3)
+    rgb = net.color(x.to(DEV), d.to(DEV), mask=mask.to(DEV), geo_feat=dens["geo_feat"])
+    rgb_ref = heads.color(x, d, mask=mask, geo_feat=ref["geo_feat"])
+    assert rgb.shape == (777, 3) and rgb.dtype == torch.float32 and (rgb[~mask.to(DEV)] == 0).all()
+    _close("rgb", rgb.detach().cpu().numpy(), rgb_ref.detach().numpy(), 4e-3, 2e-3)
+    sem = net.semantics(x.to(DEV), d.to(DEV), mask=mask.to(DEV), geo_feat=dens["geo_feat"])
+    sem_ref = heads.semantics(x, d, mask=mask, geo_feat=ref["geo_feat"])
+    assert sem.shape == (777, 40) and (sem[~mask.to(DEV)] == 0).all()
+    _close("sem", sem.detach().cpu().numpy(), sem_ref.detach().numpy(), 4e-3, 2e-3)
+    empty = torch.zeros(777, dtype=torch.bool, device=DEV)
+    assert (net.color(x.to(DEV), d.to(DEV), mask=empty, geo_feat=dens["geo_feat"]) == 0).all()
+    s2, c2, p2 = net(x.to(DEV), d.to(DEV))
+    s_ref, c_ref, p_ref = heads(x, d)
+    _close("fwd_color", c2.float().detach().cpu().numpy(), c_ref.detach().numpy(), 4e-3, 2e-3)
+    _close("fwd_sem", p2.detach().cpu().numpy(), p_ref.detach().numpy(), 4e-3, 2e-3)
+    # autograd through the module-level path reaches every parameter group
+    (s2.sum() + c2.float().sum() + (p2 ** 2).sum()).backward()
+    for p in net.parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0
+
+
+def test_optimizer_step_changes_render_and_state_dict_round_trips():
+    """Two Adam groups as at joint_train_lightning_net.py:897-919; fp16 working copies follow the masters."""
+    from ucsa_neural_rendering_b200.nerf import SemanticNeRFNetwork
+
+    net = SemanticNeRFNetwork(encoding="hashgrid", bound=4, cuda_ray=False, density_scale=1,
+                              num_semantic_classes=40).to(DEV)
+    opt = torch.optim.Adam([
+        {"name": "encoding", "params": list(net.encoder.parameters())},
+        {"name": "net", "params": list(net.sigma_net.parameters()) + list(net.color_net.parameters())
+         + list(net.semantics_net.parameters()), "weight_decay": 1e-6},
+    ], lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    n = 256
+    g = torch.Generator().manual_seed(1)
+    o = ((torch.rand(1, n, 3, generator=g) - 0.5)).to(DEV)
+    d = torch.nn.functional.normalize(torch.randn(1, n, 3, generator=g), dim=-1).to(DEV)
+    dn = torch.ones(1, n, 1, device=DEV)
+    target = torch.rand(1, n, 3, generator=g).to(DEV)
+    scaler = torch.amp.GradScaler("cuda", enabled=True)
+    losses = []
+    net.train()
+    for _ in range(12):
+        opt.zero_grad()
+        with torch.autocast("cuda", enabled=True):
+            out = net.render(o, d, direction_norms=dn, perturb=True, num_steps=32, upsample_steps=32, seed=7)
+            loss = ((out["image"] - target) ** 2).mean()
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0], losses
+    sd = net.state_dict()
+    net2 = SemanticNeRFNetwork(encoding="hashgrid", bound=4, cuda_ray=False, density_scale=1,
+                               num_semantic_classes=40).to(DEV)
+    net2.load_state_dict(sd)
+    net.eval(), net2.eval()
+    with torch.no_grad():
+        a = net.render(o, d, direction_norms=dn, staged=True, perturb=False, seed=9)
+        b = net2.render(o, d, direction_norms=dn, staged=True, perturb=False, seed=9)
+    for k in a:
+        assert torch.equal(a[k], b[k])

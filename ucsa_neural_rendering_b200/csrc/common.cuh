@@ -1,0 +1,98 @@
+// Shared helpers for libucsa_nerf.so (sm_100a).  Not part of the ABI.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ucsa_nerf.h"
+
+namespace ucsa {
+
+constexpr int kNumSMs = 148;          // B200: 2 dies x 74 SMs
+constexpr float kMaskThreshold = 1e-4f;  // renderer_semantics.py:249-250
+constexpr float kLastDelta = 1e10f;      // renderer_semantics.py:187,239
+constexpr float kTransEps = 1e-15f;      // renderer_semantics.py:193,244
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define UCSA_REQUIRE(cond, ...)                 \
+  do {                                          \
+    if (!(cond)) {                              \
+      ::ucsa::set_error(__VA_ARGS__);           \
+      return UCSA_ERR_INVALID_ARGUMENT;         \
+    }                                           \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline uint32_t ceil_div(uint64_t a, uint64_t b) { return static_cast<uint32_t>((a + b - 1) / b); }
+
+// ------------------------------------------------------------------ warp primitives
+constexpr unsigned kFullMask = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, o));
+  return v;
+}
+// inclusive scans over the 32 lanes
+__device__ __forceinline__ float warp_scan_mul(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float up = __shfl_up_sync(kFullMask, v, o);
+    if (lane >= o) v *= up;
+  }
+  return v;
+}
+__device__ __forceinline__ float warp_scan_add(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float up = __shfl_up_sync(kFullMask, v, o);
+    if (lane >= o) v += up;
+  }
+  return v;
+}
+// inclusive suffix sum: lane i gets sum over lanes >= i
+__device__ __forceinline__ float warp_rscan_add(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float dn = __shfl_down_sync(kFullMask, v, o);
+    if (lane + o < 32) v += dn;
+  }
+  return v;
+}
+
+// ------------------------------------------------------------------ counter-based uniform numbers
+// Used only when the caller does not inject its own random buffers (the reference draws them with
+// torch.rand, renderer_semantics.py:28,166; there is no stream to be compatible with).
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ float uniform01(uint64_t seed, uint32_t ray, uint32_t k, uint32_t stream) {
+  uint64_t key = (static_cast<uint64_t>(ray) << 32) | (static_cast<uint64_t>(stream) << 24) | k;
+  return static_cast<float>(mix64(mix64(seed) ^ key) >> 40) * (1.0f / 16777216.0f);
+}
+
+// ------------------------------------------------------------------ fp16 helpers
+__device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
+
+union H8 {  // eight halves as one 16-byte vector
+  uint4 v;
+  __half2 h2[4];
+  __half h[8];
+};
+
+__device__ __forceinline__ void red_add_f32x2(float* addr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+}  // namespace ucsa

@@ -1,0 +1,106 @@
+// Multiresolution hash-grid device functions (rows a4/a5 of SURVEY.md section 8).
+// Arithmetic contract (frozen in oracle/tcnn_spec.py, DESIGN.md "tcnn arithmetic spec"):
+//   pos = fma(scale_l, x01, 0.5); cell = floor(pos); frac = pos - cell;
+//   corner c adds bit d of c on axis d; weight = ((1*wx)*wy)*wz in fp32;
+//   index = dense x + y*res + z*res^2  or  x ^ y*2654435761 ^ z*805459861, then mod entries_l.
+#pragma once
+
+#include "common.cuh"
+
+namespace ucsa {
+
+struct LevelGeom {
+  float scale;
+  uint32_t res;
+  uint32_t entries;
+  uint32_t offset;
+  uint32_t hashed;
+};
+
+__device__ __forceinline__ LevelGeom level_geom(const ucsa_grid_desc& g, int l) {
+  return LevelGeom{g.scale[l], g.res[l], g.entries[l], g.offset[l], g.hashed[l]};
+}
+
+struct Cell {
+  uint32_t c[3];
+  float f[3];
+};
+
+__device__ __forceinline__ Cell locate(const LevelGeom& lv, const float x01[3]) {
+  Cell out;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float pos = fmaf(lv.scale, x01[d], 0.5f);
+    const float fl = floorf(pos);
+    out.c[d] = static_cast<uint32_t>(fl);
+    out.f[d] = pos - fl;
+  }
+  return out;
+}
+
+__device__ __forceinline__ uint32_t corner_entry(const LevelGeom& lv, const Cell& cell, int corner) {
+  const uint32_t x = cell.c[0] + (corner & 1);
+  const uint32_t y = cell.c[1] + ((corner >> 1) & 1);
+  const uint32_t z = cell.c[2] + ((corner >> 2) & 1);
+  uint32_t idx;
+  if (lv.hashed) {
+    idx = x ^ (y * 2654435761u) ^ (z * 805459861u);
+  } else {
+    idx = x + y * lv.res + z * lv.res * lv.res;
+  }
+  // hashed levels always hold 2^k entries; dense ones a multiple of 8
+  idx = ((lv.entries & (lv.entries - 1u)) == 0u) ? (idx & (lv.entries - 1u)) : (idx % lv.entries);
+  return lv.offset + idx;
+}
+
+__device__ __forceinline__ float corner_weight(const Cell& cell, int corner) {
+  float w = 1.0f;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) w *= ((corner >> d) & 1) ? cell.f[d] : (1.0f - cell.f[d]);
+  return w;
+}
+
+// One level: trilinear interpolation of the fp16 table, fp32 accumulate.
+__device__ __forceinline__ float2 interp_level(const __half2* __restrict__ table, const LevelGeom& lv,
+                                               const float x01[3]) {
+  const Cell cell = locate(lv, x01);
+  __half2 v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[c] = __ldg(table + corner_entry(lv, cell, c));
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float w = corner_weight(cell, c);
+    const float2 f = __half22float2(v[c]);
+    a0 = fmaf(w, f.x, a0);
+    a1 = fmaf(w, f.y, a1);
+  }
+  return make_float2(a0, a1);
+}
+
+// Scatter of one level's gradient: grad_table[entry] += w_c * (g0, g1).
+__device__ __forceinline__ void scatter_level(float* __restrict__ grad_table, const LevelGeom& lv,
+                                              const float x01[3], float g0, float g1) {
+  if (g0 == 0.f && g1 == 0.f) return;
+  const Cell cell = locate(lv, x01);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float w = corner_weight(cell, c);
+    red_add_f32x2(grad_table + 2ull * corner_entry(lv, cell, c), w * g0, w * g1);
+  }
+}
+
+// Sample position of slot k of ray n, exactly as renderer_semantics.py:171-173 then
+// network_tcnn_semantics.py:133 evaluate it in eager fp32 (no FMA contraction).
+__device__ __forceinline__ void sample_x01(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                           const float* __restrict__ aabb, float z, uint32_t n, float bound,
+                                           float x01[3]) {
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    float p = __fadd_rn(rays_o[3 * n + d], __fmul_rn(rays_d[3 * n + d], z));
+    p = fminf(fmaxf(p, aabb[d]), aabb[3 + d]);
+    x01[d] = __fdiv_rn(__fadd_rn(p, bound), 2.0f * bound);
+  }
+}
+
+}  // namespace ucsa

@@ -1,0 +1,216 @@
+// Ray set-up and sample placement of the LIVE path: AABB slab test, uniform / stratified coarse samples,
+// inverse-CDF importance resampling and the merge of the two sorted runs.
+// Rows a2, a3, a9, a10 of SURVEY.md section 8.
+#include "common.cuh"
+
+namespace ucsa {
+namespace {
+
+// ---------------------------------------------------------------- a2: raymarching.cu:62-115
+__global__ void near_far_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                const float* __restrict__ aabb, uint32_t n_rays, float min_near,
+                                float* __restrict__ nears, float* __restrict__ fars) {
+  const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_rays) return;
+  float t_near = 0.f, t_far = 0.f;
+  bool hit = true;
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax) {
+    const float o = rays_o[3 * n + ax];
+    const float inv = 1.0f / rays_d[3 * n + ax];
+    float lo = (aabb[ax] - o) * inv;
+    float hi = (aabb[3 + ax] - o) * inv;
+    if (lo > hi) {
+      const float tmp = lo;
+      lo = hi;
+      hi = tmp;
+    }
+    if (ax == 0) {
+      t_near = lo;
+      t_far = hi;
+    } else if (hit) {
+      if (t_near > hi || lo > t_far) {
+        hit = false;
+      } else {
+        if (lo > t_near) t_near = lo;
+        if (hi < t_far) t_far = hi;
+      }
+    }
+  }
+  if (!hit) {
+    nears[n] = fars[n] = 3.402823466e+38f;  // FLT_MAX, as std::numeric_limits<float>::max()
+    return;
+  }
+  if (t_near < min_near) t_near = min_near;
+  nears[n] = t_near;
+  fars[n] = t_far;
+}
+
+// ---------------------------------------------------------------- a3: renderer_semantics.py:154-168
+__device__ __forceinline__ float coarse_z(float near, float far, float lin) {
+  return __fadd_rn(near, __fmul_rn(__fsub_rn(far, near), lin));
+}
+
+__global__ void sample_coarse_kernel(const float* __restrict__ nears, const float* __restrict__ fars,
+                                     const float* __restrict__ lin, const float* __restrict__ t_rand,
+                                     uint64_t seed, uint32_t ray_base, int perturb, uint32_t n_rays, uint32_t tc,
+                                     uint32_t t, float* __restrict__ z_cat) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<uint64_t>(n_rays) * tc) return;
+  const uint32_t n = static_cast<uint32_t>(i / tc), k = static_cast<uint32_t>(i % tc);
+  const float near = nears[n], far = fars[n];
+  float z = coarse_z(near, far, lin[k]);
+  if (perturb) {
+    const float z_prev = k > 0 ? coarse_z(near, far, lin[k - 1]) : z;
+    const float z_next = k + 1 < tc ? coarse_z(near, far, lin[k + 1]) : z;
+    const float lower = k > 0 ? __fmul_rn(0.5f, __fadd_rn(z, z_prev)) : z;
+    const float upper = k + 1 < tc ? __fmul_rn(0.5f, __fadd_rn(z_next, z)) : z;
+    const float r = t_rand != nullptr ? t_rand[i] : uniform01(seed, ray_base + n, k, 0u);
+    z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), r));
+  }
+  z_cat[static_cast<uint64_t>(n) * t + k] = z;
+}
+
+// ---------------------------------------------------------------- a9/a10: renderer_semantics.py:182-222
+// One CTA per ray.  Shared memory: zc[Tc] sg[Tc] wt[Tc] cdf[Tc] zn[Tf] zs[Tf] (floats).
+// The cumulative product / sum run sequentially in thread 0: 2*Tc dependent flops per ray, which keeps the
+// summation order of torch.cumprod / torch.cumsum on the CPU and costs microseconds per 4096-ray batch.
+__global__ void __launch_bounds__(256)
+resample_merge_kernel(const float* __restrict__ sigma, float* __restrict__ z_cat, const float* __restrict__ u,
+                      uint64_t seed, uint32_t ray_base, uint32_t tc, uint32_t tf, float density_scale,
+                      int32_t* __restrict__ order) {
+  extern __shared__ float sm[];
+  float* zc = sm;
+  float* sg = zc + tc;
+  float* wt = sg + tc;
+  float* cdf = wt + tc;
+  float* zn = cdf + tc;
+  float* zs = zn + tf;
+  const uint32_t n = blockIdx.x, t = tc + tf;
+  const uint64_t row = static_cast<uint64_t>(n) * t;
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  for (uint32_t k = tid; k < tc; k += nt) {
+    zc[k] = z_cat[row + k];
+    sg[k] = sigma[row + k];
+  }
+  __syncthreads();
+  // alpha_k, kept in wt until the scan turns it into the weight
+  for (uint32_t k = tid; k < tc; k += nt) {
+    const float delta = k + 1 < tc ? __fsub_rn(zc[k + 1], zc[k]) : kLastDelta;
+    wt[k] = 1.0f - expf(__fmul_rn(__fmul_rn(-delta, density_scale), sg[k]));
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float trans = 1.0f;
+    for (uint32_t k = 0; k < tc; ++k) {
+      const float alpha = wt[k];
+      wt[k] = alpha * trans;
+      trans *= __fadd_rn(__fsub_rn(1.0f, alpha), kTransEps);
+    }
+    // pdf over weights[1:-1] + 1e-5 ; cdf = [0, cumsum(pdf)]  (tc-1 entries)
+    float total = 0.f;
+    for (uint32_t k = 1; k + 1 < tc; ++k) total += wt[k] + 1e-5f;
+    float run = 0.f;
+    cdf[0] = 0.f;
+    for (uint32_t k = 1; k + 1 < tc; ++k) {
+      run += __fdiv_rn(wt[k] + 1e-5f, total);
+      cdf[k] = run;
+    }
+  }
+  __syncthreads();
+  const uint32_t n_cdf = tc - 1;  // bins (mid-points) and cdf entries
+  for (uint32_t j = tid; j < tf; j += nt) {
+    const float uj = u != nullptr ? u[static_cast<uint64_t>(n) * tf + j] : uniform01(seed, ray_base + n, j, 1u);
+    // searchsorted(cdf, u, right=True): number of entries <= u
+    uint32_t lo = 0, hi = n_cdf;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (cdf[mid] <= uj) lo = mid + 1; else hi = mid;
+    }
+    const uint32_t below = lo > 0 ? lo - 1 : 0;
+    const uint32_t above = lo < n_cdf - 1 ? lo : n_cdf - 1;
+    float denom = __fsub_rn(cdf[above], cdf[below]);
+    if (denom < 1e-5f) denom = 1.0f;
+    const float frac = __fdiv_rn(__fsub_rn(uj, cdf[below]), denom);
+    // bins: z_mid_k = z_k + 0.5 * (z_{k+1} - z_k)
+    const float b_lo = __fadd_rn(zc[below], __fmul_rn(0.5f, __fsub_rn(zc[below + 1], zc[below])));
+    const float b_hi = __fadd_rn(zc[above], __fmul_rn(0.5f, __fsub_rn(zc[above + 1], zc[above])));
+    const float z_new = __fadd_rn(b_lo, __fmul_rn(frac, __fsub_rn(b_hi, b_lo)));
+    zn[j] = z_new;
+    z_cat[row + tc + j] = z_new;
+  }
+  __syncthreads();
+  // rank of every fine sample among the fine samples (stable), then scatter into the sorted run zs
+  for (uint32_t j = tid; j < tf; j += nt) {
+    const float v = zn[j];
+    uint32_t rank = 0;
+    for (uint32_t k = 0; k < tf; ++k) {
+      const float w = zn[k];
+      rank += (w < v || (w == v && k < j)) ? 1u : 0u;
+    }
+    zs[rank] = v;
+    // position in the merged order: fine samples go after coarse samples of equal depth
+    uint32_t lo = 0, hi = tc;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (zc[mid] <= v) lo = mid + 1; else hi = mid;
+    }
+    order[row + rank + lo] = static_cast<int32_t>(tc + j);
+  }
+  __syncthreads();
+  for (uint32_t k = tid; k < tc; k += nt) {
+    const float v = zc[k];
+    uint32_t lo = 0, hi = tf;  // number of fine samples strictly below v
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (zs[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    order[row + k + lo] = static_cast<int32_t>(k);
+  }
+}
+
+}  // namespace
+}  // namespace ucsa
+
+using namespace ucsa;
+
+extern "C" int ucsa_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb6,
+                                       uint32_t n_rays, float min_near, float* nears, float* fars,
+                                       void* stream) {
+  UCSA_REQUIRE(rays_o && rays_d && aabb6 && nears && fars, "near_far_from_aabb: null pointer");
+  if (n_rays == 0) return UCSA_OK;
+  near_far_kernel<<<ceil_div(n_rays, 256), 256, 0, as_stream(stream)>>>(rays_o, rays_d, aabb6, n_rays, min_near,
+                                                                        nears, fars);
+  return check_launch("near_far_from_aabb");
+}
+
+extern "C" int ucsa_sample_coarse(const float* nears, const float* fars, const float* lin, const float* t_rand,
+                                  uint64_t seed, uint32_t ray_base, int perturb, uint32_t n_rays, uint32_t tc,
+                                  uint32_t t, float* z_cat, void* stream) {
+  UCSA_REQUIRE(nears && fars && lin && z_cat, "sample_coarse: null pointer");
+  UCSA_REQUIRE(tc >= 1 && tc <= t, "sample_coarse: need 1 <= Tc <= T");
+  if (n_rays == 0) return UCSA_OK;
+  const uint64_t total = static_cast<uint64_t>(n_rays) * tc;
+  sample_coarse_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(nears, fars, lin, t_rand, seed,
+                                                                            ray_base, perturb, n_rays, tc, t,
+                                                                            z_cat);
+  return check_launch("sample_coarse");
+}
+
+extern "C" int ucsa_resample_merge(const float* sigma, float* z_cat, const float* u, uint64_t seed,
+                                   uint32_t ray_base, uint32_t n_rays, uint32_t tc, uint32_t tf,
+                                   float density_scale, int32_t* order, void* stream) {
+  UCSA_REQUIRE(sigma && z_cat && order, "resample_merge: null pointer");
+  UCSA_REQUIRE(tc >= 3 && tf >= 1 && tc <= 4096 && tf <= 4096, "resample_merge: need 3 <= Tc <= 4096, 1 <= Tf <= 4096");
+  if (n_rays == 0) return UCSA_OK;
+  const size_t smem = (4ull * tc + 2ull * tf) * sizeof(float);
+  static size_t smem_set = 48 * 1024;
+  if (smem > smem_set) {
+    cudaFuncSetAttribute(resample_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem_set = smem;
+  }
+  resample_merge_kernel<<<n_rays, 256, smem, as_stream(stream)>>>(sigma, z_cat, u, seed, ray_base, tc, tf,
+                                                                  density_scale, order);
+  return check_launch("resample_merge");
+}

@@ -1,0 +1,225 @@
+// Weights, w > 1e-4 masks, depth, and the compaction of the masked-in samples that the colour / semantic
+// heads are evaluated on.  Rows a11 (+ the masks of a12/a13) and their backward (a15) of SURVEY.md section 8.
+#include "weights.cuh"
+
+namespace ucsa {
+namespace {
+
+constexpr int kWarpsPerCta = 4;
+
+// gather a ray's (z, sigma) into sorted order in the warp's shared-memory slice
+__device__ __forceinline__ void stage_sorted(const float* __restrict__ z_cat, const float* __restrict__ sigma,
+                                             const int32_t* __restrict__ order, uint64_t row, uint32_t t,
+                                             int lane, float* zs, float* sg) {
+  for (uint32_t s = lane; s < t; s += 32) {
+    const uint32_t slot = order != nullptr ? static_cast<uint32_t>(order[row + s]) : s;
+    zs[s] = z_cat[row + slot];
+    sg[s] = sigma[row + slot];
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+weights_fwd_kernel(const float* __restrict__ z_cat, const float* __restrict__ sigma,
+                   const int32_t* __restrict__ order, const float* __restrict__ dnorm, uint32_t n_rays, uint32_t t,
+                   float density_scale, float* __restrict__ w_sorted, float* __restrict__ depth,
+                   int32_t* __restrict__ ray_count, uint8_t* __restrict__ use_geo) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t n = blockIdx.x * kWarpsPerCta + wib;
+  if (n >= n_rays) return;
+  float* zs = sm + static_cast<size_t>(wib) * 2 * t;
+  float* sg = zs + t;
+  const uint64_t row = static_cast<uint64_t>(n) * t;
+  stage_sorted(z_cat, sigma, order, row, t, lane, zs, sg);
+
+  float carry = 1.0f, dsum = 0.f;
+  int count = 0;
+  for (uint32_t base = 0; base < t; base += 32) {
+    const uint32_t s = base + lane;
+    const bool valid = s < t;
+    SampleTerms st{1.f, 0.f, 1.f, 0.f};
+    if (valid) st = sample_terms(zs, sg, s, t, density_scale);
+    const float trans = chunk_transmittance(valid ? st.keep : 1.0f, carry, lane);
+    const float w = st.alpha * trans;
+    const bool keep = valid && w > kMaskThreshold;
+    if (valid) {
+      w_sorted[row + s] = w;
+      const uint32_t slot = order != nullptr ? static_cast<uint32_t>(order[row + s]) : s;
+      use_geo[row + slot] = keep ? 1 : 0;
+    }
+    if (keep) dsum += w * zs[s];
+    count += __popc(__ballot_sync(kFullMask, keep));
+  }
+  dsum = warp_sum(dsum);
+  if (lane == 0) {
+    depth[n] = dsum / dnorm[n];
+    ray_count[n] = count;
+  }
+}
+
+// single-CTA exclusive scan; n_rays <= 2^18 in every configuration, i.e. at most 256 iterations
+__global__ void __launch_bounds__(1024)
+scan_counts_kernel(const int32_t* __restrict__ counts, uint32_t n, int32_t* __restrict__ offsets) {
+  __shared__ int warp_total[32];
+  __shared__ int carry_s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const int v = i < n ? counts[i] : 0;
+    int incl = warp_scan_add_i32(v, lane);
+    if (lane == 31) warp_total[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const int tot = warp_total[lane];
+      const int sc = warp_scan_add_i32(tot, lane);
+      warp_total[lane] = sc - tot;  // exclusive offset of each warp
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    if (i < n) offsets[i] = carry + warp_total[wid] + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_total[wid] + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[n] = carry_s;
+}
+
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+compact_masked_kernel(const float* __restrict__ w_sorted, const float* __restrict__ z_cat,
+                      const int32_t* __restrict__ order, const int32_t* __restrict__ ray_off, uint32_t n_rays,
+                      uint32_t t, int32_t* __restrict__ sel, float* __restrict__ w_sel,
+                      float* __restrict__ z_sel) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (n >= n_rays) return;
+  const uint64_t row = static_cast<uint64_t>(n) * t;
+  int out = ray_off[n];
+  for (uint32_t base = 0; base < t; base += 32) {
+    const uint32_t s = base + lane;
+    const float w = s < t ? w_sorted[row + s] : 0.f;
+    const bool keep = s < t && w > kMaskThreshold;
+    const unsigned ballot = __ballot_sync(kFullMask, keep);
+    if (keep) {
+      const int r = out + __popc(ballot & ((1u << lane) - 1u));
+      const uint32_t slot = order != nullptr ? static_cast<uint32_t>(order[row + s]) : s;
+      sel[r] = static_cast<int32_t>(row + slot);
+      w_sel[r] = w;
+      z_sel[r] = z_cat[row + slot];
+    }
+    out += __popc(ballot);
+  }
+}
+
+// d_sigma (cat order) from dL/dw of the masked-in samples (d_w_sel, compact order).
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+weights_bwd_kernel(const float* __restrict__ z_cat, const float* __restrict__ sigma,
+                   const int32_t* __restrict__ order, const float* __restrict__ w_sorted,
+                   const int32_t* __restrict__ ray_off, const float* __restrict__ d_w_sel, uint32_t n_rays,
+                   uint32_t t, float density_scale, float* __restrict__ d_sigma) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t n = blockIdx.x * kWarpsPerCta + wib;
+  if (n >= n_rays) return;
+  float* zs = sm + static_cast<size_t>(wib) * 4 * t;
+  float* sg = zs + t;
+  float* tr = sg + t;  // transmittance in front of each sample
+  float* gw = tr + t;  // dL/dw (0 where masked out)
+  const uint64_t row = static_cast<uint64_t>(n) * t;
+  stage_sorted(z_cat, sigma, order, row, t, lane, zs, sg);
+
+  float carry = 1.0f;
+  int out = ray_off[n];
+  for (uint32_t base = 0; base < t; base += 32) {
+    const uint32_t s = base + lane;
+    const bool valid = s < t;
+    float keep_f = 1.0f;
+    if (valid) keep_f = sample_terms(zs, sg, s, t, density_scale).keep;
+    const float trans = chunk_transmittance(keep_f, carry, lane);
+    const float w = valid ? w_sorted[row + s] : 0.f;
+    const bool keep = valid && w > kMaskThreshold;
+    const unsigned ballot = __ballot_sync(kFullMask, keep);
+    if (valid) {
+      tr[s] = trans;
+      gw[s] = keep ? d_w_sel[out + __popc(ballot & ((1u << lane) - 1u))] : 0.f;
+    }
+    out += __popc(ballot);
+  }
+  __syncwarp();
+  float suffix_carry = 0.f;
+  const uint32_t n_chunks = (t + 31) / 32;
+  for (uint32_t c = n_chunks; c-- > 0;) {
+    const uint32_t s = c * 32 + lane;
+    const bool valid = s < t;
+    const float g = valid ? gw[s] : 0.f;
+    const float w = valid ? w_sorted[row + s] : 0.f;
+    const float suffix = chunk_suffix(g * w, suffix_carry, lane);
+    if (valid) {
+      const SampleTerms st = sample_terms(zs, sg, s, t, density_scale);
+      const uint32_t slot = order != nullptr ? static_cast<uint32_t>(order[row + s]) : s;
+      d_sigma[row + slot] = sigma_grad(st, density_scale, g, tr[s], suffix);
+    }
+  }
+}
+
+int set_smem(const void* fn, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    if (bytes > 227 * 1024) {
+      set_error("samples per ray too large for the shared-memory staging (%zu bytes)", bytes);
+      return UCSA_ERR_UNSUPPORTED;
+    }
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  }
+  return UCSA_OK;
+}
+
+}  // namespace
+}  // namespace ucsa
+
+using namespace ucsa;
+
+extern "C" int ucsa_weights_fwd(const float* z_cat, const float* sigma, const int32_t* order,
+                                const float* direction_norms, uint32_t n_rays, uint32_t t, float density_scale,
+                                float* w_sorted, float* depth, int32_t* ray_count, uint8_t* use_geo,
+                                void* stream) {
+  UCSA_REQUIRE(z_cat && sigma && direction_norms && w_sorted && depth && ray_count && use_geo,
+               "weights_fwd: null pointer");
+  UCSA_REQUIRE(t >= 1, "weights_fwd: T must be >= 1");
+  if (n_rays == 0) return UCSA_OK;
+  const size_t smem = static_cast<size_t>(kWarpsPerCta) * 2 * t * sizeof(float);
+  if (int rc = set_smem(reinterpret_cast<const void*>(weights_fwd_kernel), smem)) return rc;
+  weights_fwd_kernel<<<ceil_div(n_rays, kWarpsPerCta), 32 * kWarpsPerCta, smem, as_stream(stream)>>>(
+      z_cat, sigma, order, direction_norms, n_rays, t, density_scale, w_sorted, depth, ray_count, use_geo);
+  return check_launch("weights_fwd");
+}
+
+extern "C" int ucsa_scan_counts(const int32_t* ray_count, uint32_t n_rays, int32_t* ray_off, void* stream) {
+  UCSA_REQUIRE(ray_count && ray_off, "scan_counts: null pointer");
+  scan_counts_kernel<<<1, 1024, 0, as_stream(stream)>>>(ray_count, n_rays, ray_off);
+  return check_launch("scan_counts");
+}
+
+extern "C" int ucsa_compact_masked(const float* w_sorted, const float* z_cat, const int32_t* order,
+                                   const int32_t* ray_off, uint32_t n_rays, uint32_t t, int32_t* sel,
+                                   float* w_sel, float* z_sel, void* stream) {
+  UCSA_REQUIRE(w_sorted && z_cat && ray_off && sel && w_sel && z_sel, "compact_masked: null pointer");
+  UCSA_REQUIRE(static_cast<uint64_t>(n_rays) * t < (1ull << 31), "compact_masked: N*T must fit int32");
+  if (n_rays == 0) return UCSA_OK;
+  compact_masked_kernel<<<ceil_div(n_rays, kWarpsPerCta), 32 * kWarpsPerCta, 0, as_stream(stream)>>>(
+      w_sorted, z_cat, order, ray_off, n_rays, t, sel, w_sel, z_sel);
+  return check_launch("compact_masked");
+}
+
+extern "C" int ucsa_weights_bwd(const float* z_cat, const float* sigma, const int32_t* order,
+                                const float* w_sorted, const int32_t* ray_off, const float* d_w_sel,
+                                uint32_t n_rays, uint32_t t, float density_scale, float* d_sigma, void* stream) {
+  UCSA_REQUIRE(z_cat && sigma && w_sorted && ray_off && d_w_sel && d_sigma, "weights_bwd: null pointer");
+  if (n_rays == 0) return UCSA_OK;
+  const size_t smem = static_cast<size_t>(kWarpsPerCta) * 4 * t * sizeof(float);
+  if (int rc = set_smem(reinterpret_cast<const void*>(weights_bwd_kernel), smem)) return rc;
+  weights_bwd_kernel<<<ceil_div(n_rays, kWarpsPerCta), 32 * kWarpsPerCta, smem, as_stream(stream)>>>(
+      z_cat, sigma, order, w_sorted, ray_off, d_w_sel, n_rays, t, density_scale, d_sigma);
+  return check_launch("weights_bwd");
+}

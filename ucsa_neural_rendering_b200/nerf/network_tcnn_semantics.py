@@ -1,0 +1,429 @@
+"""SemanticNeRFNetwork -- drop-in for nr4seg/nerf/network_tcnn_semantics.py without tiny-cuda-nn.
+
+Same constructor, attributes (``encoder``, ``sigma_net``, ``encoder_dir``, ``color_net``, ``semantics_net``,
+each an ``nn.Module`` with ``.parameters()`` for the two Adam groups of joint_train_lightning_net.py:897-919)
+and methods (``forward``, ``density``, ``color``, ``semantics``, ``run``, ``render``) as the reference
+(network_tcnn_semantics.py:10-207).  ``run`` is overridden with the fused pipeline: one autograd node whose
+forward and backward are chains of libucsa_nerf.so kernels with no eager tensor math in between.
+
+Parameters are fp32 masters (like the tcnn torch bindings keep them); kernels read an fp16 working copy that
+is refreshed whenever the master's version counter moves (i.e. after every optimizer step).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from .activation import trunc_exp  # noqa: F401  (re-exported like the reference module)
+from .renderer_semantics import SemanticNeRFRenderer
+
+
+def _pad16(n: int) -> int:
+    return (n + 15) // 16 * 16
+
+
+class _HalfCache(nn.Module):
+    """fp32 master ``params`` + lazily refreshed fp16 copy."""
+
+    def __init__(self):
+        super().__init__()
+        self._half = None
+        self._half_key = None
+
+    def half_params(self) -> torch.Tensor:
+        p = self.params
+        key = (p.data_ptr(), p._version, p.device)
+        if self._half is None or self._half_key != key or self._half.device != p.device:
+            if self._half is None or self._half.shape != p.shape or self._half.device != p.device:
+                self._half = torch.empty(p.shape, dtype=torch.float16, device=p.device)
+            ops.cast_f32_to_f16(p.detach(), self._half)
+            self._half_key = key
+        return self._half
+
+
+class _HashGridFn(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x01, params, module):
+        x01 = x01.detach().float().contiguous()
+        enc = torch.empty(x01.shape[0], 32, dtype=torch.float16, device=x01.device)
+        ops.hashgrid_fwd(x01, module.half_params(), module.grid, enc)
+        ctx.save_for_backward(x01)
+        ctx.module = module
+        return enc
+
+    @staticmethod
+    def backward(ctx, d_enc):
+        (x01,) = ctx.saved_tensors
+        m = ctx.module
+        scale = m.loss_scale
+        grad = torch.zeros_like(m.params)
+        ops.hashgrid_bwd(x01, m.grid, (d_enc.float() * scale).half().contiguous(), 1.0 / scale, grad)
+        return None, grad, None
+
+
+class HashGridEncoding(_HalfCache):
+    """tcnn.Encoding(HashGrid) of network_tcnn_semantics.py:36-46: [S,3] in [0,1] -> [S,32] fp16."""
+
+    def __init__(self, bound, seed=1337, loss_scale=128.0):
+        super().__init__()
+        self.n_input_dims = 3
+        self.n_output_dims = 32
+        self.loss_scale = loss_scale
+        self.grid = ops.make_grid_desc(bound)
+        n = int(self.grid.total_entries) * 2
+        g = torch.Generator().manual_seed(seed)
+        self.params = nn.Parameter((torch.rand(n, generator=g) * 2 - 1) * 1e-4)  # tcnn: U(-1e-4, 1e-4)
+
+    def forward(self, x):
+        return _HashGridFn.apply(x, self.params, self)
+
+
+class SHEncoding(nn.Module):
+    """tcnn.Encoding(SphericalHarmonics, degree 4) of network_tcnn_semantics.py:64-70: [K,3] in [0,1] -> [K,16] fp16."""
+
+    def __init__(self):
+        super().__init__()
+        self.n_input_dims = 3
+        self.n_output_dims = 16
+
+    def forward(self, d01):
+        d01 = d01.detach().float().contiguous()
+        out = torch.empty(d01.shape[0], 16, dtype=torch.float16, device=d01.device)
+        ops.sh4_fwd(d01, out)
+        return out
+
+
+class _MlpFn(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, params, module):
+        dims = module.dims
+        n = x.shape[0]
+        xh = x.detach().half()
+        if xh.shape[1] < dims[0]:  # tcnn pads the input with ones: the extra column acts as a bias
+            xh = torch.cat([xh, torch.ones(n, dims[0] - xh.shape[1], dtype=torch.float16, device=x.device)], 1)
+        xh = xh.contiguous()
+        y = torch.empty(n, dims[-1], dtype=torch.float16, device=x.device)
+        acts = torch.empty(n, sum(dims[1:-1]), dtype=torch.float16, device=x.device)
+        ops.mlp_fwd(xh, module.half_params(), dims, y, acts)
+        ctx.save_for_backward(xh, acts)
+        ctx.module = module
+        ctx.n_in = x.shape[1]
+        ctx.x_dtype = x.dtype
+        return y[:, :module.n_output_dims]
+
+    @staticmethod
+    def backward(ctx, dy):
+        xh, acts = ctx.saved_tensors
+        m = ctx.module
+        dims = m.dims
+        n = xh.shape[0]
+        scale = m.loss_scale
+        dyh = torch.zeros(n, dims[-1], dtype=torch.float16, device=xh.device)
+        dyh[:, :m.n_output_dims] = (dy.float() * scale).half()
+        dx = torch.empty(n, dims[0], dtype=torch.float16, device=xh.device)
+        grad = torch.zeros_like(m.params)
+        ops.mlp_bwd(xh, m.half_params(), dims, acts, dyh, 1.0 / scale, dx, grad)
+        return (dx[:, :ctx.n_in].float() / scale).to(ctx.x_dtype), grad, None
+
+
+class FusedMLP(_HalfCache):
+    """tcnn.Network(FullyFusedMLP, ReLU, no output activation): fp16 in/out, fp32 accumulate, no bias."""
+
+    def __init__(self, n_input_dims, n_output_dims, n_hidden_layers, n_neurons=64, seed=0, out_pad=None,
+                 loss_scale=128.0):
+        super().__init__()
+        assert n_neurons == 64, "FullyFusedMLP is built for 64-wide hidden layers"
+        self.n_input_dims = n_input_dims
+        self.n_output_dims = n_output_dims
+        self.loss_scale = loss_scale
+        self.dims = [_pad16(n_input_dims)] + [n_neurons] * n_hidden_layers + [out_pad or _pad16(n_output_dims)]
+        g = torch.Generator().manual_seed(seed)
+        parts = []
+        for fi, fo in zip(self.dims[:-1], self.dims[1:]):
+            s = math.sqrt(6.0 / (fi + fo))  # tcnn default: Xavier-uniform
+            parts.append((torch.rand(fo * fi, generator=g) * 2 - 1) * s)
+        self.params = nn.Parameter(torch.cat(parts))
+
+    def forward(self, x):
+        return _MlpFn.apply(x, self.params, self)
+
+
+class _DensityFn(torch.autograd.Function):
+    """density(x) for free-standing points: encode + sigma MLP + trunc_exp in one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, xyz, enc_params, sigma_params, net):
+        xyz = xyz.detach().float().contiguous()
+        s = xyz.shape[0]
+        dev = xyz.device
+        need = torch.is_grad_enabled() and (enc_params.requires_grad or sigma_params.requires_grad)
+        sigma = torch.empty(s, dtype=torch.float32, device=dev)
+        h = torch.empty(s, 16, dtype=torch.float16, device=dev)
+        enc = torch.empty(s, 32, dtype=torch.float16, device=dev) if need else None
+        hid = torch.empty(s, 64, dtype=torch.float16, device=dev) if need else None
+        ops.density_fwd(net.encoder.grid, net.encoder.half_params(), net.sigma_net.half_params(), net.bound,
+                        xyz=xyz, sigma=sigma, h=h, enc=enc, hid=hid)
+        ctx.net = net
+        if need:
+            ctx.save_for_backward(xyz, h, enc, hid)
+        geo = h[:, 1:]
+        return sigma, geo
+
+    @staticmethod
+    def backward(ctx, d_sigma, d_geo):
+        net = ctx.net
+        xyz, h, enc, hid = ctx.saved_tensors
+        s = xyz.shape[0]
+        dev = xyz.device
+        scale = net.loss_scale
+        dh = torch.zeros(s, 16, dtype=torch.float16, device=dev)
+        use_geo = None
+        if d_geo is not None:
+            dh[:, 1:] = (d_geo.float() * scale).half()
+            use_geo = torch.ones(s, dtype=torch.uint8, device=dev)
+        g_table = torch.zeros_like(net.encoder.params)
+        g_sigma = torch.zeros_like(net.sigma_net.params)
+        ops.density_bwd(net.encoder.grid, net.sigma_net.half_params(), net.bound, xyz=xyz, h=h, enc=enc, hid=hid,
+                        d_sigma=None if d_sigma is None else d_sigma.float().contiguous(), dh=dh, use_geo=use_geo,
+                        loss_scale=scale, grad_table=g_table, grad_w_sigma=g_sigma)
+        return None, g_table, g_sigma, None
+
+
+class _FusedRender(torch.autograd.Function):
+    """The whole of SemanticNeRFRenderer.run() (renderer_semantics.py:123-299) with the network heads inlined."""
+
+    @staticmethod
+    def forward(ctx, enc_params, sigma_params, color_params, sem_params, rays_o, rays_d, dnorm, net, cfg):
+        dev = rays_o.device
+        n = rays_o.shape[0]
+        tc, tf = cfg["num_steps"], cfg["upsample_steps"]
+        t = tc + tf
+        c = net.num_semantic_classes
+        aabb = cfg["aabb"]
+        need = torch.is_grad_enabled() and any(
+            p.requires_grad for p in (enc_params, sigma_params, color_params, sem_params))
+        grid = net.encoder.grid
+        table_h = net.encoder.half_params()
+        w_sig = net.sigma_net.half_params()
+        w_col = net.color_net.half_params()
+        w_sem = net.semantics_net.half_params()
+        f32 = dict(dtype=torch.float32, device=dev)
+        f16 = dict(dtype=torch.float16, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+
+        nears, fars = ops.near_far_from_aabb(rays_o, rays_d, aabb)
+        z_cat = torch.empty(n, t, **f32)
+        lin = torch.linspace(0.0, 1.0, tc, device=dev)
+        ops.sample_coarse(nears, fars, lin, z_cat, tc, perturb=cfg["perturb"], t_rand=cfg["t_rand"],
+                          seed=cfg["seed"], ray_base=cfg["ray_base"])
+        sigma = torch.empty(n, t, **f32)
+        h = torch.empty(n, t, 16, **f16)
+        enc = torch.empty(n, t, 32, **f16) if need else None
+        hid = torch.empty(n, t, 64, **f16) if need else None
+        common = dict(rays_o=rays_o, rays_d=rays_d, aabb=aabb, z_cat=z_cat, sigma=sigma, h=h, enc=enc, hid=hid)
+        ops.density_fwd(grid, table_h, w_sig, net.bound, k0=0, k1=tc, **common)
+        order = None
+        if tf > 0:
+            order = torch.empty(n, t, **i32)
+            ops.resample_merge(sigma, z_cat, order, tc, tf, net.density_scale, u=cfg["u"], seed=cfg["seed"],
+                               ray_base=cfg["ray_base"])
+            ops.density_fwd(grid, table_h, w_sig, net.bound, k0=tc, k1=t, **common)
+
+        w_sorted = torch.empty(n, t, **f32)
+        depth = torch.empty(n, **f32)
+        ray_count = torch.empty(n, **i32)
+        use_geo = torch.empty(n, t, dtype=torch.uint8, device=dev)
+        ops.weights_fwd(z_cat, sigma, order, dnorm, net.density_scale, w_sorted, depth, ray_count, use_geo)
+        ray_off = torch.empty(n + 1, **i32)
+        ops.scan_counts(ray_count, ray_off)
+        k_max = n * t  # worst case; the kernels read the true K from ray_off[n] on the device (no host sync)
+        sel = torch.empty(k_max, **i32)
+        w_sel = torch.empty(k_max, **f32)
+        z_sel = torch.empty(k_max, **f32)
+        ops.compact_masked(w_sorted, z_cat, order, ray_off, sel, w_sel, z_sel)
+
+        rgb = torch.empty(k_max, 3, **f32)
+        logits = torch.empty(k_max, ops.MAX_CLASSES, **f16)
+        hc1 = torch.empty(k_max, 64, **f16) if need else None
+        hc2 = torch.empty(k_max, 64, **f16) if need else None
+        hs = torch.empty(k_max, 64, **f16) if need else None
+        ops.heads_fwd(sel, ray_off, n, t, k_max, rays_d, h, w_col, w_sem, c, rgb, logits, hc1, hc2, hs)
+        image = torch.empty(n, 3, **f32)
+        semantics = torch.empty(n, c, **f32)
+        ops.composite_fwd(ray_off, w_sel, rgb, logits, n, c, image, semantics)
+
+        if need:
+            ctx.net = net
+            ctx.shape = (n, tc, tf, c, k_max)
+            ctx.aabb = aabb
+            ctx.order = order
+            ctx.save_for_backward(rays_o, rays_d, dnorm, z_cat, sigma, h, enc, hid, w_sorted, use_geo, ray_off, sel,
+                                  w_sel, z_sel, rgb, logits, hc1, hc2, hs)
+        return depth, image, semantics
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_depth, g_image, g_sem):
+        net = ctx.net
+        n, tc, tf, c, k_max = ctx.shape
+        t = tc + tf
+        (rays_o, rays_d, dnorm, z_cat, sigma, h, enc, hid, w_sorted, use_geo, ray_off, sel, w_sel, z_sel, rgb,
+         logits, hc1, hc2, hs) = ctx.saved_tensors
+        order = ctx.order
+        dev = rays_o.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        scale = float(net.loss_scale)
+        w_sig = net.sigma_net.half_params()
+        w_col = net.color_net.half_params()
+        w_sem = net.semantics_net.half_params()
+
+        d_rgb = torch.empty(k_max, 3, **f32)
+        d_logits = torch.empty(k_max, ops.MAX_CLASSES, **f32)
+        d_w_sel = torch.empty(k_max, **f32)
+        ops.composite_bwd(ray_off, sel, w_sel, z_sel, rgb, logits, g_image.float().contiguous(),
+                          g_depth.float().contiguous(), g_sem.float().contiguous(), dnorm, n, c, d_rgb, d_logits,
+                          d_w_sel)
+        dh = torch.empty(n, t, 16, dtype=torch.float16, device=dev)
+        g_col = torch.zeros(ops.COLOR_PARAMS, **f32)
+        g_semw = torch.zeros(ops.SEM_PARAMS, **f32)
+        ops.heads_bwd(sel, ray_off, n, t, k_max, rays_d, h, w_col, w_sem, c, rgb, hc1, hc2, hs, d_rgb, d_logits, scale,
+                      dh, g_col, g_semw)
+        d_sigma = torch.empty(n, t, **f32)
+        ops.weights_bwd(z_cat, sigma, order, w_sorted, ray_off, d_w_sel, net.density_scale, d_sigma)
+        g_table = torch.zeros(net.encoder.params.numel(), **f32)
+        g_sig = torch.zeros(ops.SIGMA_PARAMS, **f32)
+        ops.density_bwd(net.encoder.grid, w_sig, net.bound, rays_o=rays_o, rays_d=rays_d, aabb=ctx.aabb, z_cat=z_cat,
+                        k0=0, k1=t, h=h, enc=enc, hid=hid, d_sigma=d_sigma, dh=dh, use_geo=use_geo, loss_scale=scale,
+                        grad_table=g_table, grad_w_sigma=g_sig)
+        return g_table, g_sig, g_col, g_semw, None, None, None, None, None
+
+
+class SemanticNeRFNetwork(SemanticNeRFRenderer):
+
+    def __init__(self,
+                 encoding="HashGrid",
+                 encoding_dir="SphericalHarmonics",
+                 num_layers=2,
+                 hidden_dim=64,
+                 geo_feat_dim=15,
+                 num_layers_color=3,
+                 hidden_dim_color=64,
+                 num_layers_semantics=2,
+                 hidden_dim_semantics=64,
+                 bound=1,
+                 num_semantic_classes=41,
+                 **kwargs):
+        super().__init__(bound, **kwargs, num_semantic_classes=num_semantic_classes)
+        if (num_layers, hidden_dim, geo_feat_dim, num_layers_color, hidden_dim_color, num_layers_semantics,
+                hidden_dim_semantics) != (2, 64, 15, 3, 64, 2, 64):
+            raise NotImplementedError(
+                "the fused kernels are built for the reference architecture: sigma 32-64-16, colour 32-64-64-3, "
+                "semantics 16-64-C (network_tcnn_semantics.py:12-24 defaults)")
+        if not 1 <= num_semantic_classes <= ops.MAX_CLASSES:
+            raise NotImplementedError(f"num_semantic_classes must be in [1, {ops.MAX_CLASSES}]")
+
+        self.num_layers = num_layers
+        self.hidden_dim = hidden_dim
+        self.geo_feat_dim = geo_feat_dim
+        self.loss_scale = 128.0  # fp16 backward scale inside the kernels (tcnn's default for fp16)
+
+        self.encoder = HashGridEncoding(bound, seed=1337, loss_scale=self.loss_scale)
+        self.sigma_net = FusedMLP(32, 1 + geo_feat_dim, num_layers - 1, hidden_dim, seed=1338)
+
+        self.num_layers_color = num_layers_color
+        self.hidden_dim_color = hidden_dim_color
+        self.encoder_dir = SHEncoding()
+        self.in_dim_color = self.encoder_dir.n_output_dims + self.geo_feat_dim
+        self.color_net = FusedMLP(self.in_dim_color, 3, num_layers_color - 1, hidden_dim_color, seed=1339)
+
+        self.num_layers_semantics = num_layers_semantics
+        self.hidden_dim_semantics = hidden_dim_semantics
+        self.num_semantic_classes = num_semantic_classes
+        self.in_dim_semantics = self.geo_feat_dim
+        self.semantics_net = FusedMLP(self.in_dim_semantics, num_semantic_classes, num_layers_semantics - 1,
+                                      hidden_dim_semantics, seed=1340, out_pad=ops.MAX_CLASSES)
+
+    # ------------------------------------------------------------------ module-level API of the reference
+    def forward(self, x, d):
+        # x: [N, 3] in [-bound, bound]; d: [N, 3] normalised
+        dens = self.density(x)
+        sigma, geo_feat = dens["sigma"], dens["geo_feat"]
+        d = (d + 1) / 2
+        d = self.encoder_dir(d)
+        h = torch.cat([d, geo_feat], dim=-1)
+        h = self.color_net(h)
+        color = torch.sigmoid(h)
+        semantics = self.semantics_net(geo_feat)
+        semantics = F.softmax(semantics.float(), dim=-1)
+        return sigma, color, semantics
+
+    def density(self, x):
+        sigma, geo_feat = _DensityFn.apply(x, self.encoder.params, self.sigma_net.params, self)
+        return {"sigma": sigma, "geo_feat": geo_feat}
+
+    def color(self, x, d, mask=None, geo_feat=None, **kwargs):
+        # masked evaluation, network_tcnn_semantics.py:147-178
+        if mask is not None:
+            rgbs = torch.zeros(mask.shape[0], 3, dtype=torch.float32, device=x.device)
+            if not mask.any():
+                return rgbs
+            d = d[mask]
+            geo_feat = geo_feat[mask]
+        d = (d + 1) / 2
+        d = self.encoder_dir(d)
+        h = torch.cat([d, geo_feat.to(d.dtype)], dim=-1)
+        h = self.color_net(h)
+        h = torch.sigmoid(h)
+        if mask is not None:
+            rgbs[mask] = h.to(rgbs.dtype)
+        else:
+            rgbs = h
+        return rgbs
+
+    def semantics(self, x, d, mask=None, geo_feat=None, **kwargs):
+        # masked evaluation + softmax, network_tcnn_semantics.py:180-207
+        if mask is not None:
+            semantics = torch.zeros(mask.shape[0], self.num_semantic_classes, dtype=torch.float32, device=x.device)
+            if not mask.any():
+                return semantics
+            geo_feat = geo_feat[mask]
+        h = self.semantics_net(geo_feat)
+        if mask is not None:
+            semantics[mask] = F.softmax(h.to(semantics.dtype), dim=-1)
+        else:
+            semantics = F.softmax(h.float(), dim=-1)
+        return semantics
+
+    # ------------------------------------------------------------------ fused rendering
+    def run(self, rays_o, rays_d, direction_norms, num_steps=256, upsample_steps=256, bg_color=None,
+            perturb=False, epoch=None, **kwargs):
+        if kwargs.get("generic", False):
+            kwargs.pop("generic")
+            return super().run(rays_o, rays_d, direction_norms, num_steps=num_steps,
+                               upsample_steps=upsample_steps, bg_color=bg_color, perturb=perturb, epoch=epoch,
+                               **kwargs)
+        prefix = rays_o.shape[:-1]
+        o = rays_o.contiguous().view(-1, 3).float().contiguous()
+        d = rays_d.contiguous().view(-1, 3).float().contiguous()
+        dn = direction_norms.contiguous().view(-1).float().contiguous()
+        t_rand, u = kwargs.get("t_rand"), kwargs.get("u")
+        cfg = dict(
+            num_steps=int(num_steps), upsample_steps=int(upsample_steps), perturb=bool(perturb),
+            t_rand=None if t_rand is None else t_rand.float().contiguous(),
+            u=None if u is None else u.float().contiguous(),
+            seed=kwargs.get("seed", None) or self._next_seed(), ray_base=int(kwargs.get("ray_base", 0)),
+            aabb=self.aabb_train if self.training else self.aabb_infer)
+        depth, image, semantics = _FusedRender.apply(self.encoder.params, self.sigma_net.params,
+                                                     self.color_net.params, self.semantics_net.params, o, d, dn,
+                                                     self, cfg)
+        return {
+            "depth": depth.view(*prefix),
+            "image": image.view(*prefix, 3),
+            "semantics": semantics.view(*prefix, self.num_semantic_classes),
+        }

@@ -1,0 +1,289 @@
+"""SemanticNeRFRenderer -- host-side mirror of nr4seg/nerf/renderer_semantics.py on libucsa_nerf.so.
+
+Same constructor, buffers, ``run`` / ``render`` signatures, return dict and error behaviour as the reference
+(renderer_semantics.py:61-358).  ``run`` here is the *generic* form: it calls the subclass' ``density`` /
+``color`` / ``semantics`` exactly where the reference does (so any subclass written against the reference
+keeps working) and executes the renderer's own arithmetic -- AABB test, sample placement, importance
+resampling + merge, weights / masks and the three composites, forward and backward -- in CUDA kernels.
+``SemanticNeRFNetwork`` overrides it with the fully fused pipeline.
+
+Two documented liberties, both opt-in through ``**kwargs`` the reference signature already accepts:
+``t_rand=[N,num_steps]`` and ``u=[N,upsample_steps]`` inject the uniform numbers the reference draws with
+``torch.rand`` (renderer_semantics.py:166 and :28; the latter on the *CPU* generator even for inference).
+Without them a counter-based generator keyed by (module seed, call counter, ray index, sample index) is used.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+def sample_pdf(bins, weights, n_samples, det=False):
+    """Compatibility export of renderer_semantics.py:10-46 (inverse-CDF sampling) in torch ops.
+
+    ``run`` does not call it -- resampling is fused into ``ucsa_resample_merge`` -- it is kept because the
+    reference module exports it."""
+    weights = weights + 1e-5
+    pdf = weights / torch.sum(weights, -1, keepdim=True)
+    cdf = torch.cat([torch.zeros_like(pdf[..., :1]), torch.cumsum(pdf, -1)], -1)
+    if det:
+        u = torch.linspace(0.5 / n_samples, 1.0 - 0.5 / n_samples, steps=n_samples, device=weights.device)
+        u = u.expand(list(cdf.shape[:-1]) + [n_samples])
+    else:
+        u = torch.rand(list(cdf.shape[:-1]) + [n_samples]).to(weights.device)
+    u = u.contiguous()
+    hi = torch.searchsorted(cdf, u, right=True)
+    lo = (hi - 1).clamp_min(0)
+    hi = hi.clamp_max(cdf.shape[-1] - 1)
+    c_lo, c_hi = torch.gather(cdf, -1, lo), torch.gather(cdf, -1, hi)
+    b_lo, b_hi = torch.gather(bins, -1, lo), torch.gather(bins, -1, hi)
+    span = c_hi - c_lo
+    span = torch.where(span < 1e-5, torch.ones_like(span), span)
+    return b_lo + (u - c_lo) / span * (b_hi - b_lo)
+
+
+class _CompositeDense(torch.autograd.Function):
+    """weights + masks + depth / image / semantics composites (renderer_semantics.py:238-285)."""
+
+    @staticmethod
+    def forward(ctx, sigma, z, rgb, prob, direction_norms, density_scale):
+        sigma = sigma.detach().float().contiguous()
+        z = z.detach().float().contiguous()
+        rgb = rgb.detach().float().contiguous()
+        prob = prob.detach().float().contiguous()
+        dn = direction_norms.detach().float().contiguous()
+        n, t = sigma.shape
+        c = prob.shape[-1]
+        dev = sigma.device
+        weights = torch.empty(n, t, dtype=torch.float32, device=dev)
+        depth = torch.empty(n, dtype=torch.float32, device=dev)
+        image = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        semantics = torch.empty(n, c, dtype=torch.float32, device=dev)
+        ops.composite_dense_fwd(sigma, z, rgb, prob, dn, density_scale, weights, depth, image, semantics)
+        ctx.save_for_backward(sigma, z, rgb, weights, dn)
+        ctx.density_scale = density_scale
+        ctx.n_classes = c
+        return depth, image, semantics
+
+    @staticmethod
+    def backward(ctx, g_depth, g_image, g_semantics):
+        sigma, z, rgb, weights, dn = ctx.saved_tensors
+        n, t = sigma.shape
+        dev = sigma.device
+        d_sigma = torch.empty_like(sigma)
+        d_rgb = torch.empty_like(rgb)
+        d_prob = torch.empty(n, t, ctx.n_classes, dtype=torch.float32, device=dev)
+        ops.composite_dense_bwd(sigma, z, rgb, weights, dn, g_depth.float().contiguous(),
+                                g_image.float().contiguous(), g_semantics.float().contiguous(),
+                                ctx.density_scale, d_sigma, d_rgb, d_prob)
+        return d_sigma, None, d_rgb, d_prob, None, None
+
+
+composite_dense = _CompositeDense.apply
+
+
+class SemanticNeRFRenderer(nn.Module):
+
+    def __init__(
+        self,
+        bound=1,
+        cuda_ray=False,
+        density_scale=1,
+        num_semantic_classes=41,
+    ):
+        super().__init__()
+
+        self.epoch = 1
+        self.weights = np.zeros([0])
+        self.weights_sum = np.zeros([0])
+
+        self.bound = bound
+        self.cascade = 1 + math.ceil(math.log2(bound))
+        self.density_scale = density_scale
+        self.num_semantic_classes = num_semantic_classes
+
+        # (xmin, ymin, zmin, xmax, ymax, zmax); only used to place samples (renderer_semantics.py:81-87)
+        aabb_train = torch.FloatTensor([-bound, -bound, -bound, bound, bound, bound])
+        aabb_infer = aabb_train.clone()
+        self.register_buffer("aabb_train", aabb_train)
+        self.register_buffer("aabb_infer", aabb_infer)
+
+        # extra state of the occupancy-grid path (renderer_semantics.py:89-103)
+        self.cuda_ray = cuda_ray
+        if cuda_ray:
+            density_grid = torch.zeros([self.cascade] + [128] * 3)  # [CAS, H, H, H]
+            self.register_buffer("density_grid", density_grid)
+            self.mean_density = 0
+            self.iter_density = 0
+            step_counter = torch.zeros(16, 2, dtype=torch.int32)
+            self.register_buffer("step_counter", step_counter)
+            self.mean_count = 0
+            self.local_step = 0
+
+        # counter-based random numbers (see module docstring)
+        self.rng_seed = 0x5EED
+        self._rng_calls = 0
+
+    def forward(self, x, d):
+        raise NotImplementedError()
+
+    def density(self, x):
+        raise NotImplementedError()
+
+    def reset_extra_state(self):
+        if not self.cuda_ray:
+            return
+        self.density_grid.zero_()
+        self.mean_density = 0
+        self.iter_density = 0
+        self.step_counter.zero_()
+        self.mean_count = 0
+        self.local_step = 0
+
+    def _next_seed(self):
+        self._rng_calls += 1
+        return (self.rng_seed << 20) ^ self._rng_calls
+
+    def run(self,
+            rays_o,
+            rays_d,
+            direction_norms,
+            num_steps=256,
+            upsample_steps=256,
+            bg_color=None,
+            perturb=False,
+            epoch=None,
+            **kwargs):
+        # rays_o, rays_d: [B, N, 3]; direction_norms: [B, N, 1]; returns image [B,N,3], depth [B,N], semantics [B,N,C]
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3).float()
+        rays_d = rays_d.contiguous().view(-1, 3).float()
+        direction_norms = direction_norms.contiguous().view(-1).float()
+        n_rays = rays_o.shape[0]
+        device = rays_o.device
+        aabb = self.aabb_train if self.training else self.aabb_infer
+        seed = kwargs.get("seed", None) or self._next_seed()
+        ray_base = int(kwargs.get("ray_base", 0))
+        t_rand, u = kwargs.get("t_rand"), kwargs.get("u")
+
+        nears, fars = ops.near_far_from_aabb(rays_o, rays_d, aabb)
+        t_total = num_steps + upsample_steps
+        z_cat = torch.empty(n_rays, t_total, dtype=torch.float32, device=device)
+        lin = torch.linspace(0.0, 1.0, num_steps, device=device)
+        ops.sample_coarse(nears, fars, lin, z_cat, num_steps, perturb=perturb,
+                          t_rand=None if t_rand is None else t_rand.float().contiguous(), seed=seed,
+                          ray_base=ray_base)
+
+        def positions(z):
+            p = rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * z.unsqueeze(-1)
+            return torch.min(torch.max(p, aabb[:3]), aabb[3:])
+
+        z_vals = z_cat[:, :num_steps]
+        xyzs = positions(z_vals)
+        density_outputs = self.density(xyzs.reshape(-1, 3))
+        for k, v in density_outputs.items():
+            density_outputs[k] = v.view(n_rays, num_steps, -1)
+
+        if upsample_steps > 0:
+            with torch.no_grad():
+                sigma_cat = torch.zeros(n_rays, t_total, dtype=torch.float32, device=device)
+                sigma_cat[:, :num_steps] = density_outputs["sigma"].squeeze(-1).float()
+                order = torch.empty(n_rays, t_total, dtype=torch.int32, device=device)
+                ops.resample_merge(sigma_cat, z_cat, order, num_steps, upsample_steps, self.density_scale,
+                                   u=None if u is None else u.float().contiguous(), seed=seed, ray_base=ray_base)
+                new_xyzs = positions(z_cat[:, num_steps:])
+            new_density_outputs = self.density(new_xyzs.reshape(-1, 3))
+            for k, v in new_density_outputs.items():
+                new_density_outputs[k] = v.view(n_rays, upsample_steps, -1)
+            z_index = order.long()
+            z_vals = torch.gather(z_cat, 1, z_index)
+            xyzs = torch.cat([xyzs, new_xyzs], dim=1)
+            xyzs = torch.gather(xyzs, 1, z_index.unsqueeze(-1).expand_as(xyzs))
+            for k in density_outputs:
+                tmp = torch.cat([density_outputs[k], new_density_outputs[k]], dim=1)
+                density_outputs[k] = torch.gather(tmp, 1, z_index.unsqueeze(-1).expand_as(tmp))
+
+        sigma = density_outputs["sigma"].squeeze(-1).float()
+        with torch.no_grad():
+            w_tmp = torch.empty_like(sigma)
+            depth_tmp = torch.empty(n_rays, dtype=torch.float32, device=device)
+            count_tmp = torch.empty(n_rays, dtype=torch.int32, device=device)
+            mask_u8 = torch.empty(n_rays, t_total, dtype=torch.uint8, device=device)
+            ops.weights_fwd(z_vals.contiguous(), sigma.detach().contiguous(), None, direction_norms,
+                            self.density_scale, w_tmp, depth_tmp, count_tmp, mask_u8)
+            mask = mask_u8.bool()  # weights > 1e-4 (renderer_semantics.py:249-250)
+
+        dirs = rays_d.view(-1, 1, 3).expand_as(xyzs)
+        for k, v in density_outputs.items():
+            density_outputs[k] = v.reshape(-1, v.shape[-1])
+        rgbs = self.color(xyzs.reshape(-1, 3), dirs.reshape(-1, 3), mask=mask.reshape(-1), **density_outputs)
+        rgbs = rgbs.view(n_rays, -1, 3)
+        local_semantics = self.semantics(xyzs.reshape(-1, 3), dirs.reshape(-1, 3), mask=mask.reshape(-1),
+                                         **density_outputs)
+        local_semantics = local_semantics.view(n_rays, -1, self.num_semantic_classes)
+
+        depth, image, semantics = composite_dense(sigma, z_vals, rgbs, local_semantics, direction_norms,
+                                                  float(self.density_scale))
+        return {
+            "depth": depth.view(*prefix),
+            "image": image.view(*prefix, 3),
+            "semantics": semantics.view(*prefix, self.num_semantic_classes),
+        }
+
+    def render(self,
+               rays_o,
+               rays_d,
+               direction_norms,
+               staged=False,
+               max_ray_batch=4096,
+               bg_color=None,
+               perturb=False,
+               epoch=None,
+               **kwargs):
+        # rays_o, rays_d: [B, N, 3]; direction_norms: [B, N, 1]
+        _run = self.run
+        B, N = rays_o.shape[:2]
+        device = rays_o.device
+
+        # never stage when cuda_ray (renderer_semantics.py:320-321)
+        if staged and not self.cuda_ray:
+            depth = torch.empty((B, N), device=device)
+            image = torch.empty((B, N, 3), device=device)
+            semantics = torch.empty((B, N, self.num_semantic_classes), device=device)
+            t_rand, u = kwargs.pop("t_rand", None), kwargs.pop("u", None)
+            seed = kwargs.pop("seed", None) or self._next_seed()
+            for b in range(B):
+                head = 0
+                while head < N:
+                    tail = min(head + max_ray_batch, N)
+                    sl = slice(b * N + head, b * N + tail)
+                    results_ = _run(rays_o[b:b + 1, head:tail],
+                                    rays_d[b:b + 1, head:tail],
+                                    direction_norms=direction_norms[b:b + 1, head:tail],
+                                    bg_color=bg_color,
+                                    perturb=perturb,
+                                    epoch=epoch,
+                                    t_rand=None if t_rand is None else t_rand[sl],
+                                    u=None if u is None else u[sl],
+                                    seed=seed,
+                                    ray_base=b * N + head,
+                                    **kwargs)
+                    depth[b:b + 1, head:tail] = results_["depth"]
+                    image[b:b + 1, head:tail] = results_["image"]
+                    semantics[b:b + 1, head:tail] = results_["semantics"]
+                    head += max_ray_batch
+            results = {"depth": depth, "image": image, "semantics": semantics}
+        else:
+            results = _run(rays_o,
+                           rays_d,
+                           direction_norms=direction_norms,
+                           bg_color=bg_color,
+                           perturb=perturb,
+                           epoch=epoch,
+                           **kwargs)
+        return results

@@ -1,0 +1,242 @@
+"""Tensor-level wrappers over the C ABI (include/ucsa_nerf.h).
+
+Each function checks device / dtype / contiguity, passes raw device pointers plus the current CUDA stream, and
+raises ``UcsaError`` on a non-zero status.  Nothing here computes anything on the host.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+
+from ._lib import GridDesc, UcsaError, check, lib
+
+MAX_CLASSES = 48
+SIGMA_PARAMS = 3072
+COLOR_PARAMS = 7168
+SEM_PARAMS = 16 * 64 + MAX_CLASSES * 64
+
+
+def _ptr(t, dtype=None, name="tensor"):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise UcsaError(f"{name} must be a CUDA tensor (the rendering path has no CPU fallback)")
+    if not t.is_contiguous():
+        raise UcsaError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise UcsaError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def per_level_scale(bound: float) -> float:
+    # network_tcnn_semantics.py:34
+    return float(2.0 ** (math.log2(2048 * bound / 16) / (16 - 1)))
+
+
+def make_grid_desc(bound: float, base_resolution: int = 16, log2_hashmap_size: int = 19) -> GridDesc:
+    g = GridDesc()
+    check(lib().ucsa_grid_desc_init(per_level_scale(bound), base_resolution, log2_hashmap_size, ctypes.byref(g)),
+          "grid_desc_init")
+    return g
+
+
+def near_far_from_aabb(rays_o, rays_d, aabb, min_near=0.2):
+    n = rays_o.shape[0]
+    nears = torch.empty(n, dtype=torch.float32, device=rays_o.device)
+    fars = torch.empty_like(nears)
+    check(lib().ucsa_near_far_from_aabb(_ptr(rays_o, torch.float32, "rays_o"), _ptr(rays_d, torch.float32, "rays_d"),
+                                        _ptr(aabb, torch.float32, "aabb"), n, float(min_near), _ptr(nears),
+                                        _ptr(fars), _stream()), "near_far_from_aabb")
+    return nears, fars
+
+
+def sample_coarse(nears, fars, lin, z_cat, tc, *, perturb, t_rand=None, seed=0, ray_base=0):
+    n, t = z_cat.shape
+    check(lib().ucsa_sample_coarse(_ptr(nears, torch.float32), _ptr(fars, torch.float32), _ptr(lin, torch.float32),
+                                   _ptr(t_rand, torch.float32, "t_rand"), seed, ray_base, int(bool(perturb)), n, tc, t,
+                                   _ptr(z_cat, torch.float32), _stream()), "sample_coarse")
+
+
+def density_fwd(grid, table_h, w_sigma_h, bound, *, xyz=None, rays_o=None, rays_d=None, aabb=None, z_cat=None,
+                k0=0, k1=1, sigma, h, enc=None, hid=None):
+    if xyz is not None:
+        n, t = xyz.shape[0], 1
+    else:
+        n, t = z_cat.shape
+    check(lib().ucsa_density_fwd(_ptr(xyz, torch.float32, "xyz"), _ptr(rays_o, torch.float32, "rays_o"),
+                                 _ptr(rays_d, torch.float32, "rays_d"), _ptr(aabb, torch.float32, "aabb"),
+                                 _ptr(z_cat, torch.float32, "z_cat"), n, t, k0, k1, float(bound),
+                                 _ptr(table_h, torch.float16, "table_h"), ctypes.byref(grid),
+                                 _ptr(w_sigma_h, torch.float16, "w_sigma_h"), _ptr(sigma, torch.float32, "sigma"),
+                                 _ptr(h, torch.float16, "h"), _ptr(enc, torch.float16, "enc"),
+                                 _ptr(hid, torch.float16, "hid"), _stream()), "density_fwd")
+
+
+def density_bwd(grid, w_sigma_h, bound, *, xyz=None, rays_o=None, rays_d=None, aabb=None, z_cat=None, k0=0, k1=1,
+                h, enc, hid, d_sigma, dh, use_geo, loss_scale, grad_table, grad_w_sigma):
+    if xyz is not None:
+        n, t = xyz.shape[0], 1
+    else:
+        n, t = z_cat.shape
+    check(lib().ucsa_density_bwd(_ptr(xyz, torch.float32, "xyz"), _ptr(rays_o, torch.float32), _ptr(rays_d, torch.float32),
+                                 _ptr(aabb, torch.float32), _ptr(z_cat, torch.float32), n, t, k0, k1, float(bound),
+                                 ctypes.byref(grid), _ptr(w_sigma_h, torch.float16), _ptr(h, torch.float16),
+                                 _ptr(enc, torch.float16), _ptr(hid, torch.float16), _ptr(d_sigma, torch.float32, "d_sigma"),
+                                 _ptr(dh, torch.float16, "dh"), _ptr(use_geo, torch.uint8, "use_geo"),
+                                 float(loss_scale), _ptr(grad_table, torch.float32, "grad_table"),
+                                 _ptr(grad_w_sigma, torch.float32, "grad_w_sigma"), _stream()), "density_bwd")
+
+
+def resample_merge(sigma, z_cat, order, tc, tf, density_scale, *, u=None, seed=0, ray_base=0):
+    n = z_cat.shape[0]
+    check(lib().ucsa_resample_merge(_ptr(sigma, torch.float32), _ptr(z_cat, torch.float32), _ptr(u, torch.float32, "u"),
+                                    seed, ray_base, n, tc, tf, float(density_scale), _ptr(order, torch.int32, "order"),
+                                    _stream()), "resample_merge")
+
+
+def weights_fwd(z_cat, sigma, order, direction_norms, density_scale, w_sorted, depth, ray_count, use_geo):
+    n, t = z_cat.shape
+    check(lib().ucsa_weights_fwd(_ptr(z_cat, torch.float32), _ptr(sigma, torch.float32), _ptr(order, torch.int32),
+                                 _ptr(direction_norms, torch.float32), n, t, float(density_scale),
+                                 _ptr(w_sorted, torch.float32), _ptr(depth, torch.float32), _ptr(ray_count, torch.int32),
+                                 _ptr(use_geo, torch.uint8), _stream()), "weights_fwd")
+
+
+def scan_counts(ray_count, ray_off):
+    check(lib().ucsa_scan_counts(_ptr(ray_count, torch.int32), ray_count.shape[0], _ptr(ray_off, torch.int32),
+                                 _stream()), "scan_counts")
+
+
+def compact_masked(w_sorted, z_cat, order, ray_off, sel, w_sel, z_sel):
+    n, t = z_cat.shape
+    check(lib().ucsa_compact_masked(_ptr(w_sorted, torch.float32), _ptr(z_cat, torch.float32), _ptr(order, torch.int32),
+                                    _ptr(ray_off, torch.int32), n, t, _ptr(sel, torch.int32), _ptr(w_sel, torch.float32),
+                                    _ptr(z_sel, torch.float32), _stream()), "compact_masked")
+
+
+def heads_fwd(sel, ray_off, n_rays, t, k_max, rays_d, h, w_color_h, w_sem_h, n_classes, rgb, logits,
+              hc1=None, hc2=None, hs=None):
+    check(lib().ucsa_heads_fwd(_ptr(sel, torch.int32), _ptr(ray_off, torch.int32), n_rays, t, k_max,
+                               _ptr(rays_d, torch.float32), _ptr(h, torch.float16), _ptr(w_color_h, torch.float16),
+                               _ptr(w_sem_h, torch.float16), n_classes, _ptr(rgb, torch.float32),
+                               _ptr(logits, torch.float16), _ptr(hc1, torch.float16), _ptr(hc2, torch.float16),
+                               _ptr(hs, torch.float16), _stream()), "heads_fwd")
+
+
+def heads_bwd(sel, ray_off, n_rays, t, k_max, rays_d, h, w_color_h, w_sem_h, n_classes, rgb, hc1, hc2, hs, d_rgb,
+              d_logits, loss_scale, dh, grad_w_color, grad_w_sem):
+    check(lib().ucsa_heads_bwd(_ptr(sel, torch.int32), _ptr(ray_off, torch.int32), n_rays, t, k_max,
+                               _ptr(rays_d, torch.float32), _ptr(h, torch.float16), _ptr(w_color_h, torch.float16),
+                               _ptr(w_sem_h, torch.float16), n_classes, _ptr(rgb, torch.float32),
+                               _ptr(hc1, torch.float16), _ptr(hc2, torch.float16), _ptr(hs, torch.float16),
+                               _ptr(d_rgb, torch.float32), _ptr(d_logits, torch.float32), float(loss_scale),
+                               _ptr(dh, torch.float16), _ptr(grad_w_color, torch.float32),
+                               _ptr(grad_w_sem, torch.float32), _stream()), "heads_bwd")
+
+
+def composite_fwd(ray_off, w_sel, rgb, logits, n_rays, n_classes, image, semantics):
+    check(lib().ucsa_composite_fwd(_ptr(ray_off, torch.int32), _ptr(w_sel, torch.float32), _ptr(rgb, torch.float32),
+                                   _ptr(logits, torch.float16), n_rays, n_classes, _ptr(image, torch.float32),
+                                   _ptr(semantics, torch.float32), _stream()), "composite_fwd")
+
+
+def composite_bwd(ray_off, sel, w_sel, z_sel, rgb, logits, g_image, g_depth, g_semantics, direction_norms, n_rays,
+                  n_classes, d_rgb, d_logits, d_w_sel):
+    check(lib().ucsa_composite_bwd(_ptr(ray_off, torch.int32), _ptr(sel, torch.int32), _ptr(w_sel, torch.float32),
+                                   _ptr(z_sel, torch.float32), _ptr(rgb, torch.float32), _ptr(logits, torch.float16),
+                                   _ptr(g_image, torch.float32, "g_image"), _ptr(g_depth, torch.float32, "g_depth"),
+                                   _ptr(g_semantics, torch.float32, "g_semantics"),
+                                   _ptr(direction_norms, torch.float32), n_rays, n_classes,
+                                   _ptr(d_rgb, torch.float32), _ptr(d_logits, torch.float32),
+                                   _ptr(d_w_sel, torch.float32), _stream()), "composite_bwd")
+
+
+def weights_bwd(z_cat, sigma, order, w_sorted, ray_off, d_w_sel, density_scale, d_sigma):
+    n, t = z_cat.shape
+    check(lib().ucsa_weights_bwd(_ptr(z_cat, torch.float32), _ptr(sigma, torch.float32), _ptr(order, torch.int32),
+                                 _ptr(w_sorted, torch.float32), _ptr(ray_off, torch.int32), _ptr(d_w_sel, torch.float32),
+                                 n, t, float(density_scale), _ptr(d_sigma, torch.float32), _stream()), "weights_bwd")
+
+
+def composite_dense_fwd(sigma, z, rgb, prob, direction_norms, density_scale, weights, depth, image, semantics):
+    n, t = sigma.shape
+    c = prob.shape[-1]
+    check(lib().ucsa_composite_dense_fwd(_ptr(sigma, torch.float32, "sigma"), _ptr(z, torch.float32, "z"),
+                                         _ptr(rgb, torch.float32, "rgb"), _ptr(prob, torch.float32, "prob"),
+                                         _ptr(direction_norms, torch.float32, "direction_norms"), n, t, c,
+                                         float(density_scale), _ptr(weights, torch.float32), _ptr(depth, torch.float32),
+                                         _ptr(image, torch.float32), _ptr(semantics, torch.float32), _stream()),
+          "composite_dense_fwd")
+
+
+def composite_dense_bwd(sigma, z, rgb, weights, direction_norms, g_depth, g_image, g_semantics, density_scale,
+                        d_sigma, d_rgb, d_prob):
+    n, t = sigma.shape
+    c = g_semantics.shape[-1]
+    check(lib().ucsa_composite_dense_bwd(_ptr(sigma, torch.float32), _ptr(z, torch.float32), _ptr(rgb, torch.float32),
+                                         _ptr(weights, torch.float32), _ptr(direction_norms, torch.float32),
+                                         _ptr(g_depth, torch.float32, "g_depth"), _ptr(g_image, torch.float32, "g_image"),
+                                         _ptr(g_semantics, torch.float32, "g_semantics"), n, t, c,
+                                         float(density_scale), _ptr(d_sigma, torch.float32), _ptr(d_rgb, torch.float32),
+                                         _ptr(d_prob, torch.float32), _stream()), "composite_dense_bwd")
+
+
+def hashgrid_fwd(x01, table_h, grid, enc):
+    check(lib().ucsa_hashgrid_fwd(_ptr(x01, torch.float32, "x01"), x01.shape[0], _ptr(table_h, torch.float16),
+                                  ctypes.byref(grid), _ptr(enc, torch.float16), _stream()), "hashgrid_fwd")
+
+
+def hashgrid_bwd(x01, grid, d_enc, inv_loss_scale, grad_table):
+    check(lib().ucsa_hashgrid_bwd(_ptr(x01, torch.float32), x01.shape[0], ctypes.byref(grid),
+                                  _ptr(d_enc, torch.float16, "d_enc"), float(inv_loss_scale),
+                                  _ptr(grad_table, torch.float32), _stream()), "hashgrid_bwd")
+
+
+def hashgrid_indices(x01, grid):
+    idx = torch.empty(x01.shape[0], 16, 8, dtype=torch.int32, device=x01.device)
+    check(lib().ucsa_hashgrid_indices(_ptr(x01, torch.float32), x01.shape[0], ctypes.byref(grid), idx.data_ptr(),
+                                      _stream()), "hashgrid_indices")
+    return idx
+
+
+def sh4_fwd(d01, out):
+    check(lib().ucsa_sh4_fwd(_ptr(d01, torch.float32, "d01"), d01.shape[0], _ptr(out, torch.float16), _stream()),
+          "sh4_fwd")
+
+
+def _dims_array(dims):
+    return (ctypes.c_uint32 * len(dims))(*dims)
+
+
+def mlp_fwd(x_h, w_h, dims, y_h, acts_h=None):
+    arr = _dims_array(dims)
+    check(lib().ucsa_mlp_fwd(_ptr(x_h, torch.float16, "x"), x_h.shape[0], _ptr(w_h, torch.float16),
+                             ctypes.cast(arr, ctypes.c_void_p), len(dims) - 1, _ptr(y_h, torch.float16),
+                             _ptr(acts_h, torch.float16), _stream()), "mlp_fwd")
+
+
+def mlp_bwd(x_h, w_h, dims, acts_h, dy_h, inv_loss_scale, dx_h, grad_w):
+    arr = _dims_array(dims)
+    check(lib().ucsa_mlp_bwd(_ptr(x_h, torch.float16), x_h.shape[0], _ptr(w_h, torch.float16),
+                             ctypes.cast(arr, ctypes.c_void_p), len(dims) - 1, _ptr(acts_h, torch.float16),
+                             _ptr(dy_h, torch.float16, "dy"), float(inv_loss_scale), _ptr(dx_h, torch.float16),
+                             _ptr(grad_w, torch.float32), _stream()), "mlp_bwd")
+
+
+def cast_f32_to_f16(src, dst):
+    check(lib().ucsa_cast_f32_to_f16(_ptr(src, torch.float32, "src"), src.numel(), _ptr(dst, torch.float16, "dst"),
+                                     _stream()), "cast_f32_to_f16")
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, param_h, *, lr, beta1, beta2, eps, weight_decay, grad_scale_inv,
+              found_inf, step):
+    check(lib().ucsa_adam_step(_ptr(param, torch.float32), _ptr(grad, torch.float32), _ptr(exp_avg, torch.float32),
+                               _ptr(exp_avg_sq, torch.float32), _ptr(param_h, torch.float16), param.numel(), float(lr),
+                               float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale_inv),
+                               _ptr(found_inf, torch.float32), int(step), _stream()), "adam_step")
