@@ -123,7 +123,7 @@ class OracleHeads(torch.nn.Module):
         sh = spec.sh4_forward((d + 1) / 2)
         h = spec.mlp_forward(torch.cat([sh, geo_feat], dim=-1), self.color_net, self.dims_color,
                              16 + self.geo_feat_dim, 3)
-        return torch.sigmoid(h).half().float()  # fp16 sigmoid output under autocast
+        return spec._round_h(torch.sigmoid(h))  # fp16 sigmoid output under autocast
 
     # network_tcnn_semantics.py:147-178
     def color(self, x, d, mask=None, geo_feat=None, **_):

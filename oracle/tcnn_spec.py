@@ -123,9 +123,21 @@ def hash_indices(x01: np.ndarray, table) -> np.ndarray:
     return out
 
 
+class _RoundH(torch.autograd.Function):
+    """Round to fp16 and come back to fp32.  Straight-through: the gradient passes unchanged in fp32 (a plain
+    ``t.half().float()`` would round the *gradient* to fp16 at the cast, which is an artefact of the emulation)."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.half().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 def _round_h(t: torch.Tensor) -> torch.Tensor:
-    """Round to fp16 and come back to fp32; autograd treats it as identity."""
-    return t.half().float()
+    return _RoundH.apply(t)
 
 
 def hashgrid_forward(x01: torch.Tensor, params: torch.Tensor, table) -> torch.Tensor:

@@ -162,7 +162,7 @@ class _DensityFn(torch.autograd.Function):
         xyz = xyz.detach().float().contiguous()
         s = xyz.shape[0]
         dev = xyz.device
-        need = torch.is_grad_enabled() and (enc_params.requires_grad or sigma_params.requires_grad)
+        need = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]  # (grad mode is off inside forward)
         sigma = torch.empty(s, dtype=torch.float32, device=dev)
         h = torch.empty(s, 16, dtype=torch.float16, device=dev)
         enc = torch.empty(s, 32, dtype=torch.float16, device=dev) if need else None
@@ -206,8 +206,7 @@ class _FusedRender(torch.autograd.Function):
         t = tc + tf
         c = net.num_semantic_classes
         aabb = cfg["aabb"]
-        need = torch.is_grad_enabled() and any(
-            p.requires_grad for p in (enc_params, sigma_params, color_params, sem_params))
+        need = any(ctx.needs_input_grad[:4])  # (grad mode is off inside forward)
         grid = net.encoder.grid
         table_h = net.encoder.half_params()
         w_sig = net.sigma_net.half_params()
