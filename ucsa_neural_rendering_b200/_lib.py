@@ -77,6 +77,56 @@ def parse_header(path: str = HEADER):
 _lock = threading.Lock()
 _lib = None
 
+HOST_ONLY = {"ucsa_abi_version", "ucsa_last_error_string", "ucsa_grid_desc_init"}
+
+
+class LaunchStats:
+    """Counts kernel launches (every non-host entry point enqueues exactly one kernel) and, for the entry points
+    named in ``timed``, brackets each call with CUDA events on the current stream (used by bench.py only)."""
+
+    def __init__(self):
+        self.reset()
+        self.timed = set()
+
+    def reset(self):
+        self.launches = 0
+        self.by_name = {}
+        self.events = {}
+
+    def elapsed_ms(self, name):
+        """-> list of per-launch durations; call after a device synchronize"""
+        return [a.elapsed_time(b) for a, b in self.events.get(name, [])]
+
+
+stats = LaunchStats()
+
+
+class _Entry:
+    __slots__ = ("name", "fn", "is_launch")
+
+    def __init__(self, name, fn):
+        self.name, self.fn, self.is_launch = name, fn, name not in HOST_ONLY
+
+    def __call__(self, *args):
+        if not self.is_launch:
+            return self.fn(*args)
+        stats.launches += 1
+        stats.by_name[self.name] = stats.by_name.get(self.name, 0) + 1
+        if self.name in stats.timed:
+            import torch
+
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rc = self.fn(*args)
+            b.record()
+            stats.events.setdefault(self.name, []).append((a, b))
+            return rc
+        return self.fn(*args)
+
+
+class _Handle:
+    pass
+
 
 def lib():
     """The loaded library with typed entry points; raises if it is not built."""
@@ -90,14 +140,16 @@ def lib():
             raise UcsaError(
                 f"{LIB_PATH} is missing: build it with `python -m ucsa_neural_rendering_b200.build` "
                 "(there is no CPU or PyTorch fallback for the rendering path)")
-        handle = ctypes.CDLL(LIB_PATH)
+        cdll = ctypes.CDLL(LIB_PATH)
+        handle = _Handle()
         for name, (restype, argtypes, _) in parse_header().items():
             try:
-                fn = getattr(handle, name)
+                fn = getattr(cdll, name)
             except AttributeError as exc:
                 raise UcsaError(f"libucsa_nerf.so does not export {name}") from exc
             fn.restype = restype
             fn.argtypes = argtypes
+            setattr(handle, name, _Entry(name, fn))
         if handle.ucsa_abi_version() != 1:
             raise UcsaError("libucsa_nerf.so ABI version mismatch")
         _lib = handle

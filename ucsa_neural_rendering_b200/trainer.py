@@ -1,0 +1,93 @@
+"""NeRF training step of the reference (joint_train_lightning_net.py:167-223 losses, :473-513 step,
+:897-919 optimizer) around the drop-in network, plus the ray-sharded multi-GPU form of SURVEY.md section 8e.
+
+``nerf_losses`` is the loss arithmetic of ``forward_nerf_train``; ``NerfTrainer.train_step`` is one
+``training_step_nerf`` iteration without the Lightning / logging plumbing: render 4096 rays (perturb=True),
+losses, backward, Adam (two groups, weight decay on the MLPs only).  The optimizer is the fused
+``ucsa_adam_step`` kernel (row f1): one pass per parameter tensor that also refreshes the fp16 working copy.
+
+Multi-GPU: one process per GPU, each rank renders its own slice of the ray batch; after backward one NCCL
+all-reduce(sum) over a single flat gradient buffer; every rank then applies the same Adam update, so no
+parameter broadcast is needed.  Losses are means over the *global* ray count."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def nerf_losses(outputs, gt_rgb, labels, gt_depth, one_m_to_scene_uom, weight_depth=0.1, weight_semantics=0.04,
+                global_scale=1.0):
+    """joint_train_lightning_net.py:199-221 and :503-507.  Shapes [B,N,...] as rendered."""
+    pred_rgb, semantics, pred_depth = outputs["image"], outputs["semantics"], outputs["depth"]
+    labels = labels.clone()
+    invalid = torch.sum(semantics, dim=-1) == 0
+    semantics = torch.where(invalid.unsqueeze(-1), torch.ones_like(semantics), semantics)
+    semantics = semantics / torch.sum(semantics, dim=-1, keepdim=True)
+    labels[invalid] = -1
+    loss_color = torch.nn.functional.mse_loss(pred_rgb, gt_rgb.float(), reduction="none").mean()
+    logp = torch.log(semantics + 1e-15).permute(0, 2, 1)
+    loss_sem = torch.nn.functional.nll_loss(logp, labels, ignore_index=-1, reduction="none").mean()
+    valid = gt_depth != 0
+    loss_depth = torch.nn.functional.l1_loss(pred_depth[valid] / one_m_to_scene_uom, gt_depth[valid],
+                                             reduction="none").mean(-1)
+    total = loss_color + loss_sem * weight_semantics + loss_depth * weight_depth
+    return total * global_scale, (loss_color, loss_sem, loss_depth)
+
+
+class NerfTrainer:
+
+    def __init__(self, net, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, weight_decay_net=1e-6, num_steps=256,
+                 upsample_steps=256, distributed=False):
+        self.net = net
+        self.lr, self.betas, self.eps, self.wd_net = lr, betas, eps, weight_decay_net
+        self.num_steps, self.upsample_steps = num_steps, upsample_steps
+        self.distributed = distributed and dist.is_initialized() and dist.get_world_size() > 1
+        self.world = dist.get_world_size() if self.distributed else 1
+        self.rank = dist.get_rank() if self.distributed else 0
+        self.step = 0
+        # parameter tensors in a fixed order; group "encoding" has no weight decay
+        self.groups = [(net.encoder, 0.0), (net.sigma_net, weight_decay_net), (net.color_net, weight_decay_net),
+                       (net.semantics_net, weight_decay_net)]
+        dev = net.encoder.params.device
+        sizes = [m.params.numel() for m, _ in self.groups]
+        self.flat_grad = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        self.grad_views, off = [], 0
+        for s in sizes:
+            self.grad_views.append(self.flat_grad[off:off + s])
+            off += s
+        self.exp_avg = [torch.zeros_like(m.params) for m, _ in self.groups]
+        self.exp_avg_sq = [torch.zeros_like(m.params) for m, _ in self.groups]
+        for (m, _), g in zip(self.groups, self.grad_views):
+            m.params.grad = g  # autograd accumulates straight into the flat all-reduce buffer
+            m.half_params()
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def optimizer_step(self):
+        self.step += 1
+        for (m, wd), g, ea, eas in zip(self.groups, self.grad_views, self.exp_avg, self.exp_avg_sq):
+            half = m.half_params()
+            ops.adam_step(m.params.data, g, ea, eas, half, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1],
+                          eps=self.eps, weight_decay=wd, grad_scale_inv=1.0, found_inf=None, step=self.step)
+
+    def train_step(self, rays_o, rays_d, direction_norms, gt_rgb, labels, gt_depth, one_m_to_scene_uom, seed=None,
+                   ray_base=0):
+        """One optimisation step on this rank's rays ([1,n,...] tensors).  Returns the (local) loss tensor."""
+        net = self.net
+        self.zero_grad()
+        out = net.render(rays_o, rays_d, direction_norms=direction_norms, staged=False, bg_color=None, perturb=True,
+                         num_steps=self.num_steps, upsample_steps=self.upsample_steps, seed=seed,
+                         ray_base=ray_base)
+        loss, _ = nerf_losses(out, gt_rgb, labels, gt_depth, one_m_to_scene_uom, global_scale=1.0 / self.world)
+        loss.backward()
+        for (m, _), g in zip(self.groups, self.grad_views):
+            if m.params.grad is not g:  # autograd replaced the tensor: copy back into the flat buffer
+                g.copy_(m.params.grad)
+                m.params.grad = g
+        if self.distributed:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+        self.optimizer_step()
+        return loss
