@@ -176,6 +176,31 @@ UCSA_API int ucsa_mlp_bwd(const void* x_h, uint32_t n, const void* w_h, const ui
                  const void* acts_h, const void* dy_h, float inv_loss_scale, void* dx_h, float* grad_w,
                  void* stream);
 
+UCSA_API int ucsa_density_fwd_simt(const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,
+                     const float* z_cat, uint32_t n_rays, uint32_t t, uint32_t k0, uint32_t k1, float bound,
+                     const void* table_h, const ucsa_grid_desc* grid_host, const void* w_sigma_h,
+                     float* sigma, void* h, void* enc, void* hid, void* stream);
+UCSA_API int ucsa_density_bwd_simt(const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,
+                     const float* z_cat, uint32_t n_rays, uint32_t t, uint32_t k0, uint32_t k1, float bound,
+                     const ucsa_grid_desc* grid_host, const void* w_sigma_h, const void* h, const void* enc,
+                     const void* hid, const float* d_sigma, const void* dh, const uint8_t* use_geo,
+                     float loss_scale, float* grad_table, float* grad_w_sigma, void* stream);
+UCSA_API int ucsa_heads_fwd_simt(const int32_t* sel, const int32_t* ray_off, uint32_t n_rays, uint32_t t, uint32_t k_max,
+                   const float* rays_d, const void* h, const void* w_color_h, const void* w_sem_h,
+                   uint32_t n_classes, float* rgb, void* logits, void* hc1, void* hc2, void* hs, void* stream);
+UCSA_API int ucsa_heads_bwd_simt(const int32_t* sel, const int32_t* ray_off, uint32_t n_rays, uint32_t t, uint32_t k_max,
+                   const float* rays_d, const void* h, const void* w_color_h, const void* w_sem_h,
+                   uint32_t n_classes, const float* rgb, const void* hc1, const void* hc2, const void* hs,
+                   const float* d_rgb, const float* d_logits, float loss_scale, void* dh, float* grad_w_color,
+                   float* grad_w_sem, void* stream);
+/* CUDA-core (no tensor core) realisation of the same MLP contract; kept as the on-device cross-check of the
+ * tcgen05 path (tests/) -- not used by the rendering pipeline. */
+UCSA_API int ucsa_mlp_fwd_simt(const void* x_h, uint32_t n, const void* w_h, const uint32_t* dims_host,
+                               uint32_t n_layers, void* y_h, void* acts_h, void* stream);
+UCSA_API int ucsa_mlp_bwd_simt(const void* x_h, uint32_t n, const void* w_h, const uint32_t* dims_host,
+                               uint32_t n_layers, const void* acts_h, const void* dy_h, float inv_loss_scale,
+                               void* dx_h, float* grad_w, void* stream);
+
 /* ---- parameter plumbing: fp32 master -> fp16 working copy; fused Adam (row f1:
  * joint_train_lightning_net.py:897-919: lr, betas (0.9,0.99), eps 1e-15, weight_decay on the MLPs). */
 UCSA_API int ucsa_cast_f32_to_f16(const float* src, uint64_t n, void* dst_h, void* stream);

@@ -77,6 +77,7 @@ def parse_header(path: str = HEADER):
 _lock = threading.Lock()
 _lib = None
 
+_DEBUG_SYNC = os.environ.get("UCSA_DEBUG_SYNC", "0") == "1"
 HOST_ONLY = {"ucsa_abi_version", "ucsa_last_error_string", "ucsa_grid_desc_init"}
 
 
@@ -112,6 +113,18 @@ class _Entry:
             return self.fn(*args)
         stats.launches += 1
         stats.by_name[self.name] = stats.by_name.get(self.name, 0) + 1
+        if _DEBUG_SYNC:  # UCSA_DEBUG_SYNC=1: name every launch and wait for it (locates a faulting kernel)
+            import sys
+
+            import torch
+
+            sys.stderr.write(f"[ucsa] {self.name} ...")
+            sys.stderr.flush()
+            rc = self.fn(*args)
+            torch.cuda.synchronize()
+            sys.stderr.write(f" rc={rc}\n")
+            sys.stderr.flush()
+            return rc
         if self.name in stats.timed:
             import torch
 

@@ -1,4 +1,5 @@
-// density(): hash-grid encode + sigma MLP (32->64->16) + trunc_exp, forward and backward.
+// density() on CUDA cores only: hash-grid encode + sigma MLP (32->64->16) + trunc_exp, forward and backward.
+// On-device cross-check of density_tc.cu (the tcgen05 production kernels); exported as ucsa_density_*_simt.
 // Rows a4/a5/a6/a8/a15 of SURVEY.md section 8 (network_tcnn_semantics.py:130-144, activation.py:7-19).
 //
 // One kernel per direction; the encoded features never leave the SM between the gather and the MLP.
@@ -199,7 +200,7 @@ uint32_t persistent_grid(uint64_t n_samples, int ctas_per_sm) {
 
 using namespace ucsa;
 
-extern "C" int ucsa_density_fwd(const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,
+extern "C" int ucsa_density_fwd_simt(const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,
                                 const float* z_cat, uint32_t n_rays, uint32_t t, uint32_t k0, uint32_t k1,
                                 float bound, const void* table_h, const ucsa_grid_desc* grid_host,
                                 const void* w_sigma_h, float* sigma, void* h, void* enc, void* hid,
@@ -219,7 +220,7 @@ extern "C" int ucsa_density_fwd(const float* xyz, const float* rays_o, const flo
   return check_launch("density_fwd");
 }
 
-extern "C" int ucsa_density_bwd(const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,
+extern "C" int ucsa_density_bwd_simt(const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,
                                 const float* z_cat, uint32_t n_rays, uint32_t t, uint32_t k0, uint32_t k1,
                                 float bound, const ucsa_grid_desc* grid_host, const void* w_sigma_h,
                                 const void* h, const void* enc, const void* hid, const float* d_sigma,

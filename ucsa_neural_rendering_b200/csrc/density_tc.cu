@@ -1,0 +1,328 @@
+// density(): hash-grid encode + sigma MLP (32->64->16, tcgen05) + trunc_exp, forward and backward.
+// Rows a4/a5/a6/a8/a15 of SURVEY.md section 8 (network_tcnn_semantics.py:130-144, activation.py:7-19).
+//
+// Forward, per 128-sample tile of a persistent CTA (thread t = sample t = TMEM lane t):
+//   gather 16 levels x 8 corners (fp16x2, L1/L2-resident table) -> encoded row straight into the shared-memory
+//   A tile -> UMMA 128x64x32 -> TMEM -> ReLU/fp16 -> A tile of layer 2 -> UMMA 128x16x64 -> TMEM -> h, sigma.
+//   The encoded features and hidden activations reach HBM only as the copies saved for the backward pass.
+// Backward: dL/dh tile -> UMMA data gradients back to dL/d(encoded), weight gradients accumulated in TMEM over
+//   all tiles of the CTA, and the hash-table gradient scattered with vector reductions (red.global.add.v2.f32).
+// Several CTAs per SM (TMEM: 128 columns each) overlap one tile's gather/scatter phase with another's MMAs.
+#include "grid.cuh"
+#include "mlp_umma.cuh"
+
+namespace ucsa {
+namespace {
+
+using umma::Tile;
+
+struct DensityArgs {
+  const float* xyz;     // [S,3] or null
+  const float* rays_o;  // [N,3]
+  const float* rays_d;
+  const float* aabb;
+  const float* z_cat;   // [N,T]
+  uint32_t n_rays, t, k0, span;  // span = k1-k0
+  uint64_t n_samples;            // n_rays*span
+  float bound;
+  ucsa_grid_desc grid;
+};
+
+__device__ __forceinline__ uint64_t locate_sample(const DensityArgs& a, uint64_t s, float x01[3]) {
+  if (a.xyz != nullptr) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x01[d] = __fdiv_rn(__fadd_rn(a.xyz[3 * s + d], a.bound), 2.0f * a.bound);
+    return s;
+  }
+  const uint32_t n = static_cast<uint32_t>(s / a.span);
+  const uint32_t k = a.k0 + static_cast<uint32_t>(s % a.span);
+  const uint64_t flat = static_cast<uint64_t>(n) * a.t + k;
+  sample_x01(a.rays_o, a.rays_d, a.aabb, a.z_cat[flat], n, a.bound, x01);
+  return flat;
+}
+
+constexpr uint32_t kW1Bytes = 64 / 8 * Tile<32>::kGroupBytes;  // [64][32]
+constexpr uint32_t kW2Bytes = 16 / 8 * Tile<64>::kGroupBytes;  // [16][64]
+constexpr uint32_t kTmemCols = 128;
+
+__global__ void __launch_bounds__(128)
+density_fwd_tc_kernel(const DensityArgs a, const __half2* __restrict__ table, const __half* __restrict__ w_sigma,
+                      float* __restrict__ sigma, __half* __restrict__ h, __half* __restrict__ enc,
+                      __half* __restrict__ hid) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* w1 = smem;
+  unsigned char* w2 = w1 + kW1Bytes;
+  unsigned char* t_enc = w2 + kW2Bytes;
+  unsigned char* t_hid = t_enc + Tile<32>::kBytes;
+  unsigned char* tail = t_hid + Tile<64>::kBytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(tail + 8);
+  umma::load_weight_tile<32>(w1, w_sigma, 64);
+  umma::load_weight_tile<64>(w2, w_sigma + 64 * 32, 16);
+  umma::Ctx ctx = umma::ctx_init(slot, bar, kTmemCols);
+  const uint32_t s_enc = umma::smem_u32(t_enc), s_hid = umma::smem_u32(t_hid);
+  const uint32_t s_w1 = umma::smem_u32(w1), s_w2 = umma::smem_u32(w2);
+  constexpr uint32_t kAcc1 = 0, kAcc2 = 64;
+
+  const int row = threadIdx.x;
+  const uint64_t n_tiles = (a.n_samples + 127) / 128;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint64_t s = tile * 128 + row;
+    const bool valid = s < a.n_samples;
+    uint64_t flat = 0;
+    if (valid) {
+      float x01[3];
+      flat = locate_sample(a, s, x01);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {  // four levels = one 16-byte chunk of the encoded row
+        H8 o;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = interp_level(table, level_geom(a.grid, 4 * c + j), x01);
+          o.h2[j] = __floats2half2_rn(f.x, f.y);
+        }
+        *Tile<32>::chunk(t_enc, row, c) = o.v;
+        if (enc != nullptr) reinterpret_cast<uint4*>(enc + flat * 32)[c] = o.v;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) *Tile<32>::chunk(t_enc, row, c) = make_uint4(0, 0, 0, 0);
+    }
+    ctx.publish();
+    if (threadIdx.x == 0) {
+      umma::tc_fence_after();
+      umma::issue_fwd<32, 64>(ctx.tmem + kAcc1, s_enc, s_w1);
+      umma::commit(ctx.bar);
+    }
+    ctx.wait();
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) umma::acc_to_tile16<64, true>(ctx, kAcc1 + c0, t_hid, c0);
+    if (hid != nullptr && valid) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) reinterpret_cast<uint4*>(hid + flat * 64)[c] = *Tile<64>::chunk(t_hid, row, c);
+    }
+    ctx.publish();
+    if (threadIdx.x == 0) {
+      umma::tc_fence_after();
+      umma::issue_fwd<64, 16>(ctx.tmem + kAcc2, s_hid, s_w2);
+      umma::commit(ctx.bar);
+    }
+    ctx.wait();
+    float v[16];
+    umma::tmem_ld16(ctx.lane_addr(kAcc2), v);
+    if (valid) {
+      H8 lo, hi;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        lo.h[i] = __float2half_rn(v[i]);
+        hi.h[i] = __float2half_rn(v[8 + i]);
+      }
+      reinterpret_cast<uint4*>(h + flat * 16)[0] = lo.v;
+      reinterpret_cast<uint4*>(h + flat * 16)[1] = hi.v;
+      sigma[flat] = expf(__half2float(lo.h[0]));  // trunc_exp forward, fp32
+    }
+  }
+  umma::ctx_free(ctx, kTmemCols);
+}
+
+// [64 x N] weight-gradient accumulator (UMMA M = 64) -> global fp32 (see mlp_umma.cuh)
+template <int N, bool TRANSPOSED>
+__device__ __forceinline__ void flush_wgrad(const umma::Ctx& ctx, uint32_t col0, float* __restrict__ grad, int ld,
+                                            float scale) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    umma::tmem_ld16(ctx.lane_addr(col0 + c0), v);
+    if (lane < 16) {
+      const int m = warp * 16 + lane;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        atomicAdd(grad + (TRANSPOSED ? (c0 + i) * ld + m : m * ld + c0 + i), v[i] * scale);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, const __half* __restrict__ h,
+                      const __half* __restrict__ enc, const __half* __restrict__ hid,
+                      const float* __restrict__ d_sigma, const __half* __restrict__ dh,
+                      const uint8_t* __restrict__ use_geo, float loss_scale, float* __restrict__ grad_table,
+                      float* __restrict__ grad_w) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* w1 = smem;
+  unsigned char* w2 = w1 + kW1Bytes;
+  unsigned char* t_enc = w2 + kW2Bytes;
+  unsigned char* t_hid = t_enc + Tile<32>::kBytes;
+  unsigned char* t_dhid = t_hid + Tile<64>::kBytes;
+  unsigned char* t_dout = t_dhid + Tile<64>::kBytes;
+  unsigned char* tail = t_dout + Tile<16>::kBytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(tail + 8);
+  umma::load_weight_tile<32>(w1, w_sigma, 64);
+  umma::load_weight_tile<64>(w2, w_sigma + 64 * 32, 16);
+  umma::Ctx ctx = umma::ctx_init(slot, bar, kTmemCols);
+  const uint32_t s_enc = umma::smem_u32(t_enc), s_hid = umma::smem_u32(t_hid), s_dhid = umma::smem_u32(t_dhid),
+                 s_dout = umma::smem_u32(t_dout), s_w1 = umma::smem_u32(w1), s_w2 = umma::smem_u32(w2);
+  constexpr uint32_t kAcc = 0, kG1 = 64, kG2 = 96;  // scratch 64 | dW1 [64x32] | dW2^T [64x16]
+
+  const int row = threadIdx.x;
+  const float inv_scale = 1.0f / loss_scale;
+  const uint64_t n_tiles = (a.n_samples + 127) / 128;
+  bool first = true;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint64_t s = tile * 128 + row;
+    const bool valid = s < a.n_samples;
+    if (!first) ctx.wait();  // the weight-gradient MMAs of the previous tile have read the tiles
+    float x01[3] = {0.f, 0.f, 0.f};
+    if (valid) {
+      const uint64_t flat = locate_sample(a, s, x01);
+      // dL/dh: element 0 through trunc_exp (activation.py:16-19), elements 1..15 = dL/dgeo_feat from the heads
+      H8 lo, hi;
+      if (use_geo != nullptr && dh != nullptr && use_geo[flat]) {
+        lo.v = __ldg(reinterpret_cast<const uint4*>(dh + flat * 16));
+        hi.v = __ldg(reinterpret_cast<const uint4*>(dh + flat * 16 + 8));
+      } else {
+        lo.v = make_uint4(0, 0, 0, 0);
+        hi.v = make_uint4(0, 0, 0, 0);
+      }
+      const float h0 = __half2float(h[flat * 16]);
+      const float gs = d_sigma != nullptr ? d_sigma[flat] : 0.f;
+      lo.h[0] = __float2half_rn(gs * expf(fminf(fmaxf(h0, -15.f), 15.f)) * loss_scale);
+      *Tile<16>::chunk(t_dout, row, 0) = lo.v;
+      *Tile<16>::chunk(t_dout, row, 1) = hi.v;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *Tile<64>::chunk(t_hid, row, c) = __ldg(reinterpret_cast<const uint4*>(hid + flat * 64) + c);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *Tile<32>::chunk(t_enc, row, c) = __ldg(reinterpret_cast<const uint4*>(enc + flat * 32) + c);
+    } else {
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      *Tile<16>::chunk(t_dout, row, 0) = z;
+      *Tile<16>::chunk(t_dout, row, 1) = z;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) *Tile<64>::chunk(t_hid, row, c) = z;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) *Tile<32>::chunk(t_enc, row, c) = z;
+    }
+    ctx.publish();
+    if (threadIdx.x == 0) {
+      umma::tc_fence_after();
+      umma::issue_dgrad<16, 64>(ctx.tmem + kAcc, s_dout, s_w2);  // d(hidden) = dL/dh . W2
+      umma::commit(ctx.bar);
+      umma::issue_wgrad<16>(ctx.tmem + kG2, s_hid, s_dout, first);  // d(W2)^T = hidden^T . dL/dh
+    }
+    ctx.wait();
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) umma::acc_to_tile16<64, false>(ctx, kAcc + c0, t_dhid, c0, t_hid);
+    ctx.publish();
+    if (threadIdx.x == 0) {
+      umma::tc_fence_after();
+      umma::issue_dgrad<64, 32>(ctx.tmem + kAcc, s_dhid, s_w1);  // d(encoded) = d(hidden) . W1
+      umma::commit(ctx.bar);
+      umma::issue_wgrad<32>(ctx.tmem + kG1, s_dhid, s_enc, first);  // d(W1) = d(hidden)^T . encoded
+    }
+    ctx.wait();
+    float g[32];
+    {
+      float v[16];
+      umma::tmem_ld16(ctx.lane_addr(kAcc), v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) g[i] = v[i];
+      umma::tmem_ld16(ctx.lane_addr(kAcc + 16), v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) g[16 + i] = v[i];
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      umma::tc_fence_after();
+      umma::commit(ctx.bar);  // covers the two weight-gradient products; waited on at the top of the next tile
+    }
+    if (valid && grad_table != nullptr) {
+#pragma unroll
+      for (int l = 0; l < UCSA_GRID_LEVELS; ++l)
+        scatter_level(grad_table, level_geom(a.grid, l), x01, round_h(g[2 * l]) * inv_scale,
+                      round_h(g[2 * l + 1]) * inv_scale);
+    }
+    first = false;
+  }
+  ctx.wait();
+  flush_wgrad<32, false>(ctx, kG1, grad_w, 32, inv_scale);
+  flush_wgrad<16, true>(ctx, kG2, grad_w + 64 * 32, 64, inv_scale);
+  umma::ctx_free(ctx, kTmemCols);
+}
+
+constexpr size_t kFwdSmem = kW1Bytes + kW2Bytes + Tile<32>::kBytes + Tile<64>::kBytes + 64;
+constexpr size_t kBwdSmem = kW1Bytes + kW2Bytes + Tile<32>::kBytes + 2 * Tile<64>::kBytes + Tile<16>::kBytes + 64;
+
+int fill_args(DensityArgs& a, const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,
+              const float* z_cat, uint32_t n_rays, uint32_t t, uint32_t k0, uint32_t k1, float bound,
+              const ucsa_grid_desc* grid) {
+  UCSA_REQUIRE(grid != nullptr, "density: null grid descriptor");
+  UCSA_REQUIRE(bound > 0.f, "density: bound must be positive");
+  if (xyz != nullptr) {
+    a = DensityArgs{xyz, nullptr, nullptr, nullptr, nullptr, n_rays, 1u, 0u, 1u, n_rays, bound, *grid};
+    return UCSA_OK;
+  }
+  UCSA_REQUIRE(rays_o && rays_d && aabb6 && z_cat, "density: rays_o/rays_d/aabb/z_cat required without xyz");
+  UCSA_REQUIRE(k0 < k1 && k1 <= t, "density: bad slot range [%u,%u) of %u", k0, k1, t);
+  a = DensityArgs{nullptr, rays_o, rays_d, aabb6, z_cat, n_rays, t, k0, k1 - k0,
+                  static_cast<uint64_t>(n_rays) * (k1 - k0), bound, *grid};
+  return UCSA_OK;
+}
+
+uint32_t persistent_grid(uint64_t n_samples, int ctas_per_sm) {
+  const uint64_t tiles = (n_samples + 127) / 128;
+  const uint64_t cap = static_cast<uint64_t>(kNumSMs) * ctas_per_sm;
+  return static_cast<uint32_t>(tiles < cap ? tiles : cap);
+}
+
+}  // namespace
+}  // namespace ucsa
+
+using namespace ucsa;
+
+extern "C" int ucsa_density_fwd(const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,
+                                const float* z_cat, uint32_t n_rays, uint32_t t, uint32_t k0, uint32_t k1,
+                                float bound, const void* table_h, const ucsa_grid_desc* grid_host,
+                                const void* w_sigma_h, float* sigma, void* h, void* enc, void* hid,
+                                void* stream) {
+  DensityArgs a;
+  if (int rc = fill_args(a, xyz, rays_o, rays_d, aabb6, z_cat, n_rays, t, k0, k1, bound, grid_host)) return rc;
+  UCSA_REQUIRE(table_h && w_sigma_h && sigma && h, "density_fwd: null table/weights/outputs");
+  if (a.n_samples == 0) return UCSA_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(density_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
+    attr_set = true;
+  }
+  density_fwd_tc_kernel<<<persistent_grid(a.n_samples, 4), 128, kFwdSmem, as_stream(stream)>>>(
+      a, static_cast<const __half2*>(table_h), static_cast<const __half*>(w_sigma_h), sigma,
+      static_cast<__half*>(h), static_cast<__half*>(enc), static_cast<__half*>(hid));
+  return check_launch("density_fwd");
+}
+
+extern "C" int ucsa_density_bwd(const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,
+                                const float* z_cat, uint32_t n_rays, uint32_t t, uint32_t k0, uint32_t k1,
+                                float bound, const ucsa_grid_desc* grid_host, const void* w_sigma_h,
+                                const void* h, const void* enc, const void* hid, const float* d_sigma,
+                                const void* dh, const uint8_t* use_geo, float loss_scale, float* grad_table,
+                                float* grad_w_sigma, void* stream) {
+  DensityArgs a;
+  if (int rc = fill_args(a, xyz, rays_o, rays_d, aabb6, z_cat, n_rays, t, k0, k1, bound, grid_host)) return rc;
+  UCSA_REQUIRE(w_sigma_h && h && enc && hid && grad_w_sigma, "density_bwd: null saved tensors / outputs");
+  UCSA_REQUIRE(loss_scale > 0.f, "density_bwd: loss_scale must be positive");
+  if (a.n_samples == 0) return UCSA_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(density_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+    attr_set = true;
+  }
+  density_bwd_tc_kernel<<<persistent_grid(a.n_samples, 4), 128, kBwdSmem, as_stream(stream)>>>(
+      a, static_cast<const __half*>(w_sigma_h), static_cast<const __half*>(h), static_cast<const __half*>(enc),
+      static_cast<const __half*>(hid), d_sigma, static_cast<const __half*>(dh), use_geo, loss_scale, grad_table,
+      grad_w_sigma);
+  return check_launch("density_bwd");
+}

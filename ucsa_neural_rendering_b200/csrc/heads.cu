@@ -1,3 +1,4 @@
+// CUDA-core cross-check of heads_tc.cu (exported as ucsa_heads_*_simt).
 // Colour and semantic heads on the masked-in samples: SH degree-4 direction encoding, colour MLP
 // (SH16 + geo15 + 1 -> 64 -> 64 -> 3, sigmoid) and semantic MLP (geo15 + 1 -> 64 -> C).
 // Rows a7, a12, a13 and their backward of SURVEY.md section 8 (network_tcnn_semantics.py:147-207).
@@ -250,7 +251,7 @@ uint32_t heads_grid(uint32_t k_max, int ctas_per_sm) {
 
 using namespace ucsa;
 
-extern "C" int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32_t n_rays, uint32_t t,
+extern "C" int ucsa_heads_fwd_simt(const int32_t* sel, const int32_t* ray_off, uint32_t n_rays, uint32_t t,
                               uint32_t k_max, const float* rays_d, const void* h, const void* w_color_h,
                               const void* w_sem_h, uint32_t n_classes, float* rgb, void* logits, void* hc1,
                               void* hc2, void* hs, void* stream) {
@@ -269,7 +270,7 @@ extern "C" int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32
   return check_launch("heads_fwd");
 }
 
-extern "C" int ucsa_heads_bwd(const int32_t* sel, const int32_t* ray_off, uint32_t n_rays, uint32_t t,
+extern "C" int ucsa_heads_bwd_simt(const int32_t* sel, const int32_t* ray_off, uint32_t n_rays, uint32_t t,
                               uint32_t k_max, const float* rays_d, const void* h, const void* w_color_h,
                               const void* w_sem_h, uint32_t n_classes, const float* rgb, const void* hc1,
                               const void* hc2, const void* hs, const float* d_rgb, const float* d_logits,

@@ -1,0 +1,408 @@
+// Colour and semantic heads on the masked-in samples, on the tcgen05 tensor cores: SH degree-4 direction
+// encoding, colour MLP (SH16 + geo15 + 1 -> 64 -> 64 -> 3, sigmoid) and semantic MLP (geo15 + 1 -> 64 -> C).
+// Rows a7, a12, a13 and their backward of SURVEY.md section 8 (network_tcnn_semantics.py:147-207).
+//
+// The reference evaluates the heads only where w > 1e-4 (boolean-mask gather / scatter, :159-161,:174); here the
+// K surviving rows arrive as the compact list `sel` (row -> n*T+slot) built by compact_masked.  Per 128-row tile
+// the two networks advance together: one commit covers the colour and the semantic product of a stage, so the
+// forward pass needs three MMA round trips and the backward pass three data-gradient round trips; the five
+// weight gradients accumulate in TMEM across all tiles of the persistent CTA.
+#include "mlp_umma.cuh"
+#include "sh4.cuh"
+
+namespace ucsa {
+namespace {
+
+using umma::Tile;
+
+constexpr int kSemOut = UCSA_MAX_CLASSES;  // semantic output layer is always 48 wide (pad16 of 33..48 classes)
+constexpr int kColorW1 = 0, kColorW2 = 64 * 32, kColorW3 = kColorW2 + 64 * 64;  // offsets in w_color
+constexpr int kSemW1 = 0, kSemW2 = 64 * 16;                                      // offsets in w_sem
+
+// shared-memory weight tiles
+constexpr uint32_t kWc1 = 64 / 8 * Tile<32>::kGroupBytes;
+constexpr uint32_t kWc2 = 64 / 8 * Tile<64>::kGroupBytes;
+constexpr uint32_t kWc3 = 16 / 8 * Tile<64>::kGroupBytes;
+constexpr uint32_t kWs1 = 64 / 8 * Tile<16>::kGroupBytes;
+constexpr uint32_t kWs2 = kSemOut / 8 * Tile<64>::kGroupBytes;
+constexpr uint32_t kWeightBytes = kWc1 + kWc2 + kWc3 + kWs1 + kWs2;
+
+struct WeightTiles {
+  uint32_t c1, c2, c3, s1, s2;  // shared-space addresses
+};
+
+__device__ __forceinline__ WeightTiles load_weights(unsigned char* base, const __half* __restrict__ w_color,
+                                                    const __half* __restrict__ w_sem) {
+  unsigned char* c1 = base;
+  unsigned char* c2 = c1 + kWc1;
+  unsigned char* c3 = c2 + kWc2;
+  unsigned char* s1 = c3 + kWc3;
+  unsigned char* s2 = s1 + kWs1;
+  umma::load_weight_tile<32>(c1, w_color + kColorW1, 64);
+  umma::load_weight_tile<64>(c2, w_color + kColorW2, 64);
+  umma::load_weight_tile<64>(c3, w_color + kColorW3, 16);
+  umma::load_weight_tile<16>(s1, w_sem + kSemW1, 64);
+  umma::load_weight_tile<64>(s2, w_sem + kSemW2, kSemOut);
+  return WeightTiles{umma::smem_u32(c1), umma::smem_u32(c2), umma::smem_u32(c3), umma::smem_u32(s1),
+                     umma::smem_u32(s2)};
+}
+
+// colour input row [SH(16) | geo_feat(15) | 1] and semantic input row [geo_feat(15) | 1] of this thread's row
+__device__ __forceinline__ void build_inputs(const float* __restrict__ rays_d, const __half* __restrict__ h,
+                                             uint32_t flat, uint32_t t, bool valid, unsigned char* t_in_c,
+                                             unsigned char* t_in_s) {
+  const int row = threadIdx.x;
+  H8 sh_lo, sh_hi, g0, g1;
+  if (valid) {
+    const uint32_t n = flat / t;
+    float sh[16];
+    sh4_eval(rays_d[3 * n + 0], rays_d[3 * n + 1], rays_d[3 * n + 2], sh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sh_lo.h[i] = __float2half_rn(sh[i]);
+      sh_hi.h[i] = __float2half_rn(sh[8 + i]);
+    }
+    H8 lo, hi;
+    lo.v = __ldg(reinterpret_cast<const uint4*>(h + static_cast<uint64_t>(flat) * 16));
+    hi.v = __ldg(reinterpret_cast<const uint4*>(h + static_cast<uint64_t>(flat) * 16 + 8));
+#pragma unroll
+    for (int i = 0; i < 7; ++i) g0.h[i] = lo.h[i + 1];
+    g0.h[7] = hi.h[0];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) g1.h[i] = hi.h[i + 1];
+    g1.h[7] = __float2half_rn(1.0f);
+  } else {
+    sh_lo.v = sh_hi.v = g0.v = g1.v = make_uint4(0, 0, 0, 0);
+  }
+  *Tile<32>::chunk(t_in_c, row, 0) = sh_lo.v;
+  *Tile<32>::chunk(t_in_c, row, 1) = sh_hi.v;
+  *Tile<32>::chunk(t_in_c, row, 2) = g0.v;
+  *Tile<32>::chunk(t_in_c, row, 3) = g1.v;
+  *Tile<16>::chunk(t_in_s, row, 0) = g0.v;
+  *Tile<16>::chunk(t_in_s, row, 1) = g1.v;
+}
+
+template <int W>
+__device__ __forceinline__ void row_t2g(__half* __restrict__ dst, unsigned char* tile) {
+#pragma unroll
+  for (int c = 0; c < W / 8; ++c) reinterpret_cast<uint4*>(dst)[c] = *Tile<W>::chunk(tile, threadIdx.x, c);
+}
+template <int W>
+__device__ __forceinline__ void row_g2t(unsigned char* tile, const __half* __restrict__ src, bool valid) {
+#pragma unroll
+  for (int c = 0; c < W / 8; ++c)
+    *Tile<W>::chunk(tile, threadIdx.x, c) =
+        valid ? __ldg(reinterpret_cast<const uint4*>(src) + c) : make_uint4(0, 0, 0, 0);
+}
+
+constexpr uint32_t kFwdCols = 256;
+constexpr uint32_t kFwdSmem = kWeightBytes + Tile<32>::kBytes + Tile<16>::kBytes + 3 * Tile<64>::kBytes + 64;
+
+__global__ void __launch_bounds__(128)
+heads_fwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__ k_ptr, uint32_t t,
+                    const float* __restrict__ rays_d, const __half* __restrict__ h,
+                    const __half* __restrict__ w_color, const __half* __restrict__ w_sem, float* __restrict__ rgb,
+                    __half* __restrict__ logits, __half* __restrict__ hc1, __half* __restrict__ hc2,
+                    __half* __restrict__ hs) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* t_in_c = smem + kWeightBytes;
+  unsigned char* t_in_s = t_in_c + Tile<32>::kBytes;
+  unsigned char* t_h1 = t_in_s + Tile<16>::kBytes;
+  unsigned char* t_hs = t_h1 + Tile<64>::kBytes;
+  unsigned char* t_h2 = t_hs + Tile<64>::kBytes;
+  unsigned char* tail = t_h2 + Tile<64>::kBytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(tail + 8);
+  const WeightTiles w = load_weights(smem, w_color, w_sem);
+  umma::Ctx ctx = umma::ctx_init(slot, bar, kFwdCols);
+  const uint32_t s_in_c = umma::smem_u32(t_in_c), s_in_s = umma::smem_u32(t_in_s), s_h1 = umma::smem_u32(t_h1),
+                 s_hs = umma::smem_u32(t_hs), s_h2 = umma::smem_u32(t_h2);
+  constexpr uint32_t kAcc0 = 0, kAcc1 = 64, kAcc2 = 128;
+
+  const uint32_t k_rows = static_cast<uint32_t>(*k_ptr);
+  const uint32_t n_tiles = (k_rows + 127) / 128;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t r = tile * 128 + threadIdx.x;
+    const bool valid = r < k_rows;
+    build_inputs(rays_d, h, valid ? static_cast<uint32_t>(sel[r]) : 0u, t, valid, t_in_c, t_in_s);
+    ctx.publish();
+    if (threadIdx.x == 0) {
+      umma::tc_fence_after();
+      umma::issue_fwd<32, 64>(ctx.tmem + kAcc0, s_in_c, w.c1);
+      umma::issue_fwd<16, 64>(ctx.tmem + kAcc1, s_in_s, w.s1);
+      umma::commit(ctx.bar);
+    }
+    ctx.wait();
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      umma::acc_to_tile16<64, true>(ctx, kAcc0 + c0, t_h1, c0);
+      umma::acc_to_tile16<64, true>(ctx, kAcc1 + c0, t_hs, c0);
+    }
+    if (valid && hc1 != nullptr) row_t2g<64>(hc1 + static_cast<uint64_t>(r) * 64, t_h1);
+    if (valid && hs != nullptr) row_t2g<64>(hs + static_cast<uint64_t>(r) * 64, t_hs);
+    ctx.publish();
+    if (threadIdx.x == 0) {
+      umma::tc_fence_after();
+      umma::issue_fwd<64, 64>(ctx.tmem + kAcc0, s_h1, w.c2);
+      umma::issue_fwd<64, kSemOut>(ctx.tmem + kAcc2, s_hs, w.s2);
+      umma::commit(ctx.bar);
+    }
+    ctx.wait();
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) umma::acc_to_tile16<64, true>(ctx, kAcc0 + c0, t_h2, c0);
+    if (valid && hc2 != nullptr) row_t2g<64>(hc2 + static_cast<uint64_t>(r) * 64, t_h2);
+#pragma unroll
+    for (int c0 = 0; c0 < kSemOut; c0 += 16) {
+      float v[16];
+      umma::tmem_ld16(ctx.lane_addr(kAcc2 + c0), v);
+      if (valid) {
+        H8 a, b;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          a.h[i] = __float2half_rn(v[i]);
+          b.h[i] = __float2half_rn(v[8 + i]);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(logits + static_cast<uint64_t>(r) * kSemOut + c0);
+        dst[0] = a.v;
+        dst[1] = b.v;
+      }
+    }
+    ctx.publish();
+    if (threadIdx.x == 0) {
+      umma::tc_fence_after();
+      umma::issue_fwd<64, 16>(ctx.tmem + kAcc1, s_h2, w.c3);
+      umma::commit(ctx.bar);
+    }
+    ctx.wait();
+    float v[16];
+    umma::tmem_ld16(ctx.lane_addr(kAcc1), v);
+    if (valid) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float x = round_h(v[c]);
+        rgb[static_cast<uint64_t>(r) * 3 + c] = round_h(1.0f / (1.0f + expf(-x)));  // fp16 sigmoid under autocast
+      }
+    }
+  }
+  umma::ctx_free(ctx, kFwdCols);
+}
+
+template <int N, bool TRANSPOSED>
+__device__ __forceinline__ void flush_wgrad(const umma::Ctx& ctx, uint32_t col0, float* __restrict__ grad, int ld,
+                                            float scale) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    umma::tmem_ld16(ctx.lane_addr(col0 + c0), v);
+    if (lane < 16) {
+      const int m = warp * 16 + lane;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        atomicAdd(grad + (TRANSPOSED ? (c0 + i) * ld + m : m * ld + c0 + i), v[i] * scale);
+    }
+  }
+}
+
+constexpr uint32_t kBwdCols = 512;
+constexpr uint32_t kBwdSmem = kWeightBytes + Tile<32>::kBytes + Tile<16>::kBytes + 6 * Tile<64>::kBytes +
+                              Tile<16>::kBytes + Tile<kSemOut>::kBytes + 64;
+
+__global__ void __launch_bounds__(128)
+heads_bwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__ k_ptr, uint32_t t,
+                    const float* __restrict__ rays_d, const __half* __restrict__ h,
+                    const __half* __restrict__ w_color, const __half* __restrict__ w_sem,
+                    const float* __restrict__ rgb, const __half* __restrict__ hc1, const __half* __restrict__ hc2,
+                    const __half* __restrict__ hs, const float* __restrict__ d_rgb,
+                    const float* __restrict__ d_logits, float loss_scale, __half* __restrict__ dh,
+                    float* __restrict__ grad_w_color, float* __restrict__ grad_w_sem) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* t_in_c = smem + kWeightBytes;
+  unsigned char* t_in_s = t_in_c + Tile<32>::kBytes;
+  unsigned char* t_h1 = t_in_s + Tile<16>::kBytes;
+  unsigned char* t_h2 = t_h1 + Tile<64>::kBytes;
+  unsigned char* t_hs = t_h2 + Tile<64>::kBytes;
+  unsigned char* t_dh1 = t_hs + Tile<64>::kBytes;
+  unsigned char* t_dh2 = t_dh1 + Tile<64>::kBytes;
+  unsigned char* t_dhs = t_dh2 + Tile<64>::kBytes;
+  unsigned char* t_dpre = t_dhs + Tile<64>::kBytes;
+  unsigned char* t_dlog = t_dpre + Tile<16>::kBytes;
+  unsigned char* tail = t_dlog + Tile<kSemOut>::kBytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(tail + 8);
+  const WeightTiles w = load_weights(smem, w_color, w_sem);
+  umma::Ctx ctx = umma::ctx_init(slot, bar, kBwdCols);
+  const uint32_t s_in_c = umma::smem_u32(t_in_c), s_in_s = umma::smem_u32(t_in_s), s_h1 = umma::smem_u32(t_h1),
+                 s_h2 = umma::smem_u32(t_h2), s_hs = umma::smem_u32(t_hs), s_dh1 = umma::smem_u32(t_dh1),
+                 s_dh2 = umma::smem_u32(t_dh2), s_dhs = umma::smem_u32(t_dhs), s_dpre = umma::smem_u32(t_dpre),
+                 s_dlog = umma::smem_u32(t_dlog);
+  // TMEM: two data-gradient scratch accumulators, then the five weight-gradient accumulators (UMMA M = 64)
+  constexpr uint32_t kAcc0 = 0, kAcc1 = 64, kGc1 = 128, kGc2 = 160, kGc3 = 224, kGs1 = 240, kGs2 = 256;
+
+  const float inv_scale = 1.0f / loss_scale;
+  const uint32_t k_rows = static_cast<uint32_t>(*k_ptr);
+  const uint32_t n_tiles = (k_rows + 127) / 128;
+  const int row = threadIdx.x;
+  bool first = true;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t r = tile * 128 + threadIdx.x;
+    const bool valid = r < k_rows;
+    const uint32_t flat = valid ? static_cast<uint32_t>(sel[r]) : 0u;
+    if (!first) ctx.wait();  // weight-gradient MMAs of the previous tile are done with the tiles
+    build_inputs(rays_d, h, flat, t, valid, t_in_c, t_in_s);
+    row_g2t<64>(t_h1, hc1 + static_cast<uint64_t>(r) * 64, valid);
+    row_g2t<64>(t_h2, hc2 + static_cast<uint64_t>(r) * 64, valid);
+    row_g2t<64>(t_hs, hs + static_cast<uint64_t>(r) * 64, valid);
+    {
+      H8 lo, hi;
+      lo.v = make_uint4(0, 0, 0, 0);
+      hi.v = make_uint4(0, 0, 0, 0);
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {  // through the sigmoid: s * (1 - s)
+          const float s = rgb[static_cast<uint64_t>(r) * 3 + c];
+          lo.h[c] = __float2half_rn(d_rgb[static_cast<uint64_t>(r) * 3 + c] * s * (1.0f - s) * loss_scale);
+        }
+      }
+      *Tile<16>::chunk(t_dpre, row, 0) = lo.v;
+      *Tile<16>::chunk(t_dpre, row, 1) = hi.v;
+    }
+#pragma unroll
+    for (int c = 0; c < kSemOut / 8; ++c) {
+      H8 o;
+      o.v = make_uint4(0, 0, 0, 0);
+      if (valid) {
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(d_logits + static_cast<uint64_t>(r) * kSemOut) + 2 * c);
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(d_logits + static_cast<uint64_t>(r) * kSemOut) + 2 * c + 1);
+        o.h[0] = __float2half_rn(a4.x * loss_scale); o.h[1] = __float2half_rn(a4.y * loss_scale);
+        o.h[2] = __float2half_rn(a4.z * loss_scale); o.h[3] = __float2half_rn(a4.w * loss_scale);
+        o.h[4] = __float2half_rn(b4.x * loss_scale); o.h[5] = __float2half_rn(b4.y * loss_scale);
+        o.h[6] = __float2half_rn(b4.z * loss_scale); o.h[7] = __float2half_rn(b4.w * loss_scale);
+      }
+      *Tile<kSemOut>::chunk(t_dlog, row, c) = o.v;
+    }
+    // ---- stage A: through the two output layers
+    ctx.publish();
+    if (threadIdx.x == 0) {
+      umma::tc_fence_after();
+      umma::issue_dgrad<16, 64>(ctx.tmem + kAcc0, s_dpre, w.c3);
+      umma::issue_dgrad<kSemOut, 64>(ctx.tmem + kAcc1, s_dlog, w.s2);
+      umma::commit(ctx.bar);
+      umma::issue_wgrad<16>(ctx.tmem + kGc3, s_h2, s_dpre, first);       // d(Wc3)^T = h2^T . dpre
+      umma::issue_wgrad<kSemOut>(ctx.tmem + kGs2, s_hs, s_dlog, first);  // d(Ws2)^T = hs^T . dlogits
+    }
+    ctx.wait();
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      umma::acc_to_tile16<64, false>(ctx, kAcc0 + c0, t_dh2, c0, t_h2);
+      umma::acc_to_tile16<64, false>(ctx, kAcc1 + c0, t_dhs, c0, t_hs);
+    }
+    // ---- stage B: colour layer 2, semantic layer 1
+    ctx.publish();
+    if (threadIdx.x == 0) {
+      umma::tc_fence_after();
+      umma::issue_dgrad<64, 64>(ctx.tmem + kAcc0, s_dh2, w.c2);
+      umma::issue_dgrad<64, 16>(ctx.tmem + kAcc1, s_dhs, w.s1);
+      umma::commit(ctx.bar);
+      umma::issue_wgrad<64>(ctx.tmem + kGc2, s_dh2, s_h1, first);    // d(Wc2) = dh2^T . h1
+      umma::issue_wgrad<16>(ctx.tmem + kGs1, s_dhs, s_in_s, first);  // d(Ws1) = dhs^T . in_s
+    }
+    ctx.wait();
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) umma::acc_to_tile16<64, false>(ctx, kAcc0 + c0, t_dh1, c0, t_h1);
+    float d_in_s[16];
+    umma::tmem_ld16(ctx.lane_addr(kAcc1), d_in_s);
+    // ---- stage C: colour layer 1
+    ctx.publish();
+    if (threadIdx.x == 0) {
+      umma::tc_fence_after();
+      umma::issue_dgrad<64, 32>(ctx.tmem + kAcc0, s_dh1, w.c1);
+      umma::commit(ctx.bar);
+      umma::issue_wgrad<32>(ctx.tmem + kGc1, s_dh1, s_in_c, first);  // d(Wc1) = dh1^T . in_c
+    }
+    ctx.wait();
+    float d_in_c[16];
+    umma::tmem_ld16(ctx.lane_addr(kAcc0 + 16), d_in_c);  // columns 16..31 = the geo_feat (+1) inputs
+    if (valid) {
+      // dL/dgeo_feat = colour part + semantic part, handed to density_bwd as fp16 (still scaled)
+      H8 lo, hi;
+      lo.h[0] = __float2half_rn(0.f);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) lo.h[i + 1] = __float2half_rn(round_h(d_in_c[i]) + round_h(d_in_s[i]));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) hi.h[i] = __float2half_rn(round_h(d_in_c[7 + i]) + round_h(d_in_s[7 + i]));
+      reinterpret_cast<uint4*>(dh + static_cast<uint64_t>(flat) * 16)[0] = lo.v;
+      reinterpret_cast<uint4*>(dh + static_cast<uint64_t>(flat) * 16)[1] = hi.v;
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      umma::tc_fence_after();
+      umma::commit(ctx.bar);  // covers the weight-gradient products of this tile
+    }
+    first = false;
+  }
+  if (!first) {
+    ctx.wait();
+    flush_wgrad<32, false>(ctx, kGc1, grad_w_color + kColorW1, 32, inv_scale);
+    flush_wgrad<64, false>(ctx, kGc2, grad_w_color + kColorW2, 64, inv_scale);
+    flush_wgrad<16, true>(ctx, kGc3, grad_w_color + kColorW3, 64, inv_scale);
+    flush_wgrad<16, false>(ctx, kGs1, grad_w_sem + kSemW1, 16, inv_scale);
+    flush_wgrad<kSemOut, true>(ctx, kGs2, grad_w_sem + kSemW2, 64, inv_scale);
+  }
+  umma::ctx_free(ctx, kBwdCols);
+}
+
+uint32_t heads_grid(uint32_t k_max, int ctas_per_sm) {
+  const uint32_t tiles = (k_max + 127) / 128;
+  const uint32_t cap = kNumSMs * ctas_per_sm;
+  return tiles < cap ? tiles : cap;
+}
+
+}  // namespace
+}  // namespace ucsa
+
+using namespace ucsa;
+
+extern "C" int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32_t n_rays, uint32_t t,
+                              uint32_t k_max, const float* rays_d, const void* h, const void* w_color_h,
+                              const void* w_sem_h, uint32_t n_classes, float* rgb, void* logits, void* hc1,
+                              void* hc2, void* hs, void* stream) {
+  UCSA_REQUIRE(sel && ray_off && rays_d && h && w_color_h && w_sem_h && rgb && logits, "heads_fwd: null pointer");
+  UCSA_REQUIRE(n_classes >= 1 && n_classes <= UCSA_MAX_CLASSES, "heads_fwd: 1 <= classes <= %d", UCSA_MAX_CLASSES);
+  if (k_max == 0) return UCSA_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(heads_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
+    attr_set = true;
+  }
+  heads_fwd_tc_kernel<<<heads_grid(k_max, 2), 128, kFwdSmem, as_stream(stream)>>>(
+      sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h),
+      static_cast<const __half*>(w_sem_h), rgb, static_cast<__half*>(logits), static_cast<__half*>(hc1),
+      static_cast<__half*>(hc2), static_cast<__half*>(hs));
+  return check_launch("heads_fwd");
+}
+
+extern "C" int ucsa_heads_bwd(const int32_t* sel, const int32_t* ray_off, uint32_t n_rays, uint32_t t,
+                              uint32_t k_max, const float* rays_d, const void* h, const void* w_color_h,
+                              const void* w_sem_h, uint32_t n_classes, const float* rgb, const void* hc1,
+                              const void* hc2, const void* hs, const float* d_rgb, const float* d_logits,
+                              float loss_scale, void* dh, float* grad_w_color, float* grad_w_sem, void* stream) {
+  UCSA_REQUIRE(sel && ray_off && rays_d && h && w_color_h && w_sem_h && rgb && hc1 && hc2 && hs && d_rgb &&
+                   d_logits && dh && grad_w_color && grad_w_sem,
+               "heads_bwd: null pointer");
+  UCSA_REQUIRE(n_classes >= 1 && n_classes <= UCSA_MAX_CLASSES, "heads_bwd: 1 <= classes <= %d", UCSA_MAX_CLASSES);
+  UCSA_REQUIRE(loss_scale > 0.f, "heads_bwd: loss_scale must be positive");
+  if (k_max == 0) return UCSA_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(heads_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+    attr_set = true;
+  }
+  heads_bwd_tc_kernel<<<heads_grid(k_max, 1), 128, kBwdSmem, as_stream(stream)>>>(
+      sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h),
+      static_cast<const __half*>(w_sem_h), rgb, static_cast<const __half*>(hc1), static_cast<const __half*>(hc2),
+      static_cast<const __half*>(hs), d_rgb, d_logits, loss_scale, static_cast<__half*>(dh), grad_w_color,
+      grad_w_sem);
+  return check_launch("heads_bwd");
+}

@@ -276,7 +276,7 @@ extern "C" int ucsa_sh4_fwd(const float* d01, uint32_t n, void* out_h, void* str
   return check_launch("sh4_fwd");
 }
 
-extern "C" int ucsa_mlp_fwd(const void* x_h, uint32_t n, const void* w_h, const uint32_t* dims, uint32_t n_layers,
+extern "C" int ucsa_mlp_fwd_simt(const void* x_h, uint32_t n, const void* w_h, const uint32_t* dims, uint32_t n_layers,
                             void* y_h, void* acts_h, void* stream) {
   UCSA_REQUIRE(x_h && w_h && dims && y_h, "mlp_fwd: null pointer");
   if (n == 0) return UCSA_OK;
@@ -290,7 +290,7 @@ extern "C" int ucsa_mlp_fwd(const void* x_h, uint32_t n, const void* w_h, const 
   }
 }
 
-extern "C" int ucsa_mlp_bwd(const void* x_h, uint32_t n, const void* w_h, const uint32_t* dims, uint32_t n_layers,
+extern "C" int ucsa_mlp_bwd_simt(const void* x_h, uint32_t n, const void* w_h, const uint32_t* dims, uint32_t n_layers,
                             const void* acts_h, const void* dy_h, float inv_loss_scale, void* dx_h, float* grad_w,
                             void* stream) {
   UCSA_REQUIRE(x_h && w_h && dims && acts_h && dy_h && grad_w, "mlp_bwd: null pointer");

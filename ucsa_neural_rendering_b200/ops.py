@@ -64,12 +64,13 @@ def sample_coarse(nears, fars, lin, z_cat, tc, *, perturb, t_rand=None, seed=0, 
 
 
 def density_fwd(grid, table_h, w_sigma_h, bound, *, xyz=None, rays_o=None, rays_d=None, aabb=None, z_cat=None,
-                k0=0, k1=1, sigma, h, enc=None, hid=None):
+                k0=0, k1=1, sigma, h, enc=None, hid=None, simt=False):
     if xyz is not None:
         n, t = xyz.shape[0], 1
     else:
         n, t = z_cat.shape
-    check(lib().ucsa_density_fwd(_ptr(xyz, torch.float32, "xyz"), _ptr(rays_o, torch.float32, "rays_o"),
+    fn = lib().ucsa_density_fwd_simt if simt else lib().ucsa_density_fwd
+    check(fn(_ptr(xyz, torch.float32, "xyz"), _ptr(rays_o, torch.float32, "rays_o"),
                                  _ptr(rays_d, torch.float32, "rays_d"), _ptr(aabb, torch.float32, "aabb"),
                                  _ptr(z_cat, torch.float32, "z_cat"), n, t, k0, k1, float(bound),
                                  _ptr(table_h, torch.float16, "table_h"), ctypes.byref(grid),
@@ -79,12 +80,13 @@ def density_fwd(grid, table_h, w_sigma_h, bound, *, xyz=None, rays_o=None, rays_
 
 
 def density_bwd(grid, w_sigma_h, bound, *, xyz=None, rays_o=None, rays_d=None, aabb=None, z_cat=None, k0=0, k1=1,
-                h, enc, hid, d_sigma, dh, use_geo, loss_scale, grad_table, grad_w_sigma):
+                h, enc, hid, d_sigma, dh, use_geo, loss_scale, grad_table, grad_w_sigma, simt=False):
     if xyz is not None:
         n, t = xyz.shape[0], 1
     else:
         n, t = z_cat.shape
-    check(lib().ucsa_density_bwd(_ptr(xyz, torch.float32, "xyz"), _ptr(rays_o, torch.float32), _ptr(rays_d, torch.float32),
+    fn = lib().ucsa_density_bwd_simt if simt else lib().ucsa_density_bwd
+    check(fn(_ptr(xyz, torch.float32, "xyz"), _ptr(rays_o, torch.float32), _ptr(rays_d, torch.float32),
                                  _ptr(aabb, torch.float32), _ptr(z_cat, torch.float32), n, t, k0, k1, float(bound),
                                  ctypes.byref(grid), _ptr(w_sigma_h, torch.float16), _ptr(h, torch.float16),
                                  _ptr(enc, torch.float16), _ptr(hid, torch.float16), _ptr(d_sigma, torch.float32, "d_sigma"),
@@ -121,8 +123,9 @@ def compact_masked(w_sorted, z_cat, order, ray_off, sel, w_sel, z_sel):
 
 
 def heads_fwd(sel, ray_off, n_rays, t, k_max, rays_d, h, w_color_h, w_sem_h, n_classes, rgb, logits,
-              hc1=None, hc2=None, hs=None):
-    check(lib().ucsa_heads_fwd(_ptr(sel, torch.int32), _ptr(ray_off, torch.int32), n_rays, t, k_max,
+              hc1=None, hc2=None, hs=None, simt=False):
+    fn = lib().ucsa_heads_fwd_simt if simt else lib().ucsa_heads_fwd
+    check(fn(_ptr(sel, torch.int32), _ptr(ray_off, torch.int32), n_rays, t, k_max,
                                _ptr(rays_d, torch.float32), _ptr(h, torch.float16), _ptr(w_color_h, torch.float16),
                                _ptr(w_sem_h, torch.float16), n_classes, _ptr(rgb, torch.float32),
                                _ptr(logits, torch.float16), _ptr(hc1, torch.float16), _ptr(hc2, torch.float16),
@@ -130,8 +133,9 @@ def heads_fwd(sel, ray_off, n_rays, t, k_max, rays_d, h, w_color_h, w_sem_h, n_c
 
 
 def heads_bwd(sel, ray_off, n_rays, t, k_max, rays_d, h, w_color_h, w_sem_h, n_classes, rgb, hc1, hc2, hs, d_rgb,
-              d_logits, loss_scale, dh, grad_w_color, grad_w_sem):
-    check(lib().ucsa_heads_bwd(_ptr(sel, torch.int32), _ptr(ray_off, torch.int32), n_rays, t, k_max,
+              d_logits, loss_scale, dh, grad_w_color, grad_w_sem, simt=False):
+    fn = lib().ucsa_heads_bwd_simt if simt else lib().ucsa_heads_bwd
+    check(fn(_ptr(sel, torch.int32), _ptr(ray_off, torch.int32), n_rays, t, k_max,
                                _ptr(rays_d, torch.float32), _ptr(h, torch.float16), _ptr(w_color_h, torch.float16),
                                _ptr(w_sem_h, torch.float16), n_classes, _ptr(rgb, torch.float32),
                                _ptr(hc1, torch.float16), _ptr(hc2, torch.float16), _ptr(hs, torch.float16),
@@ -214,16 +218,18 @@ def _dims_array(dims):
     return (ctypes.c_uint32 * len(dims))(*dims)
 
 
-def mlp_fwd(x_h, w_h, dims, y_h, acts_h=None):
+def mlp_fwd(x_h, w_h, dims, y_h, acts_h=None, simt=False):
     arr = _dims_array(dims)
-    check(lib().ucsa_mlp_fwd(_ptr(x_h, torch.float16, "x"), x_h.shape[0], _ptr(w_h, torch.float16),
+    fn = lib().ucsa_mlp_fwd_simt if simt else lib().ucsa_mlp_fwd
+    check(fn(_ptr(x_h, torch.float16, "x"), x_h.shape[0], _ptr(w_h, torch.float16),
                              ctypes.cast(arr, ctypes.c_void_p), len(dims) - 1, _ptr(y_h, torch.float16),
                              _ptr(acts_h, torch.float16), _stream()), "mlp_fwd")
 
 
-def mlp_bwd(x_h, w_h, dims, acts_h, dy_h, inv_loss_scale, dx_h, grad_w):
+def mlp_bwd(x_h, w_h, dims, acts_h, dy_h, inv_loss_scale, dx_h, grad_w, simt=False):
     arr = _dims_array(dims)
-    check(lib().ucsa_mlp_bwd(_ptr(x_h, torch.float16), x_h.shape[0], _ptr(w_h, torch.float16),
+    fn = lib().ucsa_mlp_bwd_simt if simt else lib().ucsa_mlp_bwd
+    check(fn(_ptr(x_h, torch.float16), x_h.shape[0], _ptr(w_h, torch.float16),
                              ctypes.cast(arr, ctypes.c_void_p), len(dims) - 1, _ptr(acts_h, torch.float16),
                              _ptr(dy_h, torch.float16, "dy"), float(inv_loss_scale), _ptr(dx_h, torch.float16),
                              _ptr(grad_w, torch.float32), _stream()), "mlp_bwd")
