@@ -95,4 +95,49 @@ __device__ __forceinline__ void red_add_f32x2(float* addr, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 
+// ------------------------------------------------------------------ L2 residency control
+// The 25 MB fp16 hash table (forward) and the 52 MB fp32 gradient table (backward) are re-used by every sample and
+// fit the 126 MB L2; the per-sample activation streams (hundreds of MB per step) are touched once.  Streams are
+// tagged evict_first, tables evict_last, so that the streams do not push the tables out to HBM.
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ld_stream(const void* ptr, uint64_t policy) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(ptr), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ void st_stream(void* ptr, const uint4& v, uint64_t policy) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(ptr), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void st_stream_f32(float* ptr, float v, uint64_t policy) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(ptr), "f"(v), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t ld_keep_b32(const void* ptr, uint64_t policy) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ void red_keep_f32x2(float* addr, float a, float b, uint64_t policy) {
+  asm volatile("red.global.add.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(addr), "f"(a), "f"(b), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void red_keep_f32x4(float* addr, float a, float b, float c, float d, uint64_t policy) {
+  asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(addr), "f"(a), "f"(b),
+               "f"(c), "f"(d), "l"(policy)
+               : "memory");
+}
+
 }  // namespace ucsa

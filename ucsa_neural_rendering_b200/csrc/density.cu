@@ -69,6 +69,7 @@ density_fwd_kernel(const DensityArgs a, const __half2* __restrict__ table, const
   __half* out_t = hid_t + kTileRows * kHidLd;
   load_weights_f32(w1, w_sigma, UCSA_SIGMA_PARAMS);
   __syncthreads();
+  const uint64_t keep = l2_policy_keep();
 
   __half* enc_row = enc_t + threadIdx.x * kEncLd;
   __half* hid_row = hid_t + threadIdx.x * kHidLd;
@@ -81,7 +82,7 @@ density_fwd_kernel(const DensityArgs a, const __half2* __restrict__ table, const
     const uint64_t flat = locate_sample(a, s, x01);
 #pragma unroll 4
     for (int l = 0; l < UCSA_GRID_LEVELS; ++l) {
-      const float2 f = interp_level(table, level_geom(a.grid, l), x01);
+      const float2 f = interp_level(table, level_geom(a.grid, l), x01, keep);
       *reinterpret_cast<__half2*>(enc_row + 2 * l) = __floats2half2_rn(f.x, f.y);
     }
     dense_row_fwd<32, 64, true>(w1, enc_row, hid_row);
@@ -108,6 +109,7 @@ density_bwd_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, cons
   __half* dout_t = dhid_t + kTileRows * kHidLd;
   load_weights_f32(w1, w_sigma, UCSA_SIGMA_PARAMS);
   __syncthreads();
+  const uint64_t keep = l2_policy_keep();
 
   __half* enc_row = enc_t + threadIdx.x * kEncLd;
   __half* hid_row = hid_t + threadIdx.x * kHidLd;
@@ -150,7 +152,7 @@ density_bwd_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, cons
 #pragma unroll
         for (int l = 0; l < UCSA_GRID_LEVELS; ++l) {
           scatter_level(grad_table, level_geom(a.grid, l), x01, round_h(dx32[2 * l]) * inv_scale,
-                        round_h(dx32[2 * l + 1]) * inv_scale);
+                        round_h(dx32[2 * l + 1]) * inv_scale, keep);
         }
       }
     } else {

@@ -7,7 +7,8 @@
 //   The encoded features and hidden activations reach HBM only as the copies saved for the backward pass.
 // Backward: dL/dh tile -> UMMA data gradients back to dL/d(encoded), weight gradients accumulated in TMEM over
 //   all tiles of the CTA, and the hash-table gradient scattered with vector reductions (red.global.add.v2.f32).
-// Several CTAs per SM (TMEM: 128 columns each) overlap one tile's gather/scatter phase with another's MMAs.
+// Several CTAs per SM (TMEM: 64 / 128 columns each) overlap one tile's gather/scatter phase with another's MMAs.
+// The hash table and its gradient are tagged L2 evict_last, the per-sample streams evict_first (common.cuh).
 #include "grid.cuh"
 #include "mlp_umma.cuh"
 
@@ -43,7 +44,9 @@ __device__ __forceinline__ uint64_t locate_sample(const DensityArgs& a, uint64_t
 
 constexpr uint32_t kW1Bytes = 64 / 8 * Tile<32>::kGroupBytes;  // [64][32]
 constexpr uint32_t kW2Bytes = 16 / 8 * Tile<64>::kGroupBytes;  // [16][64]
-constexpr uint32_t kTmemCols = 128;
+constexpr uint32_t kFwdTmemCols = 64;   // layer-2 accumulator re-uses the columns of layer 1 once they are read
+constexpr uint32_t kBwdTmemCols = 128;
+constexpr int kFwdCtasPerSm = 6, kBwdCtasPerSm = 4;
 
 __global__ void __launch_bounds__(128)
 density_fwd_tc_kernel(const DensityArgs a, const __half2* __restrict__ table, const __half* __restrict__ w_sigma,
@@ -59,10 +62,11 @@ density_fwd_tc_kernel(const DensityArgs a, const __half2* __restrict__ table, co
   uint32_t* slot = reinterpret_cast<uint32_t*>(tail + 8);
   umma::load_weight_tile<32>(w1, w_sigma, 64);
   umma::load_weight_tile<64>(w2, w_sigma + 64 * 32, 16);
-  umma::Ctx ctx = umma::ctx_init(slot, bar, kTmemCols);
+  umma::Ctx ctx = umma::ctx_init(slot, bar, kFwdTmemCols);
   const uint32_t s_enc = umma::smem_u32(t_enc), s_hid = umma::smem_u32(t_hid);
   const uint32_t s_w1 = umma::smem_u32(w1), s_w2 = umma::smem_u32(w2);
-  constexpr uint32_t kAcc1 = 0, kAcc2 = 64;
+  constexpr uint32_t kAcc1 = 0, kAcc2 = 0;
+  const uint64_t keep = l2_policy_keep(), stream = l2_policy_stream();
 
   const int row = threadIdx.x;
   const uint64_t n_tiles = (a.n_samples + 127) / 128;
@@ -78,11 +82,11 @@ density_fwd_tc_kernel(const DensityArgs a, const __half2* __restrict__ table, co
         H8 o;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 f = interp_level(table, level_geom(a.grid, 4 * c + j), x01);
+          const float2 f = interp_level(table, level_geom(a.grid, 4 * c + j), x01, keep);
           o.h2[j] = __floats2half2_rn(f.x, f.y);
         }
         *Tile<32>::chunk(t_enc, row, c) = o.v;
-        if (enc != nullptr) reinterpret_cast<uint4*>(enc + flat * 32)[c] = o.v;
+        if (enc != nullptr) st_stream(enc + flat * 32 + c * 8, o.v, stream);
       }
     } else {
 #pragma unroll
@@ -99,7 +103,7 @@ density_fwd_tc_kernel(const DensityArgs a, const __half2* __restrict__ table, co
     for (int c0 = 0; c0 < 64; c0 += 16) umma::acc_to_tile16<64, true>(ctx, kAcc1 + c0, t_hid, c0);
     if (hid != nullptr && valid) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) reinterpret_cast<uint4*>(hid + flat * 64)[c] = *Tile<64>::chunk(t_hid, row, c);
+      for (int c = 0; c < 8; ++c) st_stream(hid + flat * 64 + c * 8, *Tile<64>::chunk(t_hid, row, c), stream);
     }
     ctx.publish();
     if (threadIdx.x == 0) {
@@ -117,12 +121,12 @@ density_fwd_tc_kernel(const DensityArgs a, const __half2* __restrict__ table, co
         lo.h[i] = __float2half_rn(v[i]);
         hi.h[i] = __float2half_rn(v[8 + i]);
       }
-      reinterpret_cast<uint4*>(h + flat * 16)[0] = lo.v;
-      reinterpret_cast<uint4*>(h + flat * 16)[1] = hi.v;
-      sigma[flat] = expf(__half2float(lo.h[0]));  // trunc_exp forward, fp32
+      st_stream(h + flat * 16, lo.v, stream);
+      st_stream(h + flat * 16 + 8, hi.v, stream);
+      st_stream_f32(sigma + flat, expf(__half2float(lo.h[0])), stream);  // trunc_exp forward, fp32
     }
   }
-  umma::ctx_free(ctx, kTmemCols);
+  umma::ctx_free(ctx, kFwdTmemCols);
 }
 
 // [64 x N] weight-gradient accumulator (UMMA M = 64) -> global fp32 (see mlp_umma.cuh)
@@ -161,7 +165,8 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
   uint32_t* slot = reinterpret_cast<uint32_t*>(tail + 8);
   umma::load_weight_tile<32>(w1, w_sigma, 64);
   umma::load_weight_tile<64>(w2, w_sigma + 64 * 32, 16);
-  umma::Ctx ctx = umma::ctx_init(slot, bar, kTmemCols);
+  umma::Ctx ctx = umma::ctx_init(slot, bar, kBwdTmemCols);
+  const uint64_t keep = l2_policy_keep(), stream = l2_policy_stream();
   const uint32_t s_enc = umma::smem_u32(t_enc), s_hid = umma::smem_u32(t_hid), s_dhid = umma::smem_u32(t_dhid),
                  s_dout = umma::smem_u32(t_dout), s_w1 = umma::smem_u32(w1), s_w2 = umma::smem_u32(w2);
   constexpr uint32_t kAcc = 0, kG1 = 64, kG2 = 96;  // scratch 64 | dW1 [64x32] | dW2^T [64x16]
@@ -180,8 +185,8 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
       // dL/dh: element 0 through trunc_exp (activation.py:16-19), elements 1..15 = dL/dgeo_feat from the heads
       H8 lo, hi;
       if (use_geo != nullptr && dh != nullptr && use_geo[flat]) {
-        lo.v = __ldg(reinterpret_cast<const uint4*>(dh + flat * 16));
-        hi.v = __ldg(reinterpret_cast<const uint4*>(dh + flat * 16 + 8));
+        lo.v = ld_stream(dh + flat * 16, stream);
+        hi.v = ld_stream(dh + flat * 16 + 8, stream);
       } else {
         lo.v = make_uint4(0, 0, 0, 0);
         hi.v = make_uint4(0, 0, 0, 0);
@@ -193,10 +198,10 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
       *Tile<16>::chunk(t_dout, row, 1) = hi.v;
 #pragma unroll
       for (int c = 0; c < 8; ++c)
-        *Tile<64>::chunk(t_hid, row, c) = __ldg(reinterpret_cast<const uint4*>(hid + flat * 64) + c);
+        *Tile<64>::chunk(t_hid, row, c) = ld_stream(hid + flat * 64 + c * 8, stream);
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        *Tile<32>::chunk(t_enc, row, c) = __ldg(reinterpret_cast<const uint4*>(enc + flat * 32) + c);
+        *Tile<32>::chunk(t_enc, row, c) = ld_stream(enc + flat * 32 + c * 8, stream);
     } else {
       const uint4 z = make_uint4(0, 0, 0, 0);
       *Tile<16>::chunk(t_dout, row, 0) = z;
@@ -244,14 +249,14 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
 #pragma unroll
       for (int l = 0; l < UCSA_GRID_LEVELS; ++l)
         scatter_level(grad_table, level_geom(a.grid, l), x01, round_h(g[2 * l]) * inv_scale,
-                      round_h(g[2 * l + 1]) * inv_scale);
+                      round_h(g[2 * l + 1]) * inv_scale, keep);
     }
     first = false;
   }
   ctx.wait();
   flush_wgrad<32, false>(ctx, kG1, grad_w, 32, inv_scale);
   flush_wgrad<16, true>(ctx, kG2, grad_w + 64 * 32, 64, inv_scale);
-  umma::ctx_free(ctx, kTmemCols);
+  umma::ctx_free(ctx, kBwdTmemCols);
 }
 
 constexpr size_t kFwdSmem = kW1Bytes + kW2Bytes + Tile<32>::kBytes + Tile<64>::kBytes + 64;
@@ -298,7 +303,7 @@ extern "C" int ucsa_density_fwd(const float* xyz, const float* rays_o, const flo
     cudaFuncSetAttribute(density_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
     attr_set = true;
   }
-  density_fwd_tc_kernel<<<persistent_grid(a.n_samples, 4), 128, kFwdSmem, as_stream(stream)>>>(
+  density_fwd_tc_kernel<<<persistent_grid(a.n_samples, kFwdCtasPerSm), 128, kFwdSmem, as_stream(stream)>>>(
       a, static_cast<const __half2*>(table_h), static_cast<const __half*>(w_sigma_h), sigma,
       static_cast<__half*>(h), static_cast<__half*>(enc), static_cast<__half*>(hid));
   return check_launch("density_fwd");
@@ -320,7 +325,7 @@ extern "C" int ucsa_density_bwd(const float* xyz, const float* rays_o, const flo
     cudaFuncSetAttribute(density_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
     attr_set = true;
   }
-  density_bwd_tc_kernel<<<persistent_grid(a.n_samples, 4), 128, kBwdSmem, as_stream(stream)>>>(
+  density_bwd_tc_kernel<<<persistent_grid(a.n_samples, kBwdCtasPerSm), 128, kBwdSmem, as_stream(stream)>>>(
       a, static_cast<const __half*>(w_sigma_h), static_cast<const __half*>(h), static_cast<const __half*>(enc),
       static_cast<const __half*>(hid), d_sigma, static_cast<const __half*>(dh), use_geo, loss_scale, grad_table,
       grad_w_sigma);

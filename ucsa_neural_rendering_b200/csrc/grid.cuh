@@ -60,13 +60,16 @@ __device__ __forceinline__ float corner_weight(const Cell& cell, int corner) {
   return w;
 }
 
-// One level: trilinear interpolation of the fp16 table, fp32 accumulate.
+// One level: trilinear interpolation of the fp16 table, fp32 accumulate.  `keep` = l2_policy_keep().
 __device__ __forceinline__ float2 interp_level(const __half2* __restrict__ table, const LevelGeom& lv,
-                                               const float x01[3]) {
+                                               const float x01[3], uint64_t keep) {
   const Cell cell = locate(lv, x01);
   __half2 v[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) v[c] = __ldg(table + corner_entry(lv, cell, c));
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t bits = ld_keep_b32(table + corner_entry(lv, cell, c), keep);
+    v[c] = *reinterpret_cast<const __half2*>(&bits);
+  }
   float a0 = 0.f, a1 = 0.f;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
@@ -78,15 +81,25 @@ __device__ __forceinline__ float2 interp_level(const __half2* __restrict__ table
   return make_float2(a0, a1);
 }
 
-// Scatter of one level's gradient: grad_table[entry] += w_c * (g0, g1).
+// Scatter of one level's gradient: grad_table[entry] += w_c * (g0, g1).  The x and x+1 corners of a pair land in
+// adjacent entries whenever x is even (dense levels: index = x + ...; hashed levels: x enters the XOR with prime 1),
+// and then go out as one 16-byte vector reduction.  `keep` = l2_policy_keep().
 __device__ __forceinline__ void scatter_level(float* __restrict__ grad_table, const LevelGeom& lv,
-                                              const float x01[3], float g0, float g1) {
+                                              const float x01[3], float g0, float g1, uint64_t keep) {
   if (g0 == 0.f && g1 == 0.f) return;
   const Cell cell = locate(lv, x01);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const float w = corner_weight(cell, c);
-    red_add_f32x2(grad_table + 2ull * corner_entry(lv, cell, c), w * g0, w * g1);
+  for (int c = 0; c < 8; c += 2) {
+    const uint32_t e0 = corner_entry(lv, cell, c), e1 = corner_entry(lv, cell, c + 1);
+    const float w0 = corner_weight(cell, c), w1 = corner_weight(cell, c + 1);
+    if ((e0 ^ e1) == 1u) {
+      float* p = grad_table + 2ull * (e0 & ~1u);
+      if (e0 & 1u) red_keep_f32x4(p, w1 * g0, w1 * g1, w0 * g0, w0 * g1, keep);
+      else red_keep_f32x4(p, w0 * g0, w0 * g1, w1 * g0, w1 * g1, keep);
+    } else {
+      red_keep_f32x2(grad_table + 2ull * e0, w0 * g0, w0 * g1, keep);
+      red_keep_f32x2(grad_table + 2ull * e1, w1 * g0, w1 * g1, keep);
+    }
   }
 }
 

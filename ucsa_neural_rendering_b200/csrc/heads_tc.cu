@@ -82,17 +82,19 @@ __device__ __forceinline__ void build_inputs(const float* __restrict__ rays_d, c
   *Tile<16>::chunk(t_in_s, row, 1) = g1.v;
 }
 
+// saved activations are written once and read once (backward): tag them evict_first in L2
 template <int W>
 __device__ __forceinline__ void row_t2g(__half* __restrict__ dst, unsigned char* tile) {
+  const uint64_t stream = l2_policy_stream();
 #pragma unroll
-  for (int c = 0; c < W / 8; ++c) reinterpret_cast<uint4*>(dst)[c] = *Tile<W>::chunk(tile, threadIdx.x, c);
+  for (int c = 0; c < W / 8; ++c) st_stream(dst + c * 8, *Tile<W>::chunk(tile, threadIdx.x, c), stream);
 }
 template <int W>
 __device__ __forceinline__ void row_g2t(unsigned char* tile, const __half* __restrict__ src, bool valid) {
+  const uint64_t stream = l2_policy_stream();
 #pragma unroll
   for (int c = 0; c < W / 8; ++c)
-    *Tile<W>::chunk(tile, threadIdx.x, c) =
-        valid ? __ldg(reinterpret_cast<const uint4*>(src) + c) : make_uint4(0, 0, 0, 0);
+    *Tile<W>::chunk(tile, threadIdx.x, c) = valid ? ld_stream(src + c * 8, stream) : make_uint4(0, 0, 0, 0);
 }
 
 constexpr uint32_t kFwdCols = 256;

@@ -15,7 +15,7 @@ __global__ void hashgrid_fwd_kernel(const float* __restrict__ x01, uint32_t n, c
   if (i >= static_cast<uint64_t>(n) * UCSA_GRID_LEVELS) return;
   const uint32_t s = static_cast<uint32_t>(i / UCSA_GRID_LEVELS), l = static_cast<uint32_t>(i % UCSA_GRID_LEVELS);
   const float x[3] = {x01[3ull * s], x01[3ull * s + 1], x01[3ull * s + 2]};
-  const float2 f = interp_level(table, level_geom(grid, l), x);
+  const float2 f = interp_level(table, level_geom(grid, l), x, l2_policy_keep());
   reinterpret_cast<__half2*>(enc)[i] = __floats2half2_rn(f.x, f.y);
 }
 
@@ -27,7 +27,7 @@ __global__ void hashgrid_bwd_kernel(const float* __restrict__ x01, uint32_t n, c
   const uint32_t s = static_cast<uint32_t>(i / UCSA_GRID_LEVELS), l = static_cast<uint32_t>(i % UCSA_GRID_LEVELS);
   const float x[3] = {x01[3ull * s], x01[3ull * s + 1], x01[3ull * s + 2]};
   const float2 g = __half22float2(reinterpret_cast<const __half2*>(d_enc)[i]);
-  scatter_level(grad_table, level_geom(grid, l), x, g.x * inv_scale, g.y * inv_scale);
+  scatter_level(grad_table, level_geom(grid, l), x, g.x * inv_scale, g.y * inv_scale, l2_policy_keep());
 }
 
 __global__ void hashgrid_indices_kernel(const float* __restrict__ x01, uint32_t n, const ucsa_grid_desc grid,
