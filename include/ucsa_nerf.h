@@ -159,6 +159,44 @@ UCSA_API int ucsa_composite_dense_bwd(const float* sigma, const float* z, const 
                              const float* g_semantics, uint32_t n_rays, uint32_t t, uint32_t n_classes,
                              float density_scale, float* d_sigma, float* d_rgb, float* d_prob, void* stream);
 
+/* ---- a16-a20. occupancy-grid path: replaces the bound kernels of raymarching.h:9-18 / bindings.cpp:5-18.
+ * The occupancy test reads `bitfield` when non-null (ucsa_grid_packbits), else the float `grid` [C,H,H,H] exactly like
+ * raymarching.cu:157,204-210 (density > min(0.01, mean_density)).  Sample offsets are handed out in ray order:
+ * rays[n] = (n, offset, count); counter[0] += total samples, counter[1] += n_rays.  `scratch` is int32 [2*n_rays+1]. */
+UCSA_API int ucsa_march_rays_train(const float* rays_o, const float* rays_d, const float* grid, const uint32_t* bitfield,
+                          float mean_density, float bound, float dt_gamma, uint32_t n_rays, uint32_t C, uint32_t H,
+                          uint32_t max_points, const float* nears, const float* fars, float* xyzs, float* dirs,
+                          float* deltas, int32_t* rays, int32_t* counter, uint32_t perturb, int32_t* scratch,
+                          void* stream);
+UCSA_API int ucsa_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                    const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t C, uint32_t H,
+                    const float* grid, const uint32_t* bitfield, float mean_density, const float* nears,
+                    const float* fars, float* xyzs, float* dirs, float* deltas, uint32_t perturb, void* stream);
+/* rgb + depth as raymarching.cu:318-487; local_semantics [M,C] / semantics [N,C] optional (both null or both set):
+ * the semantic kernels the reference declares (raymarching.h:12-13) but never implemented. */
+UCSA_API int ucsa_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* local_semantics,
+                                      const float* deltas, const int32_t* rays, uint32_t M, uint32_t N,
+                                      uint32_t n_classes, float* weights_sum, float* depth, float* image,
+                                      float* semantics, void* stream);
+UCSA_API int ucsa_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image,
+                                       const float* grad_semantics, const float* sigmas, const float* rgbs,
+                                       const float* deltas, const int32_t* rays, const float* weights_sum,
+                                       const float* image, uint32_t M, uint32_t N, uint32_t n_classes,
+                                       float* grad_sigmas, float* grad_rgbs, float* grad_local_semantics,
+                                       void* stream);
+/* inference wavefront: raymarching.cu:647-729 (+ semantics), order-preserving compaction for :837-855 */
+UCSA_API int ucsa_composite_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, float* rays_t,
+                        const float* sigmas, const float* rgbs, const float* local_semantics, const float* deltas,
+                        uint32_t n_classes, float* weights_sum, float* depth, float* image, float* semantics,
+                        void* stream);
+UCSA_API int ucsa_compact_rays(uint32_t n_alive, int32_t* rays_alive, const int32_t* rays_alive_old, float* rays_t,
+                      const float* rays_t_old, int32_t* alive_counter, void* stream);
+/* occupancy grid maintenance (not in the reference; torch-ngp's rule): grid = max(grid*decay, fresh) where fresh >= 0;
+ * bitfield bit i = grid[i] > min(0.01, mean_density). */
+UCSA_API int ucsa_grid_update(float* density_grid, const float* fresh, uint64_t n_cells, float decay, void* stream);
+UCSA_API int ucsa_grid_packbits(const float* density_grid, uint64_t n_cells, float mean_density, uint32_t* bitfield,
+                       void* stream);
+
 /* ---- stand-alone encoders / MLP, the module-level API the reference network exposes
  * (self.encoder, self.encoder_dir, tcnn.Network; network_tcnn_semantics.py:108,117,121,125). */
 UCSA_API int ucsa_hashgrid_fwd(const float* x01, uint32_t n, const void* table_h, const ucsa_grid_desc* grid_host,

@@ -1,0 +1,284 @@
+"""Occupancy-grid path: CUDA kernels against the C restatement of the reference's
+kernels (oracle/raymarch_ref.c) -- bit-exact for sample indices / positions / step sizes -- and, when the
+reference's own raymarching.cu could be compiled (oracle/_ref), against the reference itself.  GPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import build_oracle, raymarch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from ucsa_neural_rendering_b200 import build, ops as _ops
+
+    build.build_library()
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def rm():
+    from ucsa_neural_rendering_b200.nerf.raymarching import raymarching
+
+    return raymarching
+
+
+def make_scene(n_rays, seed, bound=4.0, cascades=3, h=128):
+    g = torch.Generator().manual_seed(seed)
+    grid = torch.zeros(cascades, h, h, h)
+    # a few occupied blobs per cascade + a thin shell, densities around the 0.01 threshold on purpose
+    for c in range(cascades):
+        for _ in range(6):
+            ctr = torch.randint(16, h - 16, (3,), generator=g)
+            r = int(torch.randint(4, 14, (1,), generator=g))
+            sl = tuple(slice(int(ctr[k]) - r, int(ctr[k]) + r) for k in range(3))
+            grid[c][sl] = torch.rand(2 * r, 2 * r, 2 * r, generator=g) * 0.05
+        grid[c, :, :, 60:62] = 0.02
+    o = (torch.rand(n_rays, 3, generator=g) - 0.5) * 1.5
+    d = torch.nn.functional.normalize(torch.randn(n_rays, 3, generator=g), dim=-1)
+    aabb = torch.tensor([-bound] * 3 + [bound] * 3)
+    return grid, o, d, aabb
+
+
+@pytest.mark.parametrize("perturb", [0, 1])
+@pytest.mark.parametrize("use_bits", [False, True])
+def test_march_rays_train_bit_exact(ops, perturb, use_bits):
+    n = 700
+    grid, o, d, aabb = make_scene(n, 3)
+    mean_density = 0.008  # below 0.01: threshold = min(0.01, mean)
+    nears, fars = raymarch.near_far(o.numpy(), d.numpy(), aabb.numpy())
+    m = n * 1024
+    ref = raymarch.march_rays_train(o.numpy(), d.numpy(), grid.numpy(), mean_density, 4.0, 1 / 128, nears, fars, m, perturb)
+    r_xyz, r_dir, r_del, r_rays, r_cnt = ref
+
+    g_near, g_far = ops.near_far_from_aabb(o.to(DEV), d.to(DEV), aabb.to(DEV))
+    assert np.array_equal(g_near.cpu().numpy(), nears) and np.array_equal(g_far.cpu().numpy(), fars)
+    gd = grid.to(DEV)
+    bits = None
+    if use_bits:
+        bits = torch.zeros(gd.numel() // 32, dtype=torch.int32, device=DEV)
+        ops.grid_packbits(gd, mean_density, bits)
+        ref_bits = np.packbits((grid.numpy().reshape(-1) > min(0.01, mean_density)), bitorder="little")
+        assert np.array_equal(bits.cpu().numpy().view(np.uint8), ref_bits), "occupancy bitfield must be bit-exact"
+    counter = torch.zeros(2, dtype=torch.int32, device=DEV)
+    xyz, dirs, deltas, rays = ops.march_rays_train(o.to(DEV), d.to(DEV), gd, bits, mean_density, 4.0, 1 / 128, g_near,
+                                                   g_far, m, counter, perturb)
+    assert np.array_equal(counter.cpu().numpy(), r_cnt)
+    assert np.array_equal(rays.cpu().numpy(), r_rays), "ray (id, offset, count) triples must be bit-exact"
+    total = int(r_cnt[0])
+    assert total > 5000
+    assert np.array_equal(xyz[:total].cpu().numpy(), r_xyz[:total])
+    assert np.array_equal(deltas[:total].cpu().numpy(), r_del[:total])
+    assert np.array_equal(dirs[:total].cpu().numpy(), r_dir[:total])
+
+
+def test_march_rays_train_overflow_and_empty(ops):
+    """rays past the M budget are dropped like the reference (offset + count >= M), empty rays have count 0"""
+    n = 64
+    grid, o, d, aabb = make_scene(n, 5)
+    o[:4] = 50.0  # miss the box: near = far = FLT_MAX -> zero steps
+    nears, fars = raymarch.near_far(o.numpy(), d.numpy(), aabb.numpy())
+    full = raymarch.march_rays_train(o.numpy(), d.numpy(), grid.numpy(), 1.0, 4.0, 0.0, nears, fars, n * 1024, 0)
+    m = int(full[4][0]) // 2  # half of what is needed
+    ref = raymarch.march_rays_train(o.numpy(), d.numpy(), grid.numpy(), 1.0, 4.0, 0.0, nears, fars, m, 0)
+    counter = torch.zeros(2, dtype=torch.int32, device=DEV)
+    xyz, dirs, deltas, rays = ops.march_rays_train(o.to(DEV), d.to(DEV), grid.to(DEV), None, 1.0, 4.0, 0.0,
+                                                   torch.from_numpy(nears).to(DEV), torch.from_numpy(fars).to(DEV), m,
+                                                   counter, 0)
+    assert np.array_equal(rays.cpu().numpy(), ref[3]) and (ref[3][:4, 2] == 0).all()
+    assert np.array_equal(xyz.cpu().numpy(), ref[0]) and np.array_equal(deltas.cpu().numpy(), ref[2])
+
+
+def _ragged_inputs(seed, n=300, c=40):
+    g = torch.Generator().manual_seed(seed)
+    counts = torch.randint(0, 60, (n,), generator=g)
+    counts[::17] = 0
+    offsets = torch.cumsum(counts, 0) - counts
+    m = int(counts.sum()) + 5
+    perm = torch.randperm(n, generator=g)  # ray ids in arbitrary order, like the reference's atomics produce
+    rays = torch.stack([perm, offsets, counts], 1).int()
+    sigmas = 30 * torch.rand(m, generator=g) ** 3
+    rgbs = torch.rand(m, 3, generator=g)
+    sem = torch.softmax(torch.randn(m, c, generator=g), -1)
+    deltas = torch.stack([0.01 + 0.05 * torch.rand(m, generator=g), 0.01 + 0.06 * torch.rand(m, generator=g)], 1)
+    return sigmas, rgbs, sem, deltas, rays, m, n
+
+
+def test_composite_rays_train_vs_oracle(rm):
+    sigmas, rgbs, sem, deltas, rays, m, n = _ragged_inputs(7)
+    ws_r, depth_r, image_r = raymarch.composite_train_fwd(sigmas.numpy(), rgbs.numpy(), deltas.numpy(), rays.numpy())
+    s = sigmas.to(DEV).requires_grad_()
+    c = rgbs.to(DEV).requires_grad_()
+    ws, depth, image = rm.composite_rays_train(s, c, deltas.to(DEV), rays.to(DEV))
+    np.testing.assert_allclose(ws.detach().cpu().numpy(), ws_r, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(depth.detach().cpu().numpy(), depth_r, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(image.detach().cpu().numpy(), image_r, rtol=1e-5, atol=1e-6)
+    g = torch.Generator().manual_seed(1)
+    gw, gi = torch.randn(n, generator=g), torch.randn(n, 3, generator=g)
+    ((ws * gw.to(DEV)).sum() + (image * gi.to(DEV)).sum()).backward()
+    gs_r, gr_r = raymarch.composite_train_bwd(gw.numpy(), gi.numpy(), sigmas.numpy(), rgbs.numpy(), deltas.numpy(),
+                                              rays.numpy(), ws_r, image_r)
+    np.testing.assert_allclose(s.grad.cpu().numpy(), gs_r, rtol=2e-5, atol=1e-5 * np.abs(gs_r).max())
+    np.testing.assert_allclose(c.grad.cpu().numpy(), gr_r, rtol=1e-5, atol=1e-6)
+
+
+def test_composite_rays_train_semantics(rm):
+    """the kernels the reference declares but never implemented: checked against the defining formula in torch"""
+    sigmas, rgbs, sem, deltas, rays, m, n = _ragged_inputs(9)
+    s = sigmas.to(DEV).requires_grad_()
+    c = rgbs.to(DEV).requires_grad_()
+    p = sem.to(DEV).requires_grad_()
+    ws, depth, image, semantics = rm.composite_rays_train_semantics(s, c, p, deltas.to(DEV), rays.to(DEV), 40)
+    ws_r, depth_r, image_r = raymarch.composite_train_fwd(sigmas.numpy(), rgbs.numpy(), deltas.numpy(), rays.numpy())
+    np.testing.assert_allclose(image.detach().cpu().numpy(), image_r, rtol=1e-5, atol=1e-6)
+    sem_ref = torch.zeros(n, 40, dtype=torch.float64)
+    w_all = torch.zeros(m, dtype=torch.float64)
+    for idx, off, cnt in rays.tolist():
+        trans = 1.0
+        for i in range(off, off + cnt):
+            a = 1 - np.exp(-float(sigmas[i]) * float(deltas[i, 0]))
+            w_all[i] = a * trans
+            sem_ref[idx] += w_all[i] * sem[i].double()
+            trans *= 1 - a
+    np.testing.assert_allclose(semantics.detach().cpu().numpy(), sem_ref.numpy(), rtol=2e-5, atol=1e-6)
+    g = torch.Generator().manual_seed(2)
+    gs = torch.randn(n, 40, generator=g)
+    (semantics * gs.to(DEV)).sum().backward()
+    ray_of = torch.zeros(m, dtype=torch.long)
+    for idx, off, cnt in rays.tolist():
+        ray_of[off:off + cnt] = idx
+    ref_gp = (w_all[:, None] * gs[ray_of].double()).numpy()
+    ref_gp[int(rays[:, 2].sum()):] = 0
+    np.testing.assert_allclose(p.grad.cpu().numpy(), ref_gp, rtol=2e-5, atol=1e-6)
+    assert float(s.grad.abs().sum()) == 0.0, "semantic weights are detached (renderer_semantics.py:270)"
+
+
+@pytest.mark.parametrize("perturb", [0, 3])
+def test_inference_wavefront_kernels(ops, perturb):
+    n, n_step = 500, 4
+    grid, o, d, aabb = make_scene(n, 11)
+    nears, fars = raymarch.near_far(o.numpy(), d.numpy(), aabb.numpy())
+    g = torch.Generator().manual_seed(5)
+    n_alive = 321
+    alive = torch.randperm(n, generator=g)[:n_alive].int()
+    rays_t = torch.from_numpy(nears)[alive.long()].clone()
+    ref = raymarch.march_rays(n_alive, n_step, alive.numpy(), rays_t.numpy(), o.numpy(), d.numpy(), 4.0, 1 / 128,
+                              grid.numpy(), 0.5, nears, fars, perturb)
+    xyz, dirs, deltas = ops.march_rays(n_alive, n_step, alive.to(DEV), rays_t.to(DEV), o.to(DEV), d.to(DEV), 4.0, 1 / 128,
+                                       grid.to(DEV), None, 0.5, torch.from_numpy(nears).to(DEV),
+                                       torch.from_numpy(fars).to(DEV), n_alive * n_step, perturb)
+    assert np.array_equal(xyz.cpu().numpy(), ref[0]) and np.array_equal(deltas.cpu().numpy(), ref[2])
+    assert np.array_equal(dirs.cpu().numpy(), ref[1])
+
+    m = n_alive * n_step
+    sigmas = 40 * torch.rand(m, generator=g) ** 2
+    rgbs = torch.rand(m, 3, generator=g)
+    ws0, dp0, im0 = torch.rand(n, generator=g) * 0.5, torch.rand(n, generator=g), torch.rand(n, 3, generator=g)
+    ws0[alive[:5].long()] = 0.99995  # nearly opaque already: terminates on T < 1e-4
+    rt_r, ws_r, dp_r, im_r = raymarch.composite_rays(n_alive, n_step, alive.numpy(), rays_t.numpy(), sigmas.numpy(),
+                                                     rgbs.numpy(), ref[2], ws0.numpy(), dp0.numpy(), im0.numpy())
+    rt, ws, dp, im = rays_t.to(DEV), ws0.to(DEV), dp0.to(DEV), im0.to(DEV)
+    ops.composite_rays(n_alive, n_step, alive.to(DEV), rt, sigmas.to(DEV), rgbs.to(DEV), None, deltas, 0, ws, dp, im,
+                       None)
+    assert np.array_equal(rt.cpu().numpy() < 0, rt_r < 0)
+    np.testing.assert_allclose(rt.cpu().numpy(), rt_r, rtol=1e-6)
+    np.testing.assert_allclose(ws.cpu().numpy(), ws_r, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(dp.cpu().numpy(), dp_r, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(im.cpu().numpy(), im_r, rtol=1e-5, atol=1e-6)
+
+    ra_r, rt2_r, cnt_r = raymarch.compact_rays(n_alive, alive.numpy(), rt_r)
+    ra = torch.zeros(n_alive, dtype=torch.int32, device=DEV)
+    rt2 = torch.zeros(n_alive, device=DEV)
+    cnt = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ops.compact_rays(n_alive, ra, alive.to(DEV), rt2, rt, cnt)
+    assert int(cnt) == cnt_r and 0 < cnt_r < n_alive
+    assert np.array_equal(ra.cpu().numpy()[:cnt_r], ra_r[:cnt_r])
+    np.testing.assert_allclose(rt2.cpu().numpy()[:cnt_r], rt2_r[:cnt_r], rtol=1e-6)
+
+
+def test_against_compiled_reference_kernels(ops):
+    """oracle/_ref = the reference's raymarching.cu compiled as is (present only when it could be built)."""
+    ref = build_oracle.load_reference()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (reference sources were not mounted at build time)")
+    n = 900
+    grid, o, d, aabb = make_scene(n, 21)
+    o, d, aabb, grid = o.to(DEV), d.to(DEV), aabb.to(DEV), grid.to(DEV)
+    nears, fars = torch.empty(n, device=DEV), torch.empty(n, device=DEV)
+    ref.near_far_from_aabb(o, d, aabb, n, 0.2, nears, fars)
+    g_near, g_far = ops.near_far_from_aabb(o, d, aabb)
+    assert torch.equal(nears, g_near) and torch.equal(fars, g_far)
+    m = n * 1024
+    for perturb in (0, 1):
+        xyzs, dirs, deltas = torch.zeros(m, 3, device=DEV), torch.zeros(m, 3, device=DEV), torch.zeros(m, 2, device=DEV)
+        rays = torch.empty(n, 3, dtype=torch.int32, device=DEV)
+        counter = torch.zeros(2, dtype=torch.int32, device=DEV)
+        ref.march_rays_train(o, d, grid, 0.008, 4.0, 1 / 128, n, 3, 128, m, nears, fars, xyzs, dirs, deltas, rays, counter,
+                             perturb)
+        counter2 = torch.zeros(2, dtype=torch.int32, device=DEV)
+        xyz2, dirs2, deltas2, rays2 = ops.march_rays_train(o, d, grid, None, 0.008, 4.0, 1 / 128, nears, fars, m, counter2,
+                                                           perturb)
+        assert torch.equal(counter, counter2)
+        # the reference hands out offsets in atomic order: compare ray by ray
+        r1 = rays[torch.argsort(rays[:, 0])].cpu().numpy()
+        r2 = rays2.cpu().numpy()
+        assert np.array_equal(r1[:, 2], r2[:, 2]), "per-ray sample counts must be bit-exact"
+        x1, x2, d1, d2 = xyzs.cpu().numpy(), xyz2.cpu().numpy(), deltas.cpu().numpy(), deltas2.cpu().numpy()
+        for ray in range(0, n, 7):
+            c = r1[ray, 2]
+            a, b = r1[ray, 1], r2[ray, 1]
+            assert np.array_equal(x1[a:a + c], x2[b:b + c]) and np.array_equal(d1[a:a + c], d2[b:b + c])
+    # rgb + depth compositing on the reference's own packed stream
+    total = int(counter[0])
+    g = torch.Generator(device=DEV).manual_seed(0)
+    sig = 30 * torch.rand(m, device=DEV, generator=g) ** 3
+    rgb = torch.rand(m, 3, device=DEV, generator=g)
+    ws1, dp1, im1 = torch.empty(n, device=DEV), torch.empty(n, device=DEV), torch.empty(n, 3, device=DEV)
+    ref.composite_rays_train_forward(sig, rgb, deltas, rays, m, n, ws1, dp1, im1)
+    ws2, dp2, im2 = torch.empty(n, device=DEV), torch.empty(n, device=DEV), torch.empty(n, 3, device=DEV)
+    ops.composite_rays_train_forward(sig, rgb, None, deltas, rays, 0, ws2, dp2, im2, None)
+    assert total > 0
+    torch.testing.assert_close(ws1, ws2, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(dp1, dp2, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(im1, im2, rtol=1e-5, atol=1e-6)
+    gw, gi = torch.randn(n, device=DEV, generator=g), torch.randn(n, 3, device=DEV, generator=g)
+    gs1, gr1 = torch.zeros(m, device=DEV), torch.zeros(m, 3, device=DEV)
+    ref.composite_rays_train_backward(gw, gi, sig, rgb, deltas, rays, ws1, im1, m, n, gs1, gr1)
+    gs2, gr2 = torch.zeros(m, device=DEV), torch.zeros(m, 3, device=DEV)
+    ops.composite_rays_train_backward(gw, gi, None, sig, rgb, deltas, rays, ws1, im1, 0, gs2, gr2, None)
+    torch.testing.assert_close(gs1, gs2, rtol=2e-5, atol=1e-5 * float(gs1.abs().max()))
+    torch.testing.assert_close(gr1, gr2, rtol=1e-5, atol=1e-6)
+
+
+def test_run_cuda_end_to_end():
+    """cuda_ray=True: grid update, training render + backward, inference wavefront (new-repo-defined path)."""
+    from ucsa_neural_rendering_b200.nerf import SemanticNeRFNetwork
+
+    net = SemanticNeRFNetwork(encoding="hashgrid", bound=4, cuda_ray=True, density_scale=1,
+                              num_semantic_classes=40).to(DEV)
+    with torch.no_grad():  # make the density field non-trivial: ~exp(N(0, 1))
+        net.encoder.params.uniform_(-1.0, 1.0)
+    net.train()
+    net.update_extra_state()
+    assert net.mean_density > 0 and int(net.density_bitfield.ne(0).sum()) > 0
+    n = 512
+    g = torch.Generator().manual_seed(3)
+    o = ((torch.rand(1, n, 3, generator=g) - 0.5)).to(DEV)
+    d = torch.nn.functional.normalize(torch.randn(1, n, 3, generator=g), dim=-1).to(DEV)
+    dn = torch.ones(1, n, 1, device=DEV)
+    out = net.render(o, d, direction_norms=dn, staged=False, perturb=False, dt_gamma=1 / 128, force_all_rays=True)
+    assert out["image"].shape == (1, n, 3) and out["semantics"].shape == (1, n, 40) and out["depth"].shape == (1, n)
+    loss = out["image"].sum() + (out["semantics"] ** 2).sum()
+    loss.backward()
+    for p in net.parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all()
+    assert float(net.encoder.params.grad.abs().sum()) > 0
+    net.eval()
+    with torch.no_grad():
+        out2 = net.render(o, d, direction_norms=dn, staged=True, perturb=False, dt_gamma=1 / 128)
+    # same samples, same weights up to the wavefront's early termination (T < 1e-4)
+    torch.testing.assert_close(out2["image"], out["image"].detach(), rtol=5e-3, atol=5e-3)
+    torch.testing.assert_close(out2["semantics"], out["semantics"].detach(), rtol=5e-3, atol=5e-3)

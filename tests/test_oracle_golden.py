@@ -99,3 +99,37 @@ def test_infer_staged_golden(golden_dir):
                                perturb=False, u=_t(g["u"]))
     for k in ("depth", "image", "semantics"):
         np.testing.assert_allclose(out[k].numpy(), g[k], rtol=2e-5, atol=2e-6, err_msg=k)
+
+
+def test_pcg32_known_answer():
+    """pcg32.h:44-116 against the published PCG32 demo stream (seed 42, stream 54)."""
+    from oracle import raymarch
+
+    u, f = raymarch.pcg32_stream(42, 54, 6)
+    assert [int(x) for x in u] == [0xa15c02b7, 0x7b47f409, 0xba1d3330, 0x83d2f293, 0xbfa4784b, 0xcbed606e]
+    assert ((f >= 0) & (f < 1)).all() and abs(float(f[0]) - ((0xa15c02b7 >> 9) / 2 ** 23)) < 1e-7
+
+
+def test_c_oracle_march_properties():
+    """C restatement of the marcher: fully occupied grid -> every step is dt = clamp(t*dt_gamma), samples stay inside
+    the box, counts are capped at 1024; empty grid -> no samples."""
+    from oracle import raymarch
+
+    g = torch.Generator().manual_seed(0)
+    n = 50
+    o = ((torch.rand(n, 3, generator=g) - 0.5)).numpy()
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).numpy()
+    aabb = np.array([-4, -4, -4, 4, 4, 4], dtype=np.float32)
+    nears, fars = raymarch.near_far(o, d, aabb)
+    ref_n, ref_f = live_path.near_far(torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(aabb))
+    assert np.array_equal(nears, ref_n.numpy()) and np.array_equal(fars, ref_f.numpy())
+    full = np.ones((3, 128, 128, 128), dtype=np.float32)
+    xyz, dirs, deltas, rays, cnt = raymarch.march_rays_train(o, d, full, 1.0, 4.0, 1 / 128, nears, fars, n * 1024, 0)
+    assert cnt[1] == n and cnt[0] == rays[:, 2].sum() and (rays[:, 2] <= 1024).all() and (rays[:, 2] > 10).all()
+    tot = cnt[0]
+    assert np.abs(xyz[:tot]).max() <= 4.0 and (deltas[:tot, 0] >= 2 * 1.73205080757 / 1024 - 1e-7).all()
+    assert (deltas[:tot, 0] <= 2 * 4.0 / 128 + 1e-7).all()
+    np.testing.assert_allclose(deltas[:tot, 0], deltas[:tot, 1], rtol=1e-4)  # no skipped voxels: the two deltas agree
+    empty = np.zeros_like(full)
+    _, _, _, rays0, cnt0 = raymarch.march_rays_train(o, d, empty, 1.0, 4.0, 1 / 128, nears, fars, n * 1024, 0)
+    assert cnt0[0] == 0 and (rays0[:, 2] == 0).all()

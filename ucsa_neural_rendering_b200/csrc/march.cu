@@ -1,0 +1,568 @@
+// Occupancy-grid ray marching, ragged compositing and the inference wavefront (rows a16-a20 of SURVEY.md section 8).
+// Replaces the kernels of nr4seg/nerf/raymarching/src/raymarching.cu:138-864 and pcg32.h.
+//
+// Differences from the reference kernels, all of them within what the reference itself can produce:
+//   * sample offsets are handed out in ray order by a count -> scan -> write sequence (warp-shuffle scan), not by
+//     atomicAdd, so the packed streams are deterministic (the reference's order depends on atomic arrival);
+//   * the occupancy test can read a bitfield (1 bit per cell, 786 KB for 3 x 128^3, L1/L2 resident) produced by
+//     ucsa_grid_packbits from the float grid with the very comparison of the reference (density > min(0.01, mean)),
+//     so the marched samples are identical to marching the float grid;
+//   * live-ray compaction keeps ray order (ballot + prefix), the reference's is atomic-order.
+// The per-sample arithmetic (clamps, frexpf mip level, the double-literal index expression, FMA contractions) is
+// written as in the reference so that positions and step sizes are bit-identical.
+#include "common.cuh"
+
+namespace ucsa {
+namespace {
+
+constexpr int kMaxSteps = 1024;
+constexpr float kSqrt3 = 1.73205080757f;
+constexpr float kDensityThresh = 0.01f;
+__host__ __device__ inline float min_stepsize() { return 2 * kSqrt3 / kMaxSteps; }
+
+// ------------------------------------------------------------------ PCG32 (pcg32.h:44-116)
+struct Pcg32 {
+  uint64_t state, inc;
+  __device__ void seed(uint64_t initstate, uint64_t initseq) {
+    state = 0u;
+    inc = (initseq << 1u) | 1u;
+    next_uint();
+    state += initstate;
+    next_uint();
+  }
+  __device__ uint32_t next_uint() {
+    const uint64_t old = state;
+    state = old * 0x5851f42d4c957f2dULL + inc;
+    const uint32_t xorshifted = static_cast<uint32_t>(((old >> 18u) ^ old) >> 27u);
+    const uint32_t rot = static_cast<uint32_t>(old >> 59u);
+    return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31));
+  }
+  __device__ float next_float() { return __uint_as_float((next_uint() >> 9) | 0x3f800000u) - 1.0f; }
+};
+
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(hi, fmaxf(lo, x)); }
+__device__ __forceinline__ float signf(float x) { return copysignf(1.0f, x); }
+
+__device__ __forceinline__ int mip_from_pos(float x, float y, float z, float max_cascade) {
+  const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+  int e;
+  frexpf(mx, &e);
+  return static_cast<int>(fminf(max_cascade - 1, fmaxf(0.f, static_cast<float>(e))));
+}
+
+struct Occupancy {
+  const float* grid;        // [C,H,H,H] float densities, or
+  const uint32_t* bits;     // packed bitfield (bit i of word i/32 = cell i occupied)
+  float thresh;
+  __device__ __forceinline__ bool occupied(uint32_t index) const {
+    if (bits != nullptr) return (__ldg(bits + (index >> 5)) >> (index & 31)) & 1u;
+    return __ldg(grid + index) > thresh;
+  }
+};
+
+struct Ray {
+  float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz, far;
+};
+
+struct March {
+  float bound, dt_gamma, dt_min, dt_max;
+  uint32_t C, H;
+  Occupancy occ;
+
+  // one probe at parameter t (raymarching.cu:187-226): occupied -> one step, else jump to the next voxel
+  __device__ __forceinline__ bool probe(const Ray& r, float& t, float& x, float& y, float& z, float& dt) const {
+    x = clampf(r.ox + t * r.dx, -bound, bound);
+    y = clampf(r.oy + t * r.dy, -bound, bound);
+    z = clampf(r.oz + t * r.dz, -bound, bound);
+    const int level = mip_from_pos(x, y, z, static_cast<float>(C));
+    const float mip_bound = fminf(exp2f(static_cast<float>(level)), bound);
+    const float mip_rbound = 1 / mip_bound;
+    const int nx = clampf(0.5 * (x * mip_rbound + 1) * H, 0.0f, static_cast<float>(H - 1));
+    const int ny = clampf(0.5 * (y * mip_rbound + 1) * H, 0.0f, static_cast<float>(H - 1));
+    const int nz = clampf(0.5 * (z * mip_rbound + 1) * H, 0.0f, static_cast<float>(H - 1));
+    const uint32_t index = level * H * H * H + nx * H * H + ny * H + nz;
+    if (occ.occupied(index)) {
+      dt = clampf(t * dt_gamma, dt_min, dt_max);
+      t += dt;
+      return true;
+    }
+    const float tx = (((nx + 0.5f + 0.5f * signf(r.dx)) / (H - 1) * 2 - 1) * mip_bound - x) * r.rdx;
+    const float ty = (((ny + 0.5f + 0.5f * signf(r.dy)) / (H - 1) * 2 - 1) * mip_bound - y) * r.rdy;
+    const float tz = (((nz + 0.5f + 0.5f * signf(r.dz)) / (H - 1) * 2 - 1) * mip_bound - z) * r.rdz;
+    const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+    do {
+      const float step = clampf(t * dt_gamma, dt_min, dt_max);
+      t += step;
+    } while (t < tt);
+    return false;
+  }
+};
+
+__device__ __forceinline__ Ray load_ray(const float* __restrict__ rays_o, const float* __restrict__ rays_d, uint32_t n,
+                                        float far) {
+  Ray r;
+  r.ox = rays_o[3 * n], r.oy = rays_o[3 * n + 1], r.oz = rays_o[3 * n + 2];
+  r.dx = rays_d[3 * n], r.dy = rays_d[3 * n + 1], r.dz = rays_d[3 * n + 2];
+  r.rdx = 1 / r.dx, r.rdy = 1 / r.dy, r.rdz = 1 / r.dz;
+  r.far = far;
+  return r;
+}
+
+__device__ __forceinline__ float train_t0(float near, uint32_t n, uint32_t perturb) {
+  float t0 = near;
+  if (perturb) {
+    Pcg32 rng;
+    rng.seed(static_cast<uint64_t>(n), 1u);
+    t0 += min_stepsize() * rng.next_float();
+  }
+  return t0;
+}
+
+// pass 1: number of occupied steps per ray
+__global__ void march_count_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, March m,
+                                   uint32_t n_rays, const float* __restrict__ nears, const float* __restrict__ fars,
+                                   uint32_t perturb, int32_t* __restrict__ counts) {
+  const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_rays) return;
+  const Ray r = load_ray(rays_o, rays_d, n, fars[n]);
+  float t = train_t0(nears[n], n, perturb), x, y, z, dt;
+  uint32_t steps = 0;
+  while (t < r.far && steps < kMaxSteps) steps += m.probe(r, t, x, y, z, dt) ? 1u : 0u;
+  counts[n] = static_cast<int32_t>(steps);
+}
+
+// pass 2: write the samples of every ray at its scanned offset; rays[n] = (n, offset, count)
+__global__ void march_write_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, March m,
+                                   uint32_t n_rays, uint32_t max_points, const float* __restrict__ nears,
+                                   const float* __restrict__ fars, uint32_t perturb, const int32_t* __restrict__ counts,
+                                   const int32_t* __restrict__ offsets, int32_t base_point, int32_t base_ray,
+                                   float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
+                                   int32_t* __restrict__ rays) {
+  const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_rays) return;
+  const uint32_t num_steps = static_cast<uint32_t>(counts[n]);
+  const uint32_t point_index = static_cast<uint32_t>(base_point + offsets[n]);
+  const uint32_t ray_index = static_cast<uint32_t>(base_ray) + n;
+  rays[ray_index * 3] = static_cast<int32_t>(n);
+  rays[ray_index * 3 + 1] = static_cast<int32_t>(point_index);
+  rays[ray_index * 3 + 2] = static_cast<int32_t>(num_steps);
+  if (num_steps == 0 || point_index + num_steps >= max_points) return;
+  const Ray r = load_ray(rays_o, rays_d, n, fars[n]);
+  float* px = xyzs + 3ull * point_index;
+  float* pd = dirs + 3ull * point_index;
+  float* pl = deltas + 2ull * point_index;
+  float t = train_t0(nears[n], n, perturb), x, y, z, dt;
+  float last_t = t;
+  uint32_t step = 0;
+  while (t < r.far && step < num_steps) {
+    if (m.probe(r, t, x, y, z, dt)) {
+      px[0] = x, px[1] = y, px[2] = z;
+      pd[0] = r.dx, pd[1] = r.dy, pd[2] = r.dz;
+      pl[0] = dt;
+      pl[1] = t - last_t;
+      last_t = t;
+      px += 3, pd += 3, pl += 2;
+      ++step;
+    }
+  }
+}
+
+// adds (total samples, number of rays) to counter[0..1] like the reference's atomicAdds do
+__global__ void march_finish_kernel(const int32_t* __restrict__ offsets, uint32_t n_rays, int32_t* __restrict__ counter) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    counter[0] += offsets[n_rays];
+    counter[1] += static_cast<int32_t>(n_rays);
+  }
+}
+
+__device__ __forceinline__ int warp_iscan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(kFullMask, v, o);
+    if (lane >= o) v += up;
+  }
+  return v;
+}
+
+// single-CTA exclusive scan (offsets[n] = total); n_rays <= 2^18 in every configuration
+__global__ void __launch_bounds__(1024)
+march_scan_kernel(const int32_t* __restrict__ counts, uint32_t n, int32_t* __restrict__ offsets) {
+  __shared__ int warp_total[32];
+  __shared__ int carry_s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const int v = i < n ? counts[i] : 0;
+    const int incl = warp_iscan(v, lane);
+    if (lane == 31) warp_total[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const int tot = warp_total[lane];
+      warp_total[lane] = warp_iscan(tot, lane) - tot;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    if (i < n) offsets[i] = carry + warp_total[wid] + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_total[wid] + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[n] = carry_s;
+}
+
+// ------------------------------------------------------------------ inference wavefront (raymarching.cu:528-634)
+__global__ void march_rays_kernel(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays_alive,
+                                  const float* __restrict__ rays_t, const float* __restrict__ rays_o,
+                                  const float* __restrict__ rays_d, March m, const float* __restrict__ nears,
+                                  const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs,
+                                  float* __restrict__ deltas, uint32_t perturb) {
+  const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_alive) return;
+  const int index = rays_alive[n];
+  const Ray r = load_ray(rays_o, rays_d, index, fars[index]);
+  float t = rays_t[n];
+  if (perturb) {
+    Pcg32 rng;
+    rng.seed(static_cast<uint64_t>(n), static_cast<uint64_t>(perturb));
+    t += min_stepsize() * rng.next_float();
+  }
+  float* px = xyzs + 3ull * n * n_step;
+  float* pd = dirs + 3ull * n * n_step;
+  float* pl = deltas + 2ull * n * n_step;
+  float last_t = t, x, y, z, dt;
+  uint32_t step = 0;
+  while (t < r.far && step < n_step) {
+    if (m.probe(r, t, x, y, z, dt)) {
+      px[0] = x, px[1] = y, px[2] = z;
+      pd[0] = r.dx, pd[1] = r.dy, pd[2] = r.dz;
+      pl[0] = dt;
+      pl[1] = t - last_t;
+      last_t = t;
+      px += 3, pd += 3, pl += 2;
+      ++step;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ ragged compositing, training
+// (raymarching.cu:318-487 for rgb + depth; the semantic channels are the kernels the reference declares but never
+//  implemented, raymarching.h:12-13: semantics_n = sum_s w_s * p_s with the weights detached on that branch like
+//  the live path, renderer_semantics.py:270)
+__global__ void composite_train_fwd_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                           const float* __restrict__ sem, const float* __restrict__ deltas,
+                                           const int32_t* __restrict__ rays, uint32_t M, uint32_t N, uint32_t C,
+                                           float* __restrict__ weights_sum, float* __restrict__ depth,
+                                           float* __restrict__ image, float* __restrict__ semantics) {
+  // one warp per ray: lanes stride over the ray's samples for the semantic channels, lane 0 carries the scan
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= N) return;
+  const uint32_t index = rays[n * 3], offset = rays[n * 3 + 1], num_steps = rays[n * 3 + 2];
+  const bool empty = num_steps == 0 || offset + num_steps >= M;
+  float T = 1.0f, r = 0, g = 0, b = 0, ws = 0, t = 0, d = 0;
+  float acc0 = 0.f, acc1 = 0.f;  // classes lane, lane + 32
+  if (!empty) {
+    for (uint32_t s = 0; s < num_steps; ++s) {
+      const uint32_t i = offset + s;
+      const float alpha = 1.0f - __expf(-sigmas[i] * deltas[2 * i]);
+      const float w = alpha * T;
+      r += w * rgbs[3 * i];
+      g += w * rgbs[3 * i + 1];
+      b += w * rgbs[3 * i + 2];
+      t += deltas[2 * i + 1];
+      d += w * t;
+      ws += w;
+      T *= 1.0f - alpha;
+      if (sem != nullptr) {
+        if (static_cast<uint32_t>(lane) < C) acc0 += w * sem[static_cast<uint64_t>(i) * C + lane];
+        if (static_cast<uint32_t>(lane) + 32 < C) acc1 += w * sem[static_cast<uint64_t>(i) * C + lane + 32];
+      }
+    }
+  }
+  if (lane == 0) {
+    weights_sum[index] = ws;
+    depth[index] = d;
+    image[index * 3] = r, image[index * 3 + 1] = g, image[index * 3 + 2] = b;
+  }
+  if (semantics != nullptr) {
+    if (static_cast<uint32_t>(lane) < C) semantics[static_cast<uint64_t>(index) * C + lane] = acc0;
+    if (static_cast<uint32_t>(lane) + 32 < C) semantics[static_cast<uint64_t>(index) * C + lane + 32] = acc1;
+  }
+}
+
+__global__ void composite_train_bwd_kernel(const float* __restrict__ grad_ws, const float* __restrict__ grad_image,
+                                           const float* __restrict__ grad_sem, const float* __restrict__ sigmas,
+                                           const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                                           const int32_t* __restrict__ rays, const float* __restrict__ weights_sum,
+                                           const float* __restrict__ image, uint32_t M, uint32_t N, uint32_t C,
+                                           float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs,
+                                           float* __restrict__ grad_local_sem) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= N) return;
+  const uint32_t index = rays[n * 3], offset = rays[n * 3 + 1], num_steps = rays[n * 3 + 2];
+  if (num_steps == 0 || offset + num_steps >= M) return;
+  const float gi0 = grad_image[3 * index], gi1 = grad_image[3 * index + 1], gi2 = grad_image[3 * index + 2];
+  const float gws = grad_ws[index];
+  const float rf = image[3 * index], gf = image[3 * index + 1], bf = image[3 * index + 2], wsf = weights_sum[index];
+  float gs0 = 0.f, gs1 = 0.f;
+  if (grad_sem != nullptr) {
+    if (static_cast<uint32_t>(lane) < C) gs0 = grad_sem[static_cast<uint64_t>(index) * C + lane];
+    if (static_cast<uint32_t>(lane) + 32 < C) gs1 = grad_sem[static_cast<uint64_t>(index) * C + lane + 32];
+  }
+  float T = 1.0f, r = 0, g = 0, b = 0, ws = 0;
+  for (uint32_t s = 0; s < num_steps; ++s) {
+    const uint32_t i = offset + s;
+    const float alpha = 1.0f - __expf(-sigmas[i] * deltas[2 * i]);
+    const float w = alpha * T;
+    r += w * rgbs[3 * i];
+    g += w * rgbs[3 * i + 1];
+    b += w * rgbs[3 * i + 2];
+    ws += w;
+    T *= 1.0f - alpha;
+    if (lane == 0) {
+      grad_rgbs[3 * i] = gi0 * w;
+      grad_rgbs[3 * i + 1] = gi1 * w;
+      grad_rgbs[3 * i + 2] = gi2 * w;
+      grad_sigmas[i] = deltas[2 * i] * (gi0 * (T * rgbs[3 * i] - (rf - r)) + gi1 * (T * rgbs[3 * i + 1] - (gf - g)) +
+                                        gi2 * (T * rgbs[3 * i + 2] - (bf - b)) + gws * (T - (wsf - ws)));
+    }
+    if (grad_local_sem != nullptr) {
+      if (static_cast<uint32_t>(lane) < C) grad_local_sem[static_cast<uint64_t>(i) * C + lane] = w * gs0;
+      if (static_cast<uint32_t>(lane) + 32 < C) grad_local_sem[static_cast<uint64_t>(i) * C + lane + 32] = w * gs1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ inference compositing (raymarching.cu:647-729)
+__global__ void composite_rays_kernel(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays_alive,
+                                      float* __restrict__ rays_t, const float* __restrict__ sigmas,
+                                      const float* __restrict__ rgbs, const float* __restrict__ sem,
+                                      const float* __restrict__ deltas, uint32_t C, float* __restrict__ weights_sum,
+                                      float* __restrict__ depth, float* __restrict__ image,
+                                      float* __restrict__ semantics) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= n_alive) return;
+  const int index = rays_alive[n];
+  float t = rays_t[n];
+  float ws = weights_sum[index], d = depth[index];
+  float r = image[3 * index], g = image[3 * index + 1], b = image[3 * index + 2];
+  float acc0 = 0.f, acc1 = 0.f;
+  if (sem != nullptr) {
+    if (static_cast<uint32_t>(lane) < C) acc0 = semantics[static_cast<uint64_t>(index) * C + lane];
+    if (static_cast<uint32_t>(lane) + 32 < C) acc1 = semantics[static_cast<uint64_t>(index) * C + lane + 32];
+  }
+  uint32_t step = 0;
+  while (step < n_step) {
+    const uint32_t i = n * n_step + step;
+    if (deltas[2 * i] == 0) break;
+    const float alpha = 1.0f - __expf(-sigmas[i] * deltas[2 * i]);
+    const float T = 1 - ws;
+    const float w = alpha * T;
+    ws += w;
+    t += deltas[2 * i + 1];
+    d += w * t;
+    r += w * rgbs[3 * i];
+    g += w * rgbs[3 * i + 1];
+    b += w * rgbs[3 * i + 2];
+    if (sem != nullptr) {
+      if (static_cast<uint32_t>(lane) < C) acc0 += w * sem[static_cast<uint64_t>(i) * C + lane];
+      if (static_cast<uint32_t>(lane) + 32 < C) acc1 += w * sem[static_cast<uint64_t>(i) * C + lane + 32];
+    }
+    if (T < 1e-4) break;
+    ++step;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    rays_t[n] = step < n_step ? -1.0f : t;
+    weights_sum[index] = ws;
+    depth[index] = d;
+    image[3 * index] = r, image[3 * index + 1] = g, image[3 * index + 2] = b;
+  }
+  if (sem != nullptr) {
+    if (static_cast<uint32_t>(lane) < C) semantics[static_cast<uint64_t>(index) * C + lane] = acc0;
+    if (static_cast<uint32_t>(lane) + 32 < C) semantics[static_cast<uint64_t>(index) * C + lane + 32] = acc1;
+  }
+}
+
+// ------------------------------------------------------------------ live-ray compaction, order preserving
+// one CTA; warp ballots + prefix inside 1024-ray chunks, running base across chunks
+__global__ void __launch_bounds__(1024)
+compact_rays_kernel(uint32_t n_alive, int32_t* __restrict__ rays_alive, const int32_t* __restrict__ rays_alive_old,
+                    float* __restrict__ rays_t, const float* __restrict__ rays_t_old, int32_t* __restrict__ alive_counter) {
+  __shared__ int warp_total[32];
+  __shared__ int carry_s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = alive_counter[0];
+  __syncthreads();
+  for (uint32_t base = 0; base < n_alive; base += 1024) {
+    const uint32_t n = base + threadIdx.x;
+    const float t_old = n < n_alive ? rays_t_old[n] : -1.0f;
+    const bool keep = n < n_alive && t_old >= 0;
+    const unsigned ballot = __ballot_sync(kFullMask, keep);
+    if (lane == 0) warp_total[wid] = __popc(ballot);
+    __syncthreads();
+    if (wid == 0) {
+      const int tot = warp_total[lane];
+      warp_total[lane] = warp_iscan(tot, lane) - tot;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    if (keep) {
+      const int dst = carry + warp_total[wid] + __popc(ballot & ((1u << lane) - 1u));
+      rays_alive[dst] = rays_alive_old[n];
+      rays_t[dst] = t_old;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_total[wid] + __popc(ballot);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) alive_counter[0] = carry_s;
+}
+
+// ------------------------------------------------------------------ occupancy grid maintenance (row a20)
+// density_grid = max(density_grid * decay, fresh) where fresh >= 0 (torch-ngp's update rule; not in the reference)
+__global__ void grid_update_kernel(float* __restrict__ grid, const float* __restrict__ fresh, uint64_t n, float decay) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float f = fresh[i];
+  if (f >= 0.f) grid[i] = fmaxf(grid[i] * decay, f);
+}
+// bit i = grid[i] > thresh, 32 cells per thread-word via ballot
+__global__ void grid_packbits_kernel(const float* __restrict__ grid, uint64_t n, float thresh, uint32_t* __restrict__ bits) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool occ = i < n && grid[i] > thresh;
+  const unsigned word = __ballot_sync(kFullMask, occ);
+  if ((threadIdx.x & 31) == 0 && i < n) bits[i >> 5] = word;
+}
+
+int make_march(March& m, const float* grid, const uint32_t* bits, float mean_density, float bound, float dt_gamma,
+               uint32_t C, uint32_t H) {
+  UCSA_REQUIRE(grid != nullptr || bits != nullptr, "march: need a density grid or a bitfield");
+  UCSA_REQUIRE(C >= 1 && H >= 2 && bound > 0.f, "march: bad grid geometry");
+  m.bound = bound;
+  m.dt_gamma = dt_gamma;
+  m.dt_min = min_stepsize();
+  m.dt_max = 2 * bound / H;
+  m.C = C;
+  m.H = H;
+  m.occ.grid = grid;
+  m.occ.bits = bits;
+  m.occ.thresh = fminf(kDensityThresh, mean_density);
+  return UCSA_OK;
+}
+
+}  // namespace
+}  // namespace ucsa
+
+using namespace ucsa;
+
+extern "C" int ucsa_march_rays_train(const float* rays_o, const float* rays_d, const float* grid,
+                                     const uint32_t* bitfield, float mean_density, float bound, float dt_gamma,
+                                     uint32_t n_rays, uint32_t C, uint32_t H, uint32_t max_points, const float* nears,
+                                     const float* fars, float* xyzs, float* dirs, float* deltas, int32_t* rays,
+                                     int32_t* counter, uint32_t perturb, int32_t* scratch, void* stream) {
+  UCSA_REQUIRE(rays_o && rays_d && nears && fars && xyzs && dirs && deltas && rays && counter && scratch,
+               "march_rays_train: null pointer");
+  March m;
+  if (int rc = make_march(m, grid, bitfield, mean_density, bound, dt_gamma, C, H)) return rc;
+  if (n_rays == 0) return UCSA_OK;
+  cudaStream_t st = as_stream(stream);
+  int32_t* counts = scratch;            // [n_rays]
+  int32_t* offsets = scratch + n_rays;  // [n_rays + 1]
+  march_count_kernel<<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, m, n_rays, nears, fars, perturb, counts);
+  march_scan_kernel<<<1, 1024, 0, st>>>(counts, n_rays, offsets);
+  // the reference accumulates into `counter`; offsets start at its current value (0 for a fresh counter)
+  march_write_kernel<<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, m, n_rays, max_points, nears, fars, perturb,
+                                                            counts, offsets, 0, 0, xyzs, dirs, deltas, rays);
+  march_finish_kernel<<<1, 32, 0, st>>>(offsets, n_rays, counter);
+  return check_launch("march_rays_train");
+}
+
+extern "C" int ucsa_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                               const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t C,
+                               uint32_t H, const float* grid, const uint32_t* bitfield, float mean_density,
+                               const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                               uint32_t perturb, void* stream) {
+  UCSA_REQUIRE(rays_alive && rays_t && rays_o && rays_d && nears && fars && xyzs && dirs && deltas,
+               "march_rays: null pointer");
+  March m;
+  if (int rc = make_march(m, grid, bitfield, mean_density, bound, dt_gamma, C, H)) return rc;
+  if (n_alive == 0) return UCSA_OK;
+  march_rays_kernel<<<ceil_div(n_alive, 128), 128, 0, as_stream(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o,
+                                                                           rays_d, m, nears, fars, xyzs, dirs, deltas,
+                                                                           perturb);
+  return check_launch("march_rays");
+}
+
+extern "C" int ucsa_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* local_semantics,
+                                                 const float* deltas, const int32_t* rays, uint32_t M, uint32_t N,
+                                                 uint32_t n_classes, float* weights_sum, float* depth, float* image,
+                                                 float* semantics, void* stream) {
+  UCSA_REQUIRE(sigmas && rgbs && deltas && rays && weights_sum && depth && image, "composite_rays_train_forward: null pointer");
+  UCSA_REQUIRE((local_semantics == nullptr) == (semantics == nullptr), "composite_rays_train_forward: semantics in/out mismatch");
+  UCSA_REQUIRE(n_classes <= 64, "composite_rays_train_forward: at most 64 classes");
+  if (N == 0) return UCSA_OK;
+  composite_train_fwd_kernel<<<ceil_div(static_cast<uint64_t>(N) * 32, 128), 128, 0, as_stream(stream)>>>(
+      sigmas, rgbs, local_semantics, deltas, rays, M, N, n_classes, weights_sum, depth, image, semantics);
+  return check_launch("composite_rays_train_forward");
+}
+
+extern "C" int ucsa_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image,
+                                                  const float* grad_semantics, const float* sigmas, const float* rgbs,
+                                                  const float* deltas, const int32_t* rays, const float* weights_sum,
+                                                  const float* image, uint32_t M, uint32_t N, uint32_t n_classes,
+                                                  float* grad_sigmas, float* grad_rgbs, float* grad_local_semantics,
+                                                  void* stream) {
+  UCSA_REQUIRE(grad_weights_sum && grad_image && sigmas && rgbs && deltas && rays && weights_sum && image &&
+                   grad_sigmas && grad_rgbs,
+               "composite_rays_train_backward: null pointer");
+  UCSA_REQUIRE(n_classes <= 64, "composite_rays_train_backward: at most 64 classes");
+  if (N == 0) return UCSA_OK;
+  composite_train_bwd_kernel<<<ceil_div(static_cast<uint64_t>(N) * 32, 128), 128, 0, as_stream(stream)>>>(
+      grad_weights_sum, grad_image, grad_semantics, sigmas, rgbs, deltas, rays, weights_sum, image, M, N, n_classes,
+      grad_sigmas, grad_rgbs, grad_local_semantics);
+  return check_launch("composite_rays_train_backward");
+}
+
+extern "C" int ucsa_composite_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, float* rays_t,
+                                   const float* sigmas, const float* rgbs, const float* local_semantics,
+                                   const float* deltas, uint32_t n_classes, float* weights_sum, float* depth,
+                                   float* image, float* semantics, void* stream) {
+  UCSA_REQUIRE(rays_alive && rays_t && sigmas && rgbs && deltas && weights_sum && depth && image, "composite_rays: null pointer");
+  UCSA_REQUIRE((local_semantics == nullptr) == (semantics == nullptr), "composite_rays: semantics in/out mismatch");
+  UCSA_REQUIRE(n_classes <= 64, "composite_rays: at most 64 classes");
+  if (n_alive == 0) return UCSA_OK;
+  composite_rays_kernel<<<ceil_div(static_cast<uint64_t>(n_alive) * 32, 128), 128, 0, as_stream(stream)>>>(
+      n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, local_semantics, deltas, n_classes, weights_sum, depth, image,
+      semantics);
+  return check_launch("composite_rays");
+}
+
+extern "C" int ucsa_compact_rays(uint32_t n_alive, int32_t* rays_alive, const int32_t* rays_alive_old, float* rays_t,
+                                 const float* rays_t_old, int32_t* alive_counter, void* stream) {
+  UCSA_REQUIRE(rays_alive && rays_alive_old && rays_t && rays_t_old && alive_counter, "compact_rays: null pointer");
+  compact_rays_kernel<<<1, 1024, 0, as_stream(stream)>>>(n_alive, rays_alive, rays_alive_old, rays_t, rays_t_old,
+                                                         alive_counter);
+  return check_launch("compact_rays");
+}
+
+extern "C" int ucsa_grid_update(float* density_grid, const float* fresh, uint64_t n_cells, float decay, void* stream) {
+  UCSA_REQUIRE(density_grid && fresh, "grid_update: null pointer");
+  if (n_cells == 0) return UCSA_OK;
+  grid_update_kernel<<<ceil_div(n_cells, 256), 256, 0, as_stream(stream)>>>(density_grid, fresh, n_cells, decay);
+  return check_launch("grid_update");
+}
+
+extern "C" int ucsa_grid_packbits(const float* density_grid, uint64_t n_cells, float mean_density, uint32_t* bitfield,
+                                  void* stream) {
+  UCSA_REQUIRE(density_grid && bitfield, "grid_packbits: null pointer");
+  UCSA_REQUIRE(n_cells % 32 == 0, "grid_packbits: cell count must be a multiple of 32");
+  if (n_cells == 0) return UCSA_OK;
+  grid_packbits_kernel<<<ceil_div(n_cells, 256), 256, 0, as_stream(stream)>>>(density_grid, n_cells,
+                                                                              fminf(kDensityThresh, mean_density), bitfield);
+  return check_launch("grid_packbits");
+}

@@ -21,6 +21,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from .raymarching import raymarching
 
 
 def sample_pdf(bins, weights, n_samples, det=False):
@@ -138,6 +139,7 @@ class SemanticNeRFRenderer(nn.Module):
     def reset_extra_state(self):
         if not self.cuda_ray:
             return
+        self.density_bitfield = None
         self.density_grid.zero_()
         self.mean_density = 0
         self.iter_density = 0
@@ -235,6 +237,111 @@ class SemanticNeRFRenderer(nn.Module):
             "semantics": semantics.view(*prefix, self.num_semantic_classes),
         }
 
+    # ------------------------------------------------------------------ occupancy-grid path (cuda_ray=True)
+    # The reference allocates density_grid / step_counter (renderer_semantics.py:89-103) but ships neither run_cuda
+    # nor update_extra_state; both are defined here after torch-ngp, which the reference is adapted
+    # from (README.md:257): march through the occupancy grid, evaluate the heads on the packed samples, composite
+    # with the ragged kernels.  Semantics are composited as probabilities with detached weights like the live path.
+    def run_cuda(self, rays_o, rays_d, direction_norms, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False,
+                 max_steps=1024, epoch=None, **kwargs):
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3).float()
+        rays_d = rays_d.contiguous().view(-1, 3).float()
+        direction_norms = direction_norms.contiguous().view(-1).float()
+        n_rays = rays_o.shape[0]
+        device = rays_o.device
+        c = self.num_semantic_classes
+        aabb = self.aabb_train if self.training else self.aabb_infer
+        nears, fars = ops.near_far_from_aabb(rays_o, rays_d, aabb)
+        bits = getattr(self, "density_bitfield", None)
+
+        if self.training:
+            counter = self.step_counter[self.local_step % 16]
+            counter.zero_()
+            self.local_step += 1
+            xyzs, dirs, deltas, rays = raymarching.march_rays_train(
+                rays_o, rays_d, self.bound, self.density_grid, self.mean_density, nears, fars, counter, self.mean_count,
+                perturb, 128, force_all_rays, dt_gamma, bitfield=bits)
+            sigmas, rgbs, sems = self(xyzs, dirs)
+            sigmas = self.density_scale * sigmas
+            weights_sum, depth, image, semantics = raymarching.composite_rays_train_semantics(
+                sigmas, rgbs.float(), sems.float(), deltas, rays, c)
+        else:
+            dtype = torch.float32
+            weights_sum = torch.zeros(n_rays, dtype=dtype, device=device)
+            depth = torch.zeros(n_rays, dtype=dtype, device=device)
+            image = torch.zeros(n_rays, 3, dtype=dtype, device=device)
+            semantics = torch.zeros(n_rays, c, dtype=dtype, device=device)
+            n_alive = n_rays
+            alive_counter = torch.zeros([1], dtype=torch.int32, device=device)
+            rays_alive = torch.zeros(2, n_rays, dtype=torch.int32, device=device)  # 2 is used to loop old/new
+            rays_t = torch.zeros(2, n_rays, dtype=dtype, device=device)
+            step = 0
+            i = 0
+            while step < max_steps:
+                if step == 0:
+                    n_alive = n_rays
+                    rays_alive[0] = torch.arange(n_alive, dtype=torch.int32, device=device)
+                    rays_t[0] = nears
+                else:
+                    alive_counter.zero_()
+                    raymarching.compact_rays(n_alive, rays_alive[i % 2], rays_alive[(i + 1) % 2], rays_t[i % 2],
+                                             rays_t[(i + 1) % 2], alive_counter)
+                    n_alive = alive_counter.item()  # the wavefront's one host read per round
+                if n_alive <= 0:
+                    break
+                n_step = max(min(n_rays // n_alive, 8), 1)  # fewer live rays -> more steps per round
+                xyzs, dirs, deltas = raymarching.march_rays(n_alive, n_step, rays_alive[i % 2], rays_t[i % 2], rays_o,
+                                                            rays_d, self.bound, self.density_grid, self.mean_density,
+                                                            nears, fars, 128, perturb, dt_gamma, bitfield=bits)
+                sigmas, rgbs, sems = self(xyzs, dirs)
+                sigmas = self.density_scale * sigmas
+                raymarching.composite_rays_semantics(n_alive, n_step, rays_alive[i % 2], rays_t[i % 2], sigmas,
+                                                     rgbs.float(), sems.float(), deltas, weights_sum, depth, image,
+                                                     semantics)
+                step += n_step
+                i += 1
+        depth = depth / direction_norms
+        return {
+            "depth": depth.view(*prefix),
+            "image": image.view(*prefix, 3),
+            "semantics": semantics.view(*prefix, c),
+        }
+
+    @torch.no_grad()
+    def update_extra_state(self, decay=0.95, S=128):
+        """Refresh the occupancy grid from the current density field (call every ~16 training steps)."""
+        if not self.cuda_ray:
+            return
+        device = self.density_grid.device
+        h = self.density_grid.shape[1]
+        fresh = -torch.ones_like(self.density_grid)
+        coords = torch.arange(h, dtype=torch.int32, device=device)
+        xs = coords.split(S)
+        for xc in xs:
+            for yc in xs:
+                for zc in xs:
+                    xx, yy, zz = torch.meshgrid(xc, yc, zc, indexing="ij")
+                    cell = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1)  # [n,3]
+                    index = (cell[:, 0].long() * h + cell[:, 1].long()) * h + cell[:, 2].long()  # raymarching.cu:204
+                    xyz = 2 * cell.float() / (h - 1) - 1
+                    for cas in range(self.cascade):
+                        cas_bound = min(2 ** cas, self.bound)
+                        half = cas_bound / h
+                        pts = xyz * (cas_bound - half) + (torch.rand_like(xyz) * 2 - 1) * half
+                        sigma = self.density(pts)["sigma"].reshape(-1).detach() * self.density_scale
+                        fresh[cas].view(-1)[index] = sigma
+        ops.grid_update(self.density_grid, fresh.contiguous(), decay)
+        self.mean_density = torch.mean(self.density_grid.clamp(min=0)).item()
+        self.iter_density += 1
+        if not hasattr(self, "density_bitfield") or self.density_bitfield is None:
+            self.density_bitfield = torch.zeros(self.density_grid.numel() // 32, dtype=torch.int32, device=device)
+        ops.grid_packbits(self.density_grid, self.mean_density, self.density_bitfield)
+        total_step = min(16, self.local_step)
+        if total_step > 0:
+            self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
+        self.local_step = 0
+
     def render(self,
                rays_o,
                rays_d,
@@ -246,7 +353,7 @@ class SemanticNeRFRenderer(nn.Module):
                epoch=None,
                **kwargs):
         # rays_o, rays_d: [B, N, 3]; direction_norms: [B, N, 1]
-        _run = self.run
+        _run = self.run_cuda if self.cuda_ray else self.run
         B, N = rays_o.shape[:2]
         device = rays_o.device
 

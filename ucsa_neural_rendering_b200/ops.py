@@ -246,3 +246,86 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, param_h, *, lr, beta1, beta2, ep
                                _ptr(exp_avg_sq, torch.float32), _ptr(param_h, torch.float16), param.numel(), float(lr),
                                float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale_inv),
                                _ptr(found_inf, torch.float32), int(step), _stream()), "adam_step")
+
+
+# ---------------------------------------------------------------------------------------------- occupancy-grid path
+def march_rays_train(rays_o, rays_d, grid, bitfield, mean_density, bound, dt_gamma, nears, fars, max_points, counter,
+                     perturb):
+    n = rays_o.shape[0]
+    dev = rays_o.device
+    c, h = grid.shape[0], grid.shape[1]
+    xyzs = torch.zeros(max_points, 3, dtype=torch.float32, device=dev)
+    dirs = torch.zeros(max_points, 3, dtype=torch.float32, device=dev)
+    deltas = torch.zeros(max_points, 2, dtype=torch.float32, device=dev)
+    rays = torch.empty(n, 3, dtype=torch.int32, device=dev)
+    scratch = torch.empty(2 * n + 1, dtype=torch.int32, device=dev)
+    check(lib().ucsa_march_rays_train(_ptr(rays_o, torch.float32), _ptr(rays_d, torch.float32),
+                                      _ptr(grid, torch.float32, "density_grid"), _ptr(bitfield, torch.int32, "bitfield"),
+                                      float(mean_density), float(bound), float(dt_gamma), n, c, h, max_points,
+                                      _ptr(nears, torch.float32), _ptr(fars, torch.float32), _ptr(xyzs), _ptr(dirs),
+                                      _ptr(deltas), _ptr(rays), _ptr(counter, torch.int32, "counter"), int(perturb),
+                                      _ptr(scratch), _stream()), "march_rays_train")
+    return xyzs, dirs, deltas, rays
+
+
+def march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, grid, bitfield, mean_density,
+               nears, fars, max_points, perturb):
+    dev = rays_o.device
+    c, h = grid.shape[0], grid.shape[1]
+    xyzs = torch.zeros(max_points, 3, dtype=torch.float32, device=dev)
+    dirs = torch.zeros(max_points, 3, dtype=torch.float32, device=dev)
+    deltas = torch.zeros(max_points, 2, dtype=torch.float32, device=dev)
+    check(lib().ucsa_march_rays(n_alive, n_step, _ptr(rays_alive, torch.int32), _ptr(rays_t, torch.float32),
+                                _ptr(rays_o, torch.float32), _ptr(rays_d, torch.float32), float(bound), float(dt_gamma),
+                                c, h, _ptr(grid, torch.float32), _ptr(bitfield, torch.int32), float(mean_density),
+                                _ptr(nears, torch.float32), _ptr(fars, torch.float32), _ptr(xyzs), _ptr(dirs),
+                                _ptr(deltas), int(perturb), _stream()), "march_rays")
+    return xyzs, dirs, deltas
+
+
+def composite_rays_train_forward(sigmas, rgbs, local_semantics, deltas, rays, n_classes, weights_sum, depth, image,
+                                 semantics):
+    check(lib().ucsa_composite_rays_train_forward(_ptr(sigmas, torch.float32), _ptr(rgbs, torch.float32),
+                                                  _ptr(local_semantics, torch.float32), _ptr(deltas, torch.float32),
+                                                  _ptr(rays, torch.int32), sigmas.shape[0], rays.shape[0], n_classes,
+                                                  _ptr(weights_sum, torch.float32), _ptr(depth, torch.float32),
+                                                  _ptr(image, torch.float32), _ptr(semantics, torch.float32),
+                                                  _stream()), "composite_rays_train_forward")
+
+
+def composite_rays_train_backward(grad_ws, grad_image, grad_sem, sigmas, rgbs, deltas, rays, weights_sum, image,
+                                  n_classes, grad_sigmas, grad_rgbs, grad_local_sem):
+    check(lib().ucsa_composite_rays_train_backward(_ptr(grad_ws, torch.float32), _ptr(grad_image, torch.float32),
+                                                   _ptr(grad_sem, torch.float32), _ptr(sigmas, torch.float32),
+                                                   _ptr(rgbs, torch.float32), _ptr(deltas, torch.float32),
+                                                   _ptr(rays, torch.int32), _ptr(weights_sum, torch.float32),
+                                                   _ptr(image, torch.float32), sigmas.shape[0], rays.shape[0], n_classes,
+                                                   _ptr(grad_sigmas, torch.float32), _ptr(grad_rgbs, torch.float32),
+                                                   _ptr(grad_local_sem, torch.float32), _stream()),
+          "composite_rays_train_backward")
+
+
+def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, local_semantics, deltas, n_classes, weights_sum,
+                   depth, image, semantics):
+    check(lib().ucsa_composite_rays(n_alive, n_step, _ptr(rays_alive, torch.int32), _ptr(rays_t, torch.float32),
+                                    _ptr(sigmas, torch.float32), _ptr(rgbs, torch.float32),
+                                    _ptr(local_semantics, torch.float32), _ptr(deltas, torch.float32), n_classes,
+                                    _ptr(weights_sum, torch.float32), _ptr(depth, torch.float32),
+                                    _ptr(image, torch.float32), _ptr(semantics, torch.float32), _stream()),
+          "composite_rays")
+
+
+def compact_rays(n_alive, rays_alive, rays_alive_old, rays_t, rays_t_old, alive_counter):
+    check(lib().ucsa_compact_rays(n_alive, _ptr(rays_alive, torch.int32), _ptr(rays_alive_old, torch.int32),
+                                  _ptr(rays_t, torch.float32), _ptr(rays_t_old, torch.float32),
+                                  _ptr(alive_counter, torch.int32), _stream()), "compact_rays")
+
+
+def grid_update(density_grid, fresh, decay):
+    check(lib().ucsa_grid_update(_ptr(density_grid, torch.float32), _ptr(fresh, torch.float32), density_grid.numel(),
+                                 float(decay), _stream()), "grid_update")
+
+
+def grid_packbits(density_grid, mean_density, bitfield):
+    check(lib().ucsa_grid_packbits(_ptr(density_grid, torch.float32), density_grid.numel(), float(mean_density),
+                                   _ptr(bitfield, torch.int32), _stream()), "grid_packbits")
