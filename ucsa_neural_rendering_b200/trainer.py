@@ -14,7 +14,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import ops, parallel
 
 
 def nerf_losses(outputs, gt_rgb, labels, gt_depth, one_m_to_scene_uom, weight_depth=0.1, weight_semantics=0.04,
@@ -88,6 +88,6 @@ class NerfTrainer:
                 g.copy_(m.params.grad)
                 m.params.grad = g
         if self.distributed:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+            parallel.all_reduce_gradients(self.flat_grad)
         self.optimizer_step()
         return loss
