@@ -115,24 +115,30 @@ UCSA_API int ucsa_scan_counts(const int32_t* ray_count, uint32_t n_rays, int32_t
 UCSA_API int ucsa_compact_masked(const float* w_sorted, const float* z_cat, const int32_t* order, const int32_t* ray_off,
                         uint32_t n_rays, uint32_t t, int32_t* sel, float* w_sel, float* z_sel, void* stream);
 
-/* ---- a7/a12/a13. colour + semantic heads on the K masked-in rows (network_tcnn_semantics.py:147-207).
- * K is read on the device from ray_off[n_rays]; k_max bounds the launch.  rgb [K,3] f32 (fp16 sigmoid
- * values), logits fp16 [K,48]; hc1,hc2,hs fp16 [K,64] saved for backward when non-null. */
+/* ---- a7/a12/a13 (+a14 fused). colour + semantic heads on the K masked-in rows (network_tcnn_semantics.py:147-207)
+ * and, when image/semantics are non-null, the compositing of renderer_semantics.py:279-285 in the same kernel:
+ * image [N,3] += sum w*rgb, semantics [N,C] += sum w*softmax(logits) (atomicAdd; the caller zero-fills them).
+ * K is read on the device from ray_off[n_rays]; k_max bounds the launch.  rgb [K,3] f32 (fp16 sigmoid values),
+ * logits fp16 [K,48]; hc1,hc2,hs fp16 [K,64] saved for backward when non-null. */
 UCSA_API int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32_t n_rays, uint32_t t, uint32_t k_max,
                    const float* rays_d, const void* h, const void* w_color_h, const void* w_sem_h,
-                   uint32_t n_classes, float* rgb, void* logits, void* hc1, void* hc2, void* hs, void* stream);
+                   uint32_t n_classes, const float* w_sel, float* rgb, void* logits, void* hc1, void* hc2, void* hs,
+                   float* image, float* semantics, void* stream);
 
-/* Backward of ucsa_heads_fwd.  d_rgb [K,3] f32 (w.r.t. the sigmoid output), d_logits f32 [K,48]
- * (w.r.t. the pre-softmax logits).  Writes dh[sel][1..15] = loss_scale * dL/dgeo_feat (fp16) and
- * accumulates grad_w_color [7168], grad_w_sem [64*16+pad16(C)*64] (fp32, unscaled). */
+/* Backward of ucsa_heads_fwd including the compositing: from g_image [N,3], g_depth [N], g_semantics [N,C] it forms
+ * dL/drgb, dL/dlogits (soft-max backward; semantic weights are detached, renderer_semantics.py:270) per row on the
+ * fly, writes d_w_sel [K] = dL/dw of every masked-in sample (for ucsa_weights_bwd), dh[sel][1..15] =
+ * loss_scale * dL/dgeo_feat (fp16), and accumulates grad_w_color [7168], grad_w_sem [4096] (fp32, unscaled). */
 UCSA_API int ucsa_heads_bwd(const int32_t* sel, const int32_t* ray_off, uint32_t n_rays, uint32_t t, uint32_t k_max,
                    const float* rays_d, const void* h, const void* w_color_h, const void* w_sem_h,
-                   uint32_t n_classes, const float* rgb, const void* hc1, const void* hc2, const void* hs,
-                   const float* d_rgb, const float* d_logits, float loss_scale, void* dh, float* grad_w_color,
-                   float* grad_w_sem, void* stream);
+                   uint32_t n_classes, const float* rgb, const void* logits, const void* hc1, const void* hc2,
+                   const void* hs, const float* w_sel, const float* z_sel, const float* g_image,
+                   const float* g_depth, const float* g_semantics, const float* direction_norms, float loss_scale,
+                   void* dh, float* d_w_sel, float* grad_w_color, float* grad_w_sem, void* stream);
 
-/* ---- a14. compositing over the compact rows (renderer_semantics.py:279-285): image = sum w*rgb,
- * semantics = sum w*softmax(logits).  One pass, fp32. */
+/* ---- a14, stand-alone form over the compact rows (renderer_semantics.py:279-285): image = sum w*rgb,
+ * semantics = sum w*softmax(logits).  One pass, fp32.  The rendering pipeline uses the fused form inside
+ * ucsa_heads_fwd/bwd; these entry points serve callers that hold rgb / logits already (and the cross-check tests). */
 UCSA_API int ucsa_composite_fwd(const int32_t* ray_off, const float* w_sel, const float* rgb, const void* logits,
                        uint32_t n_rays, uint32_t n_classes, float* image, float* semantics, void* stream);
 

@@ -94,26 +94,26 @@ def main():
     rgb = torch.empty(k_max, 3, **f32)
     logits = torch.empty(k_max, 48, **f16)
     hc1, hc2, hs = (torch.empty(k_max, 64, **f16) for _ in range(3))
-    ms = timeit(lambda: ops.heads_fwd(sel, off, n, t, k_max, d, h, w_col, w_sem, 40, rgb, logits, hc1, hc2, hs),
-                args.iters, flush)
-    rec(f"heads_fwd (K={k} rows)", ms, k, 32 + 12 + 96 + 3 * 128)
-    image = torch.empty(n, 3, **f32)
-    sem = torch.empty(n, 40, **f32)
+    image = torch.zeros(n, 3, **f32)
+    sem = torch.zeros(n, 40, **f32)
+    ms = timeit(lambda: ops.heads_fwd(sel, off, n, t, k_max, d, h, w_col, w_sem, 40, rgb, logits, hc1, hc2, hs,
+                                      w_sel=w_sel, image=image, semantics=sem), args.iters, flush)
+    rec(f"heads_fwd + composite (K={k} rows)", ms, k, 32 + 12 + 96 + 3 * 128)
     ms = timeit(lambda: ops.composite_fwd(off, w_sel, rgb, logits, n, 40, image, sem), args.iters, flush)
-    rec("composite_fwd", ms, k, 4 + 12 + 96)
+    rec("composite_fwd (stand-alone)", ms, k, 4 + 12 + 96)
     gi, gd, gs = torch.randn(n, 3, **f32), torch.randn(n, **f32), torch.randn(n, 40, **f32)
     d_rgb = torch.empty(k_max, 3, **f32)
     d_log = torch.empty(k_max, 48, **f32)
     d_w = torch.empty(k_max, **f32)
     ms = timeit(lambda: ops.composite_bwd(off, sel, w_sel, z_sel, rgb, logits, gi, gd, gs, dn.view(-1), n, 40, d_rgb,
                                           d_log, d_w), args.iters, flush)
-    rec("composite_bwd", ms, k, 4 + 4 + 12 + 96 + 12 + 192 + 4)
+    rec("composite_bwd (stand-alone)", ms, k, 4 + 4 + 12 + 96 + 12 + 192 + 4)
     dh = torch.empty(n, t, 16, **f16)
     g_col = torch.zeros(ops.COLOR_PARAMS, **f32)
     g_sem = torch.zeros(ops.SEM_PARAMS, **f32)
-    ms = timeit(lambda: ops.heads_bwd(sel, off, n, t, k_max, d, h, w_col, w_sem, 40, rgb, hc1, hc2, hs, d_rgb, d_log,
-                                      128.0, dh, g_col, g_sem), args.iters, flush)
-    rec(f"heads_bwd (K={k} rows)", ms, k, 32 + 3 * 128 + 12 + 192 + 32)
+    ms = timeit(lambda: ops.heads_bwd(sel, off, n, t, k_max, d, h, w_col, w_sem, 40, rgb, logits, hc1, hc2, hs, w_sel,
+                                      z_sel, gi, gd, gs, dn.view(-1), 128.0, dh, d_w, g_col, g_sem), args.iters, flush)
+    rec(f"heads_bwd + composite bwd (K={k} rows)", ms, k, 32 + 3 * 128 + 12 + 96 + 32)
     d_sigma = torch.empty(n, t, **f32)
     ms = timeit(lambda: ops.weights_bwd(z_cat, sigma, order, w_sorted, off, d_w, 1.0, d_sigma), args.iters, flush)
     rec("weights_bwd", ms, n * t, 20)

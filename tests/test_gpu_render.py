@@ -213,5 +213,70 @@ def test_optimizer_step_changes_render_and_state_dict_round_trips():
     with torch.no_grad():
         a = net.render(o, d, direction_norms=dn, staged=True, perturb=False, seed=9)
         b = net2.render(o, d, direction_norms=dn, staged=True, perturb=False, seed=9)
-    for k in a:
-        assert torch.equal(a[k], b[k])
+    for k in a:  # the fused compositing adds per-tile partial sums with atomics: equal up to fp32 summation order
+        torch.testing.assert_close(a[k], b[k], rtol=1e-5, atol=1e-6)
+
+
+def test_fused_heads_match_cuda_core_heads_plus_composite_kernels():
+    """tcgen05 heads with fused compositing (production) vs CUDA-core heads + stand-alone composite kernels."""
+    from ucsa_neural_rendering_b200 import ops
+
+    heads = live_path.OracleHeads(bound=4, num_semantic_classes=40, seed=9, hash_amp=0.4)
+    net = _net_from_oracle(heads)
+    n, t, c = 300, 48, 40
+    g = torch.Generator().manual_seed(8)
+    f32 = dict(dtype=torch.float32, device=DEV)
+    f16 = dict(dtype=torch.float16, device=DEV)
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).to(DEV)
+    h = (torch.randn(n, t, 16, generator=g) * 0.5).half().to(DEV)
+    w_all = torch.rand(n, t, generator=g) ** 6
+    w_all[5] = 0  # a ray without any masked-in sample
+    z = torch.sort(torch.rand(n, t, generator=g) * 4 + 0.2, dim=1).values.to(DEV)
+    w_all = w_all.to(DEV)
+    dn = (1 + 0.2 * torch.rand(n, generator=g)).to(DEV)
+    cnt = (w_all > 1e-4).sum(1).int()
+    off = torch.zeros(n + 1, dtype=torch.int32, device=DEV)
+    ops.scan_counts(cnt, off)
+    k = int(off[-1])
+    k_max = n * t
+    sel = torch.empty(k_max, dtype=torch.int32, device=DEV)
+    w_sel, z_sel = torch.empty(k_max, **f32), torch.empty(k_max, **f32)
+    ops.compact_masked(w_all, z, None, off, sel, w_sel, z_sel)
+    w_col, w_sem = net.color_net.half_params(), net.semantics_net.half_params()
+
+    rgb1, log1 = torch.zeros(k_max, 3, **f32), torch.zeros(k_max, 48, **f16)
+    a1, a2, a3 = (torch.zeros(k_max, 64, **f16) for _ in range(3))
+    img1, sem1 = torch.zeros(n, 3, **f32), torch.zeros(n, c, **f32)
+    ops.heads_fwd(sel, off, n, t, k_max, d, h, w_col, w_sem, c, rgb1, log1, a1, a2, a3, w_sel=w_sel, image=img1,
+                  semantics=sem1)
+    rgb2, log2 = torch.zeros(k_max, 3, **f32), torch.zeros(k_max, 48, **f16)
+    b1, b2, b3 = (torch.zeros(k_max, 64, **f16) for _ in range(3))
+    ops.heads_fwd_simt(sel, off, n, t, k_max, d, h, w_col, w_sem, c, rgb2, log2, b1, b2, b3)
+    img2, sem2 = torch.empty(n, 3, **f32), torch.empty(n, c, **f32)
+    ops.composite_fwd(off, w_sel, rgb2, log2, n, c, img2, sem2)
+    torch.testing.assert_close(rgb1[:k], rgb2[:k], rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(log1[:k].float(), log2[:k].float(), rtol=2e-3, atol=4e-3)
+    torch.testing.assert_close(img1, img2, rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(sem1, sem2, rtol=2e-3, atol=2e-3)
+    assert float(sem1[5].abs().sum()) == 0 and float(img1[5].abs().sum()) == 0
+
+    gi, gd, gs = torch.randn(n, 3, generator=g).to(DEV), torch.randn(n, generator=g).to(DEV), \
+        torch.randn(n, c, generator=g).to(DEV)
+    scale = 64.0
+    dh1, dw1 = torch.zeros(n, t, 16, **f16), torch.zeros(k_max, **f32)
+    gc1, gs1 = torch.zeros(ops.COLOR_PARAMS, **f32), torch.zeros(ops.SEM_PARAMS, **f32)
+    ops.heads_bwd(sel, off, n, t, k_max, d, h, w_col, w_sem, c, rgb1, log1, a1, a2, a3, w_sel, z_sel, gi, gd, gs, dn,
+                  scale, dh1, dw1, gc1, gs1)
+    d_rgb, d_log, dw2 = torch.zeros(k_max, 3, **f32), torch.zeros(k_max, 48, **f32), torch.zeros(k_max, **f32)
+    ops.composite_bwd(off, sel, w_sel, z_sel, rgb2, log2, gi, gd, gs, dn, n, c, d_rgb, d_log, dw2)
+    dh2 = torch.zeros(n, t, 16, **f16)
+    gc2, gs2 = torch.zeros(ops.COLOR_PARAMS, **f32), torch.zeros(ops.SEM_PARAMS, **f32)
+    ops.heads_bwd_simt(sel, off, n, t, k_max, d, h, w_col, w_sem, c, rgb2, b1, b2, b3, d_rgb, d_log, scale, dh2, gc2,
+                       gs2)
+    torch.testing.assert_close(dw1[:k], dw2[:k], rtol=2e-3, atol=2e-3 * float(dw2[:k].abs().max()))
+    torch.testing.assert_close(gc1, gc2, rtol=2e-2, atol=5e-3 * float(gc2.abs().max()))
+    torch.testing.assert_close(gs1, gs2, rtol=2e-2, atol=5e-3 * float(gs2.abs().max()))
+    m = (w_all > 1e-4).view(-1)
+    a = dh1.view(-1, 16)[m][:, 1:].float()
+    b = dh2.view(-1, 16)[m][:, 1:].float()
+    torch.testing.assert_close(a, b, rtol=2e-2, atol=1e-2 * float(b.abs().max()))

@@ -98,23 +98,31 @@ __device__ __forceinline__ void row_g2t(unsigned char* tile, const __half* __res
 }
 
 constexpr uint32_t kFwdCols = 256;
-constexpr uint32_t kFwdSmem = kWeightBytes + Tile<32>::kBytes + Tile<16>::kBytes + 3 * Tile<64>::kBytes + 64;
+// per-tile staging of w * (probabilities | rgb) for the fused compositing: [128 rows][kPartLd] fp32, odd stride
+constexpr int kPartLd = kSemOut + 5;
+constexpr uint32_t kPartBytes = 128 * kPartLd * sizeof(float);
+constexpr uint32_t kFwdSmem = kWeightBytes + Tile<32>::kBytes + Tile<16>::kBytes + 3 * Tile<64>::kBytes + kPartBytes +
+                              128 * sizeof(int) + 64;
 
 __global__ void __launch_bounds__(128)
 heads_fwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__ k_ptr, uint32_t t,
                     const float* __restrict__ rays_d, const __half* __restrict__ h,
-                    const __half* __restrict__ w_color, const __half* __restrict__ w_sem, float* __restrict__ rgb,
-                    __half* __restrict__ logits, __half* __restrict__ hc1, __half* __restrict__ hc2,
-                    __half* __restrict__ hs) {
+                    const __half* __restrict__ w_color, const __half* __restrict__ w_sem, int n_classes,
+                    const float* __restrict__ w_sel, float* __restrict__ rgb, __half* __restrict__ logits,
+                    __half* __restrict__ hc1, __half* __restrict__ hc2, __half* __restrict__ hs,
+                    float* __restrict__ image, float* __restrict__ semantics) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* t_in_c = smem + kWeightBytes;
   unsigned char* t_in_s = t_in_c + Tile<32>::kBytes;
   unsigned char* t_h1 = t_in_s + Tile<16>::kBytes;
   unsigned char* t_hs = t_h1 + Tile<64>::kBytes;
   unsigned char* t_h2 = t_hs + Tile<64>::kBytes;
-  unsigned char* tail = t_h2 + Tile<64>::kBytes;
+  float* part = reinterpret_cast<float*>(t_h2 + Tile<64>::kBytes);
+  int* ray_of_row = reinterpret_cast<int*>(part + 128 * kPartLd);
+  unsigned char* tail = reinterpret_cast<unsigned char*>(ray_of_row + 128);
   uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
   uint32_t* slot = reinterpret_cast<uint32_t*>(tail + 8);
+  const bool fuse_composite = image != nullptr;
   const WeightTiles w = load_weights(smem, w_color, w_sem);
   umma::Ctx ctx = umma::ctx_init(slot, bar, kFwdCols);
   const uint32_t s_in_c = umma::smem_u32(t_in_c), s_in_s = umma::smem_u32(t_in_s), s_h1 = umma::smem_u32(t_h1),
@@ -126,7 +134,10 @@ heads_fwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t r = tile * 128 + threadIdx.x;
     const bool valid = r < k_rows;
-    build_inputs(rays_d, h, valid ? static_cast<uint32_t>(sel[r]) : 0u, t, valid, t_in_c, t_in_s);
+    const uint32_t flat = valid ? static_cast<uint32_t>(sel[r]) : 0u;
+    const float w_row = (valid && fuse_composite) ? w_sel[r] : 0.f;
+    float* my_part = part + threadIdx.x * kPartLd;
+    build_inputs(rays_d, h, flat, t, valid, t_in_c, t_in_s);
     ctx.publish();
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
@@ -153,20 +164,42 @@ heads_fwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 16) umma::acc_to_tile16<64, true>(ctx, kAcc0 + c0, t_h2, c0);
     if (valid && hc2 != nullptr) row_t2g<64>(hc2 + static_cast<uint64_t>(r) * 64, t_h2);
+    {
+      // the row's logits: fp16 like the reference's network output, kept in registers for the soft-max
+      float lg[kSemOut];
+      const uint64_t stream = l2_policy_stream();
 #pragma unroll
-    for (int c0 = 0; c0 < kSemOut; c0 += 16) {
-      float v[16];
-      umma::tmem_ld16(ctx.lane_addr(kAcc2 + c0), v);
-      if (valid) {
+      for (int c0 = 0; c0 < kSemOut; c0 += 16) {
+        float v[16];
+        umma::tmem_ld16(ctx.lane_addr(kAcc2 + c0), v);
         H8 a, b;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           a.h[i] = __float2half_rn(v[i]);
           b.h[i] = __float2half_rn(v[8 + i]);
+          lg[c0 + i] = __half2float(a.h[i]);
+          lg[c0 + 8 + i] = __half2float(b.h[i]);
         }
-        uint4* dst = reinterpret_cast<uint4*>(logits + static_cast<uint64_t>(r) * kSemOut + c0);
-        dst[0] = a.v;
-        dst[1] = b.v;
+        if (valid) {
+          st_stream(logits + static_cast<uint64_t>(r) * kSemOut + c0, a.v, stream);
+          st_stream(logits + static_cast<uint64_t>(r) * kSemOut + c0 + 8, b.v, stream);
+        }
+      }
+      if (fuse_composite) {
+        // semantics_n = sum_rows w * softmax(logits)   (network_tcnn_semantics.py:202-203, renderer_semantics.py:284)
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < kSemOut; ++c)
+          if (c < n_classes) m = fmaxf(m, lg[c]);
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < kSemOut; ++c) {
+          lg[c] = c < n_classes ? expf(lg[c] - m) : 0.f;
+          sum += lg[c];
+        }
+        const float scale = w_row / sum;
+#pragma unroll
+        for (int c = 0; c < kSemOut; ++c) my_part[c] = lg[c] * scale;
       }
     }
     ctx.publish();
@@ -178,12 +211,40 @@ heads_fwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__
     ctx.wait();
     float v[16];
     umma::tmem_ld16(ctx.lane_addr(kAcc1), v);
-    if (valid) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float x = round_h(v[c]);
-        rgb[static_cast<uint64_t>(r) * 3 + c] = round_h(1.0f / (1.0f + expf(-x)));  // fp16 sigmoid under autocast
+    for (int c = 0; c < 3; ++c) {
+      const float x = round_h(v[c]);
+      const float col = round_h(1.0f / (1.0f + expf(-x)));  // fp16 sigmoid under autocast
+      if (valid) rgb[static_cast<uint64_t>(r) * 3 + c] = col;
+      if (fuse_composite) my_part[kSemOut + c] = w_row * col;
+    }
+    if (fuse_composite) {
+      // image_n = sum_rows w * rgb ; rows of a ray are contiguous, so each column thread walks its rows and flushes
+      // one atomicAdd per (ray, column) segment
+      ray_of_row[threadIdx.x] = valid ? static_cast<int>(flat / t) : -1;
+      __syncthreads();
+      const int n_col = n_classes + 3;
+      const int seg = threadIdx.x / n_col, col = threadIdx.x % n_col;
+      if (seg < 2) {
+        const int src_col = col < n_classes ? col : kSemOut + (col - n_classes);
+        int cur = -1;
+        float acc = 0.f;
+        for (int rr = seg * 64; rr < seg * 64 + 64; ++rr) {
+          const int id = ray_of_row[rr];
+          if (id != cur) {
+            if (cur >= 0)
+              atomicAdd(col < n_classes ? semantics + static_cast<uint64_t>(cur) * n_classes + col
+                                        : image + static_cast<uint64_t>(cur) * 3 + (col - n_classes), acc);
+            cur = id;
+            acc = 0.f;
+          }
+          acc += part[rr * kPartLd + src_col];
+        }
+        if (cur >= 0)
+          atomicAdd(col < n_classes ? semantics + static_cast<uint64_t>(cur) * n_classes + col
+                                    : image + static_cast<uint64_t>(cur) * 3 + (col - n_classes), acc);
       }
+      // the next tile's publish() barrier orders these reads before part[] is overwritten
     }
   }
   umma::ctx_free(ctx, kFwdCols);
@@ -214,10 +275,13 @@ __global__ void __launch_bounds__(128)
 heads_bwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__ k_ptr, uint32_t t,
                     const float* __restrict__ rays_d, const __half* __restrict__ h,
                     const __half* __restrict__ w_color, const __half* __restrict__ w_sem,
-                    const float* __restrict__ rgb, const __half* __restrict__ hc1, const __half* __restrict__ hc2,
-                    const __half* __restrict__ hs, const float* __restrict__ d_rgb,
-                    const float* __restrict__ d_logits, float loss_scale, __half* __restrict__ dh,
-                    float* __restrict__ grad_w_color, float* __restrict__ grad_w_sem) {
+                    int n_classes, const float* __restrict__ rgb, const __half* __restrict__ logits,
+                    const __half* __restrict__ hc1, const __half* __restrict__ hc2, const __half* __restrict__ hs,
+                    const float* __restrict__ w_sel, const float* __restrict__ z_sel,
+                    const float* __restrict__ g_image, const float* __restrict__ g_depth,
+                    const float* __restrict__ g_sem, const float* __restrict__ dnorm, float loss_scale,
+                    __half* __restrict__ dh, float* __restrict__ d_w_sel, float* __restrict__ grad_w_color,
+                    float* __restrict__ grad_w_sem) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* t_in_c = smem + kWeightBytes;
   unsigned char* t_in_s = t_in_c + Tile<32>::kBytes;
@@ -255,33 +319,72 @@ heads_bwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__
     row_g2t<64>(t_h1, hc1 + static_cast<uint64_t>(r) * 64, valid);
     row_g2t<64>(t_h2, hc2 + static_cast<uint64_t>(r) * 64, valid);
     row_g2t<64>(t_hs, hs + static_cast<uint64_t>(r) * 64, valid);
+    // ---- backward of the compositing, fused (renderer_semantics.py:270-285): per row, no reduction needed
+    //   image_n = sum w rgb        -> d rgb = w g_image ;  d w += g_image . rgb
+    //   depth_n = sum w z / dn     ->                      d w += g_depth z / dn
+    //   sem_n   = sum w softmax(l) -> d l = p (w g_sem - <w g_sem, p>)   (weights detached on this branch)
     {
+      const uint32_t n = flat / t;
+      const float w_row = valid ? w_sel[r] : 0.f;
       H8 lo, hi;
       lo.v = make_uint4(0, 0, 0, 0);
       hi.v = make_uint4(0, 0, 0, 0);
       if (valid) {
+        float dw = g_depth[n] / dnorm[n] * z_sel[r];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {  // through the sigmoid: s * (1 - s)
           const float s = rgb[static_cast<uint64_t>(r) * 3 + c];
-          lo.h[c] = __float2half_rn(d_rgb[static_cast<uint64_t>(r) * 3 + c] * s * (1.0f - s) * loss_scale);
+          const float gi = g_image[static_cast<uint64_t>(n) * 3 + c];
+          dw = fmaf(gi, s, dw);
+          lo.h[c] = __float2half_rn(w_row * gi * s * (1.0f - s) * loss_scale);
         }
+        d_w_sel[r] = dw;
       }
       *Tile<16>::chunk(t_dpre, row, 0) = lo.v;
       *Tile<16>::chunk(t_dpre, row, 1) = hi.v;
-    }
-#pragma unroll
-    for (int c = 0; c < kSemOut / 8; ++c) {
-      H8 o;
-      o.v = make_uint4(0, 0, 0, 0);
+
+      float p[kSemOut];
       if (valid) {
-        const float4 a4 = __ldg(reinterpret_cast<const float4*>(d_logits + static_cast<uint64_t>(r) * kSemOut) + 2 * c);
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(d_logits + static_cast<uint64_t>(r) * kSemOut) + 2 * c + 1);
-        o.h[0] = __float2half_rn(a4.x * loss_scale); o.h[1] = __float2half_rn(a4.y * loss_scale);
-        o.h[2] = __float2half_rn(a4.z * loss_scale); o.h[3] = __float2half_rn(a4.w * loss_scale);
-        o.h[4] = __float2half_rn(b4.x * loss_scale); o.h[5] = __float2half_rn(b4.y * loss_scale);
-        o.h[6] = __float2half_rn(b4.z * loss_scale); o.h[7] = __float2half_rn(b4.w * loss_scale);
+        const uint64_t stream = l2_policy_stream();
+#pragma unroll
+        for (int c0 = 0; c0 < kSemOut; c0 += 8) {
+          H8 v;
+          v.v = ld_stream(logits + static_cast<uint64_t>(r) * kSemOut + c0, stream);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) p[c0 + i] = __half2float(v.h[i]);
+        }
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < kSemOut; ++c)
+          if (c < n_classes) m = fmaxf(m, p[c]);
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < kSemOut; ++c) {
+          p[c] = c < n_classes ? expf(p[c] - m) : 0.f;
+          sum += p[c];
+        }
+        const float inv = 1.0f / sum;
+        float dot = 0.f;
+        float q[kSemOut];
+#pragma unroll
+        for (int c = 0; c < kSemOut; ++c) {
+          p[c] *= inv;
+          q[c] = c < n_classes ? w_row * __ldg(g_sem + static_cast<uint64_t>(n) * n_classes + c) : 0.f;
+          dot = fmaf(q[c], p[c], dot);
+        }
+#pragma unroll
+        for (int c = 0; c < kSemOut; ++c) p[c] = p[c] * (q[c] - dot) * loss_scale;
+      } else {
+#pragma unroll
+        for (int c = 0; c < kSemOut; ++c) p[c] = 0.f;
       }
-      *Tile<kSemOut>::chunk(t_dlog, row, c) = o.v;
+#pragma unroll
+      for (int c = 0; c < kSemOut / 8; ++c) {
+        H8 o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.h[i] = __float2half_rn(p[c * 8 + i]);
+        *Tile<kSemOut>::chunk(t_dlog, row, c) = o.v;
+      }
     }
     // ---- stage A: through the two output layers
     ctx.publish();
@@ -368,9 +471,11 @@ using namespace ucsa;
 
 extern "C" int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32_t n_rays, uint32_t t,
                               uint32_t k_max, const float* rays_d, const void* h, const void* w_color_h,
-                              const void* w_sem_h, uint32_t n_classes, float* rgb, void* logits, void* hc1,
-                              void* hc2, void* hs, void* stream) {
+                              const void* w_sem_h, uint32_t n_classes, const float* w_sel, float* rgb, void* logits,
+                              void* hc1, void* hc2, void* hs, float* image, float* semantics, void* stream) {
   UCSA_REQUIRE(sel && ray_off && rays_d && h && w_color_h && w_sem_h && rgb && logits, "heads_fwd: null pointer");
+  UCSA_REQUIRE((image == nullptr) == (semantics == nullptr) && (image == nullptr || w_sel != nullptr),
+               "heads_fwd: fused compositing needs w_sel, image and semantics together");
   UCSA_REQUIRE(n_classes >= 1 && n_classes <= UCSA_MAX_CLASSES, "heads_fwd: 1 <= classes <= %d", UCSA_MAX_CLASSES);
   if (k_max == 0) return UCSA_OK;
   static bool attr_set = false;
@@ -380,18 +485,21 @@ extern "C" int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32
   }
   heads_fwd_tc_kernel<<<heads_grid(k_max, 2), 128, kFwdSmem, as_stream(stream)>>>(
       sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h),
-      static_cast<const __half*>(w_sem_h), rgb, static_cast<__half*>(logits), static_cast<__half*>(hc1),
-      static_cast<__half*>(hc2), static_cast<__half*>(hs));
+      static_cast<const __half*>(w_sem_h), static_cast<int>(n_classes), w_sel, rgb, static_cast<__half*>(logits),
+      static_cast<__half*>(hc1), static_cast<__half*>(hc2), static_cast<__half*>(hs), image, semantics);
   return check_launch("heads_fwd");
 }
 
 extern "C" int ucsa_heads_bwd(const int32_t* sel, const int32_t* ray_off, uint32_t n_rays, uint32_t t,
                               uint32_t k_max, const float* rays_d, const void* h, const void* w_color_h,
-                              const void* w_sem_h, uint32_t n_classes, const float* rgb, const void* hc1,
-                              const void* hc2, const void* hs, const float* d_rgb, const float* d_logits,
-                              float loss_scale, void* dh, float* grad_w_color, float* grad_w_sem, void* stream) {
-  UCSA_REQUIRE(sel && ray_off && rays_d && h && w_color_h && w_sem_h && rgb && hc1 && hc2 && hs && d_rgb &&
-                   d_logits && dh && grad_w_color && grad_w_sem,
+                              const void* w_sem_h, uint32_t n_classes, const float* rgb, const void* logits,
+                              const void* hc1, const void* hc2, const void* hs, const float* w_sel,
+                              const float* z_sel, const float* g_image, const float* g_depth,
+                              const float* g_semantics, const float* direction_norms, float loss_scale, void* dh,
+                              float* d_w_sel, float* grad_w_color, float* grad_w_sem, void* stream) {
+  UCSA_REQUIRE(sel && ray_off && rays_d && h && w_color_h && w_sem_h && rgb && logits && hc1 && hc2 && hs && w_sel &&
+                   z_sel && g_image && g_depth && g_semantics && direction_norms && dh && d_w_sel && grad_w_color &&
+                   grad_w_sem,
                "heads_bwd: null pointer");
   UCSA_REQUIRE(n_classes >= 1 && n_classes <= UCSA_MAX_CLASSES, "heads_bwd: 1 <= classes <= %d", UCSA_MAX_CLASSES);
   UCSA_REQUIRE(loss_scale > 0.f, "heads_bwd: loss_scale must be positive");
@@ -403,8 +511,9 @@ extern "C" int ucsa_heads_bwd(const int32_t* sel, const int32_t* ray_off, uint32
   }
   heads_bwd_tc_kernel<<<heads_grid(k_max, 1), 128, kBwdSmem, as_stream(stream)>>>(
       sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h),
-      static_cast<const __half*>(w_sem_h), rgb, static_cast<const __half*>(hc1), static_cast<const __half*>(hc2),
-      static_cast<const __half*>(hs), d_rgb, d_logits, loss_scale, static_cast<__half*>(dh), grad_w_color,
+      static_cast<const __half*>(w_sem_h), static_cast<int>(n_classes), rgb, static_cast<const __half*>(logits),
+      static_cast<const __half*>(hc1), static_cast<const __half*>(hc2), static_cast<const __half*>(hs), w_sel, z_sel,
+      g_image, g_depth, g_semantics, direction_norms, loss_scale, static_cast<__half*>(dh), d_w_sel, grad_w_color,
       grad_w_sem);
   return check_launch("heads_bwd");
 }

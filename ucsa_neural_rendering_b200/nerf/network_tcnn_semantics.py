@@ -252,10 +252,10 @@ class _FusedRender(torch.autograd.Function):
         hc1 = torch.empty(k_max, 64, **f16) if need else None
         hc2 = torch.empty(k_max, 64, **f16) if need else None
         hs = torch.empty(k_max, 64, **f16) if need else None
-        ops.heads_fwd(sel, ray_off, n, t, k_max, rays_d, h, w_col, w_sem, c, rgb, logits, hc1, hc2, hs)
-        image = torch.empty(n, 3, **f32)
-        semantics = torch.empty(n, c, **f32)
-        ops.composite_fwd(ray_off, w_sel, rgb, logits, n, c, image, semantics)
+        image = torch.zeros(n, 3, **f32)
+        semantics = torch.zeros(n, c, **f32)
+        ops.heads_fwd(sel, ray_off, n, t, k_max, rays_d, h, w_col, w_sem, c, rgb, logits, hc1, hc2, hs, w_sel=w_sel,
+                      image=image, semantics=semantics)  # heads + compositing in one kernel
 
         if need:
             ctx.net = net
@@ -282,17 +282,13 @@ class _FusedRender(torch.autograd.Function):
         w_col = net.color_net.half_params()
         w_sem = net.semantics_net.half_params()
 
-        d_rgb = torch.empty(k_max, 3, **f32)
-        d_logits = torch.empty(k_max, ops.MAX_CLASSES, **f32)
         d_w_sel = torch.empty(k_max, **f32)
-        ops.composite_bwd(ray_off, sel, w_sel, z_sel, rgb, logits, g_image.float().contiguous(),
-                          g_depth.float().contiguous(), g_sem.float().contiguous(), dnorm, n, c, d_rgb, d_logits,
-                          d_w_sel)
         dh = torch.empty(n, t, 16, dtype=torch.float16, device=dev)
         g_col = torch.zeros(ops.COLOR_PARAMS, **f32)
         g_semw = torch.zeros(ops.SEM_PARAMS, **f32)
-        ops.heads_bwd(sel, ray_off, n, t, k_max, rays_d, h, w_col, w_sem, c, rgb, hc1, hc2, hs, d_rgb, d_logits, scale,
-                      dh, g_col, g_semw)
+        ops.heads_bwd(sel, ray_off, n, t, k_max, rays_d, h, w_col, w_sem, c, rgb, logits, hc1, hc2, hs, w_sel, z_sel,
+                      g_image.float().contiguous(), g_depth.float().contiguous(), g_sem.float().contiguous(), dnorm,
+                      scale, dh, d_w_sel, g_col, g_semw)  # compositing backward + heads backward in one kernel
         d_sigma = torch.empty(n, t, **f32)
         ops.weights_bwd(z_cat, sigma, order, w_sorted, ray_off, d_w_sel, net.density_scale, d_sigma)
         g_table = torch.zeros(net.encoder.params.numel(), **f32)

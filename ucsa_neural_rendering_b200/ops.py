@@ -123,25 +123,50 @@ def compact_masked(w_sorted, z_cat, order, ray_off, sel, w_sel, z_sel):
 
 
 def heads_fwd(sel, ray_off, n_rays, t, k_max, rays_d, h, w_color_h, w_sem_h, n_classes, rgb, logits,
-              hc1=None, hc2=None, hs=None, simt=False):
-    fn = lib().ucsa_heads_fwd_simt if simt else lib().ucsa_heads_fwd
-    check(fn(_ptr(sel, torch.int32), _ptr(ray_off, torch.int32), n_rays, t, k_max,
+              hc1=None, hc2=None, hs=None, w_sel=None, image=None, semantics=None):
+    """colour + semantic heads; with w_sel / image / semantics also the compositing (image, semantics zero-filled)"""
+    check(lib().ucsa_heads_fwd(_ptr(sel, torch.int32), _ptr(ray_off, torch.int32), n_rays, t, k_max,
+                               _ptr(rays_d, torch.float32), _ptr(h, torch.float16), _ptr(w_color_h, torch.float16),
+                               _ptr(w_sem_h, torch.float16), n_classes, _ptr(w_sel, torch.float32),
+                               _ptr(rgb, torch.float32), _ptr(logits, torch.float16), _ptr(hc1, torch.float16),
+                               _ptr(hc2, torch.float16), _ptr(hs, torch.float16), _ptr(image, torch.float32),
+                               _ptr(semantics, torch.float32), _stream()), "heads_fwd")
+
+
+def heads_bwd(sel, ray_off, n_rays, t, k_max, rays_d, h, w_color_h, w_sem_h, n_classes, rgb, logits, hc1, hc2, hs,
+              w_sel, z_sel, g_image, g_depth, g_semantics, direction_norms, loss_scale, dh, d_w_sel, grad_w_color,
+              grad_w_sem):
+    check(lib().ucsa_heads_bwd(_ptr(sel, torch.int32), _ptr(ray_off, torch.int32), n_rays, t, k_max,
                                _ptr(rays_d, torch.float32), _ptr(h, torch.float16), _ptr(w_color_h, torch.float16),
                                _ptr(w_sem_h, torch.float16), n_classes, _ptr(rgb, torch.float32),
                                _ptr(logits, torch.float16), _ptr(hc1, torch.float16), _ptr(hc2, torch.float16),
-                               _ptr(hs, torch.float16), _stream()), "heads_fwd")
+                               _ptr(hs, torch.float16), _ptr(w_sel, torch.float32), _ptr(z_sel, torch.float32),
+                               _ptr(g_image, torch.float32, "g_image"), _ptr(g_depth, torch.float32, "g_depth"),
+                               _ptr(g_semantics, torch.float32, "g_semantics"), _ptr(direction_norms, torch.float32),
+                               float(loss_scale), _ptr(dh, torch.float16), _ptr(d_w_sel, torch.float32),
+                               _ptr(grad_w_color, torch.float32), _ptr(grad_w_sem, torch.float32), _stream()),
+          "heads_bwd")
 
 
-def heads_bwd(sel, ray_off, n_rays, t, k_max, rays_d, h, w_color_h, w_sem_h, n_classes, rgb, hc1, hc2, hs, d_rgb,
-              d_logits, loss_scale, dh, grad_w_color, grad_w_sem, simt=False):
-    fn = lib().ucsa_heads_bwd_simt if simt else lib().ucsa_heads_bwd
-    check(fn(_ptr(sel, torch.int32), _ptr(ray_off, torch.int32), n_rays, t, k_max,
-                               _ptr(rays_d, torch.float32), _ptr(h, torch.float16), _ptr(w_color_h, torch.float16),
-                               _ptr(w_sem_h, torch.float16), n_classes, _ptr(rgb, torch.float32),
-                               _ptr(hc1, torch.float16), _ptr(hc2, torch.float16), _ptr(hs, torch.float16),
-                               _ptr(d_rgb, torch.float32), _ptr(d_logits, torch.float32), float(loss_scale),
-                               _ptr(dh, torch.float16), _ptr(grad_w_color, torch.float32),
-                               _ptr(grad_w_sem, torch.float32), _stream()), "heads_bwd")
+def heads_fwd_simt(sel, ray_off, n_rays, t, k_max, rays_d, h, w_color_h, w_sem_h, n_classes, rgb, logits,
+                   hc1=None, hc2=None, hs=None):
+    """CUDA-core cross-check of the heads (no fused compositing)"""
+    check(lib().ucsa_heads_fwd_simt(_ptr(sel, torch.int32), _ptr(ray_off, torch.int32), n_rays, t, k_max,
+                                    _ptr(rays_d, torch.float32), _ptr(h, torch.float16), _ptr(w_color_h, torch.float16),
+                                    _ptr(w_sem_h, torch.float16), n_classes, _ptr(rgb, torch.float32),
+                                    _ptr(logits, torch.float16), _ptr(hc1, torch.float16), _ptr(hc2, torch.float16),
+                                    _ptr(hs, torch.float16), _stream()), "heads_fwd_simt")
+
+
+def heads_bwd_simt(sel, ray_off, n_rays, t, k_max, rays_d, h, w_color_h, w_sem_h, n_classes, rgb, hc1, hc2, hs, d_rgb,
+                   d_logits, loss_scale, dh, grad_w_color, grad_w_sem):
+    check(lib().ucsa_heads_bwd_simt(_ptr(sel, torch.int32), _ptr(ray_off, torch.int32), n_rays, t, k_max,
+                                    _ptr(rays_d, torch.float32), _ptr(h, torch.float16), _ptr(w_color_h, torch.float16),
+                                    _ptr(w_sem_h, torch.float16), n_classes, _ptr(rgb, torch.float32),
+                                    _ptr(hc1, torch.float16), _ptr(hc2, torch.float16), _ptr(hs, torch.float16),
+                                    _ptr(d_rgb, torch.float32), _ptr(d_logits, torch.float32), float(loss_scale),
+                                    _ptr(dh, torch.float16), _ptr(grad_w_color, torch.float32),
+                                    _ptr(grad_w_sem, torch.float32), _stream()), "heads_bwd_simt")
 
 
 def composite_fwd(ray_off, w_sel, rgb, logits, n_rays, n_classes, image, semantics):
