@@ -170,7 +170,8 @@ def run_ours(args):
     from ucsa_neural_rendering_b200 import _lib
     from ucsa_neural_rendering_b200.nerf import SemanticNeRFNetwork
     from ucsa_neural_rendering_b200.scene import SyntheticScene
-    from ucsa_neural_rendering_b200.trainer import NerfTrainer, nerf_losses
+    from ucsa_neural_rendering_b200.engine import TrainEngine
+    from ucsa_neural_rendering_b200.trainer import nerf_losses
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -182,14 +183,17 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()  # fail loudly if the extension is missing
 
     scene = SyntheticScene(seed=0, device=dev)
     net = SemanticNeRFNetwork(encoding="hashgrid", bound=BOUND, cuda_ray=False, density_scale=1,
                               num_semantic_classes=N_CLASSES).to(dev).train()
-    trainer = NerfTrainer(net, num_steps=NUM_STEPS, upsample_steps=UPSAMPLE_STEPS, distributed=world > 1)
     uom = scene.one_m_to_scene_uom
+    engine = TrainEngine(net, RAYS_PER_GPU, num_steps=NUM_STEPS, upsample_steps=UPSAMPLE_STEPS,
+                         one_m_to_scene_uom=uom, use_graph=not args.no_graph)
 
     total_steps = args.warmup + args.steps
     g = torch.Generator(device=dev).manual_seed(123 + rank)
@@ -215,11 +219,12 @@ def run_ours(args):
         return float(t)
 
     # ---------------------------------------------------------------- value: inputs resident in HBM
-    for s in range(args.warmup):
-        trainer.train_step(*batches[s], uom, seed=1000 + s, ray_base=rank * RAYS_PER_GPU)
-    timed = {"ucsa_density_fwd", "ucsa_density_bwd", "ucsa_heads_fwd", "ucsa_heads_bwd"}
+    # One step = one replay of the captured CUDA graph (engine.TrainEngine): render + losses + backward + Adam.
     _lib.stats.reset()
-    _lib.stats.timed = set(timed)
+    engine.train_step(*batches[0])  # first call captures the graph: count the kernels of one step here
+    torch.cuda.synchronize()
+    for s in range(1, args.warmup):
+        engine.train_step(*batches[s])
     clocks = ClockSampler(local_rank)
     clocks.start()
     barrier()
@@ -227,25 +232,42 @@ def run_ours(args):
     t_wall0 = time.time()
     e0.record()
     for s in range(args.warmup, total_steps):
-        trainer.train_step(*batches[s], uom, seed=1000 + s, ray_base=rank * RAYS_PER_GPU)
+        engine.train_step(*batches[s])
     e1.record()
     barrier()
     t_wall1 = time.time()
     clock_info = clocks.stop(t_wall0, t_wall1)
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = _lib.stats.launches
+    value = world * RAYS_PER_GPU * args.steps / (ms_total * 1e-3)
+
+    # per-kernel device time: the same steps once more, launched eagerly with CUDA events around the kernels
+    timed = {"ucsa_density_fwd", "ucsa_density_bwd", "ucsa_heads_fwd", "ucsa_heads_bwd"}
+    eager = TrainEngine(net, RAYS_PER_GPU, num_steps=NUM_STEPS, upsample_steps=UPSAMPLE_STEPS,
+                        one_m_to_scene_uom=uom, use_graph=False)
+    eager.train_step(*batches[0])
+    torch.cuda.synchronize()
+    _lib.stats.reset()
+    eager.train_step(*batches[1])
+    torch.cuda.synchronize()
+    per_step_launches = _lib.stats.launches  # kernels of ONE step; the graph replays exactly these
     by_name = dict(_lib.stats.by_name)
+    launches = per_step_launches * args.steps
+    _lib.stats.reset()
+    _lib.stats.timed = set(timed)
+    for s in range(args.warmup, total_steps):
+        eager.train_step(*batches[s])
+    torch.cuda.synchronize()
     kernel_ms = {k: _lib.stats.elapsed_ms(k) for k in timed}
     _lib.stats.timed = set()
-    value = world * RAYS_PER_GPU * args.steps / (ms_total * 1e-3)
+    del eager
 
     # ---------------------------------------------------------------- e2e: public API, host buffers
     opt = torch.optim.Adam([
         {"name": "encoding", "params": list(net.encoder.parameters())},
         {"name": "net", "params": list(net.sigma_net.parameters()) + list(net.color_net.parameters())
          + list(net.semantics_net.parameters()), "weight_decay": 1e-6}], lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
-    for m, _ in trainer.groups:
-        m.params.grad = None
+    for p_ in net.parameters():
+        p_.grad = None
 
     def e2e_step(s):
         o, d, dn, rgb, label, depth = (x.to(dev, non_blocking=True) for x in host[s])
@@ -258,7 +280,7 @@ def run_ours(args):
             for p in net.parameters():
                 dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
         opt.step()
-        return float(loss)  # D2H read of the step's result
+        return float(loss.detach())  # D2H read of the step's result
 
     for s in range(args.warmup):
         e2e_step(s)
@@ -270,6 +292,17 @@ def run_ours(args):
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * RAYS_PER_GPU * args.steps / (e2e_ms * 1e-3)
+
+    # the engine fed from pinned host memory (H2D of the batch + D2H of the loss inside the timed region)
+    barrier()
+    e0.record()
+    for s in range(args.warmup, total_steps):
+        engine.load_batch(*host[s])
+        float(engine.step()[0])
+    e1.record()
+    barrier()
+    e2e_engine_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_engine_value = world * RAYS_PER_GPU * args.steps / (e2e_engine_ms * 1e-3)
 
     if rank != 0:
         if world > 1:
@@ -314,8 +347,12 @@ def run_ours(args):
         "config": dict(CONFIG, parallelism=f"ray-sharded dp{world}"),
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps,
-                "api": "SemanticNeRFNetwork.render + nerf_losses + torch.optim.Adam, pinned host inputs"},
-        "gpu_launches": launches, "gpu_launches_by_kernel": by_name,
+                "api": "SemanticNeRFNetwork.render + nerf_losses + torch.optim.Adam (the drop-in API a Lightning "
+                       "loop calls), pinned host inputs",
+                "engine": {"value": e2e_engine_value, "ms_per_step": e2e_engine_ms / args.steps,
+                           "api": "TrainEngine.load_batch(pinned host) + step() + loss readback"}},
+        "gpu_launches": launches, "gpu_launches_per_step": by_name,
+        "step_impl": "cuda-graph replay of %d kernels" % per_step_launches if not args.no_graph else "eager kernel chain",
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info,
     }
     print(json.dumps(line))
@@ -330,6 +367,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -68,10 +68,11 @@ UCSA_API int ucsa_near_far_from_aabb(const float* rays_o, const float* rays_d, c
 
 /* ---- a3. coarse sampling (renderer_semantics.py:154-168).  Writes slots [0,Tc) of z_cat [N,T].
  * lin[Tc] is torch.linspace(0,1,Tc).  perturb: stratified jitter; the uniform numbers come from t_rand [N,Tc]
- * when non-null, else from the counter-based generator keyed by (seed, ray_base+n, k). */
+ * when non-null, else from the counter-based generator keyed by (seed, ray_base+n, k).  step_dev (nullable, device
+ * int32) is mixed into the seed on the device, so a captured CUDA graph draws fresh numbers on every replay. */
 UCSA_API int ucsa_sample_coarse(const float* nears, const float* fars, const float* lin, const float* t_rand,
-                       uint64_t seed, uint32_t ray_base, int perturb, uint32_t n_rays, uint32_t tc, uint32_t t,
-                       float* z_cat, void* stream);
+                       uint64_t seed, const int32_t* step_dev, uint32_t ray_base, int perturb, uint32_t n_rays,
+                       uint32_t tc, uint32_t t, float* z_cat, void* stream);
 
 /* ---- a4/a5/a6/a8. density = hash-grid encode + sigma MLP + trunc_exp (network_tcnn_semantics.py:130-144).
  * Sample positions are either xyz [S,3] (then rays_*, z_cat are ignored and a "ray" has T=1 slot), or
@@ -97,9 +98,9 @@ UCSA_API int ucsa_density_bwd(const float* xyz, const float* rays_o, const float
 /* ---- a9/a10. importance resampling + merge (renderer_semantics.py:182-222, sample_pdf :10-46).
  * Reads coarse z / sigma (slots [0,Tc)), writes fine z into slots [Tc,Tc+Tf) and order [N,T]
  * (sorted position -> cat slot, the z_index of :222).  u [N,Tf] when non-null, else generated (seed). */
-UCSA_API int ucsa_resample_merge(const float* sigma, float* z_cat, const float* u, uint64_t seed, uint32_t ray_base,
-                        uint32_t n_rays, uint32_t tc, uint32_t tf, float density_scale, int32_t* order,
-                        void* stream);
+UCSA_API int ucsa_resample_merge(const float* sigma, float* z_cat, const float* u, uint64_t seed,
+                        const int32_t* step_dev, uint32_t ray_base, uint32_t n_rays, uint32_t tc, uint32_t tf,
+                        float density_scale, int32_t* order, void* stream);
 
 /* ---- a11. weights, masks, depth (renderer_semantics.py:238-250,270-277).  order may be null (identity).
  * Writes w_sorted [N,T] (un-masked weights), depth [N] (sum of masked w*z / direction_norm),
@@ -250,7 +251,17 @@ UCSA_API int ucsa_mlp_bwd_simt(const void* x_h, uint32_t n, const void* w_h, con
 UCSA_API int ucsa_cast_f32_to_f16(const float* src, uint64_t n, void* dst_h, void* stream);
 UCSA_API int ucsa_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_h,
                    uint64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
-                   float grad_scale_inv, const float* found_inf, uint32_t step, void* stream);
+                   float grad_scale_inv, const float* found_inf, uint32_t step, const int32_t* step_dev,
+                   void* stream);
+
+/* ---- f2. losses of forward_nerf_train (joint_train_lightning_net.py:199-221,503-507) and their gradients w.r.t.
+ * image / depth / semantics in one kernel.  gt_rgb as fp16 [N,3] (batch["img_fp16"]) or fp32; labels int64 with -1 =
+ * ignore; loss4 = (total, colour, semantics, depth).  total is multiplied by global_scale (1/world for sharded rays). */
+UCSA_API int ucsa_nerf_loss(const float* image, const float* depth, const float* semantics, const void* gt_rgb_h,
+                   const float* gt_rgb_f, const int64_t* labels, const float* gt_depth, uint32_t n_rays,
+                   uint32_t n_classes, float one_m_to_scene_uom, float weight_semantics, float weight_depth,
+                   float global_scale, float* loss4, float* g_image, float* g_depth, float* g_semantics,
+                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,7 @@ _SCALARS = {
     "uint32_t": ctypes.c_uint32,
     "uint64_t": ctypes.c_uint64,
     "int32_t": ctypes.c_int32,
+    "int64_t": ctypes.c_int64,
 }
 
 

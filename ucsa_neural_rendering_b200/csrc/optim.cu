@@ -24,8 +24,13 @@ __global__ void cast_kernel(const float* __restrict__ src, uint64_t n, __half* _
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, __half* __restrict__ p_h, uint64_t n, float lr, float b1,
                             float b2, float eps, float wd, float ginv, const float* __restrict__ found_inf,
-                            float bc1, float bc2_sqrt) {
+                            float bc1, float bc2_sqrt, const int32_t* __restrict__ step_dev) {
   if (found_inf != nullptr && *found_inf != 0.f) return;  // GradScaler: skip the step on overflow
+  if (step_dev != nullptr) {  // step count lives on the device (CUDA-graph replay): bias corrections from it
+    const float st = static_cast<float>(*step_dev);
+    bc1 = 1.0f - powf(b1, st);
+    bc2_sqrt = sqrtf(1.0f - powf(b2, st));
+  }
   const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float grad = g[i] * ginv;
@@ -57,15 +62,16 @@ extern "C" int ucsa_cast_f32_to_f16(const float* src, uint64_t n, void* dst_h, v
 
 extern "C" int ucsa_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_h,
                               uint64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
-                              float grad_scale_inv, const float* found_inf, uint32_t step, void* stream) {
+                              float grad_scale_inv, const float* found_inf, uint32_t step, const int32_t* step_dev,
+                              void* stream) {
   UCSA_REQUIRE(param && grad && exp_avg && exp_avg_sq, "adam_step: null pointer");
-  UCSA_REQUIRE(step >= 1, "adam_step: step counts from 1");
+  UCSA_REQUIRE(step >= 1 || step_dev != nullptr, "adam_step: step counts from 1");
   if (n == 0) return UCSA_OK;
   const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
   const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
   adam_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq,
                                                                static_cast<__half*>(param_h), n, lr, beta1, beta2,
                                                                eps, weight_decay, grad_scale_inv, found_inf, bc1,
-                                                               sqrtf(bc2));
+                                                               sqrtf(bc2), step_dev);
   return check_launch("adam_step");
 }

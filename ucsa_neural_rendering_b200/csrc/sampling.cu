@@ -53,10 +53,11 @@ __device__ __forceinline__ float coarse_z(float near, float far, float lin) {
 
 __global__ void sample_coarse_kernel(const float* __restrict__ nears, const float* __restrict__ fars,
                                      const float* __restrict__ lin, const float* __restrict__ t_rand,
-                                     uint64_t seed, uint32_t ray_base, int perturb, uint32_t n_rays, uint32_t tc,
-                                     uint32_t t, float* __restrict__ z_cat) {
+                                     uint64_t seed, const int32_t* __restrict__ step_dev, uint32_t ray_base, int perturb,
+                                     uint32_t n_rays, uint32_t tc, uint32_t t, float* __restrict__ z_cat) {
   const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<uint64_t>(n_rays) * tc) return;
+  if (step_dev != nullptr) seed += 0x9E3779B97F4A7C15ull * static_cast<uint64_t>(*step_dev);
   const uint32_t n = static_cast<uint32_t>(i / tc), k = static_cast<uint32_t>(i % tc);
   const float near = nears[n], far = fars[n];
   float z = coarse_z(near, far, lin[k]);
@@ -77,9 +78,10 @@ __global__ void sample_coarse_kernel(const float* __restrict__ nears, const floa
 // summation order of torch.cumprod / torch.cumsum on the CPU and costs microseconds per 4096-ray batch.
 __global__ void __launch_bounds__(256)
 resample_merge_kernel(const float* __restrict__ sigma, float* __restrict__ z_cat, const float* __restrict__ u,
-                      uint64_t seed, uint32_t ray_base, uint32_t tc, uint32_t tf, float density_scale,
-                      int32_t* __restrict__ order) {
+                      uint64_t seed, const int32_t* __restrict__ step_dev, uint32_t ray_base, uint32_t tc, uint32_t tf,
+                      float density_scale, int32_t* __restrict__ order) {
   extern __shared__ float sm[];
+  if (step_dev != nullptr) seed += 0x9E3779B97F4A7C15ull * static_cast<uint64_t>(*step_dev);
   float* zc = sm;
   float* sg = zc + tc;
   float* wt = sg + tc;
@@ -186,21 +188,21 @@ extern "C" int ucsa_near_far_from_aabb(const float* rays_o, const float* rays_d,
 }
 
 extern "C" int ucsa_sample_coarse(const float* nears, const float* fars, const float* lin, const float* t_rand,
-                                  uint64_t seed, uint32_t ray_base, int perturb, uint32_t n_rays, uint32_t tc,
-                                  uint32_t t, float* z_cat, void* stream) {
+                                  uint64_t seed, const int32_t* step_dev, uint32_t ray_base, int perturb,
+                                  uint32_t n_rays, uint32_t tc, uint32_t t, float* z_cat, void* stream) {
   UCSA_REQUIRE(nears && fars && lin && z_cat, "sample_coarse: null pointer");
   UCSA_REQUIRE(tc >= 1 && tc <= t, "sample_coarse: need 1 <= Tc <= T");
   if (n_rays == 0) return UCSA_OK;
   const uint64_t total = static_cast<uint64_t>(n_rays) * tc;
-  sample_coarse_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(nears, fars, lin, t_rand, seed,
+  sample_coarse_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(nears, fars, lin, t_rand, seed, step_dev,
                                                                             ray_base, perturb, n_rays, tc, t,
                                                                             z_cat);
   return check_launch("sample_coarse");
 }
 
 extern "C" int ucsa_resample_merge(const float* sigma, float* z_cat, const float* u, uint64_t seed,
-                                   uint32_t ray_base, uint32_t n_rays, uint32_t tc, uint32_t tf,
-                                   float density_scale, int32_t* order, void* stream) {
+                                   const int32_t* step_dev, uint32_t ray_base, uint32_t n_rays, uint32_t tc,
+                                   uint32_t tf, float density_scale, int32_t* order, void* stream) {
   UCSA_REQUIRE(sigma && z_cat && order, "resample_merge: null pointer");
   UCSA_REQUIRE(tc >= 3 && tf >= 1 && tc <= 4096 && tf <= 4096, "resample_merge: need 3 <= Tc <= 4096, 1 <= Tf <= 4096");
   if (n_rays == 0) return UCSA_OK;
@@ -210,7 +212,7 @@ extern "C" int ucsa_resample_merge(const float* sigma, float* z_cat, const float
     cudaFuncSetAttribute(resample_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     smem_set = smem;
   }
-  resample_merge_kernel<<<n_rays, 256, smem, as_stream(stream)>>>(sigma, z_cat, u, seed, ray_base, tc, tf,
+  resample_merge_kernel<<<n_rays, 256, smem, as_stream(stream)>>>(sigma, z_cat, u, seed, step_dev, ray_base, tc, tf,
                                                                   density_scale, order);
   return check_launch("resample_merge");
 }

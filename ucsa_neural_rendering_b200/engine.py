@@ -1,0 +1,152 @@
+"""TrainEngine: one NeRF optimisation step as a single CUDA graph (SURVEY.md section 7 step 6, rows f1 + f2).
+
+Work of one step = training_step_nerf of the reference (joint_train_lightning_net.py:473-513): render the ray batch
+with perturb=True, the three losses, backward, Adam on both parameter groups.  Here it is a fixed chain of
+libucsa_nerf.so kernels on a static workspace -- no autograd engine, no eager tensor math, no host synchronisation:
+
+    step counter += 1 -> zero gradients -> pipeline.forward_chain -> ucsa_nerf_loss -> pipeline.backward_chain
+    -> [NCCL all-reduce of the flat gradient buffer when world > 1] -> ucsa_adam_step x 4
+
+captured once with torch.cuda.graph and replayed every step.  Random numbers and Adam's bias correction read the
+step counter from device memory, so every replay draws fresh samples.  With world > 1 the all-reduce stays outside
+the graphs (forward/backward graph -> all-reduce -> optimizer graph)."""
+from __future__ import annotations
+
+import torch
+
+from . import ops, parallel, pipeline
+
+
+class TrainEngine:
+
+    def __init__(self, net, n_rays, num_steps=256, upsample_steps=256, lr=1e-2, betas=(0.9, 0.99), eps=1e-15,
+                 weight_decay_net=1e-6, weight_depth=0.1, weight_semantics=0.04, one_m_to_scene_uom=1.0, seed=0x5EED,
+                 use_graph=True):
+        self.net = net
+        dev = net.encoder.params.device
+        self.device = dev
+        self.rank, self.world = parallel.world()
+        self.n = n_rays
+        self.c = net.num_semantic_classes
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.w_depth, self.w_sem, self.uom = weight_depth, weight_semantics, one_m_to_scene_uom
+        self.seed = seed
+        self.use_graph = use_graph
+        self.ws = pipeline.RenderWorkspace(n_rays, num_steps, upsample_steps, self.c, dev, need_grad=True)
+        f32 = dict(dtype=torch.float32, device=dev)
+        # static inputs (the step's batch is copied in before the replay)
+        self.rays_o = torch.zeros(n_rays, 3, **f32)
+        self.rays_d = torch.zeros(n_rays, 3, **f32)
+        self.dnorm = torch.ones(n_rays, **f32)
+        self.gt_rgb = torch.zeros(n_rays, 3, dtype=torch.float16, device=dev)
+        self.labels = torch.zeros(n_rays, dtype=torch.int64, device=dev)
+        self.gt_depth = torch.zeros(n_rays, **f32)
+        self.ray_base = self.rank * n_rays
+        # loss + its gradients
+        self.loss = torch.zeros(4, **f32)
+        self.g_image = torch.empty(n_rays, 3, **f32)
+        self.g_depth = torch.empty(n_rays, **f32)
+        self.g_sem = torch.empty(n_rays, self.c, **f32)
+        # parameters: one flat gradient buffer (the all-reduce payload), Adam moments, device step counter
+        self.groups = [(net.encoder, 0.0), (net.sigma_net, weight_decay_net), (net.color_net, weight_decay_net),
+                       (net.semantics_net, weight_decay_net)]
+        sizes = [m.params.numel() for m, _ in self.groups]
+        self.flat_grad = torch.zeros(sum(sizes), **f32)
+        self.grads, off = [], 0
+        for s in sizes:
+            self.grads.append(self.flat_grad[off:off + s])
+            off += s
+        self.exp_avg = [torch.zeros_like(m.params) for m, _ in self.groups]
+        self.exp_avg_sq = [torch.zeros_like(m.params) for m, _ in self.groups]
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        for m, _ in self.groups:
+            m.half_params()
+        self._graph_fb = self._graph_opt = None
+
+    # ------------------------------------------------------------------ the two halves of a step
+    def _forward_backward(self):
+        net, ws = self.net, self.ws
+        self.step_dev.add_(1)
+        self.flat_grad.zero_()
+        aabb = net.aabb_train
+        pipeline.forward_chain(net, ws, self.rays_o, self.rays_d, self.dnorm, aabb, perturb=True, seed=self.seed,
+                               ray_base=self.ray_base, step_dev=self.step_dev)
+        ops.nerf_loss(ws.image, ws.depth, ws.semantics, self.gt_rgb, self.labels, self.gt_depth, self.uom, self.w_sem,
+                      self.w_depth, 1.0 / self.world, self.loss, self.g_image, self.g_depth, self.g_sem)
+        pipeline.backward_chain(net, ws, self.rays_o, self.rays_d, self.dnorm, aabb, self.g_image, self.g_depth,
+                                self.g_sem, *self.grads)
+
+    def _optimizer(self):
+        for (m, wd), g, ea, eas in zip(self.groups, self.grads, self.exp_avg, self.exp_avg_sq):
+            ops.adam_step(m.params.data, g, ea, eas, m.half_params(), lr=self.lr, beta1=self.betas[0],
+                          beta2=self.betas[1], eps=self.eps, weight_decay=wd, grad_scale_inv=1.0, found_inf=None,
+                          step=1, step_dev=self.step_dev)
+
+    def _capture(self):
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        state = self._snapshot()
+        with torch.cuda.stream(side):  # warm-up outside capture (lazy attribute set-up, allocator)
+            for _ in range(2):
+                self._forward_backward()
+                self._optimizer()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._restore(state)
+        self._graph_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_fb):
+            self._forward_backward()
+            if self.world == 1:
+                self._optimizer()
+        if self.world > 1:
+            self._graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_opt):
+                self._optimizer()
+        torch.cuda.synchronize()
+        self._restore(state)
+
+    def _snapshot(self):
+        return ([m.params.detach().clone() for m, _ in self.groups], [t.clone() for t in self.exp_avg],
+                [t.clone() for t in self.exp_avg_sq], self.step_dev.clone())
+
+    def _restore(self, state):
+        params, ea, eas, step = state
+        with torch.no_grad():
+            for (m, _), p in zip(self.groups, params):
+                m.params.copy_(p)
+                m.half_params()
+            for dst, src in zip(self.exp_avg, ea):
+                dst.copy_(src)
+            for dst, src in zip(self.exp_avg_sq, eas):
+                dst.copy_(src)
+            self.step_dev.copy_(step)
+
+    # ------------------------------------------------------------------ public
+    def load_batch(self, rays_o, rays_d, direction_norms, gt_rgb, labels, gt_depth, non_blocking=True):
+        """Copy one step's rays + ground truth (host or device tensors, any leading 1-dims) into the static inputs."""
+        self.rays_o.copy_(rays_o.reshape(-1, 3), non_blocking=non_blocking)
+        self.rays_d.copy_(rays_d.reshape(-1, 3), non_blocking=non_blocking)
+        self.dnorm.copy_(direction_norms.reshape(-1), non_blocking=non_blocking)
+        self.gt_rgb.copy_(gt_rgb.reshape(-1, 3), non_blocking=non_blocking)
+        self.labels.copy_(labels.reshape(-1), non_blocking=non_blocking)
+        self.gt_depth.copy_(gt_depth.reshape(-1), non_blocking=non_blocking)
+
+    def step(self):
+        """One optimisation step on the loaded batch; returns the device tensor (total, colour, semantic, depth)."""
+        if not self.use_graph:
+            self._forward_backward()
+            if self.world > 1:
+                parallel.all_reduce_gradients(self.flat_grad)
+            self._optimizer()
+            return self.loss
+        if self._graph_fb is None:
+            self._capture()
+        self._graph_fb.replay()
+        if self.world > 1:
+            parallel.all_reduce_gradients(self.flat_grad)
+            self._graph_opt.replay()
+        return self.loss
+
+    def train_step(self, rays_o, rays_d, direction_norms, gt_rgb, labels, gt_depth):
+        self.load_batch(rays_o, rays_d, direction_norms, gt_rgb, labels, gt_depth)
+        return self.step()

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .. import ops
+from .. import ops, pipeline
 from .activation import trunc_exp  # noqa: F401  (re-exported like the reference module)
 from .renderer_semantics import SemanticNeRFRenderer
 
@@ -196,106 +196,34 @@ class _DensityFn(torch.autograd.Function):
 
 
 class _FusedRender(torch.autograd.Function):
-    """The whole of SemanticNeRFRenderer.run() (renderer_semantics.py:123-299) with the network heads inlined."""
+    """The whole of SemanticNeRFRenderer.run() (renderer_semantics.py:123-299) with the network heads inlined: one
+    autograd node around pipeline.forward_chain / backward_chain."""
 
     @staticmethod
     def forward(ctx, enc_params, sigma_params, color_params, sem_params, rays_o, rays_d, dnorm, net, cfg):
-        dev = rays_o.device
-        n = rays_o.shape[0]
-        tc, tf = cfg["num_steps"], cfg["upsample_steps"]
-        t = tc + tf
-        c = net.num_semantic_classes
-        aabb = cfg["aabb"]
         need = any(ctx.needs_input_grad[:4])  # (grad mode is off inside forward)
-        grid = net.encoder.grid
-        table_h = net.encoder.half_params()
-        w_sig = net.sigma_net.half_params()
-        w_col = net.color_net.half_params()
-        w_sem = net.semantics_net.half_params()
-        f32 = dict(dtype=torch.float32, device=dev)
-        f16 = dict(dtype=torch.float16, device=dev)
-        i32 = dict(dtype=torch.int32, device=dev)
-
-        nears, fars = ops.near_far_from_aabb(rays_o, rays_d, aabb)
-        z_cat = torch.empty(n, t, **f32)
-        lin = torch.linspace(0.0, 1.0, tc, device=dev)
-        ops.sample_coarse(nears, fars, lin, z_cat, tc, perturb=cfg["perturb"], t_rand=cfg["t_rand"],
-                          seed=cfg["seed"], ray_base=cfg["ray_base"])
-        sigma = torch.empty(n, t, **f32)
-        h = torch.empty(n, t, 16, **f16)
-        enc = torch.empty(n, t, 32, **f16) if need else None
-        hid = torch.empty(n, t, 64, **f16) if need else None
-        common = dict(rays_o=rays_o, rays_d=rays_d, aabb=aabb, z_cat=z_cat, sigma=sigma, h=h, enc=enc, hid=hid)
-        ops.density_fwd(grid, table_h, w_sig, net.bound, k0=0, k1=tc, **common)
-        order = None
-        if tf > 0:
-            order = torch.empty(n, t, **i32)
-            ops.resample_merge(sigma, z_cat, order, tc, tf, net.density_scale, u=cfg["u"], seed=cfg["seed"],
-                               ray_base=cfg["ray_base"])
-            ops.density_fwd(grid, table_h, w_sig, net.bound, k0=tc, k1=t, **common)
-
-        w_sorted = torch.empty(n, t, **f32)
-        depth = torch.empty(n, **f32)
-        ray_count = torch.empty(n, **i32)
-        use_geo = torch.empty(n, t, dtype=torch.uint8, device=dev)
-        ops.weights_fwd(z_cat, sigma, order, dnorm, net.density_scale, w_sorted, depth, ray_count, use_geo)
-        ray_off = torch.empty(n + 1, **i32)
-        ops.scan_counts(ray_count, ray_off)
-        k_max = n * t  # worst case; the kernels read the true K from ray_off[n] on the device (no host sync)
-        sel = torch.empty(k_max, **i32)
-        w_sel = torch.empty(k_max, **f32)
-        z_sel = torch.empty(k_max, **f32)
-        ops.compact_masked(w_sorted, z_cat, order, ray_off, sel, w_sel, z_sel)
-
-        rgb = torch.empty(k_max, 3, **f32)
-        logits = torch.empty(k_max, ops.MAX_CLASSES, **f16)
-        hc1 = torch.empty(k_max, 64, **f16) if need else None
-        hc2 = torch.empty(k_max, 64, **f16) if need else None
-        hs = torch.empty(k_max, 64, **f16) if need else None
-        image = torch.zeros(n, 3, **f32)
-        semantics = torch.zeros(n, c, **f32)
-        ops.heads_fwd(sel, ray_off, n, t, k_max, rays_d, h, w_col, w_sem, c, rgb, logits, hc1, hc2, hs, w_sel=w_sel,
-                      image=image, semantics=semantics)  # heads + compositing in one kernel
-
+        ws = pipeline.RenderWorkspace(rays_o.shape[0], cfg["num_steps"], cfg["upsample_steps"],
+                                      net.num_semantic_classes, rays_o.device, need)
+        pipeline.forward_chain(net, ws, rays_o, rays_d, dnorm, cfg["aabb"], perturb=cfg["perturb"],
+                               t_rand=cfg["t_rand"], u=cfg["u"], seed=cfg["seed"], ray_base=cfg["ray_base"])
         if need:
-            ctx.net = net
-            ctx.shape = (n, tc, tf, c, k_max)
-            ctx.aabb = aabb
-            ctx.order = order
-            ctx.save_for_backward(rays_o, rays_d, dnorm, z_cat, sigma, h, enc, hid, w_sorted, use_geo, ray_off, sel,
-                                  w_sel, z_sel, rgb, logits, hc1, hc2, hs)
-        return depth, image, semantics
+            ctx.net, ctx.ws, ctx.aabb = net, ws, cfg["aabb"]
+            ctx.save_for_backward(rays_o, rays_d, dnorm)
+        return ws.depth, ws.image, ws.semantics
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_depth, g_image, g_sem):
-        net = ctx.net
-        n, tc, tf, c, k_max = ctx.shape
-        t = tc + tf
-        (rays_o, rays_d, dnorm, z_cat, sigma, h, enc, hid, w_sorted, use_geo, ray_off, sel, w_sel, z_sel, rgb,
-         logits, hc1, hc2, hs) = ctx.saved_tensors
-        order = ctx.order
-        dev = rays_o.device
-        f32 = dict(dtype=torch.float32, device=dev)
-        scale = float(net.loss_scale)
-        w_sig = net.sigma_net.half_params()
-        w_col = net.color_net.half_params()
-        w_sem = net.semantics_net.half_params()
-
-        d_w_sel = torch.empty(k_max, **f32)
-        dh = torch.empty(n, t, 16, dtype=torch.float16, device=dev)
-        g_col = torch.zeros(ops.COLOR_PARAMS, **f32)
-        g_semw = torch.zeros(ops.SEM_PARAMS, **f32)
-        ops.heads_bwd(sel, ray_off, n, t, k_max, rays_d, h, w_col, w_sem, c, rgb, logits, hc1, hc2, hs, w_sel, z_sel,
-                      g_image.float().contiguous(), g_depth.float().contiguous(), g_sem.float().contiguous(), dnorm,
-                      scale, dh, d_w_sel, g_col, g_semw)  # compositing backward + heads backward in one kernel
-        d_sigma = torch.empty(n, t, **f32)
-        ops.weights_bwd(z_cat, sigma, order, w_sorted, ray_off, d_w_sel, net.density_scale, d_sigma)
+        net, ws = ctx.net, ctx.ws
+        rays_o, rays_d, dnorm = ctx.saved_tensors
+        f32 = dict(dtype=torch.float32, device=rays_o.device)
         g_table = torch.zeros(net.encoder.params.numel(), **f32)
         g_sig = torch.zeros(ops.SIGMA_PARAMS, **f32)
-        ops.density_bwd(net.encoder.grid, w_sig, net.bound, rays_o=rays_o, rays_d=rays_d, aabb=ctx.aabb, z_cat=z_cat,
-                        k0=0, k1=t, h=h, enc=enc, hid=hid, d_sigma=d_sigma, dh=dh, use_geo=use_geo, loss_scale=scale,
-                        grad_table=g_table, grad_w_sigma=g_sig)
+        g_col = torch.zeros(ops.COLOR_PARAMS, **f32)
+        g_semw = torch.zeros(ops.SEM_PARAMS, **f32)
+        pipeline.backward_chain(net, ws, rays_o, rays_d, dnorm, ctx.aabb, g_image.float().contiguous(),
+                                g_depth.float().contiguous(), g_sem.float().contiguous(), g_table, g_sig, g_col, g_semw)
+        ctx.ws = None
         return g_table, g_sig, g_col, g_semw, None, None, None, None, None
 
 

@@ -56,11 +56,19 @@ def near_far_from_aabb(rays_o, rays_d, aabb, min_near=0.2):
     return nears, fars
 
 
-def sample_coarse(nears, fars, lin, z_cat, tc, *, perturb, t_rand=None, seed=0, ray_base=0):
+def near_far_from_aabb_into(rays_o, rays_d, aabb, nears, fars, min_near=0.2):
+    check(lib().ucsa_near_far_from_aabb(_ptr(rays_o, torch.float32, "rays_o"), _ptr(rays_d, torch.float32, "rays_d"),
+                                        _ptr(aabb, torch.float32, "aabb"), rays_o.shape[0], float(min_near),
+                                        _ptr(nears, torch.float32), _ptr(fars, torch.float32), _stream()),
+          "near_far_from_aabb")
+
+
+def sample_coarse(nears, fars, lin, z_cat, tc, *, perturb, t_rand=None, seed=0, ray_base=0, step_dev=None):
     n, t = z_cat.shape
     check(lib().ucsa_sample_coarse(_ptr(nears, torch.float32), _ptr(fars, torch.float32), _ptr(lin, torch.float32),
-                                   _ptr(t_rand, torch.float32, "t_rand"), seed, ray_base, int(bool(perturb)), n, tc, t,
-                                   _ptr(z_cat, torch.float32), _stream()), "sample_coarse")
+                                   _ptr(t_rand, torch.float32, "t_rand"), seed, _ptr(step_dev, torch.int32), ray_base,
+                                   int(bool(perturb)), n, tc, t, _ptr(z_cat, torch.float32), _stream()),
+          "sample_coarse")
 
 
 def density_fwd(grid, table_h, w_sigma_h, bound, *, xyz=None, rays_o=None, rays_d=None, aabb=None, z_cat=None,
@@ -95,11 +103,11 @@ def density_bwd(grid, w_sigma_h, bound, *, xyz=None, rays_o=None, rays_d=None, a
                                  _ptr(grad_w_sigma, torch.float32, "grad_w_sigma"), _stream()), "density_bwd")
 
 
-def resample_merge(sigma, z_cat, order, tc, tf, density_scale, *, u=None, seed=0, ray_base=0):
+def resample_merge(sigma, z_cat, order, tc, tf, density_scale, *, u=None, seed=0, ray_base=0, step_dev=None):
     n = z_cat.shape[0]
     check(lib().ucsa_resample_merge(_ptr(sigma, torch.float32), _ptr(z_cat, torch.float32), _ptr(u, torch.float32, "u"),
-                                    seed, ray_base, n, tc, tf, float(density_scale), _ptr(order, torch.int32, "order"),
-                                    _stream()), "resample_merge")
+                                    seed, _ptr(step_dev, torch.int32), ray_base, n, tc, tf, float(density_scale),
+                                    _ptr(order, torch.int32, "order"), _stream()), "resample_merge")
 
 
 def weights_fwd(z_cat, sigma, order, direction_norms, density_scale, w_sorted, depth, ray_count, use_geo):
@@ -266,11 +274,24 @@ def cast_f32_to_f16(src, dst):
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, param_h, *, lr, beta1, beta2, eps, weight_decay, grad_scale_inv,
-              found_inf, step):
+              found_inf, step, step_dev=None):
     check(lib().ucsa_adam_step(_ptr(param, torch.float32), _ptr(grad, torch.float32), _ptr(exp_avg, torch.float32),
                                _ptr(exp_avg_sq, torch.float32), _ptr(param_h, torch.float16), param.numel(), float(lr),
                                float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale_inv),
-                               _ptr(found_inf, torch.float32), int(step), _stream()), "adam_step")
+                               _ptr(found_inf, torch.float32), int(step), _ptr(step_dev, torch.int32), _stream()),
+          "adam_step")
+
+
+def nerf_loss(image, depth, semantics, gt_rgb, labels, gt_depth, uom, w_sem, w_depth, global_scale, loss4, g_image,
+              g_depth, g_semantics):
+    n, c = semantics.shape
+    half = gt_rgb.dtype == torch.float16
+    check(lib().ucsa_nerf_loss(_ptr(image, torch.float32), _ptr(depth, torch.float32), _ptr(semantics, torch.float32),
+                               _ptr(gt_rgb, torch.float16) if half else None,
+                               None if half else _ptr(gt_rgb, torch.float32), _ptr(labels, torch.int64, "labels"),
+                               _ptr(gt_depth, torch.float32, "gt_depth"), n, c, float(uom), float(w_sem), float(w_depth),
+                               float(global_scale), _ptr(loss4, torch.float32), _ptr(g_image, torch.float32),
+                               _ptr(g_depth, torch.float32), _ptr(g_semantics, torch.float32), _stream()), "nerf_loss")
 
 
 # ---------------------------------------------------------------------------------------------- occupancy-grid path

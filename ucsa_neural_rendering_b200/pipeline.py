@@ -1,0 +1,99 @@
+"""The fused LIVE-path pipeline as two kernel chains over an explicit workspace.
+
+``forward_chain`` is SemanticNeRFRenderer.run() (renderer_semantics.py:123-299) with the network heads inlined;
+``backward_chain`` is its gradient.  Neither allocates, synchronises or touches the host, so a chain can be replayed
+from a CUDA graph.  ``SemanticNeRFNetwork.run`` drives them through one autograd node (fresh workspace per call);
+``engine.TrainEngine`` drives them directly on a static workspace.
+
+Kernel sequence, forward:  near_far -> sample_coarse -> density (coarse) -> resample_merge -> density (fine)
+                           -> weights -> scan -> compact -> heads + compositing
+               backward:   heads + compositing backward -> weights backward -> density backward (hash scatter)
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class RenderWorkspace:
+    """Every buffer of one run() call for N rays, Tc + Tf samples, C classes."""
+
+    def __init__(self, n, tc, tf, c, device, need_grad):
+        t = tc + tf
+        f32 = dict(dtype=torch.float32, device=device)
+        f16 = dict(dtype=torch.float16, device=device)
+        i32 = dict(dtype=torch.int32, device=device)
+        self.n, self.tc, self.tf, self.t, self.c, self.need_grad = n, tc, tf, t, c, need_grad
+        self.k_max = n * t  # worst case; the kernels read the true K from ray_off[n] on the device (no host sync)
+        self.lin = torch.linspace(0.0, 1.0, tc, device=device)
+        self.nears = torch.empty(n, **f32)
+        self.fars = torch.empty(n, **f32)
+        self.z_cat = torch.empty(n, t, **f32)
+        self.sigma = torch.empty(n, t, **f32)
+        self.h = torch.empty(n, t, 16, **f16)
+        self.order = torch.empty(n, t, **i32) if tf > 0 else None
+        self.w_sorted = torch.empty(n, t, **f32)
+        self.ray_count = torch.empty(n, **i32)
+        self.use_geo = torch.empty(n, t, dtype=torch.uint8, device=device)
+        self.ray_off = torch.empty(n + 1, **i32)
+        self.sel = torch.empty(self.k_max, **i32)
+        self.w_sel = torch.empty(self.k_max, **f32)
+        self.z_sel = torch.empty(self.k_max, **f32)
+        self.rgb = torch.empty(self.k_max, 3, **f32)
+        self.logits = torch.empty(self.k_max, ops.MAX_CLASSES, **f16)
+        self.depth = torch.empty(n, **f32)
+        self.image = torch.empty(n, 3, **f32)
+        self.semantics = torch.empty(n, c, **f32)
+        if need_grad:
+            self.enc = torch.empty(n, t, 32, **f16)
+            self.hid = torch.empty(n, t, 64, **f16)
+            self.hc1 = torch.empty(self.k_max, 64, **f16)
+            self.hc2 = torch.empty(self.k_max, 64, **f16)
+            self.hs = torch.empty(self.k_max, 64, **f16)
+            self.d_w_sel = torch.empty(self.k_max, **f32)
+            self.dh = torch.empty(n, t, 16, **f16)
+            self.d_sigma = torch.empty(n, t, **f32)
+        else:
+            self.enc = self.hid = self.hc1 = self.hc2 = self.hs = None
+
+
+def forward_chain(net, ws, rays_o, rays_d, dnorm, aabb, *, perturb, t_rand=None, u=None, seed=0, ray_base=0,
+                  step_dev=None):
+    n, tc, tf, t, c = ws.n, ws.tc, ws.tf, ws.t, ws.c
+    grid = net.encoder.grid
+    table_h = net.encoder.half_params()
+    w_sig = net.sigma_net.half_params()
+    ops.near_far_from_aabb_into(rays_o, rays_d, aabb, ws.nears, ws.fars)
+    ops.sample_coarse(ws.nears, ws.fars, ws.lin, ws.z_cat, tc, perturb=perturb, t_rand=t_rand, seed=seed,
+                      ray_base=ray_base, step_dev=step_dev)
+    common = dict(rays_o=rays_o, rays_d=rays_d, aabb=aabb, z_cat=ws.z_cat, sigma=ws.sigma, h=ws.h, enc=ws.enc,
+                  hid=ws.hid)
+    ops.density_fwd(grid, table_h, w_sig, net.bound, k0=0, k1=tc, **common)
+    if tf > 0:
+        ops.resample_merge(ws.sigma, ws.z_cat, ws.order, tc, tf, net.density_scale, u=u, seed=seed, ray_base=ray_base,
+                           step_dev=step_dev)
+        ops.density_fwd(grid, table_h, w_sig, net.bound, k0=tc, k1=t, **common)
+    ops.weights_fwd(ws.z_cat, ws.sigma, ws.order, dnorm, net.density_scale, ws.w_sorted, ws.depth, ws.ray_count,
+                    ws.use_geo)
+    ops.scan_counts(ws.ray_count, ws.ray_off)
+    ops.compact_masked(ws.w_sorted, ws.z_cat, ws.order, ws.ray_off, ws.sel, ws.w_sel, ws.z_sel)
+    ws.image.zero_()
+    ws.semantics.zero_()
+    ops.heads_fwd(ws.sel, ws.ray_off, n, t, ws.k_max, rays_d, ws.h, net.color_net.half_params(),
+                  net.semantics_net.half_params(), c, ws.rgb, ws.logits, ws.hc1, ws.hc2, ws.hs, w_sel=ws.w_sel,
+                  image=ws.image, semantics=ws.semantics)  # heads + compositing in one kernel
+
+
+def backward_chain(net, ws, rays_o, rays_d, dnorm, aabb, g_image, g_depth, g_sem, grad_table, grad_sigma, grad_color,
+                   grad_sem):
+    """Accumulates into the four gradient buffers (fp32; the caller zero-fills them)."""
+    n, t, c = ws.n, ws.t, ws.c
+    scale = float(net.loss_scale)
+    ops.heads_bwd(ws.sel, ws.ray_off, n, t, ws.k_max, rays_d, ws.h, net.color_net.half_params(),
+                  net.semantics_net.half_params(), c, ws.rgb, ws.logits, ws.hc1, ws.hc2, ws.hs, ws.w_sel, ws.z_sel,
+                  g_image, g_depth, g_sem, dnorm, scale, ws.dh, ws.d_w_sel, grad_color, grad_sem)
+    ops.weights_bwd(ws.z_cat, ws.sigma, ws.order, ws.w_sorted, ws.ray_off, ws.d_w_sel, net.density_scale, ws.d_sigma)
+    ops.density_bwd(net.encoder.grid, net.sigma_net.half_params(), net.bound, rays_o=rays_o, rays_d=rays_d, aabb=aabb,
+                    z_cat=ws.z_cat, k0=0, k1=t, h=ws.h, enc=ws.enc, hid=ws.hid, d_sigma=ws.d_sigma, dh=ws.dh,
+                    use_geo=ws.use_geo, loss_scale=scale, grad_table=grad_table, grad_w_sigma=grad_sigma)
