@@ -88,12 +88,19 @@ UCSA_API int ucsa_density_fwd(const float* xyz, const float* rays_o, const float
 /* Backward of ucsa_density_fwd for slots [k0,k1).  d_sigma f32 [N,T] (cat order); dh fp16 [N,T,16] whose
  * elements 1..15 hold loss_scale * dL/dgeo_feat for samples with use_geo[n*T+k] != 0 (element 0 is ignored);
  * trunc_exp backward (activation.py:16-19) is applied here.  Accumulates (atomicAdd, fp32) into
- * grad_table [2*total] and grad_w_sigma [3072]; both already divided by loss_scale. */
+ * grad_table [2*total] and grad_w_sigma [3072]; both already divided by loss_scale.
+ * grad_replicas (nullable) = n_replicas zero-filled private copies [R][2*dense_entries] of the dense levels' part of
+ * the table: CTA b adds the dense levels into copy b % R (all rays of a batch leave one camera, so a few coarse cells
+ * take most of the adds and serialise the L2 atomic units); fold them with ucsa_reduce_grad_replicas afterwards. */
 UCSA_API int ucsa_density_bwd(const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,
                      const float* z_cat, uint32_t n_rays, uint32_t t, uint32_t k0, uint32_t k1, float bound,
                      const ucsa_grid_desc* grid_host, const void* w_sigma_h, const void* h, const void* enc,
                      const void* hid, const float* d_sigma, const void* dh, const uint8_t* use_geo,
-                     float loss_scale, float* grad_table, float* grad_w_sigma, void* stream);
+                     float loss_scale, float* grad_table, float* grad_replicas, uint32_t n_replicas,
+                     float* grad_w_sigma, void* stream);
+/* grad_table[dense part] += sum of the replicas; the replicas are zero again on return. */
+UCSA_API int ucsa_reduce_grad_replicas(float* grad_replicas, uint32_t n_replicas, const ucsa_grid_desc* grid_host,
+                              float* grad_table, void* stream);
 
 /* ---- a9/a10. importance resampling + merge (renderer_semantics.py:182-222, sample_pdf :10-46).
  * Reads coarse z / sigma (slots [0,Tc)), writes fine z into slots [Tc,Tc+Tf) and order [N,T]

@@ -74,6 +74,24 @@ __global__ void scatter_kernel(const float* __restrict__ x01, uint32_t n, ucsa_g
         red_add_f32x2(gt + 2ull * e1, w1 * g.x, w1 * g.y);
       }
     }
+  } else if (MODE == 5 || MODE == 6) {
+    // replicated coarse levels: CTA b adds into replica b % R of the dense levels, cutting same-address contention
+    const int R = MODE == 5 ? 16 : 64;
+    float* base = gt;
+    if (!lv.hashed) base = gt + 2ull * grid.total_entries + (size_t)(blockIdx.x % R) * 2ull * grid.offset[4];
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+      const uint32_t e0 = corner_entry(lv, cell, c), e1 = corner_entry(lv, cell, c + 1);
+      const float w0 = corner_weight(cell, c), w1 = corner_weight(cell, c + 1);
+      if ((e0 ^ e1) == 1u) {
+        float* p = base + 2ull * (e0 & ~1u);
+        if (e0 & 1u) red_v4(p, w1 * g.x, w1 * g.y, w0 * g.x, w0 * g.y);
+        else red_v4(p, w0 * g.x, w0 * g.y, w1 * g.x, w1 * g.y);
+      } else {
+        red_add_f32x2(base + 2ull * e0, w0 * g.x, w0 * g.y);
+        red_add_f32x2(base + 2ull * e1, w1 * g.x, w1 * g.y);
+      }
+    }
   } else if (MODE == 4) {
     // lanes of a warp that sit in the same cell of the same level: the lowest lane of each group adds for all
     const uint32_t key = (cell.c[0] * 73856093u) ^ (cell.c[1] * 19349663u) ^ (cell.c[2] * 83492791u) ^ (l << 28);
@@ -131,7 +149,7 @@ int main(int argc, char** argv) {
   cudaMemcpy(dx, x.data(), x.size() * 4, cudaMemcpyHostToDevice);
   cudaMalloc(&denc, (size_t)n * 32 * 2);
   cudaMemset(denc, 0x3c, (size_t)n * 32 * 2);
-  cudaMalloc(&gt, (size_t)grid.total_entries * 8);
+  cudaMalloc(&gt, (size_t)grid.total_entries * 8 + 64ull * grid.offset[4] * 8);
   cudaMalloc(&gth, (size_t)grid.total_entries * 4);
   float* flush;
   cudaMalloc(&flush, 256u << 20);
@@ -153,6 +171,8 @@ int main(int argc, char** argv) {
         case 2: scatter_kernel<2><<<blocks, 256>>>(dx, n, grid, denc, gt, gth, lo, hi, lm); break;
         case 3: scatter_kernel<3><<<blocks, 256>>>(dx, n, grid, denc, gt, gth, lo, hi, lm); break;
         case 4: scatter_kernel<4><<<blocks, 256>>>(dx, n, grid, denc, gt, gth, lo, hi, lm); break;
+        case 5: scatter_kernel<5><<<blocks, 256>>>(dx, n, grid, denc, gt, gth, lo, hi, lm); break;
+        case 6: scatter_kernel<6><<<blocks, 256>>>(dx, n, grid, denc, gt, gth, lo, hi, lm); break;
       }
       cudaEventRecord(e1);
       cudaEventSynchronize(e1);
@@ -170,10 +190,14 @@ int main(int argc, char** argv) {
     run("f16x2", 2, 0, 16, lm);
     run("v4 merge of aligned x pairs", 3, 0, 16, lm);
     run("warp-aggregated (match_any)", 4, 0, 16, lm);
+    run("v4 + 16 replicas of dense levels", 5, 0, 16, lm);
+    run("v4 + 64 replicas of dense levels", 6, 0, 16, lm);
   }
-  for (int l = 0; l < 16; l += 1) {
-    run("v2.f32", 0, l, l + 1, 1);
-    run("warp-aggregated", 4, l, l + 1, 1);
+  for (int l = 0; l < 5; l += 1) {
+    run("v2.f32", 0, l, l + 1, 0);
+    run("warp-aggregated", 4, l, l + 1, 0);
+    run("16 replicas", 5, l, l + 1, 0);
+    run("64 replicas", 6, l, l + 1, 0);
   }
   return 0;
 }

@@ -152,13 +152,20 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
                       const __half* __restrict__ enc, const __half* __restrict__ hid,
                       const float* __restrict__ d_sigma, const __half* __restrict__ dh,
                       const uint8_t* __restrict__ use_geo, float loss_scale, float* __restrict__ grad_table,
-                      float* __restrict__ grad_w) {
+                      float* __restrict__ grad_replicas, uint32_t n_replicas, float* __restrict__ grad_w) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* w1 = smem;
   unsigned char* w2 = w1 + kW1Bytes;
   unsigned char* t_enc = w2 + kW2Bytes;
   unsigned char* t_hid = t_enc + Tile<32>::kBytes;
   unsigned char* t_dhid = t_hid + Tile<64>::kBytes;
+  // Dense (coarse) levels: every ray of a batch starts at the camera, so a handful of coarse cells receive most of
+  // the adds and the L2 atomic units serialise on them.  Each CTA therefore adds into one of n_replicas private
+  // copies of the dense part of the table; ucsa_reduce_grad_replicas folds them afterwards.
+  const uint32_t dense_entries = dense_entry_count(a.grid);
+  float* dense_base = (grad_replicas != nullptr && n_replicas > 0)
+                          ? grad_replicas + static_cast<size_t>(blockIdx.x % n_replicas) * 2ull * dense_entries
+                          : grad_table;
   unsigned char* t_dout = t_dhid + Tile<64>::kBytes;
   unsigned char* tail = t_dout + Tile<16>::kBytes;
   uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
@@ -248,8 +255,8 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
     if (valid && grad_table != nullptr) {
 #pragma unroll
       for (int l = 0; l < UCSA_GRID_LEVELS; ++l)
-        scatter_level(grad_table, level_geom(a.grid, l), x01, round_h(g[2 * l]) * inv_scale,
-                      round_h(g[2 * l + 1]) * inv_scale, keep);
+        scatter_level(a.grid.hashed[l] ? grad_table : dense_base, level_geom(a.grid, l), x01,
+                      round_h(g[2 * l]) * inv_scale, round_h(g[2 * l + 1]) * inv_scale, keep);
     }
     first = false;
   }
@@ -314,7 +321,7 @@ extern "C" int ucsa_density_bwd(const float* xyz, const float* rays_o, const flo
                                 float bound, const ucsa_grid_desc* grid_host, const void* w_sigma_h,
                                 const void* h, const void* enc, const void* hid, const float* d_sigma,
                                 const void* dh, const uint8_t* use_geo, float loss_scale, float* grad_table,
-                                float* grad_w_sigma, void* stream) {
+                                float* grad_replicas, uint32_t n_replicas, float* grad_w_sigma, void* stream) {
   DensityArgs a;
   if (int rc = fill_args(a, xyz, rays_o, rays_d, aabb6, z_cat, n_rays, t, k0, k1, bound, grid_host)) return rc;
   UCSA_REQUIRE(w_sigma_h && h && enc && hid && grad_w_sigma, "density_bwd: null saved tensors / outputs");
@@ -328,6 +335,38 @@ extern "C" int ucsa_density_bwd(const float* xyz, const float* rays_o, const flo
   density_bwd_tc_kernel<<<persistent_grid(a.n_samples, kBwdCtasPerSm), 128, kBwdSmem, as_stream(stream)>>>(
       a, static_cast<const __half*>(w_sigma_h), static_cast<const __half*>(h), static_cast<const __half*>(enc),
       static_cast<const __half*>(hid), d_sigma, static_cast<const __half*>(dh), use_geo, loss_scale, grad_table,
-      grad_w_sigma);
+      grad_replicas, n_replicas, grad_w_sigma);
   return check_launch("density_bwd");
+}
+
+namespace ucsa {
+namespace {
+// grad_table[i] += sum_r replicas[r][i] over the dense part; replicas are left zeroed for the next step
+__global__ void reduce_replicas_kernel(float* __restrict__ replicas, uint32_t n_replicas, uint32_t n_floats,
+                                       float* __restrict__ grad_table) {
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n_floats) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (uint32_t r = 0; r < n_replicas; ++r) {
+    float4* p = reinterpret_cast<float4*>(replicas + static_cast<size_t>(r) * n_floats + i);
+    const float4 v = *p;
+    acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    *p = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float4* g = reinterpret_cast<float4*>(grad_table + i);
+  float4 cur = *g;
+  cur.x += acc.x, cur.y += acc.y, cur.z += acc.z, cur.w += acc.w;
+  *g = cur;
+}
+}  // namespace
+}  // namespace ucsa
+
+extern "C" int ucsa_reduce_grad_replicas(float* grad_replicas, uint32_t n_replicas, const ucsa_grid_desc* grid_host,
+                                         float* grad_table, void* stream) {
+  UCSA_REQUIRE(grad_replicas && grid_host && grad_table, "reduce_grad_replicas: null pointer");
+  const uint32_t n_floats = 2u * dense_entry_count(*grid_host);  // entries are multiples of 8 -> divisible by 4
+  if (n_replicas == 0 || n_floats == 0) return UCSA_OK;
+  reduce_replicas_kernel<<<ceil_div(n_floats / 4, 256), 256, 0, as_stream(stream)>>>(grad_replicas, n_replicas, n_floats,
+                                                                                    grad_table);
+  return check_launch("reduce_grad_replicas");
 }

@@ -21,6 +21,13 @@ __device__ __forceinline__ LevelGeom level_geom(const ucsa_grid_desc& g, int l) 
   return LevelGeom{g.scale[l], g.res[l], g.entries[l], g.offset[l], g.hashed[l]};
 }
 
+// number of entries of the leading dense levels (= offset of the first hashed level)
+__host__ __device__ __forceinline__ uint32_t dense_entry_count(const ucsa_grid_desc& g) {
+  for (int l = 0; l < UCSA_GRID_LEVELS; ++l)
+    if (g.hashed[l]) return g.offset[l];
+  return g.total_entries;
+}
+
 struct Cell {
   uint32_t c[3];
   float f[3];

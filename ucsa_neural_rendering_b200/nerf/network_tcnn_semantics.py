@@ -82,6 +82,14 @@ class HashGridEncoding(_HalfCache):
     def forward(self, x):
         return _HashGridFn.apply(x, self.params, self)
 
+    def grad_replicas(self, n_replicas=16):
+        """Scratch for the backward scatter of the dense levels (ops.density_bwd); allocated once, kept zero."""
+        rep = getattr(self, "_grad_replicas", None)
+        if rep is None or rep.device != self.params.device or rep.shape[0] != n_replicas:
+            rep = ops.grad_replicas(self.grid, self.params.device, n_replicas)
+            self._grad_replicas = rep
+        return rep
+
 
 class SHEncoding(nn.Module):
     """tcnn.Encoding(SphericalHarmonics, degree 4) of network_tcnn_semantics.py:64-70: [K,3] in [0,1] -> [K,16] fp16."""

@@ -88,19 +88,38 @@ def density_fwd(grid, table_h, w_sigma_h, bound, *, xyz=None, rays_o=None, rays_
 
 
 def density_bwd(grid, w_sigma_h, bound, *, xyz=None, rays_o=None, rays_d=None, aabb=None, z_cat=None, k0=0, k1=1,
-                h, enc, hid, d_sigma, dh, use_geo, loss_scale, grad_table, grad_w_sigma, simt=False):
+                h, enc, hid, d_sigma, dh, use_geo, loss_scale, grad_table, grad_w_sigma, simt=False, replicas=None):
+    """replicas: zero-filled fp32 [R, 2*dense_entries] (see grad_replicas()); folded into grad_table before returning"""
     if xyz is not None:
         n, t = xyz.shape[0], 1
     else:
         n, t = z_cat.shape
-    fn = lib().ucsa_density_bwd_simt if simt else lib().ucsa_density_bwd
-    check(fn(_ptr(xyz, torch.float32, "xyz"), _ptr(rays_o, torch.float32), _ptr(rays_d, torch.float32),
-                                 _ptr(aabb, torch.float32), _ptr(z_cat, torch.float32), n, t, k0, k1, float(bound),
-                                 ctypes.byref(grid), _ptr(w_sigma_h, torch.float16), _ptr(h, torch.float16),
-                                 _ptr(enc, torch.float16), _ptr(hid, torch.float16), _ptr(d_sigma, torch.float32, "d_sigma"),
-                                 _ptr(dh, torch.float16, "dh"), _ptr(use_geo, torch.uint8, "use_geo"),
-                                 float(loss_scale), _ptr(grad_table, torch.float32, "grad_table"),
-                                 _ptr(grad_w_sigma, torch.float32, "grad_w_sigma"), _stream()), "density_bwd")
+    head = (_ptr(xyz, torch.float32, "xyz"), _ptr(rays_o, torch.float32), _ptr(rays_d, torch.float32),
+            _ptr(aabb, torch.float32), _ptr(z_cat, torch.float32), n, t, k0, k1, float(bound), ctypes.byref(grid),
+            _ptr(w_sigma_h, torch.float16), _ptr(h, torch.float16), _ptr(enc, torch.float16), _ptr(hid, torch.float16),
+            _ptr(d_sigma, torch.float32, "d_sigma"), _ptr(dh, torch.float16, "dh"), _ptr(use_geo, torch.uint8, "use_geo"),
+            float(loss_scale), _ptr(grad_table, torch.float32, "grad_table"))
+    tail = (_ptr(grad_w_sigma, torch.float32, "grad_w_sigma"), _stream())
+    if simt:
+        check(lib().ucsa_density_bwd_simt(*head, *tail), "density_bwd_simt")
+        return
+    n_rep = 0 if replicas is None else replicas.shape[0]
+    check(lib().ucsa_density_bwd(*head, _ptr(replicas, torch.float32, "replicas"), n_rep, *tail), "density_bwd")
+    if n_rep:
+        check(lib().ucsa_reduce_grad_replicas(_ptr(replicas, torch.float32), n_rep, ctypes.byref(grid),
+                                              _ptr(grad_table, torch.float32), _stream()), "reduce_grad_replicas")
+
+
+def dense_entries(grid) -> int:
+    for lvl in range(16):
+        if grid.hashed[lvl]:
+            return int(grid.offset[lvl])
+    return int(grid.total_entries)
+
+
+def grad_replicas(grid, device, n_replicas=16):
+    """Zero-filled private copies of the dense levels' gradient (kept zero by ucsa_reduce_grad_replicas)."""
+    return torch.zeros(n_replicas, 2 * dense_entries(grid), dtype=torch.float32, device=device)
 
 
 def resample_merge(sigma, z_cat, order, tc, tf, density_scale, *, u=None, seed=0, ray_base=0, step_dev=None):

@@ -96,4 +96,5 @@ def backward_chain(net, ws, rays_o, rays_d, dnorm, aabb, g_image, g_depth, g_sem
     ops.weights_bwd(ws.z_cat, ws.sigma, ws.order, ws.w_sorted, ws.ray_off, ws.d_w_sel, net.density_scale, ws.d_sigma)
     ops.density_bwd(net.encoder.grid, net.sigma_net.half_params(), net.bound, rays_o=rays_o, rays_d=rays_d, aabb=aabb,
                     z_cat=ws.z_cat, k0=0, k1=t, h=ws.h, enc=ws.enc, hid=ws.hid, d_sigma=ws.d_sigma, dh=ws.dh,
-                    use_geo=ws.use_geo, loss_scale=scale, grad_table=grad_table, grad_w_sigma=grad_sigma)
+                    use_geo=ws.use_geo, loss_scale=scale, grad_table=grad_table, grad_w_sigma=grad_sigma,
+                    replicas=net.encoder.grad_replicas())
