@@ -101,17 +101,17 @@ __device__ __forceinline__ void red_add_f32x2(float* addr, float a, float b) {
 // tagged evict_first, tables evict_last, so that the streams do not push the tables out to HBM.
 __device__ __forceinline__ uint64_t l2_policy_stream() {
   uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
 __device__ __forceinline__ uint64_t l2_policy_keep() {
   uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
 __device__ __forceinline__ uint4 ld_stream(const void* ptr, uint64_t policy) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;"
+  uint4 v;  // (not volatile: a read-only load may be scheduled freely, which keeps many of them in flight)
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                : "l"(ptr), "l"(policy));
   return v;
@@ -127,7 +127,7 @@ __device__ __forceinline__ void st_stream_f32(float* ptr, float v, uint64_t poli
 }
 __device__ __forceinline__ uint32_t ld_keep_b32(const void* ptr, uint64_t policy) {
   uint32_t v;
-  asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(policy));
+  asm("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(policy));
   return v;
 }
 __device__ __forceinline__ void red_keep_f32x2(float* addr, float a, float b, uint64_t policy) {

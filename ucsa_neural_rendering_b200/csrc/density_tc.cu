@@ -9,6 +9,8 @@
 //   all tiles of the CTA, and the hash-table gradient scattered with vector reductions (red.global.add.v2.f32).
 // Several CTAs per SM (TMEM: 64 / 128 columns each) overlap one tile's gather/scatter phase with another's MMAs.
 // The hash table and its gradient are tagged L2 evict_last, the per-sample streams evict_first (common.cuh).
+#include <cstdlib>
+
 #include "grid.cuh"
 #include "mlp_umma.cuh"
 
@@ -46,7 +48,7 @@ constexpr uint32_t kW1Bytes = 64 / 8 * Tile<32>::kGroupBytes;  // [64][32]
 constexpr uint32_t kW2Bytes = 16 / 8 * Tile<64>::kGroupBytes;  // [16][64]
 constexpr uint32_t kFwdTmemCols = 64;   // layer-2 accumulator re-uses the columns of layer 1 once they are read
 constexpr uint32_t kBwdTmemCols = 128;
-constexpr int kFwdCtasPerSm = 6, kBwdCtasPerSm = 4;
+constexpr int kFwdCtasPerSm = 4, kBwdCtasPerSm = 4;  // fwd: more CTAs shrink L1 and lose (measured 4 > 6 > 8)
 
 __global__ void __launch_bounds__(128)
 density_fwd_tc_kernel(const DensityArgs a, const __half2* __restrict__ table, const __half* __restrict__ w_sigma,
@@ -55,8 +57,10 @@ density_fwd_tc_kernel(const DensityArgs a, const __half2* __restrict__ table, co
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* w1 = smem;
   unsigned char* w2 = w1 + kW1Bytes;
+  // the hidden tile re-uses the bytes of the encoded tile: layer 1 has consumed it (commit waited) before the
+  // epilogue writes layer 1's activations.  Less shared memory per CTA = more L1 for the coarse grid levels.
   unsigned char* t_enc = w2 + kW2Bytes;
-  unsigned char* t_hid = t_enc + Tile<32>::kBytes;
+  unsigned char* t_hid = t_enc;
   unsigned char* tail = t_hid + Tile<64>::kBytes;
   uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
   uint32_t* slot = reinterpret_cast<uint32_t*>(tail + 8);
@@ -266,7 +270,7 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
   umma::ctx_free(ctx, kBwdTmemCols);
 }
 
-constexpr size_t kFwdSmem = kW1Bytes + kW2Bytes + Tile<32>::kBytes + Tile<64>::kBytes + 64;
+constexpr size_t kFwdSmem = kW1Bytes + kW2Bytes + Tile<64>::kBytes + 64;
 constexpr size_t kBwdSmem = kW1Bytes + kW2Bytes + Tile<32>::kBytes + 2 * Tile<64>::kBytes + Tile<16>::kBytes + 64;
 
 int fill_args(DensityArgs& a, const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,
@@ -310,7 +314,13 @@ extern "C" int ucsa_density_fwd(const float* xyz, const float* rays_o, const flo
     cudaFuncSetAttribute(density_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
     attr_set = true;
   }
-  density_fwd_tc_kernel<<<persistent_grid(a.n_samples, kFwdCtasPerSm), 128, kFwdSmem, as_stream(stream)>>>(
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {  // tuning knob (bring-up): UCSA_DFWD_CTAS overrides the resident CTAs per SM
+    const char* e = getenv("UCSA_DFWD_CTAS");
+    ctas_per_sm = e ? atoi(e) : kFwdCtasPerSm;
+    if (ctas_per_sm < 1 || ctas_per_sm > 8) ctas_per_sm = kFwdCtasPerSm;
+  }
+  density_fwd_tc_kernel<<<persistent_grid(a.n_samples, ctas_per_sm), 128, kFwdSmem, as_stream(stream)>>>(
       a, static_cast<const __half2*>(table_h), static_cast<const __half*>(w_sigma_h), sigma,
       static_cast<__half*>(h), static_cast<__half*>(enc), static_cast<__half*>(hid));
   return check_launch("density_fwd");

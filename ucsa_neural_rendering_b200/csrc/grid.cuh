@@ -52,11 +52,14 @@ __device__ __forceinline__ uint32_t corner_entry(const LevelGeom& lv, const Cell
   uint32_t idx;
   if (lv.hashed) {
     idx = x ^ (y * 2654435761u) ^ (z * 805459861u);
+    // hashed levels hold 2^k entries (the cap 2^log2_hashmap_size); anything else takes the generic path
+    idx = ((lv.entries & (lv.entries - 1u)) == 0u) ? (idx & (lv.entries - 1u)) : (idx % lv.entries);
   } else {
+    // dense: coordinates are <= res, so idx <= res + res^2 + res^3 < 2 * entries (entries >= res^3, res >= 2):
+    // the modulo is one conditional subtraction
     idx = x + y * lv.res + z * lv.res * lv.res;
+    if (idx >= lv.entries) idx -= lv.entries;
   }
-  // hashed levels always hold 2^k entries; dense ones a multiple of 8
-  idx = ((lv.entries & (lv.entries - 1u)) == 0u) ? (idx & (lv.entries - 1u)) : (idx % lv.entries);
   return lv.offset + idx;
 }
 
