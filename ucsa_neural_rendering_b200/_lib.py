@@ -80,10 +80,11 @@ _lib = None
 
 _DEBUG_SYNC = os.environ.get("UCSA_DEBUG_SYNC", "0") == "1"
 HOST_ONLY = {"ucsa_abi_version", "ucsa_last_error_string", "ucsa_grid_desc_init"}
+KERNELS_PER_CALL = {"ucsa_heads_bwd": 2}  # colour + semantic kernels; every other entry point enqueues one kernel
 
 
 class LaunchStats:
-    """Counts kernel launches (every non-host entry point enqueues exactly one kernel) and, for the entry points
+    """Counts kernel launches (KERNELS_PER_CALL, default one per non-host entry point) and, for the entry points
     named in ``timed``, brackets each call with CUDA events on the current stream (used by bench.py only)."""
 
     def __init__(self):
@@ -112,7 +113,7 @@ class _Entry:
     def __call__(self, *args):
         if not self.is_launch:
             return self.fn(*args)
-        stats.launches += 1
+        stats.launches += KERNELS_PER_CALL.get(self.name, 1)
         stats.by_name[self.name] = stats.by_name.get(self.name, 0) + 1
         if _DEBUG_SYNC:  # UCSA_DEBUG_SYNC=1: name every launch and wait for it (locates a faulting kernel)
             import sys

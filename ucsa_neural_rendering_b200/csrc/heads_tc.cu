@@ -74,12 +74,16 @@ __device__ __forceinline__ void build_inputs(const float* __restrict__ rays_d, c
   } else {
     sh_lo.v = sh_hi.v = g0.v = g1.v = make_uint4(0, 0, 0, 0);
   }
-  *Tile<32>::chunk(t_in_c, row, 0) = sh_lo.v;
-  *Tile<32>::chunk(t_in_c, row, 1) = sh_hi.v;
-  *Tile<32>::chunk(t_in_c, row, 2) = g0.v;
-  *Tile<32>::chunk(t_in_c, row, 3) = g1.v;
-  *Tile<16>::chunk(t_in_s, row, 0) = g0.v;
-  *Tile<16>::chunk(t_in_s, row, 1) = g1.v;
+  if (t_in_c != nullptr) {
+    *Tile<32>::chunk(t_in_c, row, 0) = sh_lo.v;
+    *Tile<32>::chunk(t_in_c, row, 1) = sh_hi.v;
+    *Tile<32>::chunk(t_in_c, row, 2) = g0.v;
+    *Tile<32>::chunk(t_in_c, row, 3) = g1.v;
+  }
+  if (t_in_s != nullptr) {
+    *Tile<16>::chunk(t_in_s, row, 0) = g0.v;
+    *Tile<16>::chunk(t_in_s, row, 1) = g1.v;
+  }
 }
 
 // saved activations are written once and read once (backward): tag them evict_first in L2
@@ -97,12 +101,18 @@ __device__ __forceinline__ void row_g2t(unsigned char* tile, const __half* __res
     *Tile<W>::chunk(tile, threadIdx.x, c) = valid ? ld_stream(src + c * 8, stream) : make_uint4(0, 0, 0, 0);
 }
 
-constexpr uint32_t kFwdCols = 256;
+// Forward shared memory / TMEM plan (3 CTAs per SM):
+//   region A = [in_c 8K | in_s 4K | hs 16K]   later re-used as `part`, the fp32 staging of the fused compositing
+//   region B = [h1 16K]                       later re-used for h2 (layer 2 has consumed h1 by then)
+//   TMEM     = acc0 [0,64): colour layers 1,2,3 in turn; acc1 [64,128): semantic layer 1, then the 48 logits
+constexpr uint32_t kFwdCols = 128;
+constexpr int kFwdCtasPerSm = 3;
 // per-tile staging of w * (probabilities | rgb) for the fused compositing: [128 rows][kPartLd] fp32, odd stride
 constexpr int kPartLd = kSemOut + 5;
 constexpr uint32_t kPartBytes = 128 * kPartLd * sizeof(float);
-constexpr uint32_t kFwdSmem = kWeightBytes + Tile<32>::kBytes + Tile<16>::kBytes + 3 * Tile<64>::kBytes + kPartBytes +
-                              128 * sizeof(int) + 64;
+constexpr uint32_t kRegionA = Tile<32>::kBytes + Tile<16>::kBytes + Tile<64>::kBytes;
+static_assert(kPartBytes <= kRegionA, "compositing staging must fit the re-used input tiles");
+constexpr uint32_t kFwdSmem = kWeightBytes + kRegionA + Tile<64>::kBytes + 128 * sizeof(int) + 64;
 
 __global__ void __launch_bounds__(128)
 heads_fwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__ k_ptr, uint32_t t,
@@ -112,13 +122,13 @@ heads_fwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__
                     __half* __restrict__ hc1, __half* __restrict__ hc2, __half* __restrict__ hs,
                     float* __restrict__ image, float* __restrict__ semantics) {
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* t_in_c = smem + kWeightBytes;
+  unsigned char* t_in_c = smem + kWeightBytes;          // region A
   unsigned char* t_in_s = t_in_c + Tile<32>::kBytes;
-  unsigned char* t_h1 = t_in_s + Tile<16>::kBytes;
-  unsigned char* t_hs = t_h1 + Tile<64>::kBytes;
-  unsigned char* t_h2 = t_hs + Tile<64>::kBytes;
-  float* part = reinterpret_cast<float*>(t_h2 + Tile<64>::kBytes);
-  int* ray_of_row = reinterpret_cast<int*>(part + 128 * kPartLd);
+  unsigned char* t_hs = t_in_s + Tile<16>::kBytes;
+  float* part = reinterpret_cast<float*>(t_in_c);       // region A again, once its three tiles are consumed
+  unsigned char* t_h1 = t_in_c + kRegionA;              // region B
+  unsigned char* t_h2 = t_h1;
+  int* ray_of_row = reinterpret_cast<int*>(t_h1 + Tile<64>::kBytes);
   unsigned char* tail = reinterpret_cast<unsigned char*>(ray_of_row + 128);
   uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
   uint32_t* slot = reinterpret_cast<uint32_t*>(tail + 8);
@@ -127,7 +137,7 @@ heads_fwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__
   umma::Ctx ctx = umma::ctx_init(slot, bar, kFwdCols);
   const uint32_t s_in_c = umma::smem_u32(t_in_c), s_in_s = umma::smem_u32(t_in_s), s_h1 = umma::smem_u32(t_h1),
                  s_hs = umma::smem_u32(t_hs), s_h2 = umma::smem_u32(t_h2);
-  constexpr uint32_t kAcc0 = 0, kAcc1 = 64, kAcc2 = 128;
+  constexpr uint32_t kAcc0 = 0, kAcc1 = 64, kAcc2 = 64;
 
   const uint32_t k_rows = static_cast<uint32_t>(*k_ptr);
   const uint32_t n_tiles = (k_rows + 127) / 128;
@@ -205,12 +215,12 @@ heads_fwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__
     ctx.publish();
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
-      umma::issue_fwd<64, 16>(ctx.tmem + kAcc1, s_h2, w.c3);
+      umma::issue_fwd<64, 16>(ctx.tmem + kAcc0, s_h2, w.c3);
       umma::commit(ctx.bar);
     }
     ctx.wait();
     float v[16];
-    umma::tmem_ld16(ctx.lane_addr(kAcc1), v);
+    umma::tmem_ld16(ctx.lane_addr(kAcc0), v);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float x = round_h(v[c]);
@@ -244,7 +254,7 @@ heads_fwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__
           atomicAdd(col < n_classes ? semantics + static_cast<uint64_t>(cur) * n_classes + col
                                     : image + static_cast<uint64_t>(cur) * 3 + (col - n_classes), acc);
       }
-      // the next tile's publish() barrier orders these reads before part[] is overwritten
+      __syncthreads();  // part[] lives in the input tiles: the next tile may only rebuild them after the reads
     }
   }
   umma::ctx_free(ctx, kFwdCols);
@@ -267,43 +277,48 @@ __device__ __forceinline__ void flush_wgrad(const umma::Ctx& ctx, uint32_t col0,
   }
 }
 
-constexpr uint32_t kBwdCols = 512;
-constexpr uint32_t kBwdSmem = kWeightBytes + Tile<32>::kBytes + Tile<16>::kBytes + 6 * Tile<64>::kBytes +
-                              Tile<16>::kBytes + Tile<kSemOut>::kBytes + 64;
+// ---------------------------------------------------------------------------------------------- backward
+// Two kernels, colour first, then semantics, so that each fits several CTAs per SM:
+//   colour   : tiles in_c, h1, h2, dpre, dh2, dh1 (76 KB) + colour weights; TMEM 176 -> 256 columns; 2 CTAs / SM
+//   semantics: tiles in_s, hs, dlog, dhs (48 KB) + semantic weights;        TMEM 128 columns;        4 CTAs / SM
+// The colour kernel writes its share of dL/dgeo_feat into dh and the semantic kernel adds its own.
+constexpr uint32_t kBwdColorCols = 256, kBwdSemCols = 128;
+constexpr int kBwdColorCtas = 2, kBwdSemCtas = 4;
+constexpr uint32_t kColorWeightBytes = kWc1 + kWc2 + kWc3;
+constexpr uint32_t kSemWeightBytes = kWs1 + kWs2;
+constexpr uint32_t kBwdColorSmem = kColorWeightBytes + Tile<32>::kBytes + 4 * Tile<64>::kBytes + Tile<16>::kBytes + 64;
+constexpr uint32_t kBwdSemSmem = kSemWeightBytes + Tile<16>::kBytes + 2 * Tile<64>::kBytes + Tile<kSemOut>::kBytes + 64;
 
 __global__ void __launch_bounds__(128)
-heads_bwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__ k_ptr, uint32_t t,
-                    const float* __restrict__ rays_d, const __half* __restrict__ h,
-                    const __half* __restrict__ w_color, const __half* __restrict__ w_sem,
-                    int n_classes, const float* __restrict__ rgb, const __half* __restrict__ logits,
-                    const __half* __restrict__ hc1, const __half* __restrict__ hc2, const __half* __restrict__ hs,
-                    const float* __restrict__ w_sel, const float* __restrict__ z_sel,
-                    const float* __restrict__ g_image, const float* __restrict__ g_depth,
-                    const float* __restrict__ g_sem, const float* __restrict__ dnorm, float loss_scale,
-                    __half* __restrict__ dh, float* __restrict__ d_w_sel, float* __restrict__ grad_w_color,
-                    float* __restrict__ grad_w_sem) {
+heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__ k_ptr, uint32_t t,
+                       const float* __restrict__ rays_d, const __half* __restrict__ h,
+                       const __half* __restrict__ w_color, const float* __restrict__ rgb,
+                       const __half* __restrict__ hc1, const __half* __restrict__ hc2,
+                       const float* __restrict__ w_sel, const float* __restrict__ z_sel,
+                       const float* __restrict__ g_image, const float* __restrict__ g_depth,
+                       const float* __restrict__ dnorm, float loss_scale, __half* __restrict__ dh,
+                       float* __restrict__ d_w_sel, float* __restrict__ grad_w_color) {
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* t_in_c = smem + kWeightBytes;
-  unsigned char* t_in_s = t_in_c + Tile<32>::kBytes;
-  unsigned char* t_h1 = t_in_s + Tile<16>::kBytes;
+  unsigned char* wc1 = smem;
+  unsigned char* wc2 = wc1 + kWc1;
+  unsigned char* wc3 = wc2 + kWc2;
+  unsigned char* t_in_c = wc3 + kWc3;
+  unsigned char* t_h1 = t_in_c + Tile<32>::kBytes;
   unsigned char* t_h2 = t_h1 + Tile<64>::kBytes;
-  unsigned char* t_hs = t_h2 + Tile<64>::kBytes;
-  unsigned char* t_dh1 = t_hs + Tile<64>::kBytes;
+  unsigned char* t_dh1 = t_h2 + Tile<64>::kBytes;
   unsigned char* t_dh2 = t_dh1 + Tile<64>::kBytes;
-  unsigned char* t_dhs = t_dh2 + Tile<64>::kBytes;
-  unsigned char* t_dpre = t_dhs + Tile<64>::kBytes;
-  unsigned char* t_dlog = t_dpre + Tile<16>::kBytes;
-  unsigned char* tail = t_dlog + Tile<kSemOut>::kBytes;
+  unsigned char* t_dpre = t_dh2 + Tile<64>::kBytes;
+  unsigned char* tail = t_dpre + Tile<16>::kBytes;
   uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
   uint32_t* slot = reinterpret_cast<uint32_t*>(tail + 8);
-  const WeightTiles w = load_weights(smem, w_color, w_sem);
-  umma::Ctx ctx = umma::ctx_init(slot, bar, kBwdCols);
-  const uint32_t s_in_c = umma::smem_u32(t_in_c), s_in_s = umma::smem_u32(t_in_s), s_h1 = umma::smem_u32(t_h1),
-                 s_h2 = umma::smem_u32(t_h2), s_hs = umma::smem_u32(t_hs), s_dh1 = umma::smem_u32(t_dh1),
-                 s_dh2 = umma::smem_u32(t_dh2), s_dhs = umma::smem_u32(t_dhs), s_dpre = umma::smem_u32(t_dpre),
-                 s_dlog = umma::smem_u32(t_dlog);
-  // TMEM: two data-gradient scratch accumulators, then the five weight-gradient accumulators (UMMA M = 64)
-  constexpr uint32_t kAcc0 = 0, kAcc1 = 64, kGc1 = 128, kGc2 = 160, kGc3 = 224, kGs1 = 240, kGs2 = 256;
+  umma::load_weight_tile<32>(wc1, w_color + kColorW1, 64);
+  umma::load_weight_tile<64>(wc2, w_color + kColorW2, 64);
+  umma::load_weight_tile<64>(wc3, w_color + kColorW3, 16);
+  umma::Ctx ctx = umma::ctx_init(slot, bar, kBwdColorCols);
+  const uint32_t s_in_c = umma::smem_u32(t_in_c), s_h1 = umma::smem_u32(t_h1), s_h2 = umma::smem_u32(t_h2),
+                 s_dh1 = umma::smem_u32(t_dh1), s_dh2 = umma::smem_u32(t_dh2), s_dpre = umma::smem_u32(t_dpre),
+                 b1 = umma::smem_u32(wc1), b2 = umma::smem_u32(wc2), b3 = umma::smem_u32(wc3);
+  constexpr uint32_t kAcc = 0, kGc1 = 64, kGc2 = 96, kGc3 = 160;
 
   const float inv_scale = 1.0f / loss_scale;
   const uint32_t k_rows = static_cast<uint32_t>(*k_ptr);
@@ -315,36 +330,130 @@ heads_bwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__
     const bool valid = r < k_rows;
     const uint32_t flat = valid ? static_cast<uint32_t>(sel[r]) : 0u;
     if (!first) ctx.wait();  // weight-gradient MMAs of the previous tile are done with the tiles
-    build_inputs(rays_d, h, flat, t, valid, t_in_c, t_in_s);
+    build_inputs(rays_d, h, flat, t, valid, t_in_c, nullptr);
     row_g2t<64>(t_h1, hc1 + static_cast<uint64_t>(r) * 64, valid);
     row_g2t<64>(t_h2, hc2 + static_cast<uint64_t>(r) * 64, valid);
-    row_g2t<64>(t_hs, hs + static_cast<uint64_t>(r) * 64, valid);
-    // ---- backward of the compositing, fused (renderer_semantics.py:270-285): per row, no reduction needed
-    //   image_n = sum w rgb        -> d rgb = w g_image ;  d w += g_image . rgb
-    //   depth_n = sum w z / dn     ->                      d w += g_depth z / dn
-    //   sem_n   = sum w softmax(l) -> d l = p (w g_sem - <w g_sem, p>)   (weights detached on this branch)
     {
-      const uint32_t n = flat / t;
-      const float w_row = valid ? w_sel[r] : 0.f;
+      // backward of image_n = sum w rgb and depth_n = sum w z / dn (renderer_semantics.py:276-282):
+      //   d rgb = w g_image ;  d w = g_image . rgb + g_depth z / dn ; then through the sigmoid: s (1 - s)
       H8 lo, hi;
       lo.v = make_uint4(0, 0, 0, 0);
       hi.v = make_uint4(0, 0, 0, 0);
       if (valid) {
+        const uint32_t n = flat / t;
+        const float w_row = w_sel[r];
         float dw = g_depth[n] / dnorm[n] * z_sel[r];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {  // through the sigmoid: s * (1 - s)
-          const float s = rgb[static_cast<uint64_t>(r) * 3 + c];
+        for (int c = 0; c < 3; ++c) {
+          const float sg = rgb[static_cast<uint64_t>(r) * 3 + c];
           const float gi = g_image[static_cast<uint64_t>(n) * 3 + c];
-          dw = fmaf(gi, s, dw);
-          lo.h[c] = __float2half_rn(w_row * gi * s * (1.0f - s) * loss_scale);
+          dw = fmaf(gi, sg, dw);
+          lo.h[c] = __float2half_rn(w_row * gi * sg * (1.0f - sg) * loss_scale);
         }
         d_w_sel[r] = dw;
       }
       *Tile<16>::chunk(t_dpre, row, 0) = lo.v;
       *Tile<16>::chunk(t_dpre, row, 1) = hi.v;
+    }
+    ctx.publish();
+    if (threadIdx.x == 0) {
+      umma::tc_fence_after();
+      umma::issue_dgrad<16, 64>(ctx.tmem + kAcc, s_dpre, b3);
+      umma::commit(ctx.bar);
+      umma::issue_wgrad<16>(ctx.tmem + kGc3, s_h2, s_dpre, first);  // d(Wc3)^T = h2^T . dpre
+    }
+    ctx.wait();
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) umma::acc_to_tile16<64, false>(ctx, kAcc + c0, t_dh2, c0, t_h2);
+    ctx.publish();
+    if (threadIdx.x == 0) {
+      umma::tc_fence_after();
+      umma::issue_dgrad<64, 64>(ctx.tmem + kAcc, s_dh2, b2);
+      umma::commit(ctx.bar);
+      umma::issue_wgrad<64>(ctx.tmem + kGc2, s_dh2, s_h1, first);  // d(Wc2) = dh2^T . h1
+    }
+    ctx.wait();
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) umma::acc_to_tile16<64, false>(ctx, kAcc + c0, t_dh1, c0, t_h1);
+    ctx.publish();
+    if (threadIdx.x == 0) {
+      umma::tc_fence_after();
+      umma::issue_dgrad<64, 32>(ctx.tmem + kAcc, s_dh1, b1);
+      umma::commit(ctx.bar);
+      umma::issue_wgrad<32>(ctx.tmem + kGc1, s_dh1, s_in_c, first);  // d(Wc1) = dh1^T . in_c
+    }
+    ctx.wait();
+    float d_in_c[16];
+    umma::tmem_ld16(ctx.lane_addr(kAcc + 16), d_in_c);  // columns 16..31 = the geo_feat (+1) inputs
+    if (valid) {  // colour share of dL/dgeo_feat (fp16, still scaled); the semantic kernel adds its own
+      H8 lo, hi;
+      lo.h[0] = __float2half_rn(0.f);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) lo.h[i + 1] = __float2half_rn(d_in_c[i]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) hi.h[i] = __float2half_rn(d_in_c[7 + i]);
+      reinterpret_cast<uint4*>(dh + static_cast<uint64_t>(flat) * 16)[0] = lo.v;
+      reinterpret_cast<uint4*>(dh + static_cast<uint64_t>(flat) * 16)[1] = hi.v;
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      umma::tc_fence_after();
+      umma::commit(ctx.bar);  // covers the weight-gradient products of this tile
+    }
+    first = false;
+  }
+  if (!first) {
+    ctx.wait();
+    flush_wgrad<32, false>(ctx, kGc1, grad_w_color + kColorW1, 32, inv_scale);
+    flush_wgrad<64, false>(ctx, kGc2, grad_w_color + kColorW2, 64, inv_scale);
+    flush_wgrad<16, true>(ctx, kGc3, grad_w_color + kColorW3, 64, inv_scale);
+  }
+  umma::ctx_free(ctx, kBwdColorCols);
+}
 
+__global__ void __launch_bounds__(128)
+heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__ k_ptr, uint32_t t,
+                     const float* __restrict__ rays_d, const __half* __restrict__ h, const __half* __restrict__ w_sem,
+                     int n_classes, const __half* __restrict__ logits, const __half* __restrict__ hs,
+                     const float* __restrict__ w_sel, const float* __restrict__ g_sem, float loss_scale,
+                     __half* __restrict__ dh, float* __restrict__ grad_w_sem) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* ws1 = smem;
+  unsigned char* ws2 = ws1 + kWs1;
+  unsigned char* t_in_s = ws2 + kWs2;
+  unsigned char* t_hs = t_in_s + Tile<16>::kBytes;
+  unsigned char* t_dhs = t_hs + Tile<64>::kBytes;
+  unsigned char* t_dlog = t_dhs + Tile<64>::kBytes;
+  unsigned char* tail = t_dlog + Tile<kSemOut>::kBytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(tail + 8);
+  umma::load_weight_tile<16>(ws1, w_sem + kSemW1, 64);
+  umma::load_weight_tile<64>(ws2, w_sem + kSemW2, kSemOut);
+  umma::Ctx ctx = umma::ctx_init(slot, bar, kBwdSemCols);
+  const uint32_t s_in_s = umma::smem_u32(t_in_s), s_hs = umma::smem_u32(t_hs), s_dhs = umma::smem_u32(t_dhs),
+                 s_dlog = umma::smem_u32(t_dlog), b1 = umma::smem_u32(ws1), b2 = umma::smem_u32(ws2);
+  constexpr uint32_t kAcc = 0, kGs1 = 64, kGs2 = 80;
+
+  const float inv_scale = 1.0f / loss_scale;
+  const uint32_t k_rows = static_cast<uint32_t>(*k_ptr);
+  const uint32_t n_tiles = (k_rows + 127) / 128;
+  const int row = threadIdx.x;
+  bool first = true;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t r = tile * 128 + threadIdx.x;
+    const bool valid = r < k_rows;
+    const uint32_t flat = valid ? static_cast<uint32_t>(sel[r]) : 0u;
+    if (!first) ctx.wait();
+    build_inputs(rays_d, h, flat, t, valid, nullptr, t_in_s);
+    row_g2t<64>(t_hs, hs + static_cast<uint64_t>(r) * 64, valid);
+    {
+      // backward of semantics_n = sum w softmax(l) with detached weights (renderer_semantics.py:270,284):
+      //   d l = p (w g_sem - <w g_sem, p>)
       float p[kSemOut];
       if (valid) {
+        const uint32_t n = flat / t;
+        const float w_row = w_sel[r];
         const uint64_t stream = l2_policy_stream();
 #pragma unroll
         for (int c0 = 0; c0 < kSemOut; c0 += 8) {
@@ -386,56 +495,34 @@ heads_bwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__
         *Tile<kSemOut>::chunk(t_dlog, row, c) = o.v;
       }
     }
-    // ---- stage A: through the two output layers
     ctx.publish();
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
-      umma::issue_dgrad<16, 64>(ctx.tmem + kAcc0, s_dpre, w.c3);
-      umma::issue_dgrad<kSemOut, 64>(ctx.tmem + kAcc1, s_dlog, w.s2);
+      umma::issue_dgrad<kSemOut, 64>(ctx.tmem + kAcc, s_dlog, b2);
       umma::commit(ctx.bar);
-      umma::issue_wgrad<16>(ctx.tmem + kGc3, s_h2, s_dpre, first);       // d(Wc3)^T = h2^T . dpre
       umma::issue_wgrad<kSemOut>(ctx.tmem + kGs2, s_hs, s_dlog, first);  // d(Ws2)^T = hs^T . dlogits
     }
     ctx.wait();
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 16) {
-      umma::acc_to_tile16<64, false>(ctx, kAcc0 + c0, t_dh2, c0, t_h2);
-      umma::acc_to_tile16<64, false>(ctx, kAcc1 + c0, t_dhs, c0, t_hs);
-    }
-    // ---- stage B: colour layer 2, semantic layer 1
+    for (int c0 = 0; c0 < 64; c0 += 16) umma::acc_to_tile16<64, false>(ctx, kAcc + c0, t_dhs, c0, t_hs);
     ctx.publish();
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
-      umma::issue_dgrad<64, 64>(ctx.tmem + kAcc0, s_dh2, w.c2);
-      umma::issue_dgrad<64, 16>(ctx.tmem + kAcc1, s_dhs, w.s1);
+      umma::issue_dgrad<64, 16>(ctx.tmem + kAcc, s_dhs, b1);
       umma::commit(ctx.bar);
-      umma::issue_wgrad<64>(ctx.tmem + kGc2, s_dh2, s_h1, first);    // d(Wc2) = dh2^T . h1
       umma::issue_wgrad<16>(ctx.tmem + kGs1, s_dhs, s_in_s, first);  // d(Ws1) = dhs^T . in_s
     }
     ctx.wait();
-#pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 16) umma::acc_to_tile16<64, false>(ctx, kAcc0 + c0, t_dh1, c0, t_h1);
     float d_in_s[16];
-    umma::tmem_ld16(ctx.lane_addr(kAcc1), d_in_s);
-    // ---- stage C: colour layer 1
-    ctx.publish();
-    if (threadIdx.x == 0) {
-      umma::tc_fence_after();
-      umma::issue_dgrad<64, 32>(ctx.tmem + kAcc0, s_dh1, w.c1);
-      umma::commit(ctx.bar);
-      umma::issue_wgrad<32>(ctx.tmem + kGc1, s_dh1, s_in_c, first);  // d(Wc1) = dh1^T . in_c
-    }
-    ctx.wait();
-    float d_in_c[16];
-    umma::tmem_ld16(ctx.lane_addr(kAcc0 + 16), d_in_c);  // columns 16..31 = the geo_feat (+1) inputs
-    if (valid) {
-      // dL/dgeo_feat = colour part + semantic part, handed to density_bwd as fp16 (still scaled)
+    umma::tmem_ld16(ctx.lane_addr(kAcc), d_in_s);
+    if (valid) {  // dL/dgeo_feat = colour share (already in dh) + semantic share, handed to density_bwd as fp16
       H8 lo, hi;
-      lo.h[0] = __float2half_rn(0.f);
+      lo.v = reinterpret_cast<const uint4*>(dh + static_cast<uint64_t>(flat) * 16)[0];
+      hi.v = reinterpret_cast<const uint4*>(dh + static_cast<uint64_t>(flat) * 16)[1];
 #pragma unroll
-      for (int i = 0; i < 7; ++i) lo.h[i + 1] = __float2half_rn(round_h(d_in_c[i]) + round_h(d_in_s[i]));
+      for (int i = 0; i < 7; ++i) lo.h[i + 1] = __float2half_rn(__half2float(lo.h[i + 1]) + round_h(d_in_s[i]));
 #pragma unroll
-      for (int i = 0; i < 8; ++i) hi.h[i] = __float2half_rn(round_h(d_in_c[7 + i]) + round_h(d_in_s[7 + i]));
+      for (int i = 0; i < 8; ++i) hi.h[i] = __float2half_rn(__half2float(hi.h[i]) + round_h(d_in_s[7 + i]));
       reinterpret_cast<uint4*>(dh + static_cast<uint64_t>(flat) * 16)[0] = lo.v;
       reinterpret_cast<uint4*>(dh + static_cast<uint64_t>(flat) * 16)[1] = hi.v;
     }
@@ -443,19 +530,16 @@ heads_bwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__
     __syncthreads();
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
-      umma::commit(ctx.bar);  // covers the weight-gradient products of this tile
+      umma::commit(ctx.bar);
     }
     first = false;
   }
   if (!first) {
     ctx.wait();
-    flush_wgrad<32, false>(ctx, kGc1, grad_w_color + kColorW1, 32, inv_scale);
-    flush_wgrad<64, false>(ctx, kGc2, grad_w_color + kColorW2, 64, inv_scale);
-    flush_wgrad<16, true>(ctx, kGc3, grad_w_color + kColorW3, 64, inv_scale);
     flush_wgrad<16, false>(ctx, kGs1, grad_w_sem + kSemW1, 16, inv_scale);
     flush_wgrad<kSemOut, true>(ctx, kGs2, grad_w_sem + kSemW2, 64, inv_scale);
   }
-  umma::ctx_free(ctx, kBwdCols);
+  umma::ctx_free(ctx, kBwdSemCols);
 }
 
 uint32_t heads_grid(uint32_t k_max, int ctas_per_sm) {
@@ -483,7 +567,7 @@ extern "C" int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32
     cudaFuncSetAttribute(heads_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
     attr_set = true;
   }
-  heads_fwd_tc_kernel<<<heads_grid(k_max, 2), 128, kFwdSmem, as_stream(stream)>>>(
+  heads_fwd_tc_kernel<<<heads_grid(k_max, kFwdCtasPerSm), 128, kFwdSmem, as_stream(stream)>>>(
       sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h),
       static_cast<const __half*>(w_sem_h), static_cast<int>(n_classes), w_sel, rgb, static_cast<__half*>(logits),
       static_cast<__half*>(hc1), static_cast<__half*>(hc2), static_cast<__half*>(hs), image, semantics);
@@ -506,14 +590,18 @@ extern "C" int ucsa_heads_bwd(const int32_t* sel, const int32_t* ray_off, uint32
   if (k_max == 0) return UCSA_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(heads_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+    cudaFuncSetAttribute(heads_bwd_color_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdColorSmem);
+    cudaFuncSetAttribute(heads_bwd_sem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSemSmem);
     attr_set = true;
   }
-  heads_bwd_tc_kernel<<<heads_grid(k_max, 1), 128, kBwdSmem, as_stream(stream)>>>(
-      sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h),
-      static_cast<const __half*>(w_sem_h), static_cast<int>(n_classes), rgb, static_cast<const __half*>(logits),
-      static_cast<const __half*>(hc1), static_cast<const __half*>(hc2), static_cast<const __half*>(hs), w_sel, z_sel,
-      g_image, g_depth, g_semantics, direction_norms, loss_scale, static_cast<__half*>(dh), d_w_sel, grad_w_color,
-      grad_w_sem);
+  cudaStream_t st = as_stream(stream);
+  heads_bwd_color_kernel<<<heads_grid(k_max, kBwdColorCtas), 128, kBwdColorSmem, st>>>(
+      sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h), rgb,
+      static_cast<const __half*>(hc1), static_cast<const __half*>(hc2), w_sel, z_sel, g_image, g_depth,
+      direction_norms, loss_scale, static_cast<__half*>(dh), d_w_sel, grad_w_color);
+  heads_bwd_sem_kernel<<<heads_grid(k_max, kBwdSemCtas), 128, kBwdSemSmem, st>>>(
+      sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_sem_h),
+      static_cast<int>(n_classes), static_cast<const __half*>(logits), static_cast<const __half*>(hs), w_sel,
+      g_semantics, loss_scale, static_cast<__half*>(dh), grad_w_sem);
   return check_launch("heads_bwd");
 }
