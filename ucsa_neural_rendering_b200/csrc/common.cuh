@@ -130,6 +130,18 @@ __device__ __forceinline__ uint32_t ld_keep_b32(const void* ptr, uint64_t policy
   asm("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(policy));
   return v;
 }
+__device__ __forceinline__ uint4 ld_keep_b128(const void* ptr, uint64_t policy) {
+  uint4 v;
+  asm("ld.global.nc.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;"
+      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+      : "l"(ptr), "l"(policy));
+  return v;
+}
+// word k (0..3) of a 16-byte vector without indexing registers dynamically
+__device__ __forceinline__ uint32_t pick_word(const uint4& q, uint32_t k) {
+  const uint32_t lo = (k & 1u) ? q.y : q.x, hi = (k & 1u) ? q.w : q.z;
+  return (k & 2u) ? hi : lo;
+}
 __device__ __forceinline__ void red_keep_f32x2(float* addr, float a, float b, uint64_t policy) {
   asm volatile("red.global.add.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(addr), "f"(a), "f"(b), "l"(policy)
                : "memory");

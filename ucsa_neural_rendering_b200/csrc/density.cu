@@ -210,6 +210,7 @@ extern "C" int ucsa_density_fwd_simt(const float* xyz, const float* rays_o, cons
   DensityArgs a;
   if (int rc = fill_args(a, xyz, rays_o, rays_d, aabb6, z_cat, n_rays, t, k0, k1, bound, grid_host)) return rc;
   UCSA_REQUIRE(table_h && w_sigma_h && sigma && h, "density_fwd: null table/weights/outputs");
+  UCSA_REQUIRE((reinterpret_cast<uintptr_t>(table_h) & 15u) == 0, "density_fwd_simt: the fp16 table must be 16-byte aligned");
   if (a.n_samples == 0) return UCSA_OK;
   static bool attr_set = false;
   if (!attr_set) {

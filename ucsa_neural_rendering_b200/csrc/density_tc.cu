@@ -50,7 +50,7 @@ constexpr uint32_t kFwdTmemCols = 64;   // layer-2 accumulator re-uses the colum
 constexpr uint32_t kBwdTmemCols = 128;
 constexpr int kFwdCtasPerSm = 4, kBwdCtasPerSm = 4;  // fwd: more CTAs shrink L1 and lose (measured 4 > 6 > 8)
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, kFwdCtasPerSm)
 density_fwd_tc_kernel(const DensityArgs a, const __half2* __restrict__ table, const __half* __restrict__ w_sigma,
                       float* __restrict__ sigma, __half* __restrict__ h, __half* __restrict__ enc,
                       __half* __restrict__ hid) {
@@ -84,9 +84,12 @@ density_fwd_tc_kernel(const DensityArgs a, const __half2* __restrict__ table, co
 #pragma unroll
       for (int c = 0; c < 4; ++c) {  // four levels = one 16-byte chunk of the encoded row
         H8 o;
+        LevelGather g[4];  // all gathers of the four levels are issued before the first one is consumed
+#pragma unroll
+        for (int j = 0; j < 4; ++j) issue_level(table, level_geom(a.grid, 4 * c + j), x01, keep, g[j]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 f = interp_level(table, level_geom(a.grid, 4 * c + j), x01, keep);
+          const float2 f = finish_level(g[j]);
           o.h2[j] = __floats2half2_rn(f.x, f.y);
         }
         *Tile<32>::chunk(t_enc, row, c) = o.v;
@@ -308,6 +311,7 @@ extern "C" int ucsa_density_fwd(const float* xyz, const float* rays_o, const flo
   DensityArgs a;
   if (int rc = fill_args(a, xyz, rays_o, rays_d, aabb6, z_cat, n_rays, t, k0, k1, bound, grid_host)) return rc;
   UCSA_REQUIRE(table_h && w_sigma_h && sigma && h, "density_fwd: null table/weights/outputs");
+  UCSA_REQUIRE((reinterpret_cast<uintptr_t>(table_h) & 15u) == 0, "density_fwd: the fp16 table must be 16-byte aligned");
   if (a.n_samples == 0) return UCSA_OK;
   static bool attr_set = false;
   if (!attr_set) {

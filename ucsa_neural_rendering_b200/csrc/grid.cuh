@@ -70,25 +70,93 @@ __device__ __forceinline__ float corner_weight(const Cell& cell, int corner) {
   return w;
 }
 
-// One level: trilinear interpolation of the fp16 table, fp32 accumulate.  `keep` = l2_policy_keep().
-__device__ __forceinline__ float2 interp_level(const __half2* __restrict__ table, const LevelGeom& lv,
-                                               const float x01[3], uint64_t keep) {
-  const Cell cell = locate(lv, x01);
-  __half2 v[8];
+// The four (y, z) corner pairs of a cell: entries of the x corner (e0) and of the x+1 corner (e1), bit 0 of the pair
+// index = +1 in y, bit 1 = +1 in z.  Same arithmetic as corner_entry, with the level-uniform work hoisted.
+__device__ __forceinline__ void pair_entries(const LevelGeom& lv, const Cell& cell, uint32_t e0[4], uint32_t e1[4]) {
+  if (lv.hashed) {
+    const bool pow2 = (lv.entries & (lv.entries - 1u)) == 0u;
+    const uint32_t hy = cell.c[1] * 2654435761u, hz = cell.c[2] * 805459861u;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint32_t bits = ld_keep_b32(table + corner_entry(lv, cell, c), keep);
-    v[c] = *reinterpret_cast<const __half2*>(&bits);
+    for (int p = 0; p < 4; ++p) {
+      const uint32_t a = ((p & 1) ? hy + 2654435761u : hy) ^ ((p & 2) ? hz + 805459861u : hz);
+      const uint32_t i = cell.c[0] ^ a, j = (cell.c[0] + 1u) ^ a;
+      e0[p] = lv.offset + (pow2 ? (i & (lv.entries - 1u)) : (i % lv.entries));
+      e1[p] = lv.offset + (pow2 ? (j & (lv.entries - 1u)) : (j % lv.entries));
+    }
+  } else {
+    const uint32_t sy = lv.res, sz = lv.res * lv.res;
+    const uint32_t base = cell.c[0] + cell.c[1] * sy + cell.c[2] * sz;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      uint32_t i = base + ((p & 1) ? sy : 0u) + ((p & 2) ? sz : 0u);
+      uint32_t j = i + 1u;
+      if (i >= lv.entries) i -= lv.entries;
+      if (j >= lv.entries) j -= lv.entries;
+      e0[p] = lv.offset + i;
+      e1[p] = lv.offset + j;
+    }
   }
+}
+
+// One level: trilinear interpolation of the fp16 table, fp32 accumulate, split into the gather (issue) and the
+// arithmetic (finish) so that a caller can keep the loads of several levels in flight.  `keep` = l2_policy_keep().
+// The gather is bound by L1 wavefronts (one per distinct 128-byte line per load instruction), so the x and x+1
+// corners of a pair come from ONE 16-byte load whenever they share an aligned group of four entries: dense levels
+// index x contiguously, and hashed levels XOR x in with prime 1, so entry(x+1) = entry(x) ^ (x ^ (x+1)) stays in the
+// group unless x % 4 == 3.  A quarter of the pairs need a second (predicated) 4-byte load.  `table` is 16-byte
+// aligned and level offsets are multiples of 8 entries.
+struct LevelGather {
+  uint4 q[4];         // the aligned group of four entries holding e0 of each pair
+  uint32_t extra[4];  // e1 when it lies outside that group
+  uint32_t sel;       // per pair p, bits 8p..8p+4: (e0 & 3) | (e1 & 3) << 2 | outside << 4
+  float f[3];
+};
+
+__device__ __forceinline__ void issue_level(const __half2* __restrict__ table, const LevelGeom& lv,
+                                            const float x01[3], uint64_t keep, LevelGather& g) {
+  const Cell cell = locate(lv, x01);
+  uint32_t e0[4], e1[4];
+  pair_entries(lv, cell, e0, e1);
+  g.sel = 0u;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const uint32_t group = e0[p] & ~3u;
+    const bool outside = (e1[p] & ~3u) != group;
+    g.q[p] = ld_keep_b128(table + group, keep);
+    g.extra[p] = 0u;
+    if (outside) g.extra[p] = ld_keep_b32(table + e1[p], keep);
+    g.sel |= ((e0[p] & 3u) | ((e1[p] & 3u) << 2) | (outside ? 16u : 0u)) << (8 * p);
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) g.f[d] = cell.f[d];
+}
+
+__device__ __forceinline__ float2 finish_level(const LevelGather& g) {
+  Cell cell;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) cell.f[d] = g.f[d];
   float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const float w = corner_weight(cell, c);
-    const float2 f = __half22float2(v[c]);
-    a0 = fmaf(w, f.x, a0);
-    a1 = fmaf(w, f.y, a1);
+  for (int p = 0; p < 4; ++p) {  // corner order 0..7 = pairs (0,0) (1,0) (0,1) (1,1) in (y, z), x inside: as before
+    const uint32_t s = g.sel >> (8 * p);
+    const uint32_t b0 = pick_word(g.q[p], s & 3u);
+    const uint32_t b1 = (s & 16u) ? g.extra[p] : pick_word(g.q[p], (s >> 2) & 3u);
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&b0));
+    const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&b1));
+    const float w0 = corner_weight(cell, 2 * p), w1 = corner_weight(cell, 2 * p + 1);
+    a0 = fmaf(w0, f0.x, a0);
+    a1 = fmaf(w0, f0.y, a1);
+    a0 = fmaf(w1, f1.x, a0);
+    a1 = fmaf(w1, f1.y, a1);
   }
   return make_float2(a0, a1);
+}
+
+__device__ __forceinline__ float2 interp_level(const __half2* __restrict__ table, const LevelGeom& lv,
+                                               const float x01[3], uint64_t keep) {
+  LevelGather g;
+  issue_level(table, lv, x01, keep, g);
+  return finish_level(g);
 }
 
 // Scatter of one level's gradient: grad_table[entry] += w_c * (g0, g1).  The x and x+1 corners of a pair land in

@@ -243,6 +243,7 @@ using namespace ucsa;
 extern "C" int ucsa_hashgrid_fwd(const float* x01, uint32_t n, const void* table_h, const ucsa_grid_desc* grid,
                                  void* enc, void* stream) {
   UCSA_REQUIRE(x01 && table_h && grid && enc, "hashgrid_fwd: null pointer");
+  UCSA_REQUIRE((reinterpret_cast<uintptr_t>(table_h) & 15u) == 0, "hashgrid_fwd: the fp16 table must be 16-byte aligned");
   if (n == 0) return UCSA_OK;
   const uint64_t total = static_cast<uint64_t>(n) * UCSA_GRID_LEVELS;
   hashgrid_fwd_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
