@@ -43,6 +43,7 @@ extern "C" {
 #define UCSA_SIGMA_PARAMS 3072  /* 32->64->16            network_tcnn_semantics.py:48-58  */
 #define UCSA_COLOR_PARAMS 7168  /* 32->64->64->16        network_tcnn_semantics.py:74-84  */
 #define UCSA_MAX_CLASSES 48     /* semantics 16->64->pad16(C)  network_tcnn_semantics.py:90-100 */
+#define UCSA_TILE_ROWS(rows) (((rows) + 127u) / 128u * 128u) /* rows of a tile-layout activation buffer */
 
 /* Multiresolution hash grid geometry (tcnn HashGrid config at network_tcnn_semantics.py:36-46).
  * Filled by ucsa_grid_desc_init() on the host and passed BY VALUE to kernels. */
@@ -126,8 +127,11 @@ UCSA_API int ucsa_compact_masked(const float* w_sorted, const float* z_cat, cons
 /* ---- a7/a12/a13 (+a14 fused). colour + semantic heads on the K masked-in rows (network_tcnn_semantics.py:147-207)
  * and, when image/semantics are non-null, the compositing of renderer_semantics.py:279-285 in the same kernel:
  * image [N,3] += sum w*rgb, semantics [N,C] += sum w*softmax(logits) (atomicAdd; the caller zero-fills them).
- * K is read on the device from ray_off[n_rays]; k_max bounds the launch.  rgb [K,3] f32 (fp16 sigmoid values),
- * logits fp16 [K,48]; hc1,hc2,hs fp16 [K,64] saved for backward when non-null. */
+ * K is read on the device from ray_off[n_rays]; k_max bounds the launch.  rgb [K,3] f32 (fp16 sigmoid values);
+ * logits fp16 [K,48] row-major, optional (may be null: the backward pass recomputes them).
+ * hc1, hc2, hs (all three or none): hidden activations saved for ucsa_heads_bwd, OPAQUE tile-layout buffers of
+ * UCSA_TILE_ROWS(k_max) * 64 halves each - 128-row tiles stored as contiguous 16 KB blocks in the tensor-core
+ * operand layout (csrc/mlp_umma.cuh), moved with one bulk copy per tile. */
 UCSA_API int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32_t n_rays, uint32_t t, uint32_t k_max,
                    const float* rays_d, const void* h, const void* w_color_h, const void* w_sem_h,
                    uint32_t n_classes, const float* w_sel, float* rgb, void* logits, void* hc1, void* hc2, void* hs,
@@ -136,10 +140,11 @@ UCSA_API int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32_t
 /* Backward of ucsa_heads_fwd including the compositing: from g_image [N,3], g_depth [N], g_semantics [N,C] it forms
  * dL/drgb, dL/dlogits (soft-max backward; semantic weights are detached, renderer_semantics.py:270) per row on the
  * fly, writes d_w_sel [K] = dL/dw of every masked-in sample (for ucsa_weights_bwd), dh[sel][1..15] =
- * loss_scale * dL/dgeo_feat (fp16), and accumulates grad_w_color [7168], grad_w_sem [4096] (fp32, unscaled). */
+ * loss_scale * dL/dgeo_feat (fp16), and accumulates grad_w_color [7168], grad_w_sem [4096] (fp32, unscaled).
+ * hc1, hc2, hs are the tile-layout buffers ucsa_heads_fwd filled.  Two kernels: colour, then semantics. */
 UCSA_API int ucsa_heads_bwd(const int32_t* sel, const int32_t* ray_off, uint32_t n_rays, uint32_t t, uint32_t k_max,
                    const float* rays_d, const void* h, const void* w_color_h, const void* w_sem_h,
-                   uint32_t n_classes, const float* rgb, const void* logits, const void* hc1, const void* hc2,
+                   uint32_t n_classes, const float* rgb, const void* hc1, const void* hc2,
                    const void* hs, const float* w_sel, const float* z_sel, const float* g_image,
                    const float* g_depth, const float* g_semantics, const float* direction_norms, float loss_scale,
                    void* dh, float* d_w_sel, float* grad_w_color, float* grad_w_sem, void* stream);

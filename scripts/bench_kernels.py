@@ -93,7 +93,7 @@ def main():
     rec("compact_masked", ms, n * t, 16)
     rgb = torch.empty(k_max, 3, **f32)
     logits = torch.empty(k_max, 48, **f16)
-    hc1, hc2, hs = (torch.empty(k_max, 64, **f16) for _ in range(3))
+    hc1, hc2, hs = (torch.empty(ops.tile_rows(k_max), 64, **f16) for _ in range(3))
     image = torch.zeros(n, 3, **f32)
     sem = torch.zeros(n, 40, **f32)
     ms = timeit(lambda: ops.heads_fwd(sel, off, n, t, k_max, d, h, w_col, w_sem, 40, rgb, logits, hc1, hc2, hs,
@@ -111,7 +111,7 @@ def main():
     dh = torch.empty(n, t, 16, **f16)
     g_col = torch.zeros(ops.COLOR_PARAMS, **f32)
     g_sem = torch.zeros(ops.SEM_PARAMS, **f32)
-    ms = timeit(lambda: ops.heads_bwd(sel, off, n, t, k_max, d, h, w_col, w_sem, 40, rgb, logits, hc1, hc2, hs, w_sel,
+    ms = timeit(lambda: ops.heads_bwd(sel, off, n, t, k_max, d, h, w_col, w_sem, 40, rgb, hc1, hc2, hs, w_sel,
                                       z_sel, gi, gd, gs, dn.view(-1), 128.0, dh, d_w, g_col, g_sem), args.iters, flush)
     rec(f"heads_bwd + composite bwd (K={k} rows)", ms, k, 32 + 3 * 128 + 12 + 96 + 32)
     d_sigma = torch.empty(n, t, **f32)

@@ -245,7 +245,7 @@ def test_fused_heads_match_cuda_core_heads_plus_composite_kernels():
     w_col, w_sem = net.color_net.half_params(), net.semantics_net.half_params()
 
     rgb1, log1 = torch.zeros(k_max, 3, **f32), torch.zeros(k_max, 48, **f16)
-    a1, a2, a3 = (torch.zeros(k_max, 64, **f16) for _ in range(3))
+    a1, a2, a3 = (torch.zeros(ops.tile_rows(k_max), 64, **f16) for _ in range(3))  # tile-layout buffers
     img1, sem1 = torch.zeros(n, 3, **f32), torch.zeros(n, c, **f32)
     ops.heads_fwd(sel, off, n, t, k_max, d, h, w_col, w_sem, c, rgb1, log1, a1, a2, a3, w_sel=w_sel, image=img1,
                   semantics=sem1)
@@ -265,7 +265,7 @@ def test_fused_heads_match_cuda_core_heads_plus_composite_kernels():
     scale = 64.0
     dh1, dw1 = torch.zeros(n, t, 16, **f16), torch.zeros(k_max, **f32)
     gc1, gs1 = torch.zeros(ops.COLOR_PARAMS, **f32), torch.zeros(ops.SEM_PARAMS, **f32)
-    ops.heads_bwd(sel, off, n, t, k_max, d, h, w_col, w_sem, c, rgb1, log1, a1, a2, a3, w_sel, z_sel, gi, gd, gs, dn,
+    ops.heads_bwd(sel, off, n, t, k_max, d, h, w_col, w_sem, c, rgb1, a1, a2, a3, w_sel, z_sel, gi, gd, gs, dn,
                   scale, dh1, dw1, gc1, gs1)
     d_rgb, d_log, dw2 = torch.zeros(k_max, 3, **f32), torch.zeros(k_max, 48, **f32), torch.zeros(k_max, **f32)
     ops.composite_bwd(off, sel, w_sel, z_sel, rgb2, log2, gi, gd, gs, dn, n, c, d_rgb, d_log, dw2)

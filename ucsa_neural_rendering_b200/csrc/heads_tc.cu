@@ -7,6 +7,10 @@
 // the two networks advance together: one commit covers the colour and the semantic product of a stage, so the
 // forward pass needs three MMA round trips and the backward pass three data-gradient round trips; the five
 // weight gradients accumulate in TMEM across all tiles of the persistent CTA.
+//
+// The hidden activations saved for the backward pass (hc1, hc2, hs) are tile-layout buffers (mlp_umma.cuh): tile i
+// of the compact row list is one contiguous 16 KB block, written and read back with single bulk copies.  The
+// logits are not saved at all: the semantic backward kernel recomputes them from hs with one extra product.
 #include "mlp_umma.cuh"
 #include "sh4.cuh"
 
@@ -86,21 +90,6 @@ __device__ __forceinline__ void build_inputs(const float* __restrict__ rays_d, c
   }
 }
 
-// saved activations are written once and read once (backward): tag them evict_first in L2
-template <int W>
-__device__ __forceinline__ void row_t2g(__half* __restrict__ dst, unsigned char* tile) {
-  const uint64_t stream = l2_policy_stream();
-#pragma unroll
-  for (int c = 0; c < W / 8; ++c) st_stream(dst + c * 8, *Tile<W>::chunk(tile, threadIdx.x, c), stream);
-}
-template <int W>
-__device__ __forceinline__ void row_g2t(unsigned char* tile, const __half* __restrict__ src, bool valid) {
-  const uint64_t stream = l2_policy_stream();
-#pragma unroll
-  for (int c = 0; c < W / 8; ++c)
-    *Tile<W>::chunk(tile, threadIdx.x, c) = valid ? ld_stream(src + c * 8, stream) : make_uint4(0, 0, 0, 0);
-}
-
 // Forward shared memory / TMEM plan (3 CTAs per SM):
 //   region A = [in_c 8K | in_s 4K | hs 16K]   later re-used as `part`, the fp32 staging of the fused compositing
 //   region B = [h1 16K]                       later re-used for h2 (layer 2 has consumed h1 by then)
@@ -138,6 +127,7 @@ heads_fwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__
   const uint32_t s_in_c = umma::smem_u32(t_in_c), s_in_s = umma::smem_u32(t_in_s), s_h1 = umma::smem_u32(t_h1),
                  s_hs = umma::smem_u32(t_hs), s_h2 = umma::smem_u32(t_h2);
   constexpr uint32_t kAcc0 = 0, kAcc1 = 64, kAcc2 = 64;
+  const uint64_t stream = l2_policy_stream();
 
   const uint32_t k_rows = static_cast<uint32_t>(*k_ptr);
   const uint32_t n_tiles = (k_rows + 127) / 128;
@@ -161,23 +151,26 @@ heads_fwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__
       umma::acc_to_tile16<64, true>(ctx, kAcc0 + c0, t_h1, c0);
       umma::acc_to_tile16<64, true>(ctx, kAcc1 + c0, t_hs, c0);
     }
-    if (valid && hc1 != nullptr) row_t2g<64>(hc1 + static_cast<uint64_t>(r) * 64, t_h1);
-    if (valid && hs != nullptr) row_t2g<64>(hs + static_cast<uint64_t>(r) * 64, t_hs);
     ctx.publish();
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
       umma::issue_fwd<64, 64>(ctx.tmem + kAcc0, s_h1, w.c2);
       umma::issue_fwd<64, kSemOut>(ctx.tmem + kAcc2, s_hs, w.s2);
+      if (hc1 != nullptr) {
+        // save the two hidden tiles while the products run; the commit is held back until the copies have read
+        // shared memory, because the next epilogue overwrites both tiles (h2 and `part` alias them)
+        umma::bulk_store(umma::tile_block<64>(hc1, tile), s_h1, Tile<64>::kBytes, stream);
+        umma::bulk_store(umma::tile_block<64>(hs, tile), s_hs, Tile<64>::kBytes, stream);
+        umma::bulk_store_fence_reads();
+      }
       umma::commit(ctx.bar);
     }
     ctx.wait();
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 16) umma::acc_to_tile16<64, true>(ctx, kAcc0 + c0, t_h2, c0);
-    if (valid && hc2 != nullptr) row_t2g<64>(hc2 + static_cast<uint64_t>(r) * 64, t_h2);
     {
       // the row's logits: fp16 like the reference's network output, kept in registers for the soft-max
       float lg[kSemOut];
-      const uint64_t stream = l2_policy_stream();
 #pragma unroll
       for (int c0 = 0; c0 < kSemOut; c0 += 16) {
         float v[16];
@@ -190,7 +183,7 @@ heads_fwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__
           lg[c0 + i] = __half2float(a.h[i]);
           lg[c0 + 8 + i] = __half2float(b.h[i]);
         }
-        if (valid) {
+        if (valid && logits != nullptr) {  // optional output: the backward pass recomputes the logits
           st_stream(logits + static_cast<uint64_t>(r) * kSemOut + c0, a.v, stream);
           st_stream(logits + static_cast<uint64_t>(r) * kSemOut + c0 + 8, b.v, stream);
         }
@@ -216,6 +209,10 @@ heads_fwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
       umma::issue_fwd<64, 16>(ctx.tmem + kAcc0, s_h2, w.c3);
+      if (hc2 != nullptr) {
+        umma::bulk_store(umma::tile_block<64>(hc2, tile), s_h2, Tile<64>::kBytes, stream);
+        umma::bulk_store_fence_reads();  // the next tile's first epilogue overwrites h2's bytes (as h1)
+      }
       umma::commit(ctx.bar);
     }
     ctx.wait();
@@ -310,7 +307,9 @@ heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
   unsigned char* t_dpre = t_dh2 + Tile<64>::kBytes;
   unsigned char* tail = t_dpre + Tile<16>::kBytes;
   uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(tail + 8);
+  uint64_t* ld_bar = reinterpret_cast<uint64_t*>(tail + 8);  // completion of the bulk loads of the saved tiles
+  uint32_t* slot = reinterpret_cast<uint32_t*>(tail + 16);
+  if (threadIdx.x == 64) umma::mbar_init(ld_bar, 1);
   umma::load_weight_tile<32>(wc1, w_color + kColorW1, 64);
   umma::load_weight_tile<64>(wc2, w_color + kColorW2, 64);
   umma::load_weight_tile<64>(wc3, w_color + kColorW3, 16);
@@ -319,6 +318,8 @@ heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
                  s_dh1 = umma::smem_u32(t_dh1), s_dh2 = umma::smem_u32(t_dh2), s_dpre = umma::smem_u32(t_dpre),
                  b1 = umma::smem_u32(wc1), b2 = umma::smem_u32(wc2), b3 = umma::smem_u32(wc3);
   constexpr uint32_t kAcc = 0, kGc1 = 64, kGc2 = 96, kGc3 = 160;
+  const uint64_t stream = l2_policy_stream();
+  uint32_t ld_phase = 0;
 
   const float inv_scale = 1.0f / loss_scale;
   const uint32_t k_rows = static_cast<uint32_t>(*k_ptr);
@@ -330,9 +331,12 @@ heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
     const bool valid = r < k_rows;
     const uint32_t flat = valid ? static_cast<uint32_t>(sel[r]) : 0u;
     if (!first) ctx.wait();  // weight-gradient MMAs of the previous tile are done with the tiles
+    if (threadIdx.x == 0) {
+      umma::mbar_expect_tx(ld_bar, 2 * Tile<64>::kBytes);
+      umma::bulk_load(s_h1, umma::tile_block<64>(hc1, tile), Tile<64>::kBytes, ld_bar, stream);
+      umma::bulk_load(s_h2, umma::tile_block<64>(hc2, tile), Tile<64>::kBytes, ld_bar, stream);
+    }
     build_inputs(rays_d, h, flat, t, valid, t_in_c, nullptr);
-    row_g2t<64>(t_h1, hc1 + static_cast<uint64_t>(r) * 64, valid);
-    row_g2t<64>(t_h2, hc2 + static_cast<uint64_t>(r) * 64, valid);
     {
       // backward of image_n = sum w rgb and depth_n = sum w z / dn (renderer_semantics.py:276-282):
       //   d rgb = w g_image ;  d w = g_image . rgb + g_depth z / dn ; then through the sigmoid: s (1 - s)
@@ -356,6 +360,8 @@ heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
       *Tile<16>::chunk(t_dpre, row, 1) = hi.v;
     }
     ctx.publish();
+    umma::mbar_wait(ld_bar, ld_phase);  // h1 and h2 have landed (operands of the products, ReLU masks below)
+    ld_phase ^= 1u;
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
       umma::issue_dgrad<16, 64>(ctx.tmem + kAcc, s_dpre, b3);
@@ -415,7 +421,7 @@ heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
 __global__ void __launch_bounds__(128)
 heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__ k_ptr, uint32_t t,
                      const float* __restrict__ rays_d, const __half* __restrict__ h, const __half* __restrict__ w_sem,
-                     int n_classes, const __half* __restrict__ logits, const __half* __restrict__ hs,
+                     int n_classes, const __half* __restrict__ hs,
                      const float* __restrict__ w_sel, const float* __restrict__ g_sem, float loss_scale,
                      __half* __restrict__ dh, float* __restrict__ grad_w_sem) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -427,13 +433,17 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
   unsigned char* t_dlog = t_dhs + Tile<64>::kBytes;
   unsigned char* tail = t_dlog + Tile<kSemOut>::kBytes;
   uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(tail + 8);
+  uint64_t* ld_bar = reinterpret_cast<uint64_t*>(tail + 8);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(tail + 16);
+  if (threadIdx.x == 64) umma::mbar_init(ld_bar, 1);
   umma::load_weight_tile<16>(ws1, w_sem + kSemW1, 64);
   umma::load_weight_tile<64>(ws2, w_sem + kSemW2, kSemOut);
   umma::Ctx ctx = umma::ctx_init(slot, bar, kBwdSemCols);
   const uint32_t s_in_s = umma::smem_u32(t_in_s), s_hs = umma::smem_u32(t_hs), s_dhs = umma::smem_u32(t_dhs),
                  s_dlog = umma::smem_u32(t_dlog), b1 = umma::smem_u32(ws1), b2 = umma::smem_u32(ws2);
   constexpr uint32_t kAcc = 0, kGs1 = 64, kGs2 = 80;
+  const uint64_t stream = l2_policy_stream();
+  uint32_t ld_phase = 0;
 
   const float inv_scale = 1.0f / loss_scale;
   const uint32_t k_rows = static_cast<uint32_t>(*k_ptr);
@@ -445,23 +455,34 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
     const bool valid = r < k_rows;
     const uint32_t flat = valid ? static_cast<uint32_t>(sel[r]) : 0u;
     if (!first) ctx.wait();
+    if (threadIdx.x == 0) {
+      umma::mbar_expect_tx(ld_bar, Tile<64>::kBytes);
+      umma::bulk_load(s_hs, umma::tile_block<64>(hs, tile), Tile<64>::kBytes, ld_bar, stream);
+    }
     build_inputs(rays_d, h, flat, t, valid, nullptr, t_in_s);
-    row_g2t<64>(t_hs, hs + static_cast<uint64_t>(r) * 64, valid);
+    ctx.publish();
+    umma::mbar_wait(ld_bar, ld_phase);
+    ld_phase ^= 1u;
+    if (threadIdx.x == 0) {  // the logits again: hs . Ws2^T, the very product of the forward pass
+      umma::tc_fence_after();
+      umma::issue_fwd<64, kSemOut>(ctx.tmem + kAcc, s_hs, b2);
+      umma::commit(ctx.bar);
+    }
+    ctx.wait();
     {
       // backward of semantics_n = sum w softmax(l) with detached weights (renderer_semantics.py:270,284):
       //   d l = p (w g_sem - <w g_sem, p>)
       float p[kSemOut];
+#pragma unroll
+      for (int c0 = 0; c0 < kSemOut; c0 += 16) {
+        float v[16];
+        umma::tmem_ld16(ctx.lane_addr(kAcc + c0), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) p[c0 + i] = round_h(v[i]);  // fp16 network output, as in the forward pass
+      }
       if (valid) {
         const uint32_t n = flat / t;
         const float w_row = w_sel[r];
-        const uint64_t stream = l2_policy_stream();
-#pragma unroll
-        for (int c0 = 0; c0 < kSemOut; c0 += 8) {
-          H8 v;
-          v.v = ld_stream(logits + static_cast<uint64_t>(r) * kSemOut + c0, stream);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) p[c0 + i] = __half2float(v.h[i]);
-        }
         float m = -INFINITY;
 #pragma unroll
         for (int c = 0; c < kSemOut; ++c)
@@ -557,7 +578,9 @@ extern "C" int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32
                               uint32_t k_max, const float* rays_d, const void* h, const void* w_color_h,
                               const void* w_sem_h, uint32_t n_classes, const float* w_sel, float* rgb, void* logits,
                               void* hc1, void* hc2, void* hs, float* image, float* semantics, void* stream) {
-  UCSA_REQUIRE(sel && ray_off && rays_d && h && w_color_h && w_sem_h && rgb && logits, "heads_fwd: null pointer");
+  UCSA_REQUIRE(sel && ray_off && rays_d && h && w_color_h && w_sem_h && rgb, "heads_fwd: null pointer");
+  UCSA_REQUIRE((hc1 != nullptr) == (hc2 != nullptr) && (hc1 != nullptr) == (hs != nullptr),
+               "heads_fwd: pass hc1, hc2 and hs together");
   UCSA_REQUIRE((image == nullptr) == (semantics == nullptr) && (image == nullptr || w_sel != nullptr),
                "heads_fwd: fused compositing needs w_sel, image and semantics together");
   UCSA_REQUIRE(n_classes >= 1 && n_classes <= UCSA_MAX_CLASSES, "heads_fwd: 1 <= classes <= %d", UCSA_MAX_CLASSES);
@@ -576,12 +599,12 @@ extern "C" int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32
 
 extern "C" int ucsa_heads_bwd(const int32_t* sel, const int32_t* ray_off, uint32_t n_rays, uint32_t t,
                               uint32_t k_max, const float* rays_d, const void* h, const void* w_color_h,
-                              const void* w_sem_h, uint32_t n_classes, const float* rgb, const void* logits,
+                              const void* w_sem_h, uint32_t n_classes, const float* rgb,
                               const void* hc1, const void* hc2, const void* hs, const float* w_sel,
                               const float* z_sel, const float* g_image, const float* g_depth,
                               const float* g_semantics, const float* direction_norms, float loss_scale, void* dh,
                               float* d_w_sel, float* grad_w_color, float* grad_w_sem, void* stream) {
-  UCSA_REQUIRE(sel && ray_off && rays_d && h && w_color_h && w_sem_h && rgb && logits && hc1 && hc2 && hs && w_sel &&
+  UCSA_REQUIRE(sel && ray_off && rays_d && h && w_color_h && w_sem_h && rgb && hc1 && hc2 && hs && w_sel &&
                    z_sel && g_image && g_depth && g_semantics && direction_norms && dh && d_w_sel && grad_w_color &&
                    grad_w_sem,
                "heads_bwd: null pointer");
@@ -601,7 +624,7 @@ extern "C" int ucsa_heads_bwd(const int32_t* sel, const int32_t* ray_off, uint32
       direction_norms, loss_scale, static_cast<__half*>(dh), d_w_sel, grad_w_color);
   heads_bwd_sem_kernel<<<heads_grid(k_max, kBwdSemCtas), 128, kBwdSemSmem, st>>>(
       sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_sem_h),
-      static_cast<int>(n_classes), static_cast<const __half*>(logits), static_cast<const __half*>(hs), w_sel,
+      static_cast<int>(n_classes), static_cast<const __half*>(hs), w_sel,
       g_semantics, loss_scale, static_cast<__half*>(dh), grad_w_sem);
   return check_launch("heads_bwd");
 }

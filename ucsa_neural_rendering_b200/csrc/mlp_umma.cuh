@@ -49,6 +49,42 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// ---------------------------------------------------------------- bulk (TMA) tile copies, issued by ONE thread
+// The activations saved for the backward pass live in HBM in the core-matrix tile layout described above, one
+// contiguous Tile<C>::kBytes block per 128-row tile, so a tile moves as a single bulk copy instead of 128 threads
+// each storing / loading their own 2C-byte row (which costs one L1 wavefront per row and 16-byte chunk).
+// `policy` = l2_policy_stream(): written once, read once.
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+               "r"(ssrc), "r"(bytes), "l"(policy)
+               : "memory");
+}
+// closes the group of bulk stores issued so far and waits until they have READ their shared-memory source
+__device__ __forceinline__ void bulk_store_fence_reads() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// global -> shared; completion is signalled on `bar` (arm it with mbar_expect_tx first)
+__device__ __forceinline__ void bulk_load(uint32_t sdst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+                                          uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+          "r"(sdst), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+template <int C>
+__device__ __forceinline__ unsigned char* tile_block(void* base, uint64_t tile) {
+  return static_cast<unsigned char*>(base) + tile * (128 * C * 2);
+}
+template <int C>
+__device__ __forceinline__ const unsigned char* tile_block(const void* base, uint64_t tile) {
+  return static_cast<const unsigned char*>(base) + tile * (128 * C * 2);
+}
+
 // ---------------------------------------------------------------- fences
 // generic-proxy shared-memory writes -> visible to the tensor core (async proxy)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -149,9 +149,24 @@ def compact_masked(w_sorted, z_cat, order, ray_off, sel, w_sel, z_sel):
                                     _ptr(z_sel, torch.float32), _stream()), "compact_masked")
 
 
-def heads_fwd(sel, ray_off, n_rays, t, k_max, rays_d, h, w_color_h, w_sem_h, n_classes, rgb, logits,
+def tile_rows(rows):
+    """rows of a tile-layout activation buffer (UCSA_TILE_ROWS): whole 128-row tiles"""
+    return (rows + 127) // 128 * 128
+
+
+def _check_tiled(k_max, width, **bufs):
+    for name, b in bufs.items():
+        if b is not None and b.numel() < tile_rows(k_max) * width:
+            raise ValueError(f"{name}: tile-layout buffer needs tile_rows({k_max}) * {width} elements, has {b.numel()}")
+
+
+def heads_fwd(sel, ray_off, n_rays, t, k_max, rays_d, h, w_color_h, w_sem_h, n_classes, rgb, logits=None,
               hc1=None, hc2=None, hs=None, w_sel=None, image=None, semantics=None):
-    """colour + semantic heads; with w_sel / image / semantics also the compositing (image, semantics zero-filled)"""
+    """colour + semantic heads; with w_sel / image / semantics also the compositing (image, semantics zero-filled).
+    hc1 / hc2 / hs: opaque tile-layout buffers of tile_rows(k_max) * 64 halves (all three or none)."""
+    if (hc1 is None) != (hc2 is None) or (hc1 is None) != (hs is None):
+        raise ValueError("heads_fwd: pass hc1, hc2 and hs together")
+    _check_tiled(k_max, 64, hc1=hc1, hc2=hc2, hs=hs)
     check(lib().ucsa_heads_fwd(_ptr(sel, torch.int32), _ptr(ray_off, torch.int32), n_rays, t, k_max,
                                _ptr(rays_d, torch.float32), _ptr(h, torch.float16), _ptr(w_color_h, torch.float16),
                                _ptr(w_sem_h, torch.float16), n_classes, _ptr(w_sel, torch.float32),
@@ -160,13 +175,14 @@ def heads_fwd(sel, ray_off, n_rays, t, k_max, rays_d, h, w_color_h, w_sem_h, n_c
                                _ptr(semantics, torch.float32), _stream()), "heads_fwd")
 
 
-def heads_bwd(sel, ray_off, n_rays, t, k_max, rays_d, h, w_color_h, w_sem_h, n_classes, rgb, logits, hc1, hc2, hs,
+def heads_bwd(sel, ray_off, n_rays, t, k_max, rays_d, h, w_color_h, w_sem_h, n_classes, rgb, hc1, hc2, hs,
               w_sel, z_sel, g_image, g_depth, g_semantics, direction_norms, loss_scale, dh, d_w_sel, grad_w_color,
               grad_w_sem):
+    _check_tiled(k_max, 64, hc1=hc1, hc2=hc2, hs=hs)
     check(lib().ucsa_heads_bwd(_ptr(sel, torch.int32), _ptr(ray_off, torch.int32), n_rays, t, k_max,
                                _ptr(rays_d, torch.float32), _ptr(h, torch.float16), _ptr(w_color_h, torch.float16),
                                _ptr(w_sem_h, torch.float16), n_classes, _ptr(rgb, torch.float32),
-                               _ptr(logits, torch.float16), _ptr(hc1, torch.float16), _ptr(hc2, torch.float16),
+                               _ptr(hc1, torch.float16), _ptr(hc2, torch.float16),
                                _ptr(hs, torch.float16), _ptr(w_sel, torch.float32), _ptr(z_sel, torch.float32),
                                _ptr(g_image, torch.float32, "g_image"), _ptr(g_depth, torch.float32, "g_depth"),
                                _ptr(g_semantics, torch.float32, "g_semantics"), _ptr(direction_norms, torch.float32),

@@ -41,16 +41,16 @@ class RenderWorkspace:
         self.w_sel = torch.empty(self.k_max, **f32)
         self.z_sel = torch.empty(self.k_max, **f32)
         self.rgb = torch.empty(self.k_max, 3, **f32)
-        self.logits = torch.empty(self.k_max, ops.MAX_CLASSES, **f16)
         self.depth = torch.empty(n, **f32)
         self.image = torch.empty(n, 3, **f32)
         self.semantics = torch.empty(n, c, **f32)
         if need_grad:
             self.enc = torch.empty(n, t, 32, **f16)
             self.hid = torch.empty(n, t, 64, **f16)
-            self.hc1 = torch.empty(self.k_max, 64, **f16)
-            self.hc2 = torch.empty(self.k_max, 64, **f16)
-            self.hs = torch.empty(self.k_max, 64, **f16)
+            rows = ops.tile_rows(self.k_max)  # tile-layout buffers (ucsa_nerf.h: ucsa_heads_fwd)
+            self.hc1 = torch.empty(rows, 64, **f16)
+            self.hc2 = torch.empty(rows, 64, **f16)
+            self.hs = torch.empty(rows, 64, **f16)
             self.d_w_sel = torch.empty(self.k_max, **f32)
             self.dh = torch.empty(n, t, 16, **f16)
             self.d_sigma = torch.empty(n, t, **f32)
@@ -81,7 +81,7 @@ def forward_chain(net, ws, rays_o, rays_d, dnorm, aabb, *, perturb, t_rand=None,
     ws.image.zero_()
     ws.semantics.zero_()
     ops.heads_fwd(ws.sel, ws.ray_off, n, t, ws.k_max, rays_d, ws.h, net.color_net.half_params(),
-                  net.semantics_net.half_params(), c, ws.rgb, ws.logits, ws.hc1, ws.hc2, ws.hs, w_sel=ws.w_sel,
+                  net.semantics_net.half_params(), c, ws.rgb, None, ws.hc1, ws.hc2, ws.hs, w_sel=ws.w_sel,
                   image=ws.image, semantics=ws.semantics)  # heads + compositing in one kernel
 
 
@@ -91,7 +91,7 @@ def backward_chain(net, ws, rays_o, rays_d, dnorm, aabb, g_image, g_depth, g_sem
     n, t, c = ws.n, ws.t, ws.c
     scale = float(net.loss_scale)
     ops.heads_bwd(ws.sel, ws.ray_off, n, t, ws.k_max, rays_d, ws.h, net.color_net.half_params(),
-                  net.semantics_net.half_params(), c, ws.rgb, ws.logits, ws.hc1, ws.hc2, ws.hs, ws.w_sel, ws.z_sel,
+                  net.semantics_net.half_params(), c, ws.rgb, ws.hc1, ws.hc2, ws.hs, ws.w_sel, ws.z_sel,
                   g_image, g_depth, g_sem, dnorm, scale, ws.dh, ws.d_w_sel, grad_color, grad_sem)
     ops.weights_bwd(ws.z_cat, ws.sigma, ws.order, ws.w_sorted, ws.ray_off, ws.d_w_sel, net.density_scale, ws.d_sigma)
     ops.density_bwd(net.encoder.grid, net.sigma_net.half_params(), net.bound, rays_o=rays_o, rays_d=rays_d, aabb=aabb,
