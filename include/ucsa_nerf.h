@@ -80,11 +80,14 @@ UCSA_API int ucsa_sample_coarse(const float* nears, const float* fars, const flo
  * o + d*z clipped to aabb6 (renderer_semantics.py:171-173) for slots [k0,k1) of every ray.
  * table_h: fp16 [2*total_entries]; w_sigma_h: fp16 [3072], layer-major, each layer [out][in] row-major.
  * Outputs, indexed n*T+k: sigma f32; h fp16 [.,16] (h[0] = log-density, h[1:16] = geo_feat);
- * enc fp16 [.,32] and hid fp16 [.,64] are saved for the backward pass when non-null. */
+ * enc fp16 [.,32] and hid fp16 [.,64] are saved for the backward pass when non-null.
+ * tiled != 0: enc / hid are OPAQUE tile-layout buffers of UCSA_TILE_ROWS(rows) rows (128-sample tiles stored as
+ * contiguous blocks in the tensor-core operand layout and moved with one bulk copy each); in ray mode this needs
+ * T, k0 and k1-k0 to be multiples of 128.  tiled == 0: plain row-major rows.  Forward and backward must agree. */
 UCSA_API int ucsa_density_fwd(const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,
                      const float* z_cat, uint32_t n_rays, uint32_t t, uint32_t k0, uint32_t k1, float bound,
                      const void* table_h, const ucsa_grid_desc* grid_host, const void* w_sigma_h,
-                     float* sigma, void* h, void* enc, void* hid, void* stream);
+                     float* sigma, void* h, void* enc, void* hid, int tiled, void* stream);
 
 /* Backward of ucsa_density_fwd for slots [k0,k1).  d_sigma f32 [N,T] (cat order); dh fp16 [N,T,16] whose
  * elements 1..15 hold loss_scale * dL/dgeo_feat for samples with use_geo[n*T+k] != 0 (element 0 is ignored);
@@ -96,7 +99,7 @@ UCSA_API int ucsa_density_fwd(const float* xyz, const float* rays_o, const float
 UCSA_API int ucsa_density_bwd(const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,
                      const float* z_cat, uint32_t n_rays, uint32_t t, uint32_t k0, uint32_t k1, float bound,
                      const ucsa_grid_desc* grid_host, const void* w_sigma_h, const void* h, const void* enc,
-                     const void* hid, const float* d_sigma, const void* dh, const uint8_t* use_geo,
+                     const void* hid, int tiled, const float* d_sigma, const void* dh, const uint8_t* use_geo,
                      float loss_scale, float* grad_table, float* grad_replicas, uint32_t n_replicas,
                      float* grad_w_sigma, void* stream);
 /* grad_table[dense part] += sum of the replicas; the replicas are zero again on return. */

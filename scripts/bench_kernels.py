@@ -61,7 +61,7 @@ def main():
     h = torch.empty(n, t, 16, **f16)
     enc = torch.empty(n, t, 32, **f16)
     hid = torch.empty(n, t, 64, **f16)
-    common = dict(rays_o=o, rays_d=d, aabb=aabb, z_cat=z_cat, sigma=sigma, h=h, enc=enc, hid=hid)
+    common = dict(rays_o=o, rays_d=d, aabb=aabb, z_cat=z_cat, sigma=sigma, h=h, enc=enc, hid=hid, tiled=True)
     order = torch.empty(n, t, dtype=torch.int32, device=dev)
     rows = []
 
@@ -121,7 +121,8 @@ def main():
     g_sig = torch.zeros(ops.SIGMA_PARAMS, **f32)
     ms = timeit(lambda: ops.density_bwd(grid, w_sig, 4.0, rays_o=o, rays_d=d, aabb=aabb, z_cat=z_cat, k0=0, k1=t, h=h,
                                         enc=enc, hid=hid, d_sigma=d_sigma, dh=dh, use_geo=use, loss_scale=128.0,
-                                        grad_table=g_tab, grad_w_sigma=g_sig), args.iters, flush)
+                                        grad_table=g_tab, grad_w_sigma=g_sig, tiled=True,
+                                        replicas=net.encoder.grad_replicas()), args.iters, flush)
     rec("density_bwd (2.1M samples)", ms, n * t, 588)
     # the scatter alone, one thread per (sample, level)
     x01 = torch.rand(n * t, 3, **f32)

@@ -205,8 +205,9 @@ def _check_mlp(ops, dims, n_in, n_out, simt, n):
 
 
 # ----------------------------------------------------------------------------------------------- a4
-@pytest.mark.parametrize("simt", [False, True], ids=["tcgen05", "cuda-core"])
-def test_density_forward_backward(ops, simt):
+@pytest.mark.parametrize("simt,tiled", [(False, False), (False, True), (True, False)],
+                         ids=["tcgen05", "tcgen05-tile-layout", "cuda-core"])
+def test_density_forward_backward(ops, simt, tiled):
     heads = live_path.OracleHeads(bound=4, num_semantic_classes=40, seed=21, hash_amp=0.5)
     g = torch.Generator().manual_seed(9)
     xyz = (torch.rand(2500, 3, generator=g) - 0.5) * 8
@@ -217,9 +218,11 @@ def test_density_forward_backward(ops, simt):
     w_h = heads.sigma_net.detach().half().to(DEV)
     sigma = torch.empty(s, device=DEV)
     h = torch.empty(s, 16, dtype=torch.float16, device=DEV)
-    enc = torch.empty(s, 32, dtype=torch.float16, device=DEV)
-    hid = torch.empty(s, 64, dtype=torch.float16, device=DEV)
-    ops.density_fwd(grid, table_h, w_h, 4.0, xyz=xyz.to(DEV), sigma=sigma, h=h, enc=enc, hid=hid, simt=simt)
+    rows = ops.tile_rows(s) if tiled else s  # 2500 samples: the last tile is partial
+    enc = torch.empty(rows, 32, dtype=torch.float16, device=DEV)
+    hid = torch.empty(rows, 64, dtype=torch.float16, device=DEV)
+    ops.density_fwd(grid, table_h, w_h, 4.0, xyz=xyz.to(DEV), sigma=sigma, h=h, enc=enc, hid=hid, simt=simt,
+                    tiled=tiled)
     np.testing.assert_allclose(h[:, 1:].float().cpu().numpy(), dens["geo_feat"].detach().numpy(), rtol=2e-3, atol=2e-3)
     np.testing.assert_allclose(sigma.cpu().numpy(), dens["sigma"].detach().numpy(), rtol=4e-3, atol=1e-6)
 
@@ -233,7 +236,7 @@ def test_density_forward_backward(ops, simt):
     grad_table = torch.zeros(heads.encoder.numel(), device=DEV)
     grad_w = torch.zeros(3072, device=DEV)
     ops.density_bwd(grid, w_h, 4.0, xyz=xyz.to(DEV), h=h, enc=enc, hid=hid, d_sigma=g_sigma.to(DEV), dh=dh.to(DEV),
-                    use_geo=use, loss_scale=scale, grad_table=grad_table, grad_w_sigma=grad_w, simt=simt)
+                    use_geo=use, loss_scale=scale, grad_table=grad_table, grad_w_sigma=grad_w, simt=simt, tiled=tiled)
     gw = heads.sigma_net.grad.numpy()
     np.testing.assert_allclose(grad_w.cpu().numpy(), gw, rtol=1e-2, atol=3e-3 * np.abs(gw).max())
     gt = heads.encoder.grad

@@ -44,12 +44,22 @@ __device__ __forceinline__ uint64_t locate_sample(const DensityArgs& a, uint64_t
   return flat;
 }
 
+// Tile-layout saved activations (enc, hid): block index of the 128-sample tile starting at sample s0.  Requires
+// k0, span and t to be multiples of 128 in ray mode (checked on the host), so that a tile never straddles rays or
+// passes and the coarse pass, the fine pass and the backward pass agree on the block of every sample.
+__device__ __forceinline__ uint64_t saved_block(const DensityArgs& a, uint64_t s0) {
+  if (a.xyz != nullptr) return s0 / 128;
+  const uint64_t n = s0 / a.span;
+  return (n * a.t + a.k0 + (s0 % a.span)) / 128;
+}
+
 constexpr uint32_t kW1Bytes = 64 / 8 * Tile<32>::kGroupBytes;  // [64][32]
 constexpr uint32_t kW2Bytes = 16 / 8 * Tile<64>::kGroupBytes;  // [16][64]
 constexpr uint32_t kFwdTmemCols = 64;   // layer-2 accumulator re-uses the columns of layer 1 once they are read
 constexpr uint32_t kBwdTmemCols = 128;
 constexpr int kFwdCtasPerSm = 4, kBwdCtasPerSm = 4;  // fwd: more CTAs shrink L1 and lose (measured 4 > 6 > 8)
 
+template <bool TILED>  // TILED: enc / hid are tile-layout buffers written with bulk copies (else row-major rows)
 __global__ void __launch_bounds__(128, kFwdCtasPerSm)
 density_fwd_tc_kernel(const DensityArgs a, const __half2* __restrict__ table, const __half* __restrict__ w_sigma,
                       float* __restrict__ sigma, __half* __restrict__ h, __half* __restrict__ enc,
@@ -93,7 +103,7 @@ density_fwd_tc_kernel(const DensityArgs a, const __half2* __restrict__ table, co
           o.h2[j] = __floats2half2_rn(f.x, f.y);
         }
         *Tile<32>::chunk(t_enc, row, c) = o.v;
-        if (enc != nullptr) st_stream(enc + flat * 32 + c * 8, o.v, stream);
+        if (!TILED && enc != nullptr) st_stream(enc + flat * 32 + c * 8, o.v, stream);
       }
     } else {
 #pragma unroll
@@ -103,12 +113,16 @@ density_fwd_tc_kernel(const DensityArgs a, const __half2* __restrict__ table, co
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
       umma::issue_fwd<32, 64>(ctx.tmem + kAcc1, s_enc, s_w1);
+      if (TILED && enc != nullptr) {  // the commit waits for the copy's reads: the epilogue overwrites the tile
+        umma::bulk_store(umma::tile_block<32>(enc, saved_block(a, tile * 128)), s_enc, Tile<32>::kBytes, stream);
+        umma::bulk_store_fence_reads();
+      }
       umma::commit(ctx.bar);
     }
     ctx.wait();
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 16) umma::acc_to_tile16<64, true>(ctx, kAcc1 + c0, t_hid, c0);
-    if (hid != nullptr && valid) {
+    if (!TILED && hid != nullptr && valid) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) st_stream(hid + flat * 64 + c * 8, *Tile<64>::chunk(t_hid, row, c), stream);
     }
@@ -116,6 +130,10 @@ density_fwd_tc_kernel(const DensityArgs a, const __half2* __restrict__ table, co
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
       umma::issue_fwd<64, 16>(ctx.tmem + kAcc2, s_hid, s_w2);
+      if (TILED && hid != nullptr) {
+        umma::bulk_store(umma::tile_block<64>(hid, saved_block(a, tile * 128)), s_hid, Tile<64>::kBytes, stream);
+        umma::bulk_store_fence_reads();
+      }
       umma::commit(ctx.bar);
     }
     ctx.wait();
@@ -154,6 +172,7 @@ __device__ __forceinline__ void flush_wgrad(const umma::Ctx& ctx, uint32_t col0,
   }
 }
 
+template <bool TILED>
 __global__ void __launch_bounds__(128)
 density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, const __half* __restrict__ h,
                       const __half* __restrict__ enc, const __half* __restrict__ hid,
@@ -176,7 +195,10 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
   unsigned char* t_dout = t_dhid + Tile<64>::kBytes;
   unsigned char* tail = t_dout + Tile<16>::kBytes;
   uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(tail + 8);
+  uint64_t* ld_bar = reinterpret_cast<uint64_t*>(tail + 8);  // completion of the bulk loads of enc / hid
+  uint32_t* slot = reinterpret_cast<uint32_t*>(tail + 16);
+  uint32_t ld_phase = 0;
+  if (threadIdx.x == 64) umma::mbar_init(ld_bar, 1);
   umma::load_weight_tile<32>(w1, w_sigma, 64);
   umma::load_weight_tile<64>(w2, w_sigma + 64 * 32, 16);
   umma::Ctx ctx = umma::ctx_init(slot, bar, kBwdTmemCols);
@@ -193,6 +215,12 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
     const uint64_t s = tile * 128 + row;
     const bool valid = s < a.n_samples;
     if (!first) ctx.wait();  // the weight-gradient MMAs of the previous tile have read the tiles
+    if (TILED && threadIdx.x == 0) {
+      const uint64_t block = saved_block(a, tile * 128);
+      umma::mbar_expect_tx(ld_bar, Tile<32>::kBytes + Tile<64>::kBytes);
+      umma::bulk_load(s_enc, umma::tile_block<32>(enc, block), Tile<32>::kBytes, ld_bar, stream);
+      umma::bulk_load(s_hid, umma::tile_block<64>(hid, block), Tile<64>::kBytes, ld_bar, stream);
+    }
     float x01[3] = {0.f, 0.f, 0.f};
     if (valid) {
       const uint64_t flat = locate_sample(a, s, x01);
@@ -210,22 +238,30 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
       lo.h[0] = __float2half_rn(gs * expf(fminf(fmaxf(h0, -15.f), 15.f)) * loss_scale);
       *Tile<16>::chunk(t_dout, row, 0) = lo.v;
       *Tile<16>::chunk(t_dout, row, 1) = hi.v;
+      if (!TILED) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *Tile<64>::chunk(t_hid, row, c) = ld_stream(hid + flat * 64 + c * 8, stream);
+        for (int c = 0; c < 8; ++c)
+          *Tile<64>::chunk(t_hid, row, c) = ld_stream(hid + flat * 64 + c * 8, stream);
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *Tile<32>::chunk(t_enc, row, c) = ld_stream(enc + flat * 32 + c * 8, stream);
+        for (int c = 0; c < 4; ++c)
+          *Tile<32>::chunk(t_enc, row, c) = ld_stream(enc + flat * 32 + c * 8, stream);
+      }
     } else {
       const uint4 z = make_uint4(0, 0, 0, 0);
       *Tile<16>::chunk(t_dout, row, 0) = z;
       *Tile<16>::chunk(t_dout, row, 1) = z;
+      if (!TILED) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) *Tile<64>::chunk(t_hid, row, c) = z;
+        for (int c = 0; c < 8; ++c) *Tile<64>::chunk(t_hid, row, c) = z;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) *Tile<32>::chunk(t_enc, row, c) = z;
+        for (int c = 0; c < 4; ++c) *Tile<32>::chunk(t_enc, row, c) = z;
+      }
     }
     ctx.publish();
+    if (TILED) {
+      umma::mbar_wait(ld_bar, ld_phase);
+      ld_phase ^= 1u;
+    }
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
       umma::issue_dgrad<16, 64>(ctx.tmem + kAcc, s_dout, s_w2);  // d(hidden) = dL/dh . W2
@@ -292,6 +328,14 @@ int fill_args(DensityArgs& a, const float* xyz, const float* rays_o, const float
   return UCSA_OK;
 }
 
+int check_tiled(const DensityArgs& a, int tiled, const char* who) {
+  if (!tiled || a.xyz != nullptr) return UCSA_OK;
+  UCSA_REQUIRE(a.t % 128 == 0 && a.k0 % 128 == 0 && a.span % 128 == 0,
+               "%s: tile-layout enc/hid need T, k0 and k1-k0 to be multiples of 128 (T=%u, k0=%u, span=%u)", who, a.t,
+               a.k0, a.span);
+  return UCSA_OK;
+}
+
 uint32_t persistent_grid(uint64_t n_samples, int ctas_per_sm) {
   const uint64_t tiles = (n_samples + 127) / 128;
   const uint64_t cap = static_cast<uint64_t>(kNumSMs) * ctas_per_sm;
@@ -307,15 +351,17 @@ extern "C" int ucsa_density_fwd(const float* xyz, const float* rays_o, const flo
                                 const float* z_cat, uint32_t n_rays, uint32_t t, uint32_t k0, uint32_t k1,
                                 float bound, const void* table_h, const ucsa_grid_desc* grid_host,
                                 const void* w_sigma_h, float* sigma, void* h, void* enc, void* hid,
-                                void* stream) {
+                                int tiled, void* stream) {
   DensityArgs a;
   if (int rc = fill_args(a, xyz, rays_o, rays_d, aabb6, z_cat, n_rays, t, k0, k1, bound, grid_host)) return rc;
   UCSA_REQUIRE(table_h && w_sigma_h && sigma && h, "density_fwd: null table/weights/outputs");
   UCSA_REQUIRE((reinterpret_cast<uintptr_t>(table_h) & 15u) == 0, "density_fwd: the fp16 table must be 16-byte aligned");
   if (a.n_samples == 0) return UCSA_OK;
+  if (int rc = check_tiled(a, tiled, "density_fwd")) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(density_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
+    cudaFuncSetAttribute(density_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
+    cudaFuncSetAttribute(density_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
     attr_set = true;
   }
   static int ctas_per_sm = 0;
@@ -324,7 +370,8 @@ extern "C" int ucsa_density_fwd(const float* xyz, const float* rays_o, const flo
     ctas_per_sm = e ? atoi(e) : kFwdCtasPerSm;
     if (ctas_per_sm < 1 || ctas_per_sm > 8) ctas_per_sm = kFwdCtasPerSm;
   }
-  density_fwd_tc_kernel<<<persistent_grid(a.n_samples, ctas_per_sm), 128, kFwdSmem, as_stream(stream)>>>(
+  auto kernel = tiled ? density_fwd_tc_kernel<true> : density_fwd_tc_kernel<false>;
+  kernel<<<persistent_grid(a.n_samples, ctas_per_sm), 128, kFwdSmem, as_stream(stream)>>>(
       a, static_cast<const __half2*>(table_h), static_cast<const __half*>(w_sigma_h), sigma,
       static_cast<__half*>(h), static_cast<__half*>(enc), static_cast<__half*>(hid));
   return check_launch("density_fwd");
@@ -333,7 +380,7 @@ extern "C" int ucsa_density_fwd(const float* xyz, const float* rays_o, const flo
 extern "C" int ucsa_density_bwd(const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,
                                 const float* z_cat, uint32_t n_rays, uint32_t t, uint32_t k0, uint32_t k1,
                                 float bound, const ucsa_grid_desc* grid_host, const void* w_sigma_h,
-                                const void* h, const void* enc, const void* hid, const float* d_sigma,
+                                const void* h, const void* enc, const void* hid, int tiled, const float* d_sigma,
                                 const void* dh, const uint8_t* use_geo, float loss_scale, float* grad_table,
                                 float* grad_replicas, uint32_t n_replicas, float* grad_w_sigma, void* stream) {
   DensityArgs a;
@@ -341,12 +388,15 @@ extern "C" int ucsa_density_bwd(const float* xyz, const float* rays_o, const flo
   UCSA_REQUIRE(w_sigma_h && h && enc && hid && grad_w_sigma, "density_bwd: null saved tensors / outputs");
   UCSA_REQUIRE(loss_scale > 0.f, "density_bwd: loss_scale must be positive");
   if (a.n_samples == 0) return UCSA_OK;
+  if (int rc = check_tiled(a, tiled, "density_bwd")) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(density_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+    cudaFuncSetAttribute(density_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+    cudaFuncSetAttribute(density_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
     attr_set = true;
   }
-  density_bwd_tc_kernel<<<persistent_grid(a.n_samples, kBwdCtasPerSm), 128, kBwdSmem, as_stream(stream)>>>(
+  auto kernel = tiled ? density_bwd_tc_kernel<true> : density_bwd_tc_kernel<false>;
+  kernel<<<persistent_grid(a.n_samples, kBwdCtasPerSm), 128, kBwdSmem, as_stream(stream)>>>(
       a, static_cast<const __half*>(w_sigma_h), static_cast<const __half*>(h), static_cast<const __half*>(enc),
       static_cast<const __half*>(hid), d_sigma, static_cast<const __half*>(dh), use_geo, loss_scale, grad_table,
       grad_replicas, n_replicas, grad_w_sigma);

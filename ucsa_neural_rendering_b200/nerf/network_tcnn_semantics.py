@@ -173,10 +173,11 @@ class _DensityFn(torch.autograd.Function):
         need = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]  # (grad mode is off inside forward)
         sigma = torch.empty(s, dtype=torch.float32, device=dev)
         h = torch.empty(s, 16, dtype=torch.float16, device=dev)
-        enc = torch.empty(s, 32, dtype=torch.float16, device=dev) if need else None
-        hid = torch.empty(s, 64, dtype=torch.float16, device=dev) if need else None
+        rows = ops.tile_rows(s)  # enc / hid: tile-layout buffers, whole 128-row tiles
+        enc = torch.empty(rows, 32, dtype=torch.float16, device=dev) if need else None
+        hid = torch.empty(rows, 64, dtype=torch.float16, device=dev) if need else None
         ops.density_fwd(net.encoder.grid, net.encoder.half_params(), net.sigma_net.half_params(), net.bound,
-                        xyz=xyz, sigma=sigma, h=h, enc=enc, hid=hid)
+                        xyz=xyz, sigma=sigma, h=h, enc=enc, hid=hid, tiled=need)
         ctx.net = net
         if need:
             ctx.save_for_backward(xyz, h, enc, hid)
@@ -199,7 +200,7 @@ class _DensityFn(torch.autograd.Function):
         g_sigma = torch.zeros_like(net.sigma_net.params)
         ops.density_bwd(net.encoder.grid, net.sigma_net.half_params(), net.bound, xyz=xyz, h=h, enc=enc, hid=hid,
                         d_sigma=None if d_sigma is None else d_sigma.float().contiguous(), dh=dh, use_geo=use_geo,
-                        loss_scale=scale, grad_table=g_table, grad_w_sigma=g_sigma)
+                        loss_scale=scale, grad_table=g_table, grad_w_sigma=g_sigma, tiled=True)
         return None, g_table, g_sigma, None
 
 

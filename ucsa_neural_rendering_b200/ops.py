@@ -71,24 +71,50 @@ def sample_coarse(nears, fars, lin, z_cat, tc, *, perturb, t_rand=None, seed=0, 
           "sample_coarse")
 
 
+def tile_rows(rows):
+    """rows of a tile-layout activation buffer (UCSA_TILE_ROWS): whole 128-row tiles"""
+    return (rows + 127) // 128 * 128
+
+
+def _check_tiled(k_max, width, **bufs):
+    for name, b in bufs.items():
+        if b is not None and b.numel() < tile_rows(k_max) * width:
+            raise ValueError(f"{name}: tile-layout buffer needs tile_rows({k_max}) * {width} elements, has {b.numel()}")
+
+
 def density_fwd(grid, table_h, w_sigma_h, bound, *, xyz=None, rays_o=None, rays_d=None, aabb=None, z_cat=None,
-                k0=0, k1=1, sigma, h, enc=None, hid=None, simt=False):
+                k0=0, k1=1, sigma, h, enc=None, hid=None, simt=False, tiled=False):
+    """tiled: enc / hid are opaque tile-layout buffers of tile_rows(rows) rows (tensor-core kernels only; in ray
+    mode see density_tiled); the matching density_bwd call must say the same."""
     if xyz is not None:
         n, t = xyz.shape[0], 1
     else:
         n, t = z_cat.shape
-    fn = lib().ucsa_density_fwd_simt if simt else lib().ucsa_density_fwd
-    check(fn(_ptr(xyz, torch.float32, "xyz"), _ptr(rays_o, torch.float32, "rays_o"),
-                                 _ptr(rays_d, torch.float32, "rays_d"), _ptr(aabb, torch.float32, "aabb"),
-                                 _ptr(z_cat, torch.float32, "z_cat"), n, t, k0, k1, float(bound),
-                                 _ptr(table_h, torch.float16, "table_h"), ctypes.byref(grid),
-                                 _ptr(w_sigma_h, torch.float16, "w_sigma_h"), _ptr(sigma, torch.float32, "sigma"),
-                                 _ptr(h, torch.float16, "h"), _ptr(enc, torch.float16, "enc"),
-                                 _ptr(hid, torch.float16, "hid"), _stream()), "density_fwd")
+    args = (_ptr(xyz, torch.float32, "xyz"), _ptr(rays_o, torch.float32, "rays_o"),
+            _ptr(rays_d, torch.float32, "rays_d"), _ptr(aabb, torch.float32, "aabb"),
+            _ptr(z_cat, torch.float32, "z_cat"), n, t, k0, k1, float(bound),
+            _ptr(table_h, torch.float16, "table_h"), ctypes.byref(grid),
+            _ptr(w_sigma_h, torch.float16, "w_sigma_h"), _ptr(sigma, torch.float32, "sigma"),
+            _ptr(h, torch.float16, "h"), _ptr(enc, torch.float16, "enc"), _ptr(hid, torch.float16, "hid"))
+    if simt:
+        if tiled:
+            raise ValueError("the CUDA-core density kernels use row-major enc / hid")
+        check(lib().ucsa_density_fwd_simt(*args, _stream()), "density_fwd_simt")
+        return
+    if tiled:
+        _check_tiled(n * t, 32, enc=enc)
+        _check_tiled(n * t, 64, hid=hid)
+    check(lib().ucsa_density_fwd(*args, int(tiled), _stream()), "density_fwd")
+
+
+def density_tiled(tc, tf):
+    """whether the ray-mode density passes over Tc coarse + Tf fine slots may use tile-layout enc / hid"""
+    return tc % 128 == 0 and tf % 128 == 0
 
 
 def density_bwd(grid, w_sigma_h, bound, *, xyz=None, rays_o=None, rays_d=None, aabb=None, z_cat=None, k0=0, k1=1,
-                h, enc, hid, d_sigma, dh, use_geo, loss_scale, grad_table, grad_w_sigma, simt=False, replicas=None):
+                h, enc, hid, d_sigma, dh, use_geo, loss_scale, grad_table, grad_w_sigma, simt=False, replicas=None,
+                tiled=False):
     """replicas: zero-filled fp32 [R, 2*dense_entries] (see grad_replicas()); folded into grad_table before returning"""
     if xyz is not None:
         n, t = xyz.shape[0], 1
@@ -96,15 +122,21 @@ def density_bwd(grid, w_sigma_h, bound, *, xyz=None, rays_o=None, rays_d=None, a
         n, t = z_cat.shape
     head = (_ptr(xyz, torch.float32, "xyz"), _ptr(rays_o, torch.float32), _ptr(rays_d, torch.float32),
             _ptr(aabb, torch.float32), _ptr(z_cat, torch.float32), n, t, k0, k1, float(bound), ctypes.byref(grid),
-            _ptr(w_sigma_h, torch.float16), _ptr(h, torch.float16), _ptr(enc, torch.float16), _ptr(hid, torch.float16),
-            _ptr(d_sigma, torch.float32, "d_sigma"), _ptr(dh, torch.float16, "dh"), _ptr(use_geo, torch.uint8, "use_geo"),
-            float(loss_scale), _ptr(grad_table, torch.float32, "grad_table"))
+            _ptr(w_sigma_h, torch.float16), _ptr(h, torch.float16), _ptr(enc, torch.float16), _ptr(hid, torch.float16))
+    mid = (_ptr(d_sigma, torch.float32, "d_sigma"), _ptr(dh, torch.float16, "dh"), _ptr(use_geo, torch.uint8, "use_geo"),
+           float(loss_scale), _ptr(grad_table, torch.float32, "grad_table"))
     tail = (_ptr(grad_w_sigma, torch.float32, "grad_w_sigma"), _stream())
     if simt:
-        check(lib().ucsa_density_bwd_simt(*head, *tail), "density_bwd_simt")
+        if tiled:
+            raise ValueError("the CUDA-core density kernels use row-major enc / hid")
+        check(lib().ucsa_density_bwd_simt(*head, *mid, *tail), "density_bwd_simt")
         return
+    if tiled:
+        _check_tiled(n * t, 32, enc=enc)
+        _check_tiled(n * t, 64, hid=hid)
     n_rep = 0 if replicas is None else replicas.shape[0]
-    check(lib().ucsa_density_bwd(*head, _ptr(replicas, torch.float32, "replicas"), n_rep, *tail), "density_bwd")
+    check(lib().ucsa_density_bwd(*head, int(tiled), *mid, _ptr(replicas, torch.float32, "replicas"), n_rep, *tail),
+          "density_bwd")
     if n_rep:
         check(lib().ucsa_reduce_grad_replicas(_ptr(replicas, torch.float32), n_rep, ctypes.byref(grid),
                                               _ptr(grad_table, torch.float32), _stream()), "reduce_grad_replicas")
@@ -147,17 +179,6 @@ def compact_masked(w_sorted, z_cat, order, ray_off, sel, w_sel, z_sel):
     check(lib().ucsa_compact_masked(_ptr(w_sorted, torch.float32), _ptr(z_cat, torch.float32), _ptr(order, torch.int32),
                                     _ptr(ray_off, torch.int32), n, t, _ptr(sel, torch.int32), _ptr(w_sel, torch.float32),
                                     _ptr(z_sel, torch.float32), _stream()), "compact_masked")
-
-
-def tile_rows(rows):
-    """rows of a tile-layout activation buffer (UCSA_TILE_ROWS): whole 128-row tiles"""
-    return (rows + 127) // 128 * 128
-
-
-def _check_tiled(k_max, width, **bufs):
-    for name, b in bufs.items():
-        if b is not None and b.numel() < tile_rows(k_max) * width:
-            raise ValueError(f"{name}: tile-layout buffer needs tile_rows({k_max}) * {width} elements, has {b.numel()}")
 
 
 def heads_fwd(sel, ray_off, n_rays, t, k_max, rays_d, h, w_color_h, w_sem_h, n_classes, rgb, logits=None,

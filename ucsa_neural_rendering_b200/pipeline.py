@@ -25,6 +25,7 @@ class RenderWorkspace:
         f16 = dict(dtype=torch.float16, device=device)
         i32 = dict(dtype=torch.int32, device=device)
         self.n, self.tc, self.tf, self.t, self.c, self.need_grad = n, tc, tf, t, c, need_grad
+        self.tiled = ops.density_tiled(tc, tf)  # enc / hid in tile layout (bulk copies) when the passes align
         self.k_max = n * t  # worst case; the kernels read the true K from ray_off[n] on the device (no host sync)
         self.lin = torch.linspace(0.0, 1.0, tc, device=device)
         self.nears = torch.empty(n, **f32)
@@ -68,7 +69,7 @@ def forward_chain(net, ws, rays_o, rays_d, dnorm, aabb, *, perturb, t_rand=None,
     ops.sample_coarse(ws.nears, ws.fars, ws.lin, ws.z_cat, tc, perturb=perturb, t_rand=t_rand, seed=seed,
                       ray_base=ray_base, step_dev=step_dev)
     common = dict(rays_o=rays_o, rays_d=rays_d, aabb=aabb, z_cat=ws.z_cat, sigma=ws.sigma, h=ws.h, enc=ws.enc,
-                  hid=ws.hid)
+                  hid=ws.hid, tiled=ws.tiled and ws.enc is not None)
     ops.density_fwd(grid, table_h, w_sig, net.bound, k0=0, k1=tc, **common)
     if tf > 0:
         ops.resample_merge(ws.sigma, ws.z_cat, ws.order, tc, tf, net.density_scale, u=u, seed=seed, ray_base=ray_base,
@@ -97,4 +98,4 @@ def backward_chain(net, ws, rays_o, rays_d, dnorm, aabb, g_image, g_depth, g_sem
     ops.density_bwd(net.encoder.grid, net.sigma_net.half_params(), net.bound, rays_o=rays_o, rays_d=rays_d, aabb=aabb,
                     z_cat=ws.z_cat, k0=0, k1=t, h=ws.h, enc=ws.enc, hid=ws.hid, d_sigma=ws.d_sigma, dh=ws.dh,
                     use_geo=ws.use_geo, loss_scale=scale, grad_table=grad_table, grad_w_sigma=grad_sigma,
-                    replicas=net.encoder.grad_replicas())
+                    replicas=net.encoder.grad_replicas(), tiled=ws.tiled)
