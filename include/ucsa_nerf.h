@@ -107,8 +107,10 @@ UCSA_API int ucsa_reduce_grad_replicas(float* grad_replicas, uint32_t n_replicas
                               float* grad_table, void* stream);
 
 /* ---- a9/a10. importance resampling + merge (renderer_semantics.py:182-222, sample_pdf :10-46).
- * Reads coarse z / sigma (slots [0,Tc)), writes fine z into slots [Tc,Tc+Tf) and order [N,T]
- * (sorted position -> cat slot, the z_index of :222).  u [N,Tf] when non-null, else generated (seed). */
+ * Reads coarse z / sigma (slots [0,Tc)), writes the fine z into slots [Tc,Tc+Tf) IN ASCENDING ORDER (the same
+ * set of samples as sample_pdf draws; only their order inside the cat buffer differs from torch.cat, which nothing
+ * downstream observes) and order [N,T] (sorted position -> cat slot, the z_index of :222).
+ * u [N,Tf] when non-null, else generated (seed). */
 UCSA_API int ucsa_resample_merge(const float* sigma, float* z_cat, const float* u, uint64_t seed,
                         const int32_t* step_dev, uint32_t ray_base, uint32_t n_rays, uint32_t tc, uint32_t tf,
                         float density_scale, int32_t* order, void* stream);

@@ -295,11 +295,18 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
       umma::tc_fence_after();
       umma::commit(ctx.bar);  // covers the two weight-gradient products; waited on at the top of the next tile
     }
-    if (valid && grad_table != nullptr) {
+    if (grad_table != nullptr) {
 #pragma unroll
-      for (int l = 0; l < UCSA_GRID_LEVELS; ++l)
-        scatter_level(a.grid.hashed[l] ? grad_table : dense_base, level_geom(a.grid, l), x01,
-                      round_h(g[2 * l]) * inv_scale, round_h(g[2 * l + 1]) * inv_scale, keep);
+      for (int l = 0; l < UCSA_GRID_LEVELS; ++l) {
+        const LevelGeom lv = level_geom(a.grid, l);
+        float* dst = lv.hashed ? grad_table : dense_base;
+        const float g0 = round_h(g[2 * l]) * inv_scale, g1 = round_h(g[2 * l + 1]) * inv_scale;
+        if (lv.res <= kRunMaxRes) {  // level-uniform: coarse levels merge runs of samples inside one cell first
+          scatter_level_runs(dst, lv, x01, g0, g1, valid && (g0 != 0.f || g1 != 0.f), keep);
+        } else if (valid) {
+          scatter_level(dst, lv, x01, g0, g1, keep);
+        }
+      }
     }
     first = false;
   }

@@ -181,6 +181,61 @@ __device__ __forceinline__ void scatter_level(float* __restrict__ grad_table, co
   }
 }
 
+// Warp-collective scatter for the coarse levels (res <= kRunMaxRes): neighbouring lanes hold neighbouring samples of
+// a ray, and at a coarse level a run of them sits in ONE cell (16 samples per cell at level 0 of the 256+256
+// configuration).  The eight corner contributions are summed over each run of equal-cell lanes with a segmented
+// shuffle reduction and only the head lane of a run issues reductions: up to an order of magnitude fewer
+// red.global operations, which are what bounds the backward pass (about 1.3 LSU cycles per lane and operation).
+// Every lane of the warp must call this; `active` = the lane has a sample with a non-zero gradient.
+constexpr uint32_t kRunMaxRes = 128;
+
+__device__ __forceinline__ void scatter_level_runs(float* __restrict__ grad_table, const LevelGeom& lv,
+                                                   const float x01[3], float g0, float g1, bool active,
+                                                   uint64_t keep) {
+  const int lane = threadIdx.x & 31;
+  const Cell cell = locate(lv, x01);
+  const uint32_t key = active ? (cell.c[0] | (cell.c[1] << 8) | (cell.c[2] << 16)) : (0xFF000000u | lane);
+  // bit L of `links`: lanes L and L+1 are in the same cell
+  const uint32_t next_key = __shfl_down_sync(kFullMask, key, 1);
+  const uint32_t links = __ballot_sync(kFullMask, lane < 31 && next_key == key);
+  float c[16];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float w = active ? corner_weight(cell, k) : 0.f;
+    c[2 * k] = w * g0;
+    c[2 * k + 1] = w * g1;
+  }
+  bool head = active;
+  if (links != 0u) {  // warp-uniform
+    const uint32_t run = links >> lane;  // bit d-1 .. : links from this lane onwards
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const bool take = (run & ((1u << d) - 1u)) == ((1u << d) - 1u);  // lanes L .. L+d all share the cell
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float o = __shfl_down_sync(kFullMask, c[i], d);
+        if (take) c[i] += o;
+      }
+    }
+    head = active && (lane == 0 || ((links >> (lane - 1)) & 1u) == 0u);
+  }
+  if (!head) return;
+  uint32_t e0[4], e1[4];
+  pair_entries(lv, cell, e0, e1);
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const float a0 = c[4 * p], a1 = c[4 * p + 1], b0 = c[4 * p + 2], b1 = c[4 * p + 3];  // x corner, x+1 corner
+    if ((e0[p] ^ e1[p]) == 1u) {
+      float* q = grad_table + 2ull * (e0[p] & ~1u);
+      if (e0[p] & 1u) red_keep_f32x4(q, b0, b1, a0, a1, keep);
+      else red_keep_f32x4(q, a0, a1, b0, b1, keep);
+    } else {
+      red_keep_f32x2(grad_table + 2ull * e0[p], a0, a1, keep);
+      red_keep_f32x2(grad_table + 2ull * e1[p], b0, b1, keep);
+    }
+  }
+}
+
 // Sample position of slot k of ray n, exactly as renderer_semantics.py:171-173 then
 // network_tcnn_semantics.py:133 evaluate it in eager fp32 (no FMA contraction).
 __device__ __forceinline__ void sample_x01(const float* __restrict__ rays_o, const float* __restrict__ rays_d,

@@ -140,27 +140,46 @@ resample_merge_kernel(const float* __restrict__ sigma, float* __restrict__ z_cat
     const float b_hi = __fadd_rn(zc[above], __fmul_rn(0.5f, __fsub_rn(zc[above + 1], zc[above])));
     const float z_new = __fadd_rn(b_lo, __fmul_rn(frac, __fsub_rn(b_hi, b_lo)));
     zn[j] = z_new;
-    z_cat[row + tc + j] = z_new;
   }
   __syncthreads();
-  // rank of every fine sample among the fine samples (stable), then scatter into the sorted run zs
+  // Stable rank of every fine sample among the fine samples: #{k < j : z_k <= z_j} + #{k > j : z_k < z_j}.
+  // O(Tf^2) compares per ray, but one compare per element on 16-byte broadcast reads of shared memory.
+  const float4* zn4 = reinterpret_cast<const float4*>(zn);  // zn starts 16*Tc bytes into shared memory
   for (uint32_t j = tid; j < tf; j += nt) {
     const float v = zn[j];
+    const uint32_t jg = j >> 2, n_groups = tf >> 2;
     uint32_t rank = 0;
-    for (uint32_t k = 0; k < tf; ++k) {
+    for (uint32_t g = 0; g < jg; ++g) {
+      const float4 w = zn4[g];
+      rank += (w.x <= v ? 1u : 0u) + (w.y <= v ? 1u : 0u) + (w.z <= v ? 1u : 0u) + (w.w <= v ? 1u : 0u);
+    }
+    for (uint32_t k = jg * 4; k < min(jg * 4 + 4, tf); ++k) {  // the group holding j itself
       const float w = zn[k];
       rank += (w < v || (w == v && k < j)) ? 1u : 0u;
     }
+    for (uint32_t g = jg + 1; g < n_groups; ++g) {
+      const float4 w = zn4[g];
+      rank += (w.x < v ? 1u : 0u) + (w.y < v ? 1u : 0u) + (w.z < v ? 1u : 0u) + (w.w < v ? 1u : 0u);
+    }
+    for (uint32_t k = max(n_groups * 4, jg * 4 + 4); k < tf; ++k) rank += zn[k] < v ? 1u : 0u;
     zs[rank] = v;
+  }
+  __syncthreads();
+  // The fine samples are stored in ascending order (slot Tc + r = r-th smallest): the set of samples is what
+  // sample_pdf drew, only their order inside the cat buffer differs from torch.cat([z_vals, new_z_vals]), which no
+  // result depends on (every consumer goes through `order`).  Neighbouring threads of the density kernels then
+  // touch neighbouring cells in the fine pass as well.
+  for (uint32_t r = tid; r < tf; r += nt) {
+    const float v = zs[r];
+    z_cat[row + tc + r] = v;
     // position in the merged order: fine samples go after coarse samples of equal depth
     uint32_t lo = 0, hi = tc;
     while (lo < hi) {
       const uint32_t mid = (lo + hi) >> 1;
       if (zc[mid] <= v) lo = mid + 1; else hi = mid;
     }
-    order[row + rank + lo] = static_cast<int32_t>(tc + j);
+    order[row + r + lo] = static_cast<int32_t>(tc + r);
   }
-  __syncthreads();
   for (uint32_t k = tid; k < tc; k += nt) {
     const float v = zc[k];
     uint32_t lo = 0, hi = tf;  // number of fine samples strictly below v
