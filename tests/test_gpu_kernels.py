@@ -247,6 +247,47 @@ def test_density_forward_backward(ops, simt, tiled):
     np.testing.assert_allclose(got.numpy(), gt.numpy(), rtol=2e-2, atol=3e-3 * float(gt.abs().max()))
 
 
+def test_density_tcgen05_matches_cuda_core_with_many_tiles_per_cta(ops):
+    """200k samples = 1563 tiles over at most 592 persistent CTAs: every CTA loops over several tiles (barrier phases,
+    bulk-copy re-use of the shared tiles, TMEM accumulation of the weight gradients).  Sorted points along segments
+    exercise the run-merging scatter of the coarse levels."""
+    g = torch.Generator().manual_seed(33)
+    heads = live_path.OracleHeads(bound=4, num_semantic_classes=40, seed=5, hash_amp=0.5)
+    n_seg, per = 1600, 125
+    a = (torch.rand(n_seg, 1, 3, generator=g) - 0.5) * 7.5
+    b = (torch.rand(n_seg, 1, 3, generator=g) - 0.5) * 7.5
+    tt = torch.linspace(0, 1, per).view(1, per, 1)
+    xyz = (a + (b - a) * tt).reshape(-1, 3).contiguous().to(DEV)
+    s = xyz.shape[0]
+    grid = ops.make_grid_desc(4)
+    table_h = heads.encoder.detach().half().to(DEV)
+    w_h = heads.sigma_net.detach().half().to(DEV)
+    g_sigma = torch.randn(s, generator=g).to(DEV)
+    dh = torch.zeros(s, 16, dtype=torch.float16)
+    dh[:, 1:] = (torch.randn(s, 15, generator=g) * 64).half()
+    dh = dh.to(DEV)
+    use = torch.ones(s, dtype=torch.uint8, device=DEV)
+    out = {}
+    for name, simt, tiled in (("tc", False, True), ("simt", True, False)):
+        rows = ops.tile_rows(s) if tiled else s
+        sigma = torch.empty(s, device=DEV)
+        h = torch.empty(s, 16, dtype=torch.float16, device=DEV)
+        enc = torch.empty(rows, 32, dtype=torch.float16, device=DEV)
+        hid = torch.empty(rows, 64, dtype=torch.float16, device=DEV)
+        ops.density_fwd(grid, table_h, w_h, 4.0, xyz=xyz, sigma=sigma, h=h, enc=enc, hid=hid, simt=simt, tiled=tiled)
+        grad_table = torch.zeros(heads.encoder.numel(), device=DEV)
+        grad_w = torch.zeros(3072, device=DEV)
+        ops.density_bwd(grid, w_h, 4.0, xyz=xyz, h=h, enc=enc, hid=hid, d_sigma=g_sigma, dh=dh, use_geo=use,
+                        loss_scale=64.0, grad_table=grad_table, grad_w_sigma=grad_w, simt=simt, tiled=tiled)
+        out[name] = (sigma, h, grad_table, grad_w)
+    torch.testing.assert_close(out["tc"][1].float(), out["simt"][1].float(), rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(out["tc"][0], out["simt"][0], rtol=4e-3, atol=1e-6)
+    gw = out["simt"][3]
+    torch.testing.assert_close(out["tc"][3], gw, rtol=1e-2, atol=3e-3 * float(gw.abs().max()))
+    gt = out["simt"][2]
+    torch.testing.assert_close(out["tc"][2], gt, rtol=2e-2, atol=3e-3 * float(gt.abs().max()))
+
+
 # ----------------------------------------------------------------------------------------------- a14 dense
 def _dense_inputs(n, t, c, seed):
     g = torch.Generator().manual_seed(seed)

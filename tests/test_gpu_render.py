@@ -217,13 +217,16 @@ def test_optimizer_step_changes_render_and_state_dict_round_trips():
         torch.testing.assert_close(a[k], b[k], rtol=1e-5, atol=1e-6)
 
 
-def test_fused_heads_match_cuda_core_heads_plus_composite_kernels():
-    """tcgen05 heads with fused compositing (production) vs CUDA-core heads + stand-alone composite kernels."""
+@pytest.mark.parametrize("n,t", [(300, 48), (6000, 128)], ids=["one-tile-per-cta", "many-tiles-per-cta"])
+def test_fused_heads_match_cuda_core_heads_plus_composite_kernels(n, t):
+    """tcgen05 heads with fused compositing (production) vs CUDA-core heads + stand-alone composite kernels.
+    The large case gives every persistent CTA several 128-row tiles (barrier phases, tile re-use, TMEM accumulation
+    of the weight gradients across tiles)."""
     from ucsa_neural_rendering_b200 import ops
 
     heads = live_path.OracleHeads(bound=4, num_semantic_classes=40, seed=9, hash_amp=0.4)
     net = _net_from_oracle(heads)
-    n, t, c = 300, 48, 40
+    c = 40
     g = torch.Generator().manual_seed(8)
     f32 = dict(dtype=torch.float32, device=DEV)
     f16 = dict(dtype=torch.float16, device=DEV)
@@ -279,4 +282,7 @@ def test_fused_heads_match_cuda_core_heads_plus_composite_kernels():
     m = (w_all > 1e-4).view(-1)
     a = dh1.view(-1, 16)[m][:, 1:].float()
     b = dh2.view(-1, 16)[m][:, 1:].float()
-    torch.testing.assert_close(a, b, rtol=2e-2, atol=1e-2 * float(b.abs().max()))
+    # a hidden unit whose fp16 pre-activation is +0 in one implementation and -tiny in the other flips its ReLU mask
+    # for that row: tolerate a 1e-5 fraction of such elements, hold everything else to the tolerance
+    bad = (a - b).abs() > 2e-2 * b.abs() + 1e-2 * float(b.abs().max())
+    assert float(bad.float().mean()) < 1e-5, float(bad.float().mean())

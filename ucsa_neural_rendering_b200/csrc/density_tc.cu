@@ -178,7 +178,8 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
                       const __half* __restrict__ enc, const __half* __restrict__ hid,
                       const float* __restrict__ d_sigma, const __half* __restrict__ dh,
                       const uint8_t* __restrict__ use_geo, float loss_scale, float* __restrict__ grad_table,
-                      float* __restrict__ grad_replicas, uint32_t n_replicas, float* __restrict__ grad_w) {
+                      float* __restrict__ grad_replicas, uint32_t n_replicas, float* __restrict__ grad_w,
+                      uint32_t run_max_res) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* w1 = smem;
   unsigned char* w2 = w1 + kW1Bytes;
@@ -301,7 +302,7 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
         const LevelGeom lv = level_geom(a.grid, l);
         float* dst = lv.hashed ? grad_table : dense_base;
         const float g0 = round_h(g[2 * l]) * inv_scale, g1 = round_h(g[2 * l + 1]) * inv_scale;
-        if (lv.res <= kRunMaxRes) {  // level-uniform: coarse levels merge runs of samples inside one cell first
+        if (lv.res <= run_max_res) {  // level-uniform: coarse levels merge runs of samples inside one cell first
           scatter_level_runs(dst, lv, x01, g0, g1, valid && (g0 != 0.f || g1 != 0.f), keep);
         } else if (valid) {
           scatter_level(dst, lv, x01, g0, g1, keep);
@@ -402,11 +403,17 @@ extern "C" int ucsa_density_bwd(const float* xyz, const float* rays_o, const flo
     cudaFuncSetAttribute(density_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
     attr_set = true;
   }
+  static uint32_t run_max_res = 0;
+  if (run_max_res == 0) {  // tuning knob (bring-up): finest resolution that still merges same-cell runs per warp
+    const char* e = getenv("UCSA_RUN_MAX_RES");
+    run_max_res = e ? static_cast<uint32_t>(atoi(e)) : kRunMaxRes;
+    if (run_max_res < 1 || run_max_res > kRunResLimit) run_max_res = kRunMaxRes;
+  }
   auto kernel = tiled ? density_bwd_tc_kernel<true> : density_bwd_tc_kernel<false>;
   kernel<<<persistent_grid(a.n_samples, kBwdCtasPerSm), 128, kBwdSmem, as_stream(stream)>>>(
       a, static_cast<const __half*>(w_sigma_h), static_cast<const __half*>(h), static_cast<const __half*>(enc),
       static_cast<const __half*>(hid), d_sigma, static_cast<const __half*>(dh), use_geo, loss_scale, grad_table,
-      grad_replicas, n_replicas, grad_w_sigma);
+      grad_replicas, n_replicas, grad_w_sigma, run_max_res);
   return check_launch("density_bwd");
 }
 

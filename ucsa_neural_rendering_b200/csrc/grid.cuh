@@ -187,14 +187,15 @@ __device__ __forceinline__ void scatter_level(float* __restrict__ grad_table, co
 // shuffle reduction and only the head lane of a run issues reductions: up to an order of magnitude fewer
 // red.global operations, which are what bounds the backward pass (about 1.3 LSU cycles per lane and operation).
 // Every lane of the warp must call this; `active` = the lane has a sample with a non-zero gradient.
-constexpr uint32_t kRunMaxRes = 128;
+constexpr uint32_t kRunMaxRes = 128;     // default threshold
+constexpr uint32_t kRunResLimit = 1022;  // cell coordinates are packed into 10 bits each
 
 __device__ __forceinline__ void scatter_level_runs(float* __restrict__ grad_table, const LevelGeom& lv,
                                                    const float x01[3], float g0, float g1, bool active,
                                                    uint64_t keep) {
   const int lane = threadIdx.x & 31;
   const Cell cell = locate(lv, x01);
-  const uint32_t key = active ? (cell.c[0] | (cell.c[1] << 8) | (cell.c[2] << 16)) : (0xFF000000u | lane);
+  const uint32_t key = active ? (cell.c[0] | (cell.c[1] << 10) | (cell.c[2] << 20)) : (0x80000000u | lane);
   // bit L of `links`: lanes L and L+1 are in the same cell
   const uint32_t next_key = __shfl_down_sync(kFullMask, key, 1);
   const uint32_t links = __ballot_sync(kFullMask, lane < 31 && next_key == key);

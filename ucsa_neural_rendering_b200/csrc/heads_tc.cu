@@ -51,6 +51,23 @@ __device__ __forceinline__ WeightTiles load_weights(unsigned char* base, const _
                      umma::smem_u32(s2)};
 }
 
+// the semantic input row [geo_feat(15) | 1] as two 16-byte chunks
+__device__ __forceinline__ void geo_chunks(const __half* __restrict__ h, uint32_t flat, bool valid, H8& g0, H8& g1) {
+  if (!valid) {
+    g0.v = g1.v = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  H8 lo, hi;
+  lo.v = __ldg(reinterpret_cast<const uint4*>(h + static_cast<uint64_t>(flat) * 16));
+  hi.v = __ldg(reinterpret_cast<const uint4*>(h + static_cast<uint64_t>(flat) * 16 + 8));
+#pragma unroll
+  for (int i = 0; i < 7; ++i) g0.h[i] = lo.h[i + 1];
+  g0.h[7] = hi.h[0];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) g1.h[i] = hi.h[i + 1];
+  g1.h[7] = __float2half_rn(1.0f);
+}
+
 // colour input row [SH(16) | geo_feat(15) | 1] and semantic input row [geo_feat(15) | 1] of this thread's row
 __device__ __forceinline__ void build_inputs(const float* __restrict__ rays_d, const __half* __restrict__ h,
                                              uint32_t flat, uint32_t t, bool valid, unsigned char* t_in_c,
@@ -277,14 +294,15 @@ __device__ __forceinline__ void flush_wgrad(const umma::Ctx& ctx, uint32_t col0,
 // ---------------------------------------------------------------------------------------------- backward
 // Two kernels, colour first, then semantics, so that each fits several CTAs per SM:
 //   colour   : tiles in_c, h1, h2, dpre, dh2, dh1 (76 KB) + colour weights; TMEM 176 -> 256 columns; 2 CTAs / SM
-//   semantics: tiles in_s, hs, dlog, dhs (48 KB) + semantic weights;        TMEM 128 columns;        4 CTAs / SM
+//   semantics: tiles hs, dhs, dlog (in_s re-uses dlog) (44 KB) + weights;   TMEM 128 columns;        4 CTAs / SM
 // The colour kernel writes its share of dL/dgeo_feat into dh and the semantic kernel adds its own.
 constexpr uint32_t kBwdColorCols = 256, kBwdSemCols = 128;
 constexpr int kBwdColorCtas = 2, kBwdSemCtas = 4;
 constexpr uint32_t kColorWeightBytes = kWc1 + kWc2 + kWc3;
 constexpr uint32_t kSemWeightBytes = kWs1 + kWs2;
 constexpr uint32_t kBwdColorSmem = kColorWeightBytes + Tile<32>::kBytes + 4 * Tile<64>::kBytes + Tile<16>::kBytes + 64;
-constexpr uint32_t kBwdSemSmem = kSemWeightBytes + Tile<16>::kBytes + 2 * Tile<64>::kBytes + Tile<kSemOut>::kBytes + 64;
+constexpr uint32_t kBwdSemSmem = kSemWeightBytes + 2 * Tile<64>::kBytes + Tile<kSemOut>::kBytes + 64;
+static_assert(kBwdSemCtas * (kBwdSemSmem + 1024) <= 227 * 1024, "semantic backward: shared memory of the resident CTAs");
 
 __global__ void __launch_bounds__(128)
 heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__ k_ptr, uint32_t t,
@@ -418,7 +436,7 @@ heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
   umma::ctx_free(ctx, kBwdColorCols);
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, kBwdSemCtas)
 heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__ k_ptr, uint32_t t,
                      const float* __restrict__ rays_d, const __half* __restrict__ h, const __half* __restrict__ w_sem,
                      int n_classes, const __half* __restrict__ hs,
@@ -427,10 +445,10 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* ws1 = smem;
   unsigned char* ws2 = ws1 + kWs1;
-  unsigned char* t_in_s = ws2 + kWs2;
-  unsigned char* t_hs = t_in_s + Tile<16>::kBytes;
+  unsigned char* t_hs = ws2 + kWs2;
   unsigned char* t_dhs = t_hs + Tile<64>::kBytes;
   unsigned char* t_dlog = t_dhs + Tile<64>::kBytes;
+  unsigned char* t_in_s = t_dlog;  // built once every product reading dlog has completed (four CTAs per SM fit)
   unsigned char* tail = t_dlog + Tile<kSemOut>::kBytes;
   uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* ld_bar = reinterpret_cast<uint64_t*>(tail + 8);
@@ -459,7 +477,8 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
       umma::mbar_expect_tx(ld_bar, Tile<64>::kBytes);
       umma::bulk_load(s_hs, umma::tile_block<64>(hs, tile), Tile<64>::kBytes, ld_bar, stream);
     }
-    build_inputs(rays_d, h, flat, t, valid, nullptr, t_in_s);
+    // CTA barrier: two waits on `bar` in a row (above and below) would let a warp that is late for the first one
+    // miss its phase - mbarrier parity cannot tell phase k from k+2.  First tile: also publishes the weight tiles.
     ctx.publish();
     umma::mbar_wait(ld_bar, ld_phase);
     ld_phase ^= 1u;
@@ -531,9 +550,12 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
       umma::tc_fence_after();
       umma::issue_dgrad<64, 16>(ctx.tmem + kAcc, s_dhs, b1);
       umma::commit(ctx.bar);
-      umma::issue_wgrad<16>(ctx.tmem + kGs1, s_dhs, s_in_s, first);  // d(Ws1) = dhs^T . in_s
     }
-    ctx.wait();
+    H8 g0, g1;
+    geo_chunks(h, flat, valid, g0, g1);
+    ctx.wait();  // every product issued so far is complete: the dlog tile may be re-used for the layer-1 input
+    *Tile<16>::chunk(t_in_s, row, 0) = g0.v;
+    *Tile<16>::chunk(t_in_s, row, 1) = g1.v;
     float d_in_s[16];
     umma::tmem_ld16(ctx.lane_addr(kAcc), d_in_s);
     if (valid) {  // dL/dgeo_feat = colour share (already in dh) + semantic share, handed to density_bwd as fp16
@@ -547,11 +569,11 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
       reinterpret_cast<uint4*>(dh + static_cast<uint64_t>(flat) * 16)[0] = lo.v;
       reinterpret_cast<uint4*>(dh + static_cast<uint64_t>(flat) * 16)[1] = hi.v;
     }
-    umma::tc_fence_before();
-    __syncthreads();
+    ctx.publish();
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
-      umma::commit(ctx.bar);
+      umma::issue_wgrad<16>(ctx.tmem + kGs1, s_dhs, s_in_s, first);  // d(Ws1) = dhs^T . in_s
+      umma::commit(ctx.bar);  // waited on at the top of the next tile
     }
     first = false;
   }

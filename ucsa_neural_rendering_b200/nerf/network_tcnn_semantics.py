@@ -11,6 +11,8 @@ is refreshed whenever the master's version counter moves (i.e. after every optim
 """
 from __future__ import annotations
 
+import os
+
 import math
 
 import torch
@@ -82,8 +84,14 @@ class HashGridEncoding(_HalfCache):
     def forward(self, x):
         return _HashGridFn.apply(x, self.params, self)
 
-    def grad_replicas(self, n_replicas=16):
+    def grad_replicas(self, n_replicas=None):
         """Scratch for the backward scatter of the dense levels (ops.density_bwd); allocated once, kept zero."""
+        if n_replicas is None:
+            # 0 since the backward scatter merges same-cell runs per warp (grid.cuh: scatter_level_runs): the few coarse
+            # cells next to the camera no longer serialise the L2 atomic units.  Kept as a knob for other ray sets.
+            n_replicas = int(os.environ.get("UCSA_GRAD_REPLICAS", "0"))
+        if n_replicas == 0:
+            return None
         rep = getattr(self, "_grad_replicas", None)
         if rep is None or rep.device != self.params.device or rep.shape[0] != n_replicas:
             rep = ops.grad_replicas(self.grid, self.params.device, n_replicas)
