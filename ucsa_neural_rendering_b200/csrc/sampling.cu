@@ -73,54 +73,101 @@ __global__ void sample_coarse_kernel(const float* __restrict__ nears, const floa
 }
 
 // ---------------------------------------------------------------- a9/a10: renderer_semantics.py:182-222
-// One CTA per ray.  Shared memory: zc[Tc] sg[Tc] wt[Tc] cdf[Tc] zn[Tf] zs[Tf] (floats).
-// The cumulative product / sum run sequentially in thread 0: 2*Tc dependent flops per ray, which keeps the
-// summation order of torch.cumprod / torch.cumsum on the CPU and costs microseconds per 4096-ray batch.
+// One WARP per ray, several rays per CTA and no CTA-wide barrier: the cumulative product / sum run sequentially in
+// lane 0 (3*Tc dependent flops per ray, which keeps the summation order of torch.cumprod / torch.cumsum on the
+// CPU) while the other warps of the SM are in their parallel phases.  Shared memory per warp:
+// zc[Tc] sg[Tc] wt[Tc] cdf[Tc] zn[Tf] zs[Tf] (floats), padded to 16 bytes.
 __global__ void __launch_bounds__(256)
 resample_merge_kernel(const float* __restrict__ sigma, float* __restrict__ z_cat, const float* __restrict__ u,
                       uint64_t seed, const int32_t* __restrict__ step_dev, uint32_t ray_base, uint32_t tc, uint32_t tf,
-                      float density_scale, int32_t* __restrict__ order) {
-  extern __shared__ float sm[];
+                      float density_scale, int32_t* __restrict__ order, uint32_t n_rays, uint32_t warp_floats) {
+  extern __shared__ __align__(16) float sm_all[];
   if (step_dev != nullptr) seed += 0x9E3779B97F4A7C15ull * static_cast<uint64_t>(*step_dev);
+  const uint32_t n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= n_rays) return;  // whole warps leave; nothing below synchronises across warps
+  float* sm = sm_all + static_cast<size_t>(threadIdx.x >> 5) * warp_floats;
   float* zc = sm;
   float* sg = zc + tc;
   float* wt = sg + tc;
   float* cdf = wt + tc;
   float* zn = cdf + tc;
   float* zs = zn + tf;
-  const uint32_t n = blockIdx.x, t = tc + tf;
+  const uint32_t t = tc + tf;
   const uint64_t row = static_cast<uint64_t>(n) * t;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x & 31, nt = 32;
 
   for (uint32_t k = tid; k < tc; k += nt) {
     zc[k] = z_cat[row + k];
     sg[k] = sigma[row + k];
   }
-  __syncthreads();
-  // alpha_k, kept in wt until the scan turns it into the weight
+  __syncwarp();
+  // alpha_k -> wt, and the transmittance factor (1 - alpha_k) + 1e-15 -> cdf (scratch for now)
   for (uint32_t k = tid; k < tc; k += nt) {
     const float delta = k + 1 < tc ? __fsub_rn(zc[k + 1], zc[k]) : kLastDelta;
-    wt[k] = 1.0f - expf(__fmul_rn(__fmul_rn(-delta, density_scale), sg[k]));
+    const float alpha = 1.0f - expf(__fmul_rn(__fmul_rn(-delta, density_scale), sg[k]));
+    wt[k] = alpha;
+    cdf[k] = __fadd_rn(__fsub_rn(1.0f, alpha), kTransEps);
   }
-  __syncthreads();
-  if (tid == 0) {
+  __syncwarp();
+  // The three scans below run in lane 0, in index order, so that every product / sum rounds exactly like
+  // torch.cumprod / cumsum on the CPU.  Only the one dependent operation per element stays on the chain: each batch
+  // of eight operands is loaded before the chain touches it and everything else is done by all lanes in between.
+  if (tid == 0) {  // sg[k] := transmittance in front of sample k
     float trans = 1.0f;
-    for (uint32_t k = 0; k < tc; ++k) {
-      const float alpha = wt[k];
-      wt[k] = alpha * trans;
-      trans *= __fadd_rn(__fsub_rn(1.0f, alpha), kTransEps);
+    for (uint32_t k = 0; k < tc; k += 8) {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = k + i < tc ? cdf[k + i] : 1.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float before = trans;
+        trans *= f[i];
+        f[i] = before;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (k + i < tc) sg[k + i] = f[i];
     }
-    // pdf over weights[1:-1] + 1e-5 ; cdf = [0, cumsum(pdf)]  (tc-1 entries)
-    float total = 0.f;
-    for (uint32_t k = 1; k + 1 < tc; ++k) total += wt[k] + 1e-5f;
+  }
+  __syncwarp();
+  for (uint32_t k = tid; k < tc; k += nt) {
+    const float w = __fmul_rn(wt[k], sg[k]);
+    wt[k] = w;
+    sg[k] = __fadd_rn(w, 1e-5f);  // pdf numerator over weights[1:-1] (no FMA contraction: w is rounded first)
+  }
+  __syncwarp();
+  float total = 0.f;
+  if (tid == 0) {
+    for (uint32_t k = 1; k + 1 < tc; k += 8) {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = k + i + 1 < tc ? sg[k + i] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (k + i + 1 < tc) total += f[i];
+    }
+  }
+  total = __shfl_sync(kFullMask, total, 0);
+  for (uint32_t k = tid; k < tc; k += nt) sg[k] = __fdiv_rn(sg[k], total);
+  __syncwarp();
+  if (tid == 0) {  // cdf = [0, cumsum(pdf)]  (tc-1 entries)
     float run = 0.f;
     cdf[0] = 0.f;
-    for (uint32_t k = 1; k + 1 < tc; ++k) {
-      run += __fdiv_rn(wt[k] + 1e-5f, total);
-      cdf[k] = run;
+    for (uint32_t k = 1; k + 1 < tc; k += 8) {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = k + i + 1 < tc ? sg[k + i] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (k + i + 1 < tc) run += f[i];
+        f[i] = run;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (k + i + 1 < tc) cdf[k + i] = f[i];
     }
   }
-  __syncthreads();
+  __syncwarp();
   const uint32_t n_cdf = tc - 1;  // bins (mid-points) and cdf entries
   for (uint32_t j = tid; j < tf; j += nt) {
     const float uj = u != nullptr ? u[static_cast<uint64_t>(n) * tf + j] : uniform01(seed, ray_base + n, j, 1u);
@@ -141,7 +188,7 @@ resample_merge_kernel(const float* __restrict__ sigma, float* __restrict__ z_cat
     const float z_new = __fadd_rn(b_lo, __fmul_rn(frac, __fsub_rn(b_hi, b_lo)));
     zn[j] = z_new;
   }
-  __syncthreads();
+  __syncwarp();
   // Stable rank of every fine sample among the fine samples: #{k < j : z_k <= z_j} + #{k > j : z_k < z_j}.
   // O(Tf^2) compares per ray, but one compare per element on 16-byte broadcast reads of shared memory.
   const float4* zn4 = reinterpret_cast<const float4*>(zn);  // zn starts 16*Tc bytes into shared memory
@@ -164,7 +211,7 @@ resample_merge_kernel(const float* __restrict__ sigma, float* __restrict__ z_cat
     for (uint32_t k = max(n_groups * 4, jg * 4 + 4); k < tf; ++k) rank += zn[k] < v ? 1u : 0u;
     zs[rank] = v;
   }
-  __syncthreads();
+  __syncwarp();
   // The fine samples are stored in ascending order (slot Tc + r = r-th smallest): the set of samples is what
   // sample_pdf drew, only their order inside the cat buffer differs from torch.cat([z_vals, new_z_vals]), which no
   // result depends on (every consumer goes through `order`).  Neighbouring threads of the density kernels then
@@ -225,13 +272,17 @@ extern "C" int ucsa_resample_merge(const float* sigma, float* z_cat, const float
   UCSA_REQUIRE(sigma && z_cat && order, "resample_merge: null pointer");
   UCSA_REQUIRE(tc >= 3 && tf >= 1 && tc <= 4096 && tf <= 4096, "resample_merge: need 3 <= Tc <= 4096, 1 <= Tf <= 4096");
   if (n_rays == 0) return UCSA_OK;
-  const size_t smem = (4ull * tc + 2ull * tf) * sizeof(float);
+  const uint32_t warp_floats = (4u * tc + 2u * tf + 3u) & ~3u;
+  const size_t warp_bytes = warp_floats * sizeof(float);
+  uint32_t warps = static_cast<uint32_t>((48u * 1024u) / warp_bytes);  // rays per CTA
+  warps = warps > 8 ? 8 : (warps < 1 ? 1 : warps);
+  const size_t smem = warps * warp_bytes;
   static size_t smem_set = 48 * 1024;
   if (smem > smem_set) {
     cudaFuncSetAttribute(resample_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     smem_set = smem;
   }
-  resample_merge_kernel<<<n_rays, 256, smem, as_stream(stream)>>>(sigma, z_cat, u, seed, step_dev, ray_base, tc, tf,
-                                                                  density_scale, order);
+  resample_merge_kernel<<<ceil_div(n_rays, warps), 32 * warps, smem, as_stream(stream)>>>(
+      sigma, z_cat, u, seed, step_dev, ray_base, tc, tf, density_scale, order, n_rays, warp_floats);
   return check_launch("resample_merge");
 }

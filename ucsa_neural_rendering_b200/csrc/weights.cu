@@ -123,12 +123,16 @@ weights_bwd_kernel(const float* __restrict__ z_cat, const float* __restrict__ si
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t n = blockIdx.x * kWarpsPerCta + wib;
   if (n >= n_rays) return;
-  float* zs = sm + static_cast<size_t>(wib) * 4 * t;
+  float* zs = sm + static_cast<size_t>(wib) * 5 * t;
   float* sg = zs + t;
   float* tr = sg + t;  // transmittance in front of each sample
   float* gw = tr + t;  // dL/dw (0 where masked out)
+  float* ws = gw + t;  // the weights, staged so that no global load sits on the scan's dependency chain
   const uint64_t row = static_cast<uint64_t>(n) * t;
   stage_sorted(z_cat, sigma, order, row, t, lane, zs, sg);
+#pragma unroll 4
+  for (uint32_t s = lane; s < t; s += 32) ws[s] = w_sorted[row + s];
+  __syncwarp();
 
   float carry = 1.0f;
   int out = ray_off[n];
@@ -138,14 +142,19 @@ weights_bwd_kernel(const float* __restrict__ z_cat, const float* __restrict__ si
     float keep_f = 1.0f;
     if (valid) keep_f = sample_terms(zs, sg, s, t, density_scale).keep;
     const float trans = chunk_transmittance(keep_f, carry, lane);
-    const float w = valid ? w_sorted[row + s] : 0.f;
-    const bool keep = valid && w > kMaskThreshold;
+    const bool keep = valid && ws[s] > kMaskThreshold;
     const unsigned ballot = __ballot_sync(kFullMask, keep);
     if (valid) {
       tr[s] = trans;
-      gw[s] = keep ? d_w_sel[out + __popc(ballot & ((1u << lane) - 1u))] : 0.f;
+      gw[s] = __int_as_float(keep ? out + __popc(ballot & ((1u << lane) - 1u)) : -1);  // compact row, for now
     }
     out += __popc(ballot);
+  }
+  __syncwarp();
+#pragma unroll 4
+  for (uint32_t s = lane; s < t; s += 32) {  // independent gathers: several in flight per lane
+    const int idx = __float_as_int(gw[s]);
+    gw[s] = idx >= 0 ? d_w_sel[idx] : 0.f;
   }
   __syncwarp();
   float suffix_carry = 0.f;
@@ -154,7 +163,7 @@ weights_bwd_kernel(const float* __restrict__ z_cat, const float* __restrict__ si
     const uint32_t s = c * 32 + lane;
     const bool valid = s < t;
     const float g = valid ? gw[s] : 0.f;
-    const float w = valid ? w_sorted[row + s] : 0.f;
+    const float w = valid ? ws[s] : 0.f;
     const float suffix = chunk_suffix(g * w, suffix_carry, lane);
     if (valid) {
       const SampleTerms st = sample_terms(zs, sg, s, t, density_scale);
@@ -217,7 +226,7 @@ extern "C" int ucsa_weights_bwd(const float* z_cat, const float* sigma, const in
                                 uint32_t n_rays, uint32_t t, float density_scale, float* d_sigma, void* stream) {
   UCSA_REQUIRE(z_cat && sigma && w_sorted && ray_off && d_w_sel && d_sigma, "weights_bwd: null pointer");
   if (n_rays == 0) return UCSA_OK;
-  const size_t smem = static_cast<size_t>(kWarpsPerCta) * 4 * t * sizeof(float);
+  const size_t smem = static_cast<size_t>(kWarpsPerCta) * 5 * t * sizeof(float);
   if (int rc = set_smem(reinterpret_cast<const void*>(weights_bwd_kernel), smem)) return rc;
   weights_bwd_kernel<<<ceil_div(n_rays, kWarpsPerCta), 32 * kWarpsPerCta, smem, as_stream(stream)>>>(
       z_cat, sigma, order, w_sorted, ray_off, d_w_sel, n_rays, t, density_scale, d_sigma);
