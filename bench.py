@@ -183,8 +183,9 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            # keep stdout to the one JSON line: NCCL writes its "NCCL version ..." banner to stdout
+            os.environ.setdefault("NCCL_DEBUG_FILE", os.devnull)
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()  # fail loudly if the extension is missing
 

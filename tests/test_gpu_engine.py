@@ -44,7 +44,7 @@ def test_loss_kernel_matches_reference_losses():
     sem = sem.to(DEV).requires_grad_()
     _, _, _, rgb, labels, gt_depth = _batch(n, c, 3)
     total, (lc, ls, ld) = nerf_losses({"image": image, "semantics": sem, "depth": depth}, rgb, labels, gt_depth, 0.6,
-                                      global_scale=0.5)
+                                      global_scale=0.5, fused=False)  # the reference's torch expression
     total.backward()
     loss4 = torch.zeros(4, device=DEV)
     gi, gd, gs = torch.empty(n, 3, device=DEV), torch.empty(n, device=DEV), torch.empty(n, c, device=DEV)
@@ -55,6 +55,16 @@ def test_loss_kernel_matches_reference_losses():
     torch.testing.assert_close(gi, image.grad.view(n, 3), rtol=1e-5, atol=1e-9)
     torch.testing.assert_close(gd, depth.grad.view(n), rtol=1e-5, atol=1e-9)
     torch.testing.assert_close(gs, sem.grad.view(n, c), rtol=1e-4, atol=1e-9)
+    # the autograd wrapper nerf_losses uses on CUDA tensors, with an upstream factor (GradScaler)
+    img2, dep2, sem2 = (x.detach().clone().requires_grad_() for x in (image, depth, sem))
+    total2, parts2 = nerf_losses({"image": img2, "semantics": sem2, "depth": dep2}, rgb, labels, gt_depth, 0.6,
+                                 global_scale=0.5)
+    (total2 * 8.0).backward()
+    torch.testing.assert_close(total2.detach(), total.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(torch.stack(list(parts2)), torch.stack([lc, ls, ld]).detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(img2.grad, 8.0 * image.grad, rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(dep2.grad, 8.0 * depth.grad, rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(sem2.grad, 8.0 * sem.grad, rtol=1e-4, atol=1e-9)
 
 
 def test_engine_step_matches_autograd_path():

@@ -17,10 +17,52 @@ import torch.distributed as dist
 from . import ops, parallel
 
 
+class _FusedLosses(torch.autograd.Function):
+    """The three losses and their gradients in one kernel (ucsa_nerf_loss); backward only scales the stored
+    gradients by the incoming scalar (GradScaler's scale, 1/world ...)."""
+
+    @staticmethod
+    def forward(ctx, image, depth, semantics, gt_rgb, labels, gt_depth, uom, w_sem, w_depth, global_scale):
+        n, c = semantics.shape
+        dev = image.device
+        loss4 = torch.empty(4, dtype=torch.float32, device=dev)
+        grads = torch.empty(n * (4 + c), dtype=torch.float32, device=dev)
+        g_image, g_depth, g_sem = grads[:3 * n].view(n, 3), grads[3 * n:4 * n], grads[4 * n:].view(n, c)
+        ops.nerf_loss(image, depth, semantics, gt_rgb, labels, gt_depth, uom, w_sem, w_depth, global_scale, loss4,
+                      g_image, g_depth, g_sem)
+        ctx.save_for_backward(grads)
+        ctx.n, ctx.c = n, c
+        parts = loss4[1:]
+        ctx.mark_non_differentiable(parts)
+        return loss4[0], parts
+
+    @staticmethod
+    def backward(ctx, g_total, _g_parts):
+        (grads,) = ctx.saved_tensors
+        n, c = ctx.n, ctx.c
+        g = grads * g_total
+        return g[:3 * n].view(n, 3), g[3 * n:4 * n], g[4 * n:].view(n, c), None, None, None, None, None, None, None
+
+
 def nerf_losses(outputs, gt_rgb, labels, gt_depth, one_m_to_scene_uom, weight_depth=0.1, weight_semantics=0.04,
-                global_scale=1.0):
-    """joint_train_lightning_net.py:199-221 and :503-507.  Shapes [B,N,...] as rendered."""
+                global_scale=1.0, fused=None):
+    """joint_train_lightning_net.py:199-221 and :503-507.  Shapes [B,N,...] as rendered.
+    On CUDA tensors the losses and their gradients come from one kernel (fused=None: automatic); fused=False keeps the
+    reference's torch expression (also the CPU path of the host-logic tests)."""
     pred_rgb, semantics, pred_depth = outputs["image"], outputs["semantics"], outputs["depth"]
+    if fused is None:
+        fused = pred_rgb.is_cuda and semantics.shape[-1] <= ops.MAX_CLASSES
+    if fused:
+        c = semantics.shape[-1]
+        rgb = gt_rgb.reshape(-1, 3)
+        if rgb.dtype not in (torch.float16, torch.float32):
+            rgb = rgb.float()
+        total, parts = _FusedLosses.apply(
+            pred_rgb.reshape(-1, 3).float().contiguous(), pred_depth.reshape(-1).float().contiguous(),
+            semantics.reshape(-1, c).float().contiguous(), rgb.contiguous(), labels.reshape(-1).long().contiguous(),
+            gt_depth.reshape(-1).float().contiguous(), float(one_m_to_scene_uom), float(weight_semantics),
+            float(weight_depth), float(global_scale))
+        return total, (parts[0], parts[1], parts[2])
     labels = labels.clone()
     invalid = torch.sum(semantics, dim=-1) == 0
     semantics = torch.where(invalid.unsqueeze(-1), torch.ones_like(semantics), semantics)
