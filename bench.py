@@ -194,7 +194,7 @@ def run_ours(args):
                               num_semantic_classes=N_CLASSES).to(dev).train()
     uom = scene.one_m_to_scene_uom
     engine = TrainEngine(net, RAYS_PER_GPU, num_steps=NUM_STEPS, upsample_steps=UPSAMPLE_STEPS,
-                         one_m_to_scene_uom=uom, use_graph=not args.no_graph)
+                         one_m_to_scene_uom=uom, use_graph=not args.no_graph, exchange=args.exchange)
 
     total_steps = args.warmup + args.steps
     g = torch.Generator(device=dev).manual_seed(123 + rank)
@@ -242,9 +242,10 @@ def run_ours(args):
     value = world * RAYS_PER_GPU * args.steps / (ms_total * 1e-3)
 
     # per-kernel device time: the same steps once more, launched eagerly with CUDA events around the kernels
-    timed = {"ucsa_density_fwd", "ucsa_density_bwd", "ucsa_heads_fwd", "ucsa_heads_bwd"}
-    eager = TrainEngine(net, RAYS_PER_GPU, num_steps=NUM_STEPS, upsample_steps=UPSAMPLE_STEPS,
-                        one_m_to_scene_uom=uom, use_graph=False)
+    timed = {"ucsa_density_fwd", "ucsa_density_bwd", "ucsa_heads_fwd", "ucsa_heads_bwd", "ucsa_adam_step",
+             "ucsa_adam_exchange", "ucsa_resample_merge"}
+    eager = engine  # same engine, same buffers, launched kernel by kernel instead of replaying the graph
+    was_graph, engine.use_graph = engine.use_graph, False
     eager.train_step(*batches[0])
     torch.cuda.synchronize()
     _lib.stats.reset()
@@ -260,7 +261,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     kernel_ms = {k: _lib.stats.elapsed_ms(k) for k in timed}
     _lib.stats.timed = set()
-    del eager
+    engine.use_graph = was_graph
 
     # ---------------------------------------------------------------- e2e: public API, host buffers
     opt = torch.optim.Adam([
@@ -354,6 +355,10 @@ def run_ours(args):
                            "api": "TrainEngine.load_batch(pinned host) + step() + loss readback"}},
         "gpu_launches": launches, "gpu_launches_per_step": by_name,
         "step_impl": "cuda-graph replay of %d kernels" % per_step_launches if not args.no_graph else "eager kernel chain",
+        "gradient_exchange": {"none": "single GPU", "nccl": "NCCL all-reduce + replicated Adam",
+                              "peer": "ucsa_adam_exchange over symmetric memory (%s)" % (
+                                  "multimem.ld_reduce / multimem.st via NVSwitch" if engine.peer is not None
+                                  and engine.peer.multicast else "peer loads / stores")}[engine.exchange],
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info,
     }
     print(json.dumps(line))
@@ -367,6 +372,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--exchange", choices=["peer", "nccl"], default=None,
+                    help="multi-GPU gradient exchange (default: peer memory when available)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -43,6 +43,7 @@ extern "C" {
 #define UCSA_SIGMA_PARAMS 3072  /* 32->64->16            network_tcnn_semantics.py:48-58  */
 #define UCSA_COLOR_PARAMS 7168  /* 32->64->64->16        network_tcnn_semantics.py:74-84  */
 #define UCSA_MAX_CLASSES 48     /* semantics 16->64->pad16(C)  network_tcnn_semantics.py:90-100 */
+#define UCSA_MAX_PEERS 16       /* ranks of one NVLink domain in ucsa_adam_exchange */
 #define UCSA_TILE_ROWS(rows) (((rows) + 127u) / 128u * 128u) /* rows of a tile-layout activation buffer */
 
 /* Multiresolution hash grid geometry (tcnn HashGrid config at network_tcnn_semantics.py:36-46).
@@ -270,6 +271,19 @@ UCSA_API int ucsa_adam_step(float* param, const float* grad, float* exp_avg, flo
                    uint64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
                    float grad_scale_inv, const float* found_inf, uint32_t step, const int32_t* step_dev,
                    void* stream);
+
+/* ---- (e)+f1. gradient exchange fused into Adam over peer memory (the reference: DDP all-reduce inside Lightning,
+ * then torch.optim.Adam).  All ranks keep parameters (fp32 masters + fp16 copy) and the gradient buffer in symmetric
+ * memory; *_ptrs_host are host arrays of `world` device addresses (rank order) of those flat buffers, mc_* their
+ * multicast addresses (NVLS; all three or all null -> plain peer loads / stores).  The calling rank owns parameters
+ * [begin, end): it sums the gradients of all ranks, applies Adam (moments exp_avg / exp_avg_sq hold end-begin
+ * entries; weight decay applies to parameters >= wd_begin) and writes the new values into every rank's buffers.
+ * Bracket the launch with cross-rank barriers: gradients complete before, parameters visible after. */
+UCSA_API int ucsa_adam_exchange(const uint64_t* grad_ptrs_host, const uint64_t* param_ptrs_host,
+                   const uint64_t* param_h_ptrs_host, const float* mc_grad, float* mc_param, void* mc_param_h,
+                   uint32_t world, uint32_t rank, uint64_t begin, uint64_t end, uint64_t wd_begin, float* exp_avg,
+                   float* exp_avg_sq, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   uint32_t step, const int32_t* step_dev, void* stream);
 
 /* ---- f2. losses of forward_nerf_train (joint_train_lightning_net.py:199-221,503-507) and their gradients w.r.t.
  * image / depth / semantics in one kernel.  gt_rgb as fp16 [N,3] (batch["img_fp16"]) or fp32; labels int64 with -1 =

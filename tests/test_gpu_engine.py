@@ -118,3 +118,36 @@ def test_graph_replay_equals_eager_and_trains():
         close = ((a - b).abs() <= 1e-3 + 1e-2 * b.abs()).float().mean()
         assert float(close) > 0.9, float(close)
     assert losses[1][-1] < losses[1][0], losses[1]
+
+
+def test_adam_exchange_kernel_equals_adam_step_on_one_rank():
+    """ucsa_adam_exchange with world = 1 (peer loads / stores on the rank's own buffers) must reproduce
+    ucsa_adam_step on each parameter group: same arithmetic, weight decay only past wd_begin, owned slice only."""
+    from types import SimpleNamespace
+
+    from ucsa_neural_rendering_b200 import ops
+
+    g = torch.Generator().manual_seed(4)
+    n, wd_begin = 40000, 30000
+    p0 = torch.randn(n, generator=g).to(DEV)
+    grad = torch.randn(n, generator=g).to(DEV)
+    step_dev = torch.tensor([3], dtype=torch.int32, device=DEV)
+    hyper = dict(lr=1e-2, beta1=0.9, beta2=0.99, eps=1e-15)
+    # reference: two groups through ucsa_adam_step
+    ref_p, ref_h = p0.clone(), torch.empty(n, dtype=torch.float16, device=DEV)
+    m_ref, v_ref = torch.rand(n, generator=g).to(DEV) * 0.1, torch.rand(n, generator=g).to(DEV) * 0.01
+    m0, v0 = m_ref.clone(), v_ref.clone()
+    for lo, hi, wd in ((0, wd_begin, 0.0), (wd_begin, n, 1e-3)):
+        ops.adam_step(ref_p[lo:hi], grad[lo:hi], m_ref[lo:hi], v_ref[lo:hi], ref_h[lo:hi], weight_decay=wd,
+                      grad_scale_inv=1.0, found_inf=None, step=1, step_dev=step_dev, **hyper)
+    # fused exchange on the slice [8000, 36000) of a one-rank "world"
+    begin, end = 8000, 36000
+    p, h = p0.clone(), torch.zeros(n, dtype=torch.float16, device=DEV)
+    peer = SimpleNamespace(world=1, rank=0, begin=begin, end=end, multicast=False, grad_ptrs=[grad.data_ptr()],
+                           param_ptrs=[p.data_ptr()], param_h_ptrs=[h.data_ptr()], mc_grad=0, mc_param=0, mc_param_h=0)
+    m, v = m0[begin:end].clone(), v0[begin:end].clone()
+    ops.adam_exchange(peer, m, v, wd_begin=wd_begin, weight_decay=1e-3, step=1, step_dev=step_dev, **hyper)
+    torch.cuda.synchronize()
+    assert torch.equal(p[begin:end], ref_p[begin:end]) and torch.equal(h[begin:end], ref_h[begin:end])
+    assert torch.equal(m, m_ref[begin:end]) and torch.equal(v, v_ref[begin:end])
+    assert torch.equal(p[:begin], p0[:begin]) and torch.equal(p[end:], p0[end:])  # outside the owned slice: untouched

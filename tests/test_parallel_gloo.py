@@ -67,3 +67,16 @@ def test_shard_range_partitions_exactly():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_owner_slices_cover_the_flat_parameter_space_once():
+    """host logic of the fused exchange: equal float4-aligned slices, every parameter owned by exactly one rank"""
+    for n in (13_089_248, 4096, 40, 4, 1004):
+        for world in (1, 2, 3, 4, 8, 16):
+            covered = 0
+            for rank in range(world):
+                lo, hi = parallel.owner_slice(n, rank, world)
+                assert lo == covered and lo % 4 == 0 and lo <= hi <= n
+                assert hi % 4 == 0 or hi == n
+                covered = hi
+            assert covered == n

@@ -85,6 +85,119 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gradient exchange fused into the optimizer, over NVLink / NVSwitch peer memory (row (e) of SURVEY.md section 8).
+// Every rank holds the full parameters (fp32 masters + fp16 working copy) and a full gradient buffer in SYMMETRIC
+// memory.  Rank r owns the slice [begin, end) of the flat parameter space:
+//     g      = sum over ranks of grad[i]            one multimem.ld_reduce (the switch adds) or P2P loads
+//     p, m, v -> Adam                               moments exist only for the owned slice
+//     p'     -> every rank's masters and fp16 copy  one multimem.st each (the switch replicates) or P2P stores
+// i.e. reduce-scatter + optimizer + all-gather in one pass, 1/world of the Adam work per rank, and every copy of a
+// parameter comes from the same arithmetic (bit-identical replicas).  The caller brackets the launch with two
+// cross-rank barriers (gradients complete before, parameters visible after).
+// Measured on B200 (bench.py, 13.1 M parameters): kernel 0.108 ms with peer loads / stores vs 0.187 ms with multimem
+// at 2 GPUs, 0.205 ms vs 0.181 ms at 8 GPUs (step 3.26 -> 3.18 ms; NCCL all-reduce + replicated Adam: 3.27 ms):
+// the multimem operations cost more per 16 bytes but their traffic does not grow with the world size.
+constexpr int kMaxPeers = UCSA_MAX_PEERS;
+struct PeerPtrs {
+  float* grad[kMaxPeers];
+  float* param[kMaxPeers];
+  __half* param_h[kMaxPeers];
+};
+
+__device__ __forceinline__ float4 mc_ld_reduce_add(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.weak.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void mc_st_f32x4(float* mc, const float4& v) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void mc_st_f16x4(__half* mc, uint32_t lo, uint32_t hi) {
+  asm volatile("multimem.st.weak.global.v2.f16x2 [%0], {%1,%2};" ::"l"(mc), "r"(lo), "r"(hi) : "memory");
+}
+
+template <bool MC_LOAD, bool MC_STORE>
+__global__ void __launch_bounds__(256)
+adam_exchange_kernel(const PeerPtrs peers, const float* __restrict__ mc_grad, float* __restrict__ mc_param,
+                     __half* __restrict__ mc_param_h, uint32_t world, uint32_t rank, uint64_t begin, uint64_t end,
+                     uint64_t wd_begin, float* __restrict__ m, float* __restrict__ v, float lr, float b1, float b2,
+                     float eps, float wd, float bc1, float bc2_sqrt, const int32_t* __restrict__ step_dev) {
+  __shared__ float bc[2];
+  if (threadIdx.x == 0) {
+    if (step_dev != nullptr) {
+      const float st = static_cast<float>(*step_dev);
+      bc1 = 1.0f - powf(b1, st);
+      bc2_sqrt = sqrtf(1.0f - powf(b2, st));
+    }
+    bc[0] = bc1;
+    bc[1] = bc2_sqrt;
+  }
+  __syncthreads();
+  // kUnroll float4 groups per thread and iteration, all remote gradient loads issued before the first use: the
+  // loads cross NVLink (microseconds of latency), so the bytes in flight per SM decide the throughput
+  constexpr int kUnroll = 4;
+  const uint64_t tile = static_cast<uint64_t>(blockDim.x) * 4 * kUnroll;  // parameters per CTA and iteration
+  for (uint64_t base = begin + static_cast<uint64_t>(blockIdx.x) * tile; base < end;
+       base += static_cast<uint64_t>(gridDim.x) * tile) {
+    float4 g[kUnroll];
+    uint64_t idx[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      idx[u] = base + (static_cast<uint64_t>(u) * blockDim.x + threadIdx.x) * 4;
+      g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (MC_LOAD) {
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        if (idx[u] < end) g[u] = mc_ld_reduce_add(mc_grad + idx[u]);
+    } else {
+      for (uint32_t r = 0; r < world; ++r) {  // fixed order: the sum does not depend on the owner
+        float4 t[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+          t[u] = idx[u] < end ? *reinterpret_cast<const float4*>(peers.grad[r] + idx[u])
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) g[u].x += t[u].x, g[u].y += t[u].y, g[u].z += t[u].z, g[u].w += t[u].w;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint64_t i = idx[u];
+      if (i >= end) continue;
+      const AdamCoef c{lr / bc[0], b1, b2, eps, i >= wd_begin ? wd : 0.f, 1.0f, bc[1]};
+      float4 pp = *reinterpret_cast<const float4*>(peers.param[rank] + i);
+      const uint64_t k = i - begin;
+      float4 mm = *reinterpret_cast<const float4*>(m + k);
+      float4 vv = *reinterpret_cast<const float4*>(v + k);
+      adam_one(pp.x, g[u].x, mm.x, vv.x, c);
+      adam_one(pp.y, g[u].y, mm.y, vv.y, c);
+      adam_one(pp.z, g[u].z, mm.z, vv.z, c);
+      adam_one(pp.w, g[u].w, mm.w, vv.w, c);
+      *reinterpret_cast<float4*>(m + k) = mm;
+      *reinterpret_cast<float4*>(v + k) = vv;
+      const __half2 lo = __floats2half2_rn(pp.x, pp.y), hi = __floats2half2_rn(pp.z, pp.w);
+      const uint32_t lo_b = *reinterpret_cast<const uint32_t*>(&lo), hi_b = *reinterpret_cast<const uint32_t*>(&hi);
+      if (MC_STORE) {
+        mc_st_f32x4(mc_param + i, pp);
+        mc_st_f16x4(mc_param_h + i, lo_b, hi_b);
+      } else {
+        for (uint32_t r = 0; r < world; ++r) {
+          *reinterpret_cast<float4*>(peers.param[r] + i) = pp;
+          *reinterpret_cast<uint2*>(peers.param_h[r] + i) = make_uint2(lo_b, hi_b);
+        }
+      }
+    }
+  }
+}
+
 }  // namespace
 }  // namespace ucsa
 
@@ -117,4 +230,39 @@ extern "C" int ucsa_adam_step(float* param, const float* grad, float* exp_avg, f
                                                                eps, weight_decay, grad_scale_inv, found_inf, bc1,
                                                                sqrtf(bc2), step_dev);
   return check_launch("adam_step");
+}
+
+extern "C" int ucsa_adam_exchange(const uint64_t* grad_ptrs_host, const uint64_t* param_ptrs_host,
+                                  const uint64_t* param_h_ptrs_host, const float* mc_grad, float* mc_param,
+                                  void* mc_param_h, uint32_t world, uint32_t rank, uint64_t begin, uint64_t end,
+                                  uint64_t wd_begin, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
+                                  float beta2, float eps, float weight_decay, uint32_t step, const int32_t* step_dev,
+                                  void* stream) {
+  UCSA_REQUIRE(grad_ptrs_host && param_ptrs_host && param_h_ptrs_host && exp_avg && exp_avg_sq,
+               "adam_exchange: null pointer");
+  UCSA_REQUIRE(world >= 1 && world <= UCSA_MAX_PEERS && rank < world, "adam_exchange: 1 <= world <= %d, rank < world",
+               UCSA_MAX_PEERS);
+  UCSA_REQUIRE(begin % 4 == 0 && end % 4 == 0 && begin <= end && wd_begin % 4 == 0,
+               "adam_exchange: slice bounds must be multiples of 4 parameters");
+  UCSA_REQUIRE(step >= 1 || step_dev != nullptr, "adam_exchange: step counts from 1");
+  const bool multicast = mc_grad != nullptr;
+  UCSA_REQUIRE(!multicast || (mc_param && mc_param_h), "adam_exchange: give all three multicast addresses or none");
+  if (begin == end) return UCSA_OK;
+  PeerPtrs peers{};
+  for (uint32_t r = 0; r < world; ++r) {
+    peers.grad[r] = reinterpret_cast<float*>(grad_ptrs_host[r]);
+    peers.param[r] = reinterpret_cast<float*>(param_ptrs_host[r]);
+    peers.param_h[r] = reinterpret_cast<__half*>(param_h_ptrs_host[r]);
+    UCSA_REQUIRE(peers.grad[r] && peers.param[r] && peers.param_h[r], "adam_exchange: null peer pointer");
+  }
+  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+  const uint64_t tiles = ((end - begin) + 256 * 4 * 4 - 1) / (256 * 4 * 4);  // 256 threads x float4 x kUnroll
+  const uint32_t cap = kNumSMs * 8;
+  const uint32_t blocks = static_cast<uint32_t>(tiles < cap ? tiles : cap);
+  auto kernel = multicast ? adam_exchange_kernel<true, true> : adam_exchange_kernel<false, false>;
+  kernel<<<blocks, 256, 0, as_stream(stream)>>>(peers, mc_grad, mc_param, static_cast<__half*>(mc_param_h), world, rank,
+                                               begin, end, wd_begin, exp_avg, exp_avg_sq, lr, beta1, beta2, eps,
+                                               weight_decay, bc1, sqrtf(bc2), step_dev);
+  return check_launch("adam_exchange");
 }

@@ -5,10 +5,17 @@ with perturb=True, the three losses, backward, Adam on both parameter groups.  H
 libucsa_nerf.so kernels on a static workspace -- no autograd engine, no eager tensor math, no host synchronisation:
 
     step counter += 1 -> zero gradients -> pipeline.forward_chain -> ucsa_nerf_loss -> pipeline.backward_chain
-    -> [NCCL all-reduce of the flat gradient buffer when world > 1] -> ucsa_adam_step x 4
+    -> world == 1 : ucsa_adam_step x 4
+       world  > 1 : barrier -> ucsa_adam_exchange -> barrier           (exchange = "peer", one NVLink domain)
+                    NCCL all-reduce of the flat gradients -> ucsa_adam_step x 4          (exchange = "nccl")
 
 captured once with torch.cuda.graph and replayed every step.  Random numbers and Adam's bias correction read the
-step counter from device memory, so every replay draws fresh samples.  With world > 1 the all-reduce stays outside
+step counter from device memory, so every replay draws fresh samples.
+
+exchange = "peer": gradients, fp32 masters and the fp16 working copies live in symmetric memory; each rank sums the
+gradients of, updates and re-broadcasts 1/world of the flat parameter space in ONE kernel (multimem.ld_reduce /
+multimem.st through the NVSwitch when multicast is available, plain peer loads / stores otherwise), so the whole step
+is one graph and the Adam work per rank shrinks with the world size.  exchange = "nccl" keeps the all-reduce outside
 the graphs (forward/backward graph -> all-reduce -> optimizer graph)."""
 from __future__ import annotations
 
@@ -21,7 +28,7 @@ class TrainEngine:
 
     def __init__(self, net, n_rays, num_steps=256, upsample_steps=256, lr=1e-2, betas=(0.9, 0.99), eps=1e-15,
                  weight_decay_net=1e-6, weight_depth=0.1, weight_semantics=0.04, one_m_to_scene_uom=1.0, seed=0x5EED,
-                 use_graph=True):
+                 use_graph=True, exchange=None):
         self.net = net
         dev = net.encoder.params.device
         self.device = dev
@@ -51,13 +58,39 @@ class TrainEngine:
         self.groups = [(net.encoder, 0.0), (net.sigma_net, weight_decay_net), (net.color_net, weight_decay_net),
                        (net.semantics_net, weight_decay_net)]
         sizes = [m.params.numel() for m, _ in self.groups]
-        self.flat_grad = torch.zeros(sum(sizes), **f32)
+        if exchange is None:
+            exchange = "peer" if parallel.peer_exchange_available() else "nccl"
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer', 'nccl' or None")
+        self.exchange = exchange if self.world > 1 else "none"
+        self.wd_net = weight_decay_net
+        if self.world > 1:  # replicas must start identical (both exchange modes rely on it)
+            for m, _ in self.groups:
+                torch.distributed.broadcast(m.params.data, src=0)
+        if self.exchange == "peer":
+            self.peer = parallel.PeerExchange(sum(sizes), dev)
+            self.flat_grad = self.peer.grad
+            off = 0
+            with torch.no_grad():
+                for (m, _), s in zip(self.groups, sizes):  # re-home masters and fp16 copies in symmetric memory
+                    view = self.peer.param[off:off + s]
+                    view.copy_(m.params.data.reshape(-1))
+                    m.params.data = view.view(m.params.shape)
+                    m._half = self.peer.param_h[off:off + s].view(m.params.shape)
+                    m._half_key = None
+                    off += s
+            n_own = self.peer.end - self.peer.begin
+            self.exp_avg = [torch.zeros(n_own, **f32)]
+            self.exp_avg_sq = [torch.zeros(n_own, **f32)]
+        else:
+            self.peer = None
+            self.flat_grad = torch.zeros(sum(sizes), **f32)
+            self.exp_avg = [torch.zeros_like(m.params) for m, _ in self.groups]
+            self.exp_avg_sq = [torch.zeros_like(m.params) for m, _ in self.groups]
         self.grads, off = [], 0
         for s in sizes:
             self.grads.append(self.flat_grad[off:off + s])
             off += s
-        self.exp_avg = [torch.zeros_like(m.params) for m, _ in self.groups]
-        self.exp_avg_sq = [torch.zeros_like(m.params) for m, _ in self.groups]
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         for m, _ in self.groups:
             m.half_params()
@@ -77,6 +110,13 @@ class TrainEngine:
                                 self.g_sem, *self.grads)
 
     def _optimizer(self):
+        if self.exchange == "peer":
+            self.peer.barrier(0)  # every rank's gradients are complete
+            ops.adam_exchange(self.peer, self.exp_avg[0], self.exp_avg_sq[0], wd_begin=self.groups[0][0].params.numel(),
+                              lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
+                              weight_decay=self.wd_net, step=1, step_dev=self.step_dev)
+            self.peer.barrier(1)  # every rank's parameters are written; gradients may be zeroed again
+            return
         for (m, wd), g, ea, eas in zip(self.groups, self.grads, self.exp_avg, self.exp_avg_sq):
             ops.adam_step(m.params.data, g, ea, eas, m.half_params(), lr=self.lr, beta1=self.betas[0],
                           beta2=self.betas[1], eps=self.eps, weight_decay=wd, grad_scale_inv=1.0, found_inf=None,
@@ -89,6 +129,8 @@ class TrainEngine:
         with torch.cuda.stream(side):  # warm-up outside capture (lazy attribute set-up, allocator)
             for _ in range(2):
                 self._forward_backward()
+                if self.exchange == "nccl":
+                    parallel.all_reduce_gradients(self.flat_grad)
                 self._optimizer()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
@@ -96,9 +138,9 @@ class TrainEngine:
         self._graph_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph_fb):
             self._forward_backward()
-            if self.world == 1:
+            if self.exchange != "nccl":
                 self._optimizer()
-        if self.world > 1:
+        if self.exchange == "nccl":
             self._graph_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph_opt):
                 self._optimizer()
@@ -135,14 +177,14 @@ class TrainEngine:
         """One optimisation step on the loaded batch; returns the device tensor (total, colour, semantic, depth)."""
         if not self.use_graph:
             self._forward_backward()
-            if self.world > 1:
+            if self.exchange == "nccl":
                 parallel.all_reduce_gradients(self.flat_grad)
             self._optimizer()
             return self.loss
         if self._graph_fb is None:
             self._capture()
         self._graph_fb.replay()
-        if self.world > 1:
+        if self.exchange == "nccl":
             parallel.all_reduce_gradients(self.flat_grad)
             self._graph_opt.replay()
         return self.loss

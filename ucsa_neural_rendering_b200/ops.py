@@ -338,6 +338,19 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, param_h, *, lr, beta1, beta2, ep
           "adam_step")
 
 
+def adam_exchange(peer, exp_avg, exp_avg_sq, *, wd_begin, lr, beta1, beta2, eps, weight_decay, step, step_dev=None):
+    """Fused reduce-scatter + Adam + all-gather over peer memory; `peer` is a parallel.PeerExchange.  The caller puts a
+    cross-rank barrier before (gradients complete) and after (parameters visible)."""
+    arr = ctypes.c_uint64 * peer.world
+    mc = peer.multicast
+    check(lib().ucsa_adam_exchange(arr(*peer.grad_ptrs), arr(*peer.param_ptrs), arr(*peer.param_h_ptrs),
+                                   peer.mc_grad if mc else None, peer.mc_param if mc else None,
+                                   peer.mc_param_h if mc else None, peer.world, peer.rank, peer.begin, peer.end,
+                                   int(wd_begin), _ptr(exp_avg, torch.float32), _ptr(exp_avg_sq, torch.float32),
+                                   float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+                                   _ptr(step_dev, torch.int32), _stream()), "adam_exchange")
+
+
 def nerf_loss(image, depth, semantics, gt_rgb, labels, gt_depth, uom, w_sem, w_depth, global_scale, loss4, g_image,
               g_depth, g_semantics):
     n, c = semantics.shape

@@ -1,12 +1,16 @@
 """Multi-GPU plumbing of SURVEY.md section 8(e): one process per GPU, torch.distributed (NCCL on GPUs, gloo in the
 CPU tests).  Host logic only -- no kernel is launched here.
 
-* training  : rays shard (contiguous slice per rank), parameters replicate; ONE all-reduce(sum) over the flat
-              gradient buffer per step, identical optimizer step on every rank, no broadcast afterwards;
+* training  : rays shard (contiguous slice per rank), parameters replicate.  On one NVLink domain the gradient exchange
+              is fused into the optimizer kernel over symmetric (peer-mapped, multicast) memory: each rank sums and
+              updates 1/world of the parameters and writes them to every rank (ucsa_adam_exchange, PeerExchange
+              below).  Fallback: ONE NCCL all-reduce(sum) over the flat gradient buffer + identical Adam everywhere;
 * occupancy : every 16 steps all-reduce(max) of the density grid (ranks see different samples);
 * rendering : views shard round-robin (view % world == rank), no collective on the data path.
 """
 from __future__ import annotations
+
+import os
 
 import torch
 import torch.distributed as dist
@@ -54,3 +58,63 @@ def max_over_ranks(value: float, device=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t)
+
+
+def owner_slice(n_params: int, rank: int, world_size: int):
+    """Parameters [lo, hi) that `rank` sums, updates and broadcasts in the fused exchange: equal slices of whole
+    float4 groups, every parameter exactly once."""
+    quads = (n_params + 3) // 4
+    per = (quads + world_size - 1) // world_size * 4
+    lo = min(rank * per, n_params)
+    return lo, min(lo + per, n_params)
+
+
+class PeerExchange:
+    """Symmetric-memory buffers of one flat parameter space (gradients, fp32 masters, fp16 working copy) and the peer /
+    multicast addresses ucsa_adam_exchange needs.  torch.distributed._symmetric_memory is the plumbing (allocation,
+    handle exchange, the cross-rank barrier kernel); the data path is our kernel."""
+
+    def __init__(self, n_params: int, device):
+        import torch.distributed._symmetric_memory as symm
+
+        self.rank, self.world = world()
+        self.n = n_params
+        self.grad = symm.empty(n_params, dtype=torch.float32, device=device)
+        self.param = symm.empty(n_params, dtype=torch.float32, device=device)
+        self.param_h = symm.empty(n_params, dtype=torch.float16, device=device)
+        self.grad.zero_()
+        self._handles = [symm.rendezvous(t, dist.group.WORLD) for t in (self.grad, self.param, self.param_h)]
+        self.grad_ptrs, self.mc_grad = self._addresses(self.grad, self._handles[0])
+        self.param_ptrs, self.mc_param = self._addresses(self.param, self._handles[1])
+        self.param_h_ptrs, self.mc_param_h = self._addresses(self.param_h, self._handles[2])
+        # multimem through the NVSwitch pays off from about 8 ranks on (see csrc/optim.cu); below that plain peer
+        # loads / stores are faster.  UCSA_PEER_MULTICAST=0/1 overrides.
+        have_mc = bool(self.mc_grad and self.mc_param and self.mc_param_h)
+        want = os.environ.get("UCSA_PEER_MULTICAST", "auto")
+        self.multicast = have_mc and (want == "1" or (want != "0" and self.world > 4))
+        self.begin, self.end = owner_slice(n_params, self.rank, self.world)
+
+    def _addresses(self, tensor, handle):
+        ptrs = [int(p) for p in handle.buffer_ptrs]
+        delta = tensor.data_ptr() - ptrs[self.rank]
+        if not 0 <= delta < handle.buffer_size:
+            raise RuntimeError("symmetric tensor lies outside its rendezvoused buffer")
+        mc = int(handle.multicast_ptr) if handle.multicast_ptr else 0
+        return [p + delta for p in ptrs], (mc + delta if mc else 0)
+
+    def barrier(self, channel: int):
+        """Device-side barrier over all ranks on the current stream (CUDA-graph capturable)."""
+        self._handles[0].barrier(channel=channel)
+
+
+def peer_exchange_available() -> bool:
+    """Symmetric memory needs an initialised NCCL group whose ranks share one NVLink / P2P domain."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return False
+    if dist.get_backend() != "nccl":
+        return False
+    try:
+        import torch.distributed._symmetric_memory  # noqa: F401
+    except Exception:  # noqa: BLE001
+        return False
+    return True
