@@ -159,7 +159,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ CUDA arm
@@ -361,12 +361,35 @@ def run_ours(args):
                                   and engine.peer.multicast else "peer loads / stores")}[engine.exchange],
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result: everything else a library writes there (NCCL's version
+    banner, warnings) is sent to stderr by re-pointing file descriptor 1 for the rest of the run."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
