@@ -306,6 +306,33 @@ def run_ours(args):
     e2e_engine_ms = max_over_ranks(e0.elapsed_time(e1))
     e2e_engine_value = world * RAYS_PER_GPU * args.steps / (e2e_engine_ms * 1e-3)
 
+    # ---------------------------------------------------------------- extra: full-frame rendering
+    # one 640x480 view per rank (views shard, no collective), staged in chunks, no perturbation; reported beside the
+    # headline, not part of it
+    render_chunk = 65536
+    view_pix = torch.arange(scene.W * scene.H, device=dev)
+    net.eval()
+    with torch.no_grad():
+        vo, vd, vdn = scene.rays(rank % scene.n_views, view_pix)
+        render_args = dict(direction_norms=vdn.view(1, -1, 1), staged=True, max_ray_batch=render_chunk, bg_color=None,
+                           perturb=False, seed=99)
+        for _ in range(2):
+            out = net.render(vo[None], vd[None], **render_args)
+        n_views = 3
+        barrier()
+        e0.record()
+        for _ in range(n_views):
+            out = net.render(vo[None], vd[None], **render_args)
+            labels_u8 = out["semantics"].argmax(-1).to(torch.uint8)  # the label map a caller writes out
+        e1.record()
+        barrier()
+    net.train()
+    render_ms = max_over_ranks(e0.elapsed_time(e1)) / n_views
+    render_info = {"rays_per_s": world * scene.W * scene.H / (render_ms * 1e-3), "views_per_s": world / (render_ms * 1e-3),
+                   "ms_per_view": render_ms, "rays_per_view": scene.W * scene.H, "chunk": render_chunk,
+                   "samples_per_ray": NUM_STEPS + UPSAMPLE_STEPS, "api": "SemanticNeRFNetwork.render(staged=True)"}
+    del labels_u8
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -323,12 +350,24 @@ def run_ours(args):
     dur_ms = statistics.mean(kernel_ms[dominant])
     alg_bytes = ENCODE_BYTES_PER_SAMPLE * samples_per_launch[dominant]
     achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes per launch of the same kernel from the committed ncu capture (scripts/summarize_ncu.py traffic)
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            tj = json.load(fh)
+        traffic = tj["bytes_per_launch"].get(dominant.replace("ucsa_", "") + "_tc_kernel")
+        traffic_src = tj["source"]
+    except (OSError, ValueError, KeyError):
+        pass
+    compulsory = 76 * samples_per_launch[dominant] + 13_074_912 * (2 if dominant == "ucsa_density_fwd" else 4)
     roofline = {
-        "bound": "hbm", "kernel": dominant.replace("ucsa_", "") + "_kernel", "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": dur_ms,
-        "note": "588 B/sample counts the 512 B of table gathers/scatters, which hit the L2-resident fp16 table "
-                "rather than HBM; see DESIGN.md",
+        "bound": "hbm", "kernel": dominant.replace("ucsa_", "") + "_tc_kernel", "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": dur_ms,
+        "hbm_compulsory": {"bytes_per_launch": compulsory, "achieved": compulsory / (dur_ms * 1e-3) / 1e9,
+                           "note": "76 B/sample (xyz, features, saved activations) + the table once (SURVEY 8d)"},
+        "note": "588 B/sample counts the 512 B of table gathers/scatters, which hit the L2-resident table rather "
+                "than HBM (traffic = measured DRAM bytes of the launch); the kernel is bound by L2 reduction / L1 "
+                "gather throughput, see DESIGN.md sections 5 and 9",
         "kernel_ms_per_step": {k.replace("ucsa_", ""): totals[k] / args.steps for k in totals},
     }
 
@@ -355,6 +394,7 @@ def run_ours(args):
                            "api": "TrainEngine.load_batch(pinned host) + step() + loss readback"}},
         "gpu_launches": launches, "gpu_launches_per_step": by_name,
         "step_impl": "cuda-graph replay of %d kernels" % per_step_launches if not args.no_graph else "eager kernel chain",
+        "render": render_info,
         "gradient_exchange": {"none": "single GPU", "nccl": "NCCL all-reduce + replicated Adam",
                               "peer": "ucsa_adam_exchange over symmetric memory (%s)" % (
                                   "multimem.ld_reduce / multimem.st via NVSwitch" if engine.peer is not None

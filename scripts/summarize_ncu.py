@@ -79,5 +79,28 @@ def full(src, dst):
     print(open(dst).read())
 
 
+def traffic(src, dst):
+    """DRAM bytes (read + write) per launch of every profiled kernel -> JSON that bench.py reports as roofline.traffic"""
+    import json
+
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    acc = {}
+    for row in rows[2:]:
+        name = row[hdr.index("Kernel Name")].split("(")[0].split("::")[-1].split("<")[0]
+        total = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(m)
+            total += float(row[i].replace(",", "")) * scale[units[i]]
+        acc.setdefault(name, []).append(total)
+    out = {"source": src, "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full), mean over "
+           "the profiled launches", "bytes_per_launch": {k: sum(v) / len(v) for k, v in acc.items()}}
+    with open(dst, "w") as fh:
+        json.dump(out, fh, indent=1)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
