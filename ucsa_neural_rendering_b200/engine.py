@@ -67,8 +67,22 @@ class TrainEngine:
         if self.world > 1:  # replicas must start identical (both exchange modes rely on it)
             for m, _ in self.groups:
                 torch.distributed.broadcast(m.params.data, src=0)
+        self.peer = None
         if self.exchange == "peer":
-            self.peer = parallel.PeerExchange(sum(sizes), dev)
+            # symmetric memory needs peer access between all ranks; agree on the outcome before relying on it
+            try:
+                self.peer = parallel.PeerExchange(sum(sizes), dev)
+                ok = 1.0
+            except Exception as exc:  # noqa: BLE001 - any failure means "use NCCL", never a silent CPU path
+                import sys
+
+                sys.stderr.write(f"[ucsa] peer-memory gradient exchange unavailable ({exc!r}); using NCCL all-reduce\n")
+                ok = 0.0
+            flag = torch.tensor([ok], device=dev)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+            if float(flag) == 0.0:
+                self.peer, self.exchange = None, "nccl"
+        if self.exchange == "peer":
             self.flat_grad = self.peer.grad
             off = 0
             with torch.no_grad():
@@ -83,7 +97,6 @@ class TrainEngine:
             self.exp_avg = [torch.zeros(n_own, **f32)]
             self.exp_avg_sq = [torch.zeros(n_own, **f32)]
         else:
-            self.peer = None
             self.flat_grad = torch.zeros(sum(sizes), **f32)
             self.exp_avg = [torch.zeros_like(m.params) for m, _ in self.groups]
             self.exp_avg_sq = [torch.zeros_like(m.params) for m, _ in self.groups]
