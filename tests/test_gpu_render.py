@@ -286,3 +286,51 @@ def test_fused_heads_match_cuda_core_heads_plus_composite_kernels(n, t):
     # for that row: tolerate a 1e-5 fraction of such elements, hold everything else to the tolerance
     bad = (a - b).abs() > 2e-2 * b.abs() + 1e-2 * float(b.abs().max())
     assert float(bad.float().mean()) < 1e-5, float(bad.float().mean())
+
+
+def test_config2_full_size_properties():
+    """BASELINE config 2 sizes (4096 rays x 256+256 samples, 40 classes) through size-independent properties:
+    determinism for a fixed seed, value ranges, the opacity checksum linking semantics and depth, and linearity of the
+    backward pass (the oracle needs minutes at this size)."""
+    from ucsa_neural_rendering_b200 import ops
+    from ucsa_neural_rendering_b200.scene import SyntheticScene
+
+    heads = live_path.OracleHeads(bound=4, num_semantic_classes=40, seed=3, hash_amp=0.3)
+    net = _net_from_oracle(heads)
+    net.train()
+    scene = SyntheticScene(seed=0, device=DEV)
+    n = 4096
+    g = torch.Generator(device=DEV).manual_seed(2)
+    pix = torch.randint(0, scene.W * scene.H, (n,), device=DEV, generator=g)
+    o, d, dn = scene.rays(3, pix)
+    args = dict(direction_norms=dn.view(1, n, 1), staged=False, perturb=True, seed=77)
+
+    def run(weights):
+        net.zero_grad(set_to_none=True)
+        out = net.render(o[None], d[None], **args)
+        loss = sum(w * out[k].sum() for k, w in weights.items())
+        loss.backward()
+        return {k: v.detach()[0] for k, v in out.items()}, torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+
+    out1, g_img = run({"image": 1.0})
+    out2, g_dep = run({"depth": 1.0})
+    out3, g_mix = run({"image": 1.0, "depth": 2.0})
+    for k in out1:  # same seed, same samples: equal up to the order of the fused compositing's atomics
+        assert torch.isfinite(out1[k]).all()
+        torch.testing.assert_close(out1[k], out2[k], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(out1[k], out3[k], rtol=1e-5, atol=1e-6)
+    image, sem, depth = out1["image"], out1["semantics"], out1["depth"]
+    assert float(image.min()) >= 0 and float(image.max()) <= 1 + 1e-4
+    assert float(sem.min()) >= 0
+    opacity = sem.sum(-1)  # soft-max rows sum to one: sum_c semantics = sum of the masked-in weights
+    assert float(opacity.max()) <= 1 + 1e-4 and float(opacity.mean()) > 0.5
+    nears, fars = ops.near_far_from_aabb(o, d, net.aabb_train)
+    wz = depth * dn.view(-1)  # = sum of masked-in w * z, which lies between near * opacity and far * opacity
+    assert bool((wz <= fars * opacity * (1 + 1e-4) + 1e-4).all()) and bool((wz >= nears * opacity * (1 - 1e-4) - 1e-4).all())
+    # backward is linear in the output gradients
+    assert torch.isfinite(g_mix).all()
+    want = g_img + 2.0 * g_dep
+    scale = float(want.abs().max())
+    bad = (g_mix - want).abs() > 3e-2 * want.abs() + 1e-2 * scale
+    assert float(bad.float().mean()) < 1e-5, float(bad.float().mean())
+    assert float(g_img.abs().max()) > 0 and float(g_dep.abs().max()) > 0
