@@ -131,7 +131,8 @@ UCSA_API int ucsa_compact_masked(const float* w_sorted, const float* z_cat, cons
                         uint32_t n_rays, uint32_t t, int32_t* sel, float* w_sel, float* z_sel, void* stream);
 
 /* ---- a7/a12/a13 (+a14 fused). colour + semantic heads on the K masked-in rows (network_tcnn_semantics.py:147-207)
- * and, when image/semantics are non-null, the compositing of renderer_semantics.py:279-285 in the same kernel:
+ * (two kernels: colour, then semantics) and, when image/semantics are non-null, the compositing of
+ * renderer_semantics.py:279-285 fused into them:
  * image [N,3] += sum w*rgb, semantics [N,C] += sum w*softmax(logits) (atomicAdd; the caller zero-fills them).
  * K is read on the device from ray_off[n_rays]; k_max bounds the launch.  rgb [K,3] f32 (fp16 sigmoid values);
  * logits fp16 [K,48] row-major, optional (may be null: the backward pass recomputes them).

@@ -80,7 +80,7 @@ _lib = None
 
 _DEBUG_SYNC = os.environ.get("UCSA_DEBUG_SYNC", "0") == "1"
 HOST_ONLY = {"ucsa_abi_version", "ucsa_last_error_string", "ucsa_grid_desc_init"}
-KERNELS_PER_CALL = {"ucsa_heads_bwd": 2}  # colour + semantic kernels; every other entry point enqueues one kernel
+KERNELS_PER_CALL = {"ucsa_heads_fwd": 2, "ucsa_heads_bwd": 2}  # colour + semantic kernels; all others enqueue one
 
 
 class LaunchStats:

@@ -3,10 +3,10 @@
 // Rows a7, a12, a13 and their backward of SURVEY.md section 8 (network_tcnn_semantics.py:147-207).
 //
 // The reference evaluates the heads only where w > 1e-4 (boolean-mask gather / scatter, :159-161,:174); here the
-// K surviving rows arrive as the compact list `sel` (row -> n*T+slot) built by compact_masked.  Per 128-row tile
-// the two networks advance together: one commit covers the colour and the semantic product of a stage, so the
-// forward pass needs three MMA round trips and the backward pass three data-gradient round trips; the five
-// weight gradients accumulate in TMEM across all tiles of the persistent CTA.
+// K surviving rows arrive as the compact list `sel` (row -> n*T+slot) built by compact_masked.  Colour and semantic
+// networks run in separate kernels, forward and backward, so that each CTA carries only its own weights, tiles and
+// TMEM columns and four to five CTAs are resident per SM; the weight gradients accumulate in TMEM across all tiles
+// of a persistent CTA.
 //
 // The hidden activations saved for the backward pass (hc1, hc2, hs) are tile-layout buffers (mlp_umma.cuh): tile i
 // of the compact row list is one contiguous 16 KB block, written and read back with single bulk copies.  The
@@ -29,27 +29,7 @@ constexpr uint32_t kWc2 = 64 / 8 * Tile<64>::kGroupBytes;
 constexpr uint32_t kWc3 = 16 / 8 * Tile<64>::kGroupBytes;
 constexpr uint32_t kWs1 = 64 / 8 * Tile<16>::kGroupBytes;
 constexpr uint32_t kWs2 = kSemOut / 8 * Tile<64>::kGroupBytes;
-constexpr uint32_t kWeightBytes = kWc1 + kWc2 + kWc3 + kWs1 + kWs2;
-
-struct WeightTiles {
-  uint32_t c1, c2, c3, s1, s2;  // shared-space addresses
-};
-
-__device__ __forceinline__ WeightTiles load_weights(unsigned char* base, const __half* __restrict__ w_color,
-                                                    const __half* __restrict__ w_sem) {
-  unsigned char* c1 = base;
-  unsigned char* c2 = c1 + kWc1;
-  unsigned char* c3 = c2 + kWc2;
-  unsigned char* s1 = c3 + kWc3;
-  unsigned char* s2 = s1 + kWs1;
-  umma::load_weight_tile<32>(c1, w_color + kColorW1, 64);
-  umma::load_weight_tile<64>(c2, w_color + kColorW2, 64);
-  umma::load_weight_tile<64>(c3, w_color + kColorW3, 16);
-  umma::load_weight_tile<16>(s1, w_sem + kSemW1, 64);
-  umma::load_weight_tile<64>(s2, w_sem + kSemW2, kSemOut);
-  return WeightTiles{umma::smem_u32(c1), umma::smem_u32(c2), umma::smem_u32(c3), umma::smem_u32(s1),
-                     umma::smem_u32(s2)};
-}
+constexpr uint32_t kColorWeightBytesFwd = kWc1 + kWc2 + kWc3, kSemWeightBytesFwd = kWs1 + kWs2;
 
 // the semantic input row [geo_feat(15) | 1] as two 16-byte chunks
 __device__ __forceinline__ void geo_chunks(const __half* __restrict__ h, uint32_t flat, bool valid, H8& g0, H8& g1) {
@@ -107,43 +87,111 @@ __device__ __forceinline__ void build_inputs(const float* __restrict__ rays_d, c
   }
 }
 
-// Forward shared memory / TMEM plan (3 CTAs per SM):
-//   region A = [in_c 8K | in_s 4K | hs 16K]   later re-used as `part`, the fp32 staging of the fused compositing
-//   region B = [h1 16K]                       later re-used for h2 (layer 2 has consumed h1 by then)
-//   TMEM     = acc0 [0,64): colour layers 1,2,3 in turn; acc1 [64,128): semantic layer 1, then the 48 logits
-constexpr uint32_t kFwdCols = 128;
-constexpr int kFwdCtasPerSm = 3;
-// per-tile staging of w * (probabilities | rgb) for the fused compositing: [128 rows][kPartLd] fp32, odd stride
-constexpr int kPartLd = kSemOut + 5;
+// ---------------------------------------------------------------------------------------------- forward
+// Two kernels (colour, semantics), like the backward pass: each keeps only its own weights and tiles, so that five /
+// six CTAs are resident per SM instead of three and the dependent stages of more tiles overlap.
+//   colour   : weights 14 KB, tiles in_c 8 KB + h 16 KB (h1, later h2);            TMEM 64 columns; 5 CTAs / SM
+//   semantics: weights  8 KB, tiles in_s 4 KB + hs 16 KB, re-used (plus 7 KB) as the fp32 staging `part` of the
+//              fused compositing;                                                   TMEM 64 columns; 5 CTAs / SM
+// Fused compositing (renderer_semantics.py:279-285): every thread stages w * value of its row, then one thread per
+// (row segment, column) walks the rows - the rows of a ray are contiguous - and flushes one atomicAdd per
+// (ray, column) run.
+constexpr uint32_t kFwdTmemCols = 64;
+constexpr int kFwdColorCtas = 5, kFwdSemCtas = 5;
+constexpr int kPartLd = kSemOut + 1;  // odd stride: conflict-free row-wise writes and column-wise reads
 constexpr uint32_t kPartBytes = 128 * kPartLd * sizeof(float);
-constexpr uint32_t kRegionA = Tile<32>::kBytes + Tile<16>::kBytes + Tile<64>::kBytes;
-static_assert(kPartBytes <= kRegionA, "compositing staging must fit the re-used input tiles");
-constexpr uint32_t kFwdSmem = kWeightBytes + kRegionA + Tile<64>::kBytes + 128 * sizeof(int) + 64;
+constexpr uint32_t kFwdColorSmem = kColorWeightBytesFwd + Tile<32>::kBytes + Tile<64>::kBytes + 128 * 4 * sizeof(float) +
+                                   128 * sizeof(int) + 64;
+constexpr uint32_t kFwdSemSmem = kSemWeightBytesFwd + kPartBytes + 128 * sizeof(int) + 64;
+static_assert(Tile<16>::kBytes + Tile<64>::kBytes <= kPartBytes, "the semantic tiles live inside the staging region");
+static_assert(kFwdColorCtas * (kFwdColorSmem + 1024) <= 227 * 1024 && kFwdSemCtas * (kFwdSemSmem + 1024) <= 227 * 1024,
+              "forward heads: shared memory of the resident CTAs");
 
-__global__ void __launch_bounds__(128)
-heads_fwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__ k_ptr, uint32_t t,
-                    const float* __restrict__ rays_d, const __half* __restrict__ h,
-                    const __half* __restrict__ w_color, const __half* __restrict__ w_sem, int n_classes,
-                    const float* __restrict__ w_sel, float* __restrict__ rgb, __half* __restrict__ logits,
-                    __half* __restrict__ hc1, __half* __restrict__ hc2, __half* __restrict__ hs,
-                    float* __restrict__ image, float* __restrict__ semantics) {
+// Run structure of a tile for the fused compositing.  Rows of a ray are contiguous in the compact list, so a tile is
+// a few runs of equal ray id.  Each thread publishes its row's ray id; bit `row` of heads[row / 32] says "this row
+// starts a new run" (the id of the previous row comes from the neighbouring lane, or from sel[] for a warp's first
+// lane).  Rows past K carry id -1 and form a last run that is skipped.
+__device__ __forceinline__ void publish_runs(const int32_t* __restrict__ sel, uint32_t r, uint32_t k_rows, uint32_t t,
+                                             int id, int* ray_of_row, uint32_t* heads) {
+  const int lane = threadIdx.x & 31;
+  int prev = __shfl_up_sync(kFullMask, id, 1);
+  if (lane == 0) {
+    if (threadIdx.x == 0) prev = -2;  // the first row of a tile always starts a run
+    else prev = (r - 1 < k_rows) ? static_cast<int>(static_cast<uint32_t>(sel[r - 1]) / t) : -1;
+  }
+  const uint32_t mask = __ballot_sync(kFullMask, id != prev);
+  ray_of_row[threadIdx.x] = id;
+  if (lane == 0) heads[threadIdx.x >> 5] = mask;
+}
+
+// first row in (a, r1) that starts a run, or r1
+__device__ __forceinline__ int next_run(const uint32_t* heads, int a, int r1) {
+  int row = a + 1;
+  while (row < r1) {
+    const uint32_t w = heads[row >> 5] >> (row & 31);
+    if (w != 0u) {
+      row += __ffs(w) - 1;
+      return row < r1 ? row : r1;
+    }
+    row = (row | 31) + 1;
+  }
+  return r1;
+}
+
+// dst[ray][col] += sum over the ray's rows of part[row][col]: one thread per (row segment, column); inside a run the
+// sum is branch-free with four independent accumulators, one atomicAdd per (run, column, segment)
+__device__ __forceinline__ void composite_flush(const float* part, int ld, const int* ray_of_row, const uint32_t* heads,
+                                                int n_col, float* __restrict__ dst, int dst_ld) {
+  const int n_seg = 128 / n_col > 4 ? 4 : (128 / n_col > 0 ? 128 / n_col : 1);  // 40 classes: 3 segments
+  const int rows = (128 + n_seg - 1) / n_seg;
+  const int seg = threadIdx.x / n_col, col = threadIdx.x % n_col;
+  if (seg >= n_seg) return;
+  const int r0 = seg * rows, r1 = r0 + rows < 128 ? r0 + rows : 128;
+  int a = r0;
+  while (a < r1) {
+    const int b = next_run(heads, a, r1);
+    const int id = ray_of_row[a];
+    if (id >= 0) {
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+      const float* p = part + a * ld + col;
+      int rr = a;
+      for (; rr + 3 < b; rr += 4, p += 4 * ld) {
+        acc0 += p[0];
+        acc1 += p[ld];
+        acc2 += p[2 * ld];
+        acc3 += p[3 * ld];
+      }
+      for (; rr < b; ++rr, p += ld) acc0 += p[0];
+      atomicAdd(dst + static_cast<uint64_t>(id) * dst_ld + col, (acc0 + acc1) + (acc2 + acc3));
+    }
+    a = b;
+  }
+}
+
+__global__ void __launch_bounds__(128, kFwdColorCtas)
+heads_fwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__ k_ptr, uint32_t t,
+                       const float* __restrict__ rays_d, const __half* __restrict__ h,
+                       const __half* __restrict__ w_color, const float* __restrict__ w_sel, float* __restrict__ rgb,
+                       __half* __restrict__ hc1, __half* __restrict__ hc2, float* __restrict__ image) {
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* t_in_c = smem + kWeightBytes;          // region A
-  unsigned char* t_in_s = t_in_c + Tile<32>::kBytes;
-  unsigned char* t_hs = t_in_s + Tile<16>::kBytes;
-  float* part = reinterpret_cast<float*>(t_in_c);       // region A again, once its three tiles are consumed
-  unsigned char* t_h1 = t_in_c + kRegionA;              // region B
-  unsigned char* t_h2 = t_h1;
-  int* ray_of_row = reinterpret_cast<int*>(t_h1 + Tile<64>::kBytes);
+  unsigned char* wc1 = smem;
+  unsigned char* wc2 = wc1 + kWc1;
+  unsigned char* wc3 = wc2 + kWc2;
+  unsigned char* t_in_c = wc3 + kWc3;
+  unsigned char* t_h = t_in_c + Tile<32>::kBytes;  // h1, then h2 (layer 2 has consumed h1 by then)
+  float* part = reinterpret_cast<float*>(t_h + Tile<64>::kBytes);  // [128][4]: w * rgb
+  int* ray_of_row = reinterpret_cast<int*>(part + 128 * 4);
   unsigned char* tail = reinterpret_cast<unsigned char*>(ray_of_row + 128);
   uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
   uint32_t* slot = reinterpret_cast<uint32_t*>(tail + 8);
+  uint32_t* heads = reinterpret_cast<uint32_t*>(tail + 16);  // [4] run-start bits of the tile's rows
+  umma::load_weight_tile<32>(wc1, w_color + kColorW1, 64);
+  umma::load_weight_tile<64>(wc2, w_color + kColorW2, 64);
+  umma::load_weight_tile<64>(wc3, w_color + kColorW3, 16);
+  umma::Ctx ctx = umma::ctx_init(slot, bar, kFwdTmemCols);
+  const uint32_t s_in_c = umma::smem_u32(t_in_c), s_h = umma::smem_u32(t_h), b1 = umma::smem_u32(wc1),
+                 b2 = umma::smem_u32(wc2), b3 = umma::smem_u32(wc3);
   const bool fuse_composite = image != nullptr;
-  const WeightTiles w = load_weights(smem, w_color, w_sem);
-  umma::Ctx ctx = umma::ctx_init(slot, bar, kFwdCols);
-  const uint32_t s_in_c = umma::smem_u32(t_in_c), s_in_s = umma::smem_u32(t_in_s), s_h1 = umma::smem_u32(t_h1),
-                 s_hs = umma::smem_u32(t_hs), s_h2 = umma::smem_u32(t_h2);
-  constexpr uint32_t kAcc0 = 0, kAcc1 = 64, kAcc2 = 64;
   const uint64_t stream = l2_policy_stream();
 
   const uint32_t k_rows = static_cast<uint32_t>(*k_ptr);
@@ -153,45 +201,123 @@ heads_fwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__
     const bool valid = r < k_rows;
     const uint32_t flat = valid ? static_cast<uint32_t>(sel[r]) : 0u;
     const float w_row = (valid && fuse_composite) ? w_sel[r] : 0.f;
-    float* my_part = part + threadIdx.x * kPartLd;
-    build_inputs(rays_d, h, flat, t, valid, t_in_c, t_in_s);
+    build_inputs(rays_d, h, flat, t, valid, t_in_c, nullptr);
     ctx.publish();
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
-      umma::issue_fwd<32, 64>(ctx.tmem + kAcc0, s_in_c, w.c1);
-      umma::issue_fwd<16, 64>(ctx.tmem + kAcc1, s_in_s, w.s1);
+      umma::issue_fwd<32, 64>(ctx.tmem, s_in_c, b1);
       umma::commit(ctx.bar);
     }
     ctx.wait();
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 16) {
-      umma::acc_to_tile16<64, true>(ctx, kAcc0 + c0, t_h1, c0);
-      umma::acc_to_tile16<64, true>(ctx, kAcc1 + c0, t_hs, c0);
-    }
+    for (int c0 = 0; c0 < 64; c0 += 16) umma::acc_to_tile16<64, true>(ctx, c0, t_h, c0);
     ctx.publish();
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
-      umma::issue_fwd<64, 64>(ctx.tmem + kAcc0, s_h1, w.c2);
-      umma::issue_fwd<64, kSemOut>(ctx.tmem + kAcc2, s_hs, w.s2);
-      if (hc1 != nullptr) {
-        // save the two hidden tiles while the products run; the commit is held back until the copies have read
-        // shared memory, because the next epilogue overwrites both tiles (h2 and `part` alias them)
-        umma::bulk_store(umma::tile_block<64>(hc1, tile), s_h1, Tile<64>::kBytes, stream);
-        umma::bulk_store(umma::tile_block<64>(hs, tile), s_hs, Tile<64>::kBytes, stream);
+      umma::issue_fwd<64, 64>(ctx.tmem, s_h, b2);
+      if (hc1 != nullptr) {  // the commit waits for the copy's reads: the next epilogue overwrites the tile
+        umma::bulk_store(umma::tile_block<64>(hc1, tile), s_h, Tile<64>::kBytes, stream);
         umma::bulk_store_fence_reads();
       }
       umma::commit(ctx.bar);
     }
     ctx.wait();
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 16) umma::acc_to_tile16<64, true>(ctx, kAcc0 + c0, t_h2, c0);
+    for (int c0 = 0; c0 < 64; c0 += 16) umma::acc_to_tile16<64, true>(ctx, c0, t_h, c0);
+    ctx.publish();
+    if (threadIdx.x == 0) {
+      umma::tc_fence_after();
+      umma::issue_fwd<64, 16>(ctx.tmem, s_h, b3);
+      if (hc2 != nullptr) {
+        umma::bulk_store(umma::tile_block<64>(hc2, tile), s_h, Tile<64>::kBytes, stream);
+        umma::bulk_store_fence_reads();
+      }
+      umma::commit(ctx.bar);
+    }
+    ctx.wait();
+    float v[16];
+    umma::tmem_ld16(ctx.lane_addr(0), v);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float x = round_h(v[c]);
+      const float col = round_h(1.0f / (1.0f + expf(-x)));  // fp16 sigmoid under autocast
+      if (valid) rgb[static_cast<uint64_t>(r) * 3 + c] = col;
+      if (fuse_composite) part[threadIdx.x * 4 + c] = w_row * col;
+    }
+    if (fuse_composite) {  // image_n = sum_rows w * rgb
+      publish_runs(sel, r, k_rows, t, valid ? static_cast<int>(flat / t) : -1, ray_of_row, heads);
+      __syncthreads();
+      composite_flush(part, 4, ray_of_row, heads, 3, image, 3);
+      // the next tile reaches two CTA barriers before it writes part / ray_of_row again
+    }
+  }
+  umma::ctx_free(ctx, kFwdTmemCols);
+}
+
+__global__ void __launch_bounds__(128, kFwdSemCtas)
+heads_fwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__ k_ptr, uint32_t t,
+                     const __half* __restrict__ h, const __half* __restrict__ w_sem, int n_classes,
+                     const float* __restrict__ w_sel, __half* __restrict__ logits, __half* __restrict__ hs,
+                     float* __restrict__ semantics) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* ws1 = smem;
+  unsigned char* ws2 = ws1 + kWs1;
+  unsigned char* t_in_s = ws2 + kWs2;                     // staging region: [in_s 4 KB | hs 16 KB | ...]
+  unsigned char* t_hs = t_in_s + Tile<16>::kBytes;
+  float* part = reinterpret_cast<float*>(t_in_s);         // ... re-used as w * softmax once both tiles are consumed
+  int* ray_of_row = reinterpret_cast<int*>(t_in_s + kPartBytes);
+  unsigned char* tail = reinterpret_cast<unsigned char*>(ray_of_row + 128);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(tail + 8);
+  uint32_t* heads = reinterpret_cast<uint32_t*>(tail + 16);
+  umma::load_weight_tile<16>(ws1, w_sem + kSemW1, 64);
+  umma::load_weight_tile<64>(ws2, w_sem + kSemW2, kSemOut);
+  umma::Ctx ctx = umma::ctx_init(slot, bar, kFwdTmemCols);
+  const uint32_t s_in_s = umma::smem_u32(t_in_s), s_hs = umma::smem_u32(t_hs), b1 = umma::smem_u32(ws1),
+                 b2 = umma::smem_u32(ws2);
+  const bool fuse_composite = semantics != nullptr;
+  const uint64_t stream = l2_policy_stream();
+
+  const uint32_t k_rows = static_cast<uint32_t>(*k_ptr);
+  const uint32_t n_tiles = (k_rows + 127) / 128;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t r = tile * 128 + threadIdx.x;
+    const bool valid = r < k_rows;
+    const uint32_t flat = valid ? static_cast<uint32_t>(sel[r]) : 0u;
+    const float w_row = (valid && fuse_composite) ? w_sel[r] : 0.f;
+    {
+      H8 g0, g1;
+      geo_chunks(h, flat, valid, g0, g1);
+      *Tile<16>::chunk(t_in_s, threadIdx.x, 0) = g0.v;
+      *Tile<16>::chunk(t_in_s, threadIdx.x, 1) = g1.v;
+    }
+    ctx.publish();
+    if (threadIdx.x == 0) {
+      umma::tc_fence_after();
+      umma::issue_fwd<16, 64>(ctx.tmem, s_in_s, b1);
+      umma::commit(ctx.bar);
+    }
+    ctx.wait();
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) umma::acc_to_tile16<64, true>(ctx, c0, t_hs, c0);
+    ctx.publish();
+    if (threadIdx.x == 0) {
+      umma::tc_fence_after();
+      umma::issue_fwd<64, kSemOut>(ctx.tmem, s_hs, b2);
+      if (hs != nullptr) {  // the commit waits for the copy's reads: `part` overwrites the tile below
+        umma::bulk_store(umma::tile_block<64>(hs, tile), s_hs, Tile<64>::kBytes, stream);
+        umma::bulk_store_fence_reads();
+      }
+      umma::commit(ctx.bar);
+    }
+    ctx.wait();
     {
       // the row's logits: fp16 like the reference's network output, kept in registers for the soft-max
       float lg[kSemOut];
 #pragma unroll
       for (int c0 = 0; c0 < kSemOut; c0 += 16) {
         float v[16];
-        umma::tmem_ld16(ctx.lane_addr(kAcc2 + c0), v);
+        umma::tmem_ld16(ctx.lane_addr(c0), v);
         H8 a, b;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -214,64 +340,26 @@ heads_fwd_tc_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__
         float sum = 0.f;
 #pragma unroll
         for (int c = 0; c < kSemOut; ++c) {
-          lg[c] = c < n_classes ? expf(lg[c] - m) : 0.f;
-          sum += lg[c];
+          if (c < n_classes) {  // (uniform) columns past the class count are never staged nor read
+            lg[c] = __expf(lg[c] - m);
+            sum += lg[c];
+          }
         }
         const float scale = w_row / sum;
+        float* my_part = part + threadIdx.x * kPartLd;
 #pragma unroll
-        for (int c = 0; c < kSemOut; ++c) my_part[c] = lg[c] * scale;
+        for (int c = 0; c < kSemOut; ++c)
+          if (c < n_classes) my_part[c] = lg[c] * scale;
       }
-    }
-    ctx.publish();
-    if (threadIdx.x == 0) {
-      umma::tc_fence_after();
-      umma::issue_fwd<64, 16>(ctx.tmem + kAcc0, s_h2, w.c3);
-      if (hc2 != nullptr) {
-        umma::bulk_store(umma::tile_block<64>(hc2, tile), s_h2, Tile<64>::kBytes, stream);
-        umma::bulk_store_fence_reads();  // the next tile's first epilogue overwrites h2's bytes (as h1)
-      }
-      umma::commit(ctx.bar);
-    }
-    ctx.wait();
-    float v[16];
-    umma::tmem_ld16(ctx.lane_addr(kAcc0), v);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float x = round_h(v[c]);
-      const float col = round_h(1.0f / (1.0f + expf(-x)));  // fp16 sigmoid under autocast
-      if (valid) rgb[static_cast<uint64_t>(r) * 3 + c] = col;
-      if (fuse_composite) my_part[kSemOut + c] = w_row * col;
     }
     if (fuse_composite) {
-      // image_n = sum_rows w * rgb ; rows of a ray are contiguous, so each column thread walks its rows and flushes
-      // one atomicAdd per (ray, column) segment
-      ray_of_row[threadIdx.x] = valid ? static_cast<int>(flat / t) : -1;
+      publish_runs(sel, r, k_rows, t, valid ? static_cast<int>(flat / t) : -1, ray_of_row, heads);
       __syncthreads();
-      const int n_col = n_classes + 3;
-      const int seg = threadIdx.x / n_col, col = threadIdx.x % n_col;
-      if (seg < 2) {
-        const int src_col = col < n_classes ? col : kSemOut + (col - n_classes);
-        int cur = -1;
-        float acc = 0.f;
-        for (int rr = seg * 64; rr < seg * 64 + 64; ++rr) {
-          const int id = ray_of_row[rr];
-          if (id != cur) {
-            if (cur >= 0)
-              atomicAdd(col < n_classes ? semantics + static_cast<uint64_t>(cur) * n_classes + col
-                                        : image + static_cast<uint64_t>(cur) * 3 + (col - n_classes), acc);
-            cur = id;
-            acc = 0.f;
-          }
-          acc += part[rr * kPartLd + src_col];
-        }
-        if (cur >= 0)
-          atomicAdd(col < n_classes ? semantics + static_cast<uint64_t>(cur) * n_classes + col
-                                    : image + static_cast<uint64_t>(cur) * 3 + (col - n_classes), acc);
-      }
+      composite_flush(part, kPartLd, ray_of_row, heads, n_classes, semantics, n_classes);
       __syncthreads();  // part[] lives in the input tiles: the next tile may only rebuild them after the reads
     }
   }
-  umma::ctx_free(ctx, kFwdCols);
+  umma::ctx_free(ctx, kFwdTmemCols);
 }
 
 template <int N, bool TRANSPOSED>
@@ -509,7 +597,7 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
         float sum = 0.f;
 #pragma unroll
         for (int c = 0; c < kSemOut; ++c) {
-          p[c] = c < n_classes ? expf(p[c] - m) : 0.f;
+          p[c] = c < n_classes ? __expf(p[c] - m) : 0.f;  // same soft-max arithmetic as the forward kernel
           sum += p[c];
         }
         const float inv = 1.0f / sum;
@@ -609,13 +697,17 @@ extern "C" int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32
   if (k_max == 0) return UCSA_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(heads_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
+    cudaFuncSetAttribute(heads_fwd_color_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdColorSmem);
+    cudaFuncSetAttribute(heads_fwd_sem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSemSmem);
     attr_set = true;
   }
-  heads_fwd_tc_kernel<<<heads_grid(k_max, kFwdCtasPerSm), 128, kFwdSmem, as_stream(stream)>>>(
-      sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h),
-      static_cast<const __half*>(w_sem_h), static_cast<int>(n_classes), w_sel, rgb, static_cast<__half*>(logits),
-      static_cast<__half*>(hc1), static_cast<__half*>(hc2), static_cast<__half*>(hs), image, semantics);
+  cudaStream_t st = as_stream(stream);
+  heads_fwd_color_kernel<<<heads_grid(k_max, kFwdColorCtas), 128, kFwdColorSmem, st>>>(
+      sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h), w_sel,
+      rgb, static_cast<__half*>(hc1), static_cast<__half*>(hc2), image);
+  heads_fwd_sem_kernel<<<heads_grid(k_max, kFwdSemCtas), 128, kFwdSemSmem, st>>>(
+      sel, ray_off + n_rays, t, static_cast<const __half*>(h), static_cast<const __half*>(w_sem_h),
+      static_cast<int>(n_classes), w_sel, static_cast<__half*>(logits), static_cast<__half*>(hs), semantics);
   return check_launch("heads_fwd");
 }
 
