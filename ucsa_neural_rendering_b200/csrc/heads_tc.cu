@@ -48,32 +48,63 @@ __device__ __forceinline__ void geo_chunks(const __half* __restrict__ h, uint32_
   g1.h[7] = __float2half_rn(1.0f);
 }
 
+// Raw per-row inputs of the heads, loaded one tile AHEAD into registers: sel -> (h row, ray direction) is a chain of
+// dependent global loads, and with only a few CTAs per SM nothing else hides it (it was 45 % of the stall samples of
+// the colour backward kernel).  The loop holds the inputs of the current tile, issues the loads of the next one and
+// reads sel[] two tiles ahead.
+struct RowInputs {
+  uint4 h_lo, h_hi;  // the fp16 h row [log-density | geo_feat(15)]
+  float dir[3];
+};
+
+__device__ __forceinline__ void load_row_inputs(RowInputs& x, const float* __restrict__ rays_d,
+                                                const __half* __restrict__ h, uint32_t flat, uint32_t t, bool valid,
+                                                bool want_dir) {
+  x.h_lo = x.h_hi = make_uint4(0, 0, 0, 0);
+  x.dir[0] = x.dir[1] = x.dir[2] = 0.f;
+  if (!valid) return;
+  x.h_lo = __ldg(reinterpret_cast<const uint4*>(h + static_cast<uint64_t>(flat) * 16));
+  x.h_hi = __ldg(reinterpret_cast<const uint4*>(h + static_cast<uint64_t>(flat) * 16 + 8));
+  if (want_dir) {
+    const uint32_t n = flat / t;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x.dir[d] = __ldg(rays_d + 3 * n + d);
+  }
+}
+
+// [geo_feat(15) | 1] as two 16-byte chunks from a loaded h row
+__device__ __forceinline__ void geo_from_row(const RowInputs& x, bool valid, H8& g0, H8& g1) {
+  if (!valid) {
+    g0.v = g1.v = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  H8 lo, hi;
+  lo.v = x.h_lo;
+  hi.v = x.h_hi;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) g0.h[i] = lo.h[i + 1];
+  g0.h[7] = hi.h[0];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) g1.h[i] = hi.h[i + 1];
+  g1.h[7] = __float2half_rn(1.0f);
+}
+
 // colour input row [SH(16) | geo_feat(15) | 1] and semantic input row [geo_feat(15) | 1] of this thread's row
-__device__ __forceinline__ void build_inputs(const float* __restrict__ rays_d, const __half* __restrict__ h,
-                                             uint32_t flat, uint32_t t, bool valid, unsigned char* t_in_c,
+__device__ __forceinline__ void write_inputs(const RowInputs& x, bool valid, unsigned char* t_in_c,
                                              unsigned char* t_in_s) {
   const int row = threadIdx.x;
   H8 sh_lo, sh_hi, g0, g1;
-  if (valid) {
-    const uint32_t n = flat / t;
+  geo_from_row(x, valid, g0, g1);
+  if (valid && t_in_c != nullptr) {
     float sh[16];
-    sh4_eval(rays_d[3 * n + 0], rays_d[3 * n + 1], rays_d[3 * n + 2], sh);
+    sh4_eval(x.dir[0], x.dir[1], x.dir[2], sh);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       sh_lo.h[i] = __float2half_rn(sh[i]);
       sh_hi.h[i] = __float2half_rn(sh[8 + i]);
     }
-    H8 lo, hi;
-    lo.v = __ldg(reinterpret_cast<const uint4*>(h + static_cast<uint64_t>(flat) * 16));
-    hi.v = __ldg(reinterpret_cast<const uint4*>(h + static_cast<uint64_t>(flat) * 16 + 8));
-#pragma unroll
-    for (int i = 0; i < 7; ++i) g0.h[i] = lo.h[i + 1];
-    g0.h[7] = hi.h[0];
-#pragma unroll
-    for (int i = 0; i < 7; ++i) g1.h[i] = hi.h[i + 1];
-    g1.h[7] = __float2half_rn(1.0f);
   } else {
-    sh_lo.v = sh_hi.v = g0.v = g1.v = make_uint4(0, 0, 0, 0);
+    sh_lo.v = sh_hi.v = make_uint4(0, 0, 0, 0);
   }
   if (t_in_c != nullptr) {
     *Tile<32>::chunk(t_in_c, row, 0) = sh_lo.v;
@@ -85,6 +116,21 @@ __device__ __forceinline__ void build_inputs(const float* __restrict__ rays_d, c
     *Tile<16>::chunk(t_in_s, row, 0) = g0.v;
     *Tile<16>::chunk(t_in_s, row, 1) = g1.v;
   }
+}
+
+__device__ __forceinline__ void build_inputs(const float* __restrict__ rays_d, const __half* __restrict__ h,
+                                             uint32_t flat, uint32_t t, bool valid, unsigned char* t_in_c,
+                                             unsigned char* t_in_s) {
+  RowInputs x;
+  load_row_inputs(x, rays_d, h, flat, t, valid, t_in_c != nullptr);
+  write_inputs(x, valid, t_in_c, t_in_s);
+}
+
+// compact row r of tile `tile` -> its flat sample index (0 past the end)
+__device__ __forceinline__ uint32_t flat_of(const int32_t* __restrict__ sel, uint32_t tile, uint32_t n_tiles,
+                                            uint32_t k_rows) {
+  const uint32_t r = tile * 128 + threadIdx.x;
+  return (tile < n_tiles && r < k_rows) ? static_cast<uint32_t>(__ldg(sel + r)) : 0u;
 }
 
 // ---------------------------------------------------------------------------------------------- forward
@@ -392,7 +438,7 @@ constexpr uint32_t kBwdColorSmem = kColorWeightBytes + Tile<32>::kBytes + 4 * Ti
 constexpr uint32_t kBwdSemSmem = kSemWeightBytes + 2 * Tile<64>::kBytes + Tile<kSemOut>::kBytes + 64;
 static_assert(kBwdSemCtas * (kBwdSemSmem + 1024) <= 227 * 1024, "semantic backward: shared memory of the resident CTAs");
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, kBwdColorCtas)
 heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__ k_ptr, uint32_t t,
                        const float* __restrict__ rays_d, const __half* __restrict__ h,
                        const __half* __restrict__ w_color, const float* __restrict__ rgb,
@@ -432,17 +478,48 @@ heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
   const uint32_t n_tiles = (k_rows + 127) / 128;
   const int row = threadIdx.x;
   bool first = true;
+  // per-row scalars of the compositing backward, also one tile ahead
+  struct Scalars {
+    float w, z, gd_over_dn, rgb[3], gi[3];
+  };
+  auto load_scalars = [&](Scalars& q, uint32_t tile_, uint32_t flat_) {
+    const uint32_t r_ = tile_ * 128 + threadIdx.x;
+    q = Scalars{};
+    if (tile_ < n_tiles && r_ < k_rows) {
+      const uint32_t n = flat_ / t;
+      q.w = __ldg(w_sel + r_);
+      q.z = __ldg(z_sel + r_);
+      q.gd_over_dn = __ldg(g_depth + n) / __ldg(dnorm + n);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        q.rgb[c] = __ldg(rgb + static_cast<uint64_t>(r_) * 3 + c);
+        q.gi[c] = __ldg(g_image + static_cast<uint64_t>(n) * 3 + c);
+      }
+    }
+  };
+  uint32_t flat = flat_of(sel, blockIdx.x, n_tiles, k_rows);
+  uint32_t flat_next = flat_of(sel, blockIdx.x + gridDim.x, n_tiles, k_rows);
+  RowInputs in_cur, in_next;
+  Scalars sc_cur, sc_next;
+  load_row_inputs(in_cur, rays_d, h, flat, t, blockIdx.x * 128 + threadIdx.x < k_rows, true);
+  load_scalars(sc_cur, blockIdx.x, flat);
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t r = tile * 128 + threadIdx.x;
     const bool valid = r < k_rows;
-    const uint32_t flat = valid ? static_cast<uint32_t>(sel[r]) : 0u;
+    {  // issue the next tile's loads now; they land while this tile is processed
+      const uint32_t tile_next = tile + gridDim.x;
+      const bool valid_next = tile_next < n_tiles && tile_next * 128 + threadIdx.x < k_rows;
+      load_row_inputs(in_next, rays_d, h, flat_next, t, valid_next, true);
+      load_scalars(sc_next, tile_next, flat_next);
+    }
+    const uint32_t flat_next2 = flat_of(sel, tile + 2 * gridDim.x, n_tiles, k_rows);
     if (!first) ctx.wait();  // weight-gradient MMAs of the previous tile are done with the tiles
     if (threadIdx.x == 0) {
       umma::mbar_expect_tx(ld_bar, 2 * Tile<64>::kBytes);
       umma::bulk_load(s_h1, umma::tile_block<64>(hc1, tile), Tile<64>::kBytes, ld_bar, stream);
       umma::bulk_load(s_h2, umma::tile_block<64>(hc2, tile), Tile<64>::kBytes, ld_bar, stream);
     }
-    build_inputs(rays_d, h, flat, t, valid, t_in_c, nullptr);
+    write_inputs(in_cur, valid, t_in_c, nullptr);
     {
       // backward of image_n = sum w rgb and depth_n = sum w z / dn (renderer_semantics.py:276-282):
       //   d rgb = w g_image ;  d w = g_image . rgb + g_depth z / dn ; then through the sigmoid: s (1 - s)
@@ -450,15 +527,13 @@ heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
       lo.v = make_uint4(0, 0, 0, 0);
       hi.v = make_uint4(0, 0, 0, 0);
       if (valid) {
-        const uint32_t n = flat / t;
-        const float w_row = w_sel[r];
-        float dw = g_depth[n] / dnorm[n] * z_sel[r];
+        float dw = sc_cur.gd_over_dn * sc_cur.z;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float sg = rgb[static_cast<uint64_t>(r) * 3 + c];
-          const float gi = g_image[static_cast<uint64_t>(n) * 3 + c];
+          const float sg = sc_cur.rgb[c];
+          const float gi = sc_cur.gi[c];
           dw = fmaf(gi, sg, dw);
-          lo.h[c] = __float2half_rn(w_row * gi * sg * (1.0f - sg) * loss_scale);
+          lo.h[c] = __float2half_rn(sc_cur.w * gi * sg * (1.0f - sg) * loss_scale);
         }
         d_w_sel[r] = dw;
       }
@@ -514,6 +589,10 @@ heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
       umma::commit(ctx.bar);  // covers the weight-gradient products of this tile
     }
     first = false;
+    in_cur = in_next;
+    sc_cur = sc_next;
+    flat = flat_next;
+    flat_next = flat_next2;
   }
   if (!first) {
     ctx.wait();
