@@ -130,6 +130,9 @@ __device__ __forceinline__ uint32_t ld_keep_b32(const void* ptr, uint64_t policy
   asm("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(policy));
   return v;
 }
+__device__ __forceinline__ void prefetch_l1(const void* ptr) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+}
 __device__ __forceinline__ uint4 ld_keep_b128(const void* ptr, uint64_t policy) {
   uint4 v;
   asm("ld.global.nc.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;"

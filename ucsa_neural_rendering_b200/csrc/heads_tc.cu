@@ -118,14 +118,6 @@ __device__ __forceinline__ void write_inputs(const RowInputs& x, bool valid, uns
   }
 }
 
-__device__ __forceinline__ void build_inputs(const float* __restrict__ rays_d, const __half* __restrict__ h,
-                                             uint32_t flat, uint32_t t, bool valid, unsigned char* t_in_c,
-                                             unsigned char* t_in_s) {
-  RowInputs x;
-  load_row_inputs(x, rays_d, h, flat, t, valid, t_in_c != nullptr);
-  write_inputs(x, valid, t_in_c, t_in_s);
-}
-
 // compact row r of tile `tile` -> its flat sample index (0 past the end)
 __device__ __forceinline__ uint32_t flat_of(const int32_t* __restrict__ sel, uint32_t tile, uint32_t n_tiles,
                                             uint32_t k_rows) {
@@ -242,12 +234,22 @@ heads_fwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
 
   const uint32_t k_rows = static_cast<uint32_t>(*k_ptr);
   const uint32_t n_tiles = (k_rows + 127) / 128;
+  // row inputs one tile ahead, sel[] two tiles ahead (see RowInputs)
+  uint32_t flat = flat_of(sel, blockIdx.x, n_tiles, k_rows);
+  uint32_t flat_next = flat_of(sel, blockIdx.x + gridDim.x, n_tiles, k_rows);
+  RowInputs in_cur, in_next;
+  load_row_inputs(in_cur, rays_d, h, flat, t, blockIdx.x * 128 + threadIdx.x < k_rows, true);
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t r = tile * 128 + threadIdx.x;
     const bool valid = r < k_rows;
-    const uint32_t flat = valid ? static_cast<uint32_t>(sel[r]) : 0u;
+    {
+      const uint32_t tile_next = tile + gridDim.x;
+      load_row_inputs(in_next, rays_d, h, flat_next, t, tile_next < n_tiles && tile_next * 128 + threadIdx.x < k_rows,
+                      true);
+    }
+    const uint32_t flat_next2 = flat_of(sel, tile + 2 * gridDim.x, n_tiles, k_rows);
     const float w_row = (valid && fuse_composite) ? w_sel[r] : 0.f;
-    build_inputs(rays_d, h, flat, t, valid, t_in_c, nullptr);
+    write_inputs(in_cur, valid, t_in_c, nullptr);
     ctx.publish();
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
@@ -296,6 +298,9 @@ heads_fwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
       composite_flush(part, 4, ray_of_row, heads, 3, image, 3);
       // the next tile reaches two CTA barriers before it writes part / ray_of_row again
     }
+    in_cur = in_next;
+    flat = flat_next;
+    flat_next = flat_next2;
   }
   umma::ctx_free(ctx, kFwdTmemCols);
 }
@@ -326,17 +331,21 @@ heads_fwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
 
   const uint32_t k_rows = static_cast<uint32_t>(*k_ptr);
   const uint32_t n_tiles = (k_rows + 127) / 128;
+  uint32_t flat = flat_of(sel, blockIdx.x, n_tiles, k_rows);
+  uint32_t flat_next = flat_of(sel, blockIdx.x + gridDim.x, n_tiles, k_rows);
+  RowInputs in_cur, in_next;
+  load_row_inputs(in_cur, nullptr, h, flat, t, blockIdx.x * 128 + threadIdx.x < k_rows, false);
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t r = tile * 128 + threadIdx.x;
     const bool valid = r < k_rows;
-    const uint32_t flat = valid ? static_cast<uint32_t>(sel[r]) : 0u;
-    const float w_row = (valid && fuse_composite) ? w_sel[r] : 0.f;
     {
-      H8 g0, g1;
-      geo_chunks(h, flat, valid, g0, g1);
-      *Tile<16>::chunk(t_in_s, threadIdx.x, 0) = g0.v;
-      *Tile<16>::chunk(t_in_s, threadIdx.x, 1) = g1.v;
+      const uint32_t tile_next = tile + gridDim.x;
+      load_row_inputs(in_next, nullptr, h, flat_next, t, tile_next < n_tiles && tile_next * 128 + threadIdx.x < k_rows,
+                      false);
     }
+    const uint32_t flat_next2 = flat_of(sel, tile + 2 * gridDim.x, n_tiles, k_rows);
+    const float w_row = (valid && fuse_composite) ? w_sel[r] : 0.f;
+    write_inputs(in_cur, valid, nullptr, t_in_s);
     ctx.publish();
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
@@ -404,6 +413,9 @@ heads_fwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
       composite_flush(part, kPartLd, ray_of_row, heads, n_classes, semantics, n_classes);
       __syncthreads();  // part[] lives in the input tiles: the next tile may only rebuild them after the reads
     }
+    in_cur = in_next;
+    flat = flat_next;
+    flat_next = flat_next2;
   }
   umma::ctx_free(ctx, kFwdTmemCols);
 }
@@ -635,15 +647,28 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
   const uint32_t n_tiles = (k_rows + 127) / 128;
   const int row = threadIdx.x;
   bool first = true;
+  // Latency plan: sel[] is read two tiles ahead and the hs tile of the next tile is requested as soon as this tile's
+  // products have released the buffer, so neither the sel -> h chain nor the bulk load is waited for at the top of a
+  // tile; the row's own h / dh values and the ray's output gradients are requested early and used late.
+  uint32_t flat = flat_of(sel, blockIdx.x, n_tiles, k_rows);
+  uint32_t flat_next = flat_of(sel, blockIdx.x + gridDim.x, n_tiles, k_rows);
+  if (threadIdx.x == 0 && blockIdx.x < n_tiles) {
+    umma::mbar_expect_tx(ld_bar, Tile<64>::kBytes);
+    umma::bulk_load(s_hs, umma::tile_block<64>(hs, blockIdx.x), Tile<64>::kBytes, ld_bar, stream);
+  }
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t r = tile * 128 + threadIdx.x;
     const bool valid = r < k_rows;
-    const uint32_t flat = valid ? static_cast<uint32_t>(sel[r]) : 0u;
-    if (!first) ctx.wait();
-    if (threadIdx.x == 0) {
-      umma::mbar_expect_tx(ld_bar, Tile<64>::kBytes);
-      umma::bulk_load(s_hs, umma::tile_block<64>(hs, tile), Tile<64>::kBytes, ld_bar, stream);
+    const uint32_t flat_next2 = flat_of(sel, tile + 2 * gridDim.x, n_tiles, k_rows);
+    if (valid) {  // used later in the tile: pull the rows into L1 now (no registers held)
+      prefetch_l1(h + static_cast<uint64_t>(flat) * 16);
+      prefetch_l1(dh + static_cast<uint64_t>(flat) * 16);
+      const float* g_row = g_sem + static_cast<uint64_t>(flat / t) * n_classes;  // the ray's dL/dsemantics
+      prefetch_l1(g_row);
+      prefetch_l1(g_row + n_classes - 1);
     }
+    const float w_row = valid ? __ldg(w_sel + r) : 0.f;
+    if (!first) ctx.wait();
     // CTA barrier: two waits on `bar` in a row (above and below) would let a warp that is late for the first one
     // miss its phase - mbarrier parity cannot tell phase k from k+2.  First tile: also publishes the weight tiles.
     ctx.publish();
@@ -667,8 +692,6 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
         for (int i = 0; i < 16; ++i) p[c0 + i] = round_h(v[i]);  // fp16 network output, as in the forward pass
       }
       if (valid) {
-        const uint32_t n = flat / t;
-        const float w_row = w_sel[r];
         float m = -INFINITY;
 #pragma unroll
         for (int c = 0; c < kSemOut; ++c)
@@ -682,10 +705,11 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
         const float inv = 1.0f / sum;
         float dot = 0.f;
         float q[kSemOut];
+        const float* g_row = g_sem + static_cast<uint64_t>(flat / t) * n_classes;
 #pragma unroll
         for (int c = 0; c < kSemOut; ++c) {
           p[c] *= inv;
-          q[c] = c < n_classes ? w_row * __ldg(g_sem + static_cast<uint64_t>(n) * n_classes + c) : 0.f;
+          q[c] = c < n_classes ? w_row * __ldg(g_row + c) : 0.f;
           dot = fmaf(q[c], p[c], dot);
         }
 #pragma unroll
@@ -718,11 +742,17 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
       umma::issue_dgrad<64, 16>(ctx.tmem + kAcc, s_dhs, b1);
       umma::commit(ctx.bar);
     }
-    H8 g0, g1;
-    geo_chunks(h, flat, valid, g0, g1);
     ctx.wait();  // every product issued so far is complete: the dlog tile may be re-used for the layer-1 input
-    *Tile<16>::chunk(t_in_s, row, 0) = g0.v;
-    *Tile<16>::chunk(t_in_s, row, 1) = g1.v;
+    if (threadIdx.x == 0 && tile + gridDim.x < n_tiles) {  // ... and the hs buffer for the next tile's activations
+      umma::mbar_expect_tx(ld_bar, Tile<64>::kBytes);
+      umma::bulk_load(s_hs, umma::tile_block<64>(hs, tile + gridDim.x), Tile<64>::kBytes, ld_bar, stream);
+    }
+    {
+      H8 g0, g1;
+      geo_chunks(h, flat, valid, g0, g1);
+      *Tile<16>::chunk(t_in_s, row, 0) = g0.v;
+      *Tile<16>::chunk(t_in_s, row, 1) = g1.v;
+    }
     float d_in_s[16];
     umma::tmem_ld16(ctx.lane_addr(kAcc), d_in_s);
     if (valid) {  // dL/dgeo_feat = colour share (already in dh) + semantic share, handed to density_bwd as fp16
@@ -743,6 +773,8 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
       umma::commit(ctx.bar);  // waited on at the top of the next tile
     }
     first = false;
+    flat = flat_next;
+    flat_next = flat_next2;
   }
   if (!first) {
     ctx.wait();
