@@ -31,23 +31,6 @@ constexpr uint32_t kWs1 = 64 / 8 * Tile<16>::kGroupBytes;
 constexpr uint32_t kWs2 = kSemOut / 8 * Tile<64>::kGroupBytes;
 constexpr uint32_t kColorWeightBytesFwd = kWc1 + kWc2 + kWc3, kSemWeightBytesFwd = kWs1 + kWs2;
 
-// the semantic input row [geo_feat(15) | 1] as two 16-byte chunks
-__device__ __forceinline__ void geo_chunks(const __half* __restrict__ h, uint32_t flat, bool valid, H8& g0, H8& g1) {
-  if (!valid) {
-    g0.v = g1.v = make_uint4(0, 0, 0, 0);
-    return;
-  }
-  H8 lo, hi;
-  lo.v = __ldg(reinterpret_cast<const uint4*>(h + static_cast<uint64_t>(flat) * 16));
-  hi.v = __ldg(reinterpret_cast<const uint4*>(h + static_cast<uint64_t>(flat) * 16 + 8));
-#pragma unroll
-  for (int i = 0; i < 7; ++i) g0.h[i] = lo.h[i + 1];
-  g0.h[7] = hi.h[0];
-#pragma unroll
-  for (int i = 0; i < 7; ++i) g1.h[i] = hi.h[i + 1];
-  g1.h[7] = __float2half_rn(1.0f);
-}
-
 // Raw per-row inputs of the heads, loaded one tile AHEAD into registers: sel -> (h row, ray direction) is a chain of
 // dependent global loads, and with only a few CTAs per SM nothing else hides it (it was 45 % of the stall samples of
 // the colour backward kernel).  The loop holds the inputs of the current tile, issues the loads of the next one and
@@ -242,14 +225,15 @@ heads_fwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t r = tile * 128 + threadIdx.x;
     const bool valid = r < k_rows;
-    {
+    const float w_row = (valid && fuse_composite) ? w_sel[r] : 0.f;
+    write_inputs(in_cur, valid, t_in_c, nullptr);
+    {  // only now the next tile's loads: issued before the consumer above they would share its scoreboard and be
+       // waited for right here
       const uint32_t tile_next = tile + gridDim.x;
       load_row_inputs(in_next, rays_d, h, flat_next, t, tile_next < n_tiles && tile_next * 128 + threadIdx.x < k_rows,
                       true);
     }
     const uint32_t flat_next2 = flat_of(sel, tile + 2 * gridDim.x, n_tiles, k_rows);
-    const float w_row = (valid && fuse_composite) ? w_sel[r] : 0.f;
-    write_inputs(in_cur, valid, t_in_c, nullptr);
     ctx.publish();
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
@@ -338,14 +322,14 @@ heads_fwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t r = tile * 128 + threadIdx.x;
     const bool valid = r < k_rows;
-    {
+    const float w_row = (valid && fuse_composite) ? w_sel[r] : 0.f;
+    write_inputs(in_cur, valid, nullptr, t_in_s);
+    {  // after the consumer (scoreboards, see the colour kernel)
       const uint32_t tile_next = tile + gridDim.x;
       load_row_inputs(in_next, nullptr, h, flat_next, t, tile_next < n_tiles && tile_next * 128 + threadIdx.x < k_rows,
                       false);
     }
     const uint32_t flat_next2 = flat_of(sel, tile + 2 * gridDim.x, n_tiles, k_rows);
-    const float w_row = (valid && fuse_composite) ? w_sel[r] : 0.f;
-    write_inputs(in_cur, valid, nullptr, t_in_s);
     ctx.publish();
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
@@ -518,13 +502,6 @@ heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t r = tile * 128 + threadIdx.x;
     const bool valid = r < k_rows;
-    {  // issue the next tile's loads now; they land while this tile is processed
-      const uint32_t tile_next = tile + gridDim.x;
-      const bool valid_next = tile_next < n_tiles && tile_next * 128 + threadIdx.x < k_rows;
-      load_row_inputs(in_next, rays_d, h, flat_next, t, valid_next, true);
-      load_scalars(sc_next, tile_next, flat_next);
-    }
-    const uint32_t flat_next2 = flat_of(sel, tile + 2 * gridDim.x, n_tiles, k_rows);
     if (!first) ctx.wait();  // weight-gradient MMAs of the previous tile are done with the tiles
     if (threadIdx.x == 0) {
       umma::mbar_expect_tx(ld_bar, 2 * Tile<64>::kBytes);
@@ -552,6 +529,14 @@ heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
       *Tile<16>::chunk(t_dpre, row, 0) = lo.v;
       *Tile<16>::chunk(t_dpre, row, 1) = hi.v;
     }
+    {  // the next tile's loads, issued AFTER this tile's values are consumed (before them they would share the
+       // consumers' scoreboards and be waited for at once); they land while this tile is processed
+      const uint32_t tile_next = tile + gridDim.x;
+      const bool valid_next = tile_next < n_tiles && tile_next * 128 + threadIdx.x < k_rows;
+      load_row_inputs(in_next, rays_d, h, flat_next, t, valid_next, true);
+      load_scalars(sc_next, tile_next, flat_next);
+    }
+    const uint32_t flat_next2 = flat_of(sel, tile + 2 * gridDim.x, n_tiles, k_rows);
     ctx.publish();
     umma::mbar_wait(ld_bar, ld_phase);  // h1 and h2 have landed (operands of the products, ReLU masks below)
     ld_phase ^= 1u;
@@ -660,9 +645,7 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
     const uint32_t r = tile * 128 + threadIdx.x;
     const bool valid = r < k_rows;
     const uint32_t flat_next2 = flat_of(sel, tile + 2 * gridDim.x, n_tiles, k_rows);
-    if (valid) {  // used later in the tile: pull the rows into L1 now (no registers held)
-      prefetch_l1(h + static_cast<uint64_t>(flat) * 16);
-      prefetch_l1(dh + static_cast<uint64_t>(flat) * 16);
+    if (valid) {  // used in the soft-max block below: pull the ray's row into L1 now (no registers held)
       const float* g_row = g_sem + static_cast<uint64_t>(flat / t) * n_classes;  // the ray's dL/dsemantics
       prefetch_l1(g_row);
       prefetch_l1(g_row + n_classes - 1);
@@ -726,6 +709,15 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
         *Tile<kSemOut>::chunk(t_dlog, row, c) = o.v;
       }
     }
+    // the row's h and dh values are needed after the two products below: request them now, while few registers
+    // are live (plain loads for dh: the colour kernel wrote it)
+    RowInputs in_row;
+    load_row_inputs(in_row, nullptr, h, flat, t, valid, false);
+    uint4 dh_lo = make_uint4(0, 0, 0, 0), dh_hi = make_uint4(0, 0, 0, 0);
+    if (valid) {
+      dh_lo = reinterpret_cast<const uint4*>(dh + static_cast<uint64_t>(flat) * 16)[0];
+      dh_hi = reinterpret_cast<const uint4*>(dh + static_cast<uint64_t>(flat) * 16)[1];
+    }
     ctx.publish();
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
@@ -749,7 +741,7 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
     }
     {
       H8 g0, g1;
-      geo_chunks(h, flat, valid, g0, g1);
+      geo_from_row(in_row, valid, g0, g1);
       *Tile<16>::chunk(t_in_s, row, 0) = g0.v;
       *Tile<16>::chunk(t_in_s, row, 1) = g1.v;
     }
@@ -757,8 +749,8 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
     umma::tmem_ld16(ctx.lane_addr(kAcc), d_in_s);
     if (valid) {  // dL/dgeo_feat = colour share (already in dh) + semantic share, handed to density_bwd as fp16
       H8 lo, hi;
-      lo.v = reinterpret_cast<const uint4*>(dh + static_cast<uint64_t>(flat) * 16)[0];
-      hi.v = reinterpret_cast<const uint4*>(dh + static_cast<uint64_t>(flat) * 16)[1];
+      lo.v = dh_lo;
+      hi.v = dh_hi;
 #pragma unroll
       for (int i = 0; i < 7; ++i) lo.h[i + 1] = __float2half_rn(__half2float(lo.h[i + 1]) + round_h(d_in_s[i]));
 #pragma unroll
