@@ -172,56 +172,8 @@ __device__ __forceinline__ void flush_wgrad(const umma::Ctx& ctx, uint32_t col0,
   }
 }
 
-// Per-sample inputs of the backward pass, loaded one tile ahead into registers (the loads of a tile would otherwise
-// be waited for at its top, with four CTAs per SM to hide a DRAM round trip).  dh is fetched whether or not the
-// sample is masked in - the mask is applied when the row is used - so that nothing depends on a loaded value.
-struct BwdRow {
-  uint64_t flat;
-  float raw[3];  // xyz, or z in raw[0]
-  uint32_t use;
-  uint4 d_lo, d_hi;
-  float h0, gs;
-};
-
-__device__ __forceinline__ void load_bwd_row(BwdRow& x, const DensityArgs& a, uint64_t s, bool valid,
-                                             const __half* __restrict__ h, const float* __restrict__ d_sigma,
-                                             const __half* __restrict__ dh, const uint8_t* __restrict__ use_geo,
-                                             uint64_t stream) {
-  x.flat = 0;
-  x.raw[0] = x.raw[1] = x.raw[2] = 0.f;
-  x.use = 0;
-  x.d_lo = x.d_hi = make_uint4(0, 0, 0, 0);
-  x.h0 = x.gs = 0.f;
-  if (!valid) return;
-  if (a.xyz != nullptr) {
-    x.flat = s;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) x.raw[d] = a.xyz[3 * s + d];
-  } else {
-    const uint32_t n = static_cast<uint32_t>(s / a.span);
-    x.flat = static_cast<uint64_t>(n) * a.t + a.k0 + static_cast<uint32_t>(s % a.span);
-    x.raw[0] = a.z_cat[x.flat];
-  }
-  if (use_geo != nullptr && dh != nullptr) {
-    x.use = use_geo[x.flat];
-    x.d_lo = ld_stream(dh + x.flat * 16, stream);
-    x.d_hi = ld_stream(dh + x.flat * 16 + 8, stream);
-  }
-  x.h0 = __half2float(h[x.flat * 16]);
-  x.gs = d_sigma != nullptr ? d_sigma[x.flat] : 0.f;
-}
-
-__device__ __forceinline__ void bwd_row_x01(const BwdRow& x, const DensityArgs& a, uint64_t s, float x01[3]) {
-  if (a.xyz != nullptr) {
-#pragma unroll
-    for (int d = 0; d < 3; ++d) x01[d] = __fdiv_rn(__fadd_rn(x.raw[d], a.bound), 2.0f * a.bound);
-  } else {
-    sample_x01(a.rays_o, a.rays_d, a.aabb, x.raw[0], static_cast<uint32_t>(s / a.span), a.bound, x01);
-  }
-}
-
 template <bool TILED>
-__global__ void __launch_bounds__(128, kBwdCtasPerSm)
+__global__ void __launch_bounds__(128)
 density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, const __half* __restrict__ h,
                       const __half* __restrict__ enc, const __half* __restrict__ hid,
                       const float* __restrict__ d_sigma, const __half* __restrict__ dh,
@@ -260,17 +212,9 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
   const float inv_scale = 1.0f / loss_scale;
   const uint64_t n_tiles = (a.n_samples + 127) / 128;
   bool first = true;
-  BwdRow cur, next;
-  load_bwd_row(cur, a, static_cast<uint64_t>(blockIdx.x) * 128 + row,
-               static_cast<uint64_t>(blockIdx.x) * 128 + row < a.n_samples, h, d_sigma, dh, use_geo, stream);
   for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint64_t s = tile * 128 + row;
     const bool valid = s < a.n_samples;
-    {
-      const uint64_t s_next = (tile + gridDim.x) * 128 + row;
-      load_bwd_row(next, a, s_next, tile + gridDim.x < n_tiles && s_next < a.n_samples, h, d_sigma, dh, use_geo,
-                   stream);
-    }
     if (!first) ctx.wait();  // the weight-gradient MMAs of the previous tile have read the tiles
     if (TILED && threadIdx.x == 0) {
       const uint64_t block = saved_block(a, tile * 128);
@@ -280,19 +224,18 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
     }
     float x01[3] = {0.f, 0.f, 0.f};
     if (valid) {
-      const uint64_t flat = cur.flat;
-      bwd_row_x01(cur, a, s, x01);
+      const uint64_t flat = locate_sample(a, s, x01);
       // dL/dh: element 0 through trunc_exp (activation.py:16-19), elements 1..15 = dL/dgeo_feat from the heads
       H8 lo, hi;
-      if (cur.use) {
-        lo.v = cur.d_lo;
-        hi.v = cur.d_hi;
+      if (use_geo != nullptr && dh != nullptr && use_geo[flat]) {
+        lo.v = ld_stream(dh + flat * 16, stream);
+        hi.v = ld_stream(dh + flat * 16 + 8, stream);
       } else {
         lo.v = make_uint4(0, 0, 0, 0);
         hi.v = make_uint4(0, 0, 0, 0);
       }
-      const float h0 = cur.h0;
-      const float gs = cur.gs;
+      const float h0 = __half2float(h[flat * 16]);
+      const float gs = d_sigma != nullptr ? d_sigma[flat] : 0.f;
       lo.h[0] = __float2half_rn(gs * expf(fminf(fmaxf(h0, -15.f), 15.f)) * loss_scale);
       *Tile<16>::chunk(t_dout, row, 0) = lo.v;
       *Tile<16>::chunk(t_dout, row, 1) = hi.v;
@@ -367,7 +310,6 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
       }
     }
     first = false;
-    cur = next;
   }
   ctx.wait();
   flush_wgrad<32, false>(ctx, kG1, grad_w, 32, inv_scale);
