@@ -91,7 +91,8 @@ density_fwd_tc_kernel(const DensityArgs a, const __half2* __restrict__ table, co
     if (valid) {
       float x01[3];
       flat = locate_sample(a, s, x01);
-#pragma unroll
+      // (rolled on purpose: fully unrolled the kernel was 127 KB of SASS and its largest stall was "no instruction")
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {  // four levels = one 16-byte chunk of the encoded row
         H8 o;
         LevelGather g[4];  // all gathers of the four levels are issued before the first one is consumed
@@ -280,15 +281,17 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
       umma::issue_wgrad<32>(ctx.tmem + kG1, s_dhid, s_enc, first);  // d(W1) = d(hidden)^T . encoded
     }
     ctx.wait();
-    float g[32];
-    {
+    // dL/d(encoded) of this thread's sample -> (g0, g1) per level, parked in the hidden-activation tile (free by now:
+    // every product that read it has completed) so that the level loop below can stay ROLLED.  Unrolled, with both
+    // scatter variants per level, the kernel was 290 KB of SASS and "no instruction" its second largest stall.
+    float2* stash = reinterpret_cast<float2*>(t_hid);  // [16 levels][128 threads]
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
       float v[16];
-      umma::tmem_ld16(ctx.lane_addr(kAcc), v);
+      umma::tmem_ld16(ctx.lane_addr(kAcc + 16 * half), v);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) g[i] = v[i];
-      umma::tmem_ld16(ctx.lane_addr(kAcc + 16), v);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) g[16 + i] = v[i];
+      for (int i = 0; i < 8; ++i)
+        stash[(8 * half + i) * 128 + row] = make_float2(round_h(v[2 * i]) * inv_scale, round_h(v[2 * i + 1]) * inv_scale);
     }
     umma::tc_fence_before();
     __syncthreads();
@@ -297,18 +300,21 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
       umma::commit(ctx.bar);  // covers the two weight-gradient products; waited on at the top of the next tile
     }
     if (grad_table != nullptr) {
-#pragma unroll
+#pragma unroll 1
       for (int l = 0; l < UCSA_GRID_LEVELS; ++l) {
         const LevelGeom lv = level_geom(a.grid, l);
         float* dst = lv.hashed ? grad_table : dense_base;
-        const float g0 = round_h(g[2 * l]) * inv_scale, g1 = round_h(g[2 * l + 1]) * inv_scale;
+        const float2 gl = stash[l * 128 + row];
         if (lv.res <= run_max_res) {  // level-uniform: coarse levels merge runs of samples inside one cell first
-          scatter_level_runs(dst, lv, x01, g0, g1, valid && (g0 != 0.f || g1 != 0.f), keep);
+          scatter_level_runs(dst, lv, x01, gl.x, gl.y, valid && (gl.x != 0.f || gl.y != 0.f), keep);
         } else if (valid) {
-          scatter_level(dst, lv, x01, g0, g1, keep);
+          scatter_level(dst, lv, x01, gl.x, gl.y, keep);
         }
       }
     }
+    // the stash lives in the hidden tile, which the next tile refills (bulk copy or row stores of other threads)
+    umma::fence_async_smem();
+    __syncthreads();
     first = false;
   }
   ctx.wait();
