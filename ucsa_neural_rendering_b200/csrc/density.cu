@@ -178,7 +178,7 @@ constexpr size_t kBwdSmem = UCSA_SIGMA_PARAMS * sizeof(float) +
 int fill_args(DensityArgs& a, const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,
               const float* z_cat, uint32_t n_rays, uint32_t t, uint32_t k0, uint32_t k1, float bound,
               const ucsa_grid_desc* grid) {
-  UCSA_REQUIRE(grid != nullptr, "density: null grid descriptor");
+  UCSA_REQUIRE_GRID(grid, "density");
   UCSA_REQUIRE(bound > 0.f, "density: bound must be positive");
   if (xyz != nullptr) {
     a = DensityArgs{xyz, nullptr, nullptr, nullptr, nullptr, n_rays, 1u, 0u, 1u, n_rays, bound, *grid};

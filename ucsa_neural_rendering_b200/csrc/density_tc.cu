@@ -57,7 +57,7 @@ constexpr uint32_t kW1Bytes = 64 / 8 * Tile<32>::kGroupBytes;  // [64][32]
 constexpr uint32_t kW2Bytes = 16 / 8 * Tile<64>::kGroupBytes;  // [16][64]
 constexpr uint32_t kFwdTmemCols = 64;   // layer-2 accumulator re-uses the columns of layer 1 once they are read
 constexpr uint32_t kBwdTmemCols = 128;
-constexpr int kFwdCtasPerSm = 4, kBwdCtasPerSm = 4;  // fwd: more CTAs shrink L1 and lose (measured 4 > 6 > 8)
+constexpr int kFwdCtasPerSm = 6, kBwdCtasPerSm = 4;  // fwd: 0.478 ms (4) / 0.459 ms (6) per step with the rolled level loop
 
 template <bool TILED>  // TILED: enc / hid are tile-layout buffers written with bulk copies (else row-major rows)
 __global__ void __launch_bounds__(128, kFwdCtasPerSm)
@@ -91,20 +91,24 @@ density_fwd_tc_kernel(const DensityArgs a, const __half2* __restrict__ table, co
     if (valid) {
       float x01[3];
       flat = locate_sample(a, s, x01);
-      // (rolled on purpose: fully unrolled the kernel was 127 KB of SASS and its largest stall was "no instruction")
+      // Two levels per trip of a ROLLED loop: fully unrolled the kernel was 127 KB of SASS and "no instruction" its
+      // largest stall; eight gathers in flight per thread are enough to reach the L2 request rate
+      // (scripts/gather_probe.cu: the rate is flat from 4 loads per thread on).
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {  // four levels = one 16-byte chunk of the encoded row
-        H8 o;
-        LevelGather g[4];  // all gathers of the four levels are issued before the first one is consumed
+      for (int c = 0; c < 8; ++c) {
+        LevelGather g[2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) issue_level(table, level_geom(a.grid, 4 * c + j), x01, keep, g[j]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = finish_level(g[j]);
-          o.h2[j] = __floats2half2_rn(f.x, f.y);
+        for (int j = 0; j < 2; ++j) issue_level(table, level_geom(a.grid, 2 * c + j), x01, keep, g[j]);
+        uint2 o;
+        {
+          const float2 f0 = finish_level(g[0]), f1 = finish_level(g[1]);
+          const __half2 h0 = __floats2half2_rn(f0.x, f0.y), h1 = __floats2half2_rn(f1.x, f1.y);
+          o.x = *reinterpret_cast<const uint32_t*>(&h0);
+          o.y = *reinterpret_cast<const uint32_t*>(&h1);
         }
-        *Tile<32>::chunk(t_enc, row, c) = o.v;
-        if (!TILED && enc != nullptr) st_stream(enc + flat * 32 + c * 8, o.v, stream);
+        // levels 2c, 2c+1 = columns 4c .. 4c+3 of the encoded row = half of the 16-byte chunk c / 2
+        reinterpret_cast<uint2*>(Tile<32>::chunk(t_enc, row, c >> 1))[c & 1] = o;
+        if (!TILED && enc != nullptr) *reinterpret_cast<uint2*>(enc + flat * 32 + c * 4) = o;
       }
     } else {
 #pragma unroll
@@ -329,7 +333,7 @@ constexpr size_t kBwdSmem = kW1Bytes + kW2Bytes + Tile<32>::kBytes + 2 * Tile<64
 int fill_args(DensityArgs& a, const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,
               const float* z_cat, uint32_t n_rays, uint32_t t, uint32_t k0, uint32_t k1, float bound,
               const ucsa_grid_desc* grid) {
-  UCSA_REQUIRE(grid != nullptr, "density: null grid descriptor");
+  UCSA_REQUIRE_GRID(grid, "density");
   UCSA_REQUIRE(bound > 0.f, "density: bound must be positive");
   if (xyz != nullptr) {
     a = DensityArgs{xyz, nullptr, nullptr, nullptr, nullptr, n_rays, 1u, 0u, 1u, n_rays, bound, *grid};
@@ -448,6 +452,7 @@ __global__ void reduce_replicas_kernel(float* __restrict__ replicas, uint32_t n_
 extern "C" int ucsa_reduce_grad_replicas(float* grad_replicas, uint32_t n_replicas, const ucsa_grid_desc* grid_host,
                                          float* grad_table, void* stream) {
   UCSA_REQUIRE(grad_replicas && grid_host && grad_table, "reduce_grad_replicas: null pointer");
+  UCSA_REQUIRE_GRID(grid_host, "reduce_grad_replicas");
   const uint32_t n_floats = 2u * dense_entry_count(*grid_host);  // entries are multiples of 8 -> divisible by 4
   if (n_replicas == 0 || n_floats == 0) return UCSA_OK;
   reduce_replicas_kernel<<<ceil_div(n_floats / 4, 256), 256, 0, as_stream(stream)>>>(grad_replicas, n_replicas, n_floats,

@@ -28,6 +28,19 @@ __host__ __device__ __forceinline__ uint32_t dense_entry_count(const ucsa_grid_d
   return g.total_entries;
 }
 
+// Host-side check every entry point that takes a descriptor runs first: the kernels reduce a hash modulo the level
+// size with a mask, and address 16-byte groups of entries.
+inline bool grid_desc_ok(const ucsa_grid_desc* g) {
+  if (g == nullptr) return false;
+  for (int l = 0; l < UCSA_GRID_LEVELS; ++l) {
+    if (g->entries[l] == 0u || g->entries[l] % 8u != 0u || g->offset[l] % 8u != 0u || g->res[l] < 2u) return false;
+    if (g->hashed[l] && (g->entries[l] & (g->entries[l] - 1u)) != 0u) return false;
+  }
+  return true;
+}
+#define UCSA_REQUIRE_GRID(g, who) \
+  UCSA_REQUIRE(grid_desc_ok(g), who ": bad grid descriptor (hashed levels need 2^k entries, sizes multiples of 8)")
+
 struct Cell {
   uint32_t c[3];
   float f[3];
@@ -52,8 +65,7 @@ __device__ __forceinline__ uint32_t corner_entry(const LevelGeom& lv, const Cell
   uint32_t idx;
   if (lv.hashed) {
     idx = x ^ (y * 2654435761u) ^ (z * 805459861u);
-    // hashed levels hold 2^k entries (the cap 2^log2_hashmap_size); anything else takes the generic path
-    idx = ((lv.entries & (lv.entries - 1u)) == 0u) ? (idx & (lv.entries - 1u)) : (idx % lv.entries);
+    idx &= lv.entries - 1u;  // hashed levels hold 2^k entries (the cap 2^log2_hashmap_size; grid_desc_ok checks it)
   } else {
     // dense: coordinates are <= res, so idx <= res + res^2 + res^3 < 2 * entries (entries >= res^3, res >= 2):
     // the modulo is one conditional subtraction
@@ -74,14 +86,13 @@ __device__ __forceinline__ float corner_weight(const Cell& cell, int corner) {
 // index = +1 in y, bit 1 = +1 in z.  Same arithmetic as corner_entry, with the level-uniform work hoisted.
 __device__ __forceinline__ void pair_entries(const LevelGeom& lv, const Cell& cell, uint32_t e0[4], uint32_t e1[4]) {
   if (lv.hashed) {
-    const bool pow2 = (lv.entries & (lv.entries - 1u)) == 0u;
     const uint32_t hy = cell.c[1] * 2654435761u, hz = cell.c[2] * 805459861u;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const uint32_t a = ((p & 1) ? hy + 2654435761u : hy) ^ ((p & 2) ? hz + 805459861u : hz);
       const uint32_t i = cell.c[0] ^ a, j = (cell.c[0] + 1u) ^ a;
-      e0[p] = lv.offset + (pow2 ? (i & (lv.entries - 1u)) : (i % lv.entries));
-      e1[p] = lv.offset + (pow2 ? (j & (lv.entries - 1u)) : (j % lv.entries));
+      e0[p] = lv.offset + (i & (lv.entries - 1u));  // 2^k entries (grid_desc_ok)
+      e1[p] = lv.offset + (j & (lv.entries - 1u));
     }
   } else {
     const uint32_t sy = lv.res, sz = lv.res * lv.res;

@@ -243,6 +243,7 @@ using namespace ucsa;
 extern "C" int ucsa_hashgrid_fwd(const float* x01, uint32_t n, const void* table_h, const ucsa_grid_desc* grid,
                                  void* enc, void* stream) {
   UCSA_REQUIRE(x01 && table_h && grid && enc, "hashgrid_fwd: null pointer");
+  UCSA_REQUIRE_GRID(grid, "hashgrid_fwd");
   UCSA_REQUIRE((reinterpret_cast<uintptr_t>(table_h) & 15u) == 0, "hashgrid_fwd: the fp16 table must be 16-byte aligned");
   if (n == 0) return UCSA_OK;
   const uint64_t total = static_cast<uint64_t>(n) * UCSA_GRID_LEVELS;
@@ -254,6 +255,7 @@ extern "C" int ucsa_hashgrid_fwd(const float* x01, uint32_t n, const void* table
 extern "C" int ucsa_hashgrid_bwd(const float* x01, uint32_t n, const ucsa_grid_desc* grid, const void* d_enc,
                                  float inv_loss_scale, float* grad_table, void* stream) {
   UCSA_REQUIRE(x01 && grid && d_enc && grad_table, "hashgrid_bwd: null pointer");
+  UCSA_REQUIRE_GRID(grid, "hashgrid_bwd");
   if (n == 0) return UCSA_OK;
   const uint64_t total = static_cast<uint64_t>(n) * UCSA_GRID_LEVELS;
   hashgrid_bwd_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
@@ -264,6 +266,7 @@ extern "C" int ucsa_hashgrid_bwd(const float* x01, uint32_t n, const ucsa_grid_d
 extern "C" int ucsa_hashgrid_indices(const float* x01, uint32_t n, const ucsa_grid_desc* grid, uint32_t* idx,
                                      void* stream) {
   UCSA_REQUIRE(x01 && grid && idx, "hashgrid_indices: null pointer");
+  UCSA_REQUIRE_GRID(grid, "hashgrid_indices");
   if (n == 0) return UCSA_OK;
   const uint64_t total = static_cast<uint64_t>(n) * UCSA_GRID_LEVELS;
   hashgrid_indices_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(x01, n, *grid, idx);
