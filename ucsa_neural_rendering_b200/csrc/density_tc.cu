@@ -304,16 +304,20 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
       umma::commit(ctx.bar);  // covers the two weight-gradient products; waited on at the top of the next tile
     }
     if (grad_table != nullptr) {
+      // two rolled loops, one scatter variant each (resolutions grow with the level): every loop body stays small
+      int l = 0;
 #pragma unroll 1
-      for (int l = 0; l < UCSA_GRID_LEVELS; ++l) {
+      for (; l < UCSA_GRID_LEVELS && a.grid.res[l] <= run_max_res; ++l) {  // coarse: merge same-cell runs per warp
         const LevelGeom lv = level_geom(a.grid, l);
-        float* dst = lv.hashed ? grad_table : dense_base;
         const float2 gl = stash[l * 128 + row];
-        if (lv.res <= run_max_res) {  // level-uniform: coarse levels merge runs of samples inside one cell first
-          scatter_level_runs(dst, lv, x01, gl.x, gl.y, valid && (gl.x != 0.f || gl.y != 0.f), keep);
-        } else if (valid) {
-          scatter_level(dst, lv, x01, gl.x, gl.y, keep);
-        }
+        scatter_level_runs(lv.hashed ? grad_table : dense_base, lv, x01, gl.x, gl.y,
+                           valid && (gl.x != 0.f || gl.y != 0.f), keep);
+      }
+#pragma unroll 1
+      for (; l < UCSA_GRID_LEVELS; ++l) {  // fine: every sample has its own cell
+        const LevelGeom lv = level_geom(a.grid, l);
+        const float2 gl = stash[l * 128 + row];
+        if (valid) scatter_level(lv.hashed ? grad_table : dense_base, lv, x01, gl.x, gl.y, keep);
       }
     }
     // the stash lives in the hidden tile, which the next tile refills (bulk copy or row stores of other threads)
