@@ -177,17 +177,19 @@ __device__ __forceinline__ void scatter_level(float* __restrict__ grad_table, co
                                               const float x01[3], float g0, float g1, uint64_t keep) {
   if (g0 == 0.f && g1 == 0.f) return;
   const Cell cell = locate(lv, x01);
+  uint32_t e0[4], e1[4];
+  pair_entries(lv, cell, e0, e1);  // pair p = corners 2p (x) and 2p+1 (x+1)
 #pragma unroll
-  for (int c = 0; c < 8; c += 2) {
-    const uint32_t e0 = corner_entry(lv, cell, c), e1 = corner_entry(lv, cell, c + 1);
-    const float w0 = corner_weight(cell, c), w1 = corner_weight(cell, c + 1);
-    if ((e0 ^ e1) == 1u) {
-      float* p = grad_table + 2ull * (e0 & ~1u);
-      if (e0 & 1u) red_keep_f32x4(p, w1 * g0, w1 * g1, w0 * g0, w0 * g1, keep);
-      else red_keep_f32x4(p, w0 * g0, w0 * g1, w1 * g0, w1 * g1, keep);
+  for (int p = 0; p < 4; ++p) {
+    const float w0 = corner_weight(cell, 2 * p), w1 = corner_weight(cell, 2 * p + 1);
+    if ((e0[p] ^ e1[p]) == 1u) {
+      float* q = grad_table + 2ull * (e0[p] & ~1u);
+      const bool first = (e0[p] & 1u) == 0u;  // one reduction, operands selected (less code than two call sites)
+      const float wa = first ? w0 : w1, wb = first ? w1 : w0;
+      red_keep_f32x4(q, wa * g0, wa * g1, wb * g0, wb * g1, keep);
     } else {
-      red_keep_f32x2(grad_table + 2ull * e0, w0 * g0, w0 * g1, keep);
-      red_keep_f32x2(grad_table + 2ull * e1, w1 * g0, w1 * g1, keep);
+      red_keep_f32x2(grad_table + 2ull * e0[p], w0 * g0, w0 * g1, keep);
+      red_keep_f32x2(grad_table + 2ull * e1[p], w1 * g0, w1 * g1, keep);
     }
   }
 }
