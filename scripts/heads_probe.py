@@ -1,3 +1,5 @@
+"""Bring-up probe: where does ucsa_heads_fwd spend its time?  Times the call with / without the saved activations and
+with / without the fused compositing at config-2 sizes.   python scripts/heads_probe.py"""
 import sys, torch
 sys.path.insert(0, ".")
 from ucsa_neural_rendering_b200 import ops
