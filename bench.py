@@ -365,6 +365,17 @@ def run_ours(args):
         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": dur_ms,
         "hbm_compulsory": {"bytes_per_launch": compulsory, "achieved": compulsory / (dur_ms * 1e-3) / 1e9,
                            "note": "76 B/sample (xyz, features, saved activations) + the table once (SURVEY 8d)"},
+        # what actually binds the density kernels: the L2 request rate (scripts/gather_probe.cu, measured on B200:
+        # 285 G 16-byte gathers/s, 192 G reductions/s whatever their width); operation counts per sample from
+        # DESIGN.md section 5 (forward: 12 hashed levels x 4 corner pairs x 1.25; backward: ~68 after run-merging)
+        "l2_request_roofline": {
+            "ops_per_launch_est": (60 if dominant == "ucsa_density_fwd" else 68) * samples_per_launch[dominant],
+            "peak_gops": 285.0 if dominant == "ucsa_density_fwd" else 192.0,
+            "achieved_gops": (60 if dominant == "ucsa_density_fwd" else 68) * samples_per_launch[dominant]
+            / (dur_ms * 1e-3) / 1e9,
+            "frac": (60 if dominant == "ucsa_density_fwd" else 68) * samples_per_launch[dominant]
+            / (dur_ms * 1e-3) / 1e9 / (285.0 if dominant == "ucsa_density_fwd" else 192.0),
+            "note": "operation counts are analytic estimates; peaks measured by scripts/gather_probe.cu"},
         "note": "588 B/sample counts the 512 B of table gathers/scatters, which hit the L2-resident table rather "
                 "than HBM (traffic = measured DRAM bytes of the launch); the kernel is bound by L2 reduction / L1 "
                 "gather throughput, see DESIGN.md sections 5 and 9",

@@ -62,3 +62,37 @@ def test_facade_constructs_without_gpu_and_refuses_cpu_render():
     assert set(net.state_dict()) >= {"aabb_train", "aabb_infer", "encoder.params"}
     with pytest.raises(_lib.UcsaError):
         net.render(torch.zeros(1, 4, 3), torch.ones(1, 4, 3), torch.ones(1, 4, 1))
+
+
+def test_host_side_argument_checks_run_before_any_launch(handle):
+    """Entry points validate on the host and return -1 with a message (no GPU needed: they fail before launching)."""
+    from ucsa_neural_rendering_b200 import ops
+
+    g = ops.make_grid_desc(4)
+    one = ctypes.c_void_p(16)  # a non-null, 16-byte aligned dummy address; never dereferenced on these paths
+    # a hashed level whose size is not a power of two (kernels reduce the hash with a mask)
+    bad = _lib.GridDesc.from_buffer_copy(g)
+    bad.entries[15] = 524288 - 8
+    rc = handle.ucsa_hashgrid_indices(one, 4, ctypes.byref(bad), one, None)
+    assert rc == -1 and b"grid descriptor" in handle.ucsa_last_error_string()
+    # tile-layout activations need T, k0 and k1-k0 to be multiples of 128 in ray mode
+    rc = handle.ucsa_density_fwd(None, one, one, one, one, 8, 96, 0, 48, 4.0, one, ctypes.byref(g), one, one, one,
+                                 one, one, 1, None)
+    assert rc == -1 and b"multiples of 128" in handle.ucsa_last_error_string()
+    # the fused exchange: slice bounds in whole float4 groups, rank inside the world
+    arr = (ctypes.c_uint64 * 2)(16, 16)
+    rc = handle.ucsa_adam_exchange(arr, arr, arr, None, None, None, 2, 0, 2, 8, 0, one, one, 1e-2, 0.9, 0.99, 1e-15,
+                                   0.0, 1, None, None)
+    assert rc == -1 and b"multiples of 4" in handle.ucsa_last_error_string()
+    rc = handle.ucsa_adam_exchange(arr, arr, arr, None, None, None, 2, 2, 0, 8, 0, one, one, 1e-2, 0.9, 0.99, 1e-15,
+                                   0.0, 1, None, None)
+    assert rc == -1 and b"rank < world" in handle.ucsa_last_error_string()
+
+
+def test_tile_layout_helpers_and_launch_accounting():
+    from ucsa_neural_rendering_b200 import ops
+
+    assert [ops.tile_rows(n) for n in (0, 1, 128, 129, 4096 * 512)] == [0, 128, 128, 256, 4096 * 512]
+    assert ops.density_tiled(256, 256) and ops.density_tiled(128, 0) and not ops.density_tiled(64, 64)
+    # ucsa_heads_fwd / ucsa_heads_bwd enqueue two kernels each (colour, semantics); bench.py's gpu_launches uses this
+    assert _lib.KERNELS_PER_CALL == {"ucsa_heads_fwd": 2, "ucsa_heads_bwd": 2}
