@@ -9,6 +9,11 @@
 //   all tiles of the CTA, and the hash-table gradient scattered with vector reductions (red.global.add.v2.f32).
 // Several CTAs per SM (TMEM: 64 / 128 columns each) overlap one tile's gather/scatter phase with another's MMAs.
 // The hash table and its gradient are tagged L2 evict_last, the per-sample streams evict_first (common.cuh).
+//
+// Both kernels are bound by the L2 REQUEST rate (scripts/gather_probe.cu: 285 G gathers/s, 192 G reductions/s, the
+// same for 4-, 8- and 16-byte operations), hence one 16-byte request per (x, x+1) corner pair, same-cell runs merged
+// per warp before they are reduced (grid.cuh) - and by instruction fetch when the 16 levels are unrolled (127 KB /
+// 290 KB of SASS, "no instruction" the largest stall), hence the ROLLED level loops below.
 #include <cstdlib>
 
 #include "grid.cuh"
