@@ -10,7 +10,6 @@
 from __future__ import annotations
 
 import os
-import shutil
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))

@@ -6,7 +6,6 @@
 Prints one line per kernel: ms per launch (CUDA events), samples/s and GB/s against SURVEY.md 8(d) bytes."""
 import argparse
 import sys
-import time
 
 import torch
 
