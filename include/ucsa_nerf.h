@@ -295,6 +295,25 @@ UCSA_API int ucsa_nerf_loss(const float* image, const float* depth, const float*
                    float global_scale, float* loss4, float* g_image, float* g_depth, float* g_semantics,
                    void* stream);
 
+/* ---- f2 (front). pinhole rays of the pixels `inds` [N] (row-major, may repeat; null = pixels 0..N-1) of one view:
+ * dataset/ngp_utils.py:28-70 (get_rays), lightning/joint_train_lightning_net.py:109-151 (get_rays_train).
+ * pose16 = cam2world 4x4 row-major on the device (nerf_matrix_to_ngp convention).  Outputs rays_o, rays_d [N,3],
+ * direction_norms [N] (the norm of the un-normalised camera-frame direction). */
+UCSA_API int ucsa_generate_rays(const float* pose16, float fx, float fy, float cx, float cy, uint32_t width,
+                   uint32_t height, const int64_t* inds, uint32_t n, float* rays_o, float* rays_d,
+                   float* direction_norms, void* stream);
+/* ground truth of those pixels (joint_train_lightning_net.py:180-187: three torch.gather): image fp16 channel planes
+ * [C,H*W] (batch["img_fp16"]), labels int64 [H*W] and depth f32 [H*W] (either may be null with its output)
+ * -> gt_rgb fp16 [N,C], gt_labels [N], gt_depth [N]. */
+UCSA_API int ucsa_gather_gt(const void* image_h, const int64_t* labels, const float* depth, uint64_t hw, uint32_t channels,
+                   const int64_t* inds, uint32_t n, void* gt_rgb_h, int64_t* gt_labels, float* gt_depth, void* stream);
+
+/* ---- f3. pseudo-label epilogue of a rendered view (joint_train_lightning_net.py:246-250,755-768): rows of semantics
+ * [N,C] without mass become uniform, rows are normalised, label_u8 = argmax + 1 (lowest index on ties);
+ * rgb_u8 [N,3] = (image * 255) truncated to u8, channel order RGB or BGR (cv2).  Either output may be null. */
+UCSA_API int ucsa_label_epilogue(const float* image, const float* semantics, uint32_t n_pixels, uint32_t n_classes, int bgr,
+                   uint8_t* label_u8, uint8_t* rgb_u8, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

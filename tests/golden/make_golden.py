@@ -249,6 +249,71 @@ def case_sample_pdf(name, *, n, bins, n_samples, seed):
     print(name, "ok")
 
 
+def case_frontend(name, *, height, width, n, seed):
+    """Rows f2 / f3 / f4: ray generation, ground-truth gather, pseudo-label epilogue, pose conventions.
+    Executed from the reference: nr4seg/dataset/ngp_utils.py (get_rays, nerf_matrix_to_ngp; loaded by file path - the
+    package __init__ pulls in imageio / cv2).  get_rays_train (joint_train_lightning_net.py:109-151) is get_rays
+    followed by a gather of the sampled pixels, and the epilogue (:246-250, :755-768) and the Slerp interpolation
+    (scannet_ngp_joint.py:229-262) are methods of classes that need Lightning / OpenCV: those few lines are replayed
+    here with the same torch / scipy calls."""
+    import importlib.util
+
+    from scipy.spatial.transform import Rotation, Slerp
+
+    spec_ = importlib.util.spec_from_file_location("ref_ngp_utils", "/root/reference/nr4seg/dataset/ngp_utils.py")
+    ngp_utils = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(ngp_utils)
+
+    g = torch.Generator().manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    nerf_poses = []
+    for _ in range(6):
+        p = np.eye(4, dtype=np.float32)
+        p[:3, :3] = Rotation.random(random_state=int(rng.integers(1 << 30))).as_matrix()
+        p[:3, 3] = rng.normal(size=3)
+        nerf_poses.append(p)
+    ngp_poses = np.stack([ngp_utils.nerf_matrix_to_ngp(p) for p in nerf_poses])
+    intrinsics = np.array([0.9 * width, 0.95 * width, width / 2 - 0.3, height / 2 + 0.7])
+    rays = ngp_utils.get_rays(torch.from_numpy(ngp_poses[:2]), intrinsics, height, width)
+    inds = torch.randint(0, height * width, size=[n], generator=g)  # may duplicate, as :142
+    # ground truth planes and the three gathers of forward_nerf_train (:180-187)
+    image = torch.rand(1, 3, height, width, generator=g).half()
+    labels = torch.randint(0, 40, (1, height, width), generator=g)
+    depth = torch.rand(1, height, width, generator=g) * 4
+    b_inds = inds.expand([1, n])
+    gt_rgb = torch.gather(image.reshape(1, 3, -1).permute(0, 2, 1), 1, torch.stack(3 * [b_inds], -1))
+    gt_labels = torch.gather(labels.view(1, -1), 1, b_inds)
+    gt_depth = torch.gather(depth.view(1, -1), 1, b_inds)
+    # pseudo-label epilogue (:246-250, :755-768)
+    semantics = torch.rand(n, 40, generator=g) ** 3
+    semantics[::7] = 0  # pixels without semantic mass
+    rgb = torch.rand(n, 3, generator=g)
+    sem = semantics.clone()
+    invalid = torch.sum(sem, dim=-1) == 0
+    sem[invalid] = 1
+    sem = sem / torch.sum(sem, dim=-1, keepdim=True)
+    label_u8 = (torch.argmax(sem, dim=-1) + 1).numpy().astype(np.uint8)
+    rgb_u8 = (rgb.numpy() * 255).astype(np.uint8)
+    # novel view points (scannet_ngp_joint.py:229-262)
+    ring = nerf_poses + [nerf_poses[0]]
+    slerp = Slerp(times=[*range(len(ring))], rotations=Rotation.from_matrix([p[:3, :3] for p in ring]))
+    rots = slerp(times=[0.5 + i for i in range(len(ring) - 1)]).as_matrix()
+    novel = []
+    for i in range(len(ring) - 1):
+        q = np.eye(4)
+        q[:3, :3] = rots[i]
+        q[:3, 3] = (ring[i][:3, 3] + ring[i + 1][:3, 3]) / 2.0
+        novel.append(q)
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"), height=height, width=width, intrinsics=intrinsics,
+        nerf_poses=np.stack(nerf_poses), ngp_poses=ngp_poses, rays_o=rays["rays_o"].numpy(),
+        rays_d=rays["rays_d"].numpy(), direction_norms=rays["direction_norms"].numpy(), inds=inds.numpy(),
+        image_h=image[0].numpy(), labels=labels[0].numpy(), depth=depth[0].numpy(), gt_rgb=gt_rgb[0].numpy(),
+        gt_labels=gt_labels[0].numpy(), gt_depth=gt_depth[0].numpy(), semantics=semantics.numpy(), rgb=rgb.numpy(),
+        label_u8=label_u8, rgb_u8=rgb_u8, novel_poses=np.stack(novel))
+    print(name, "rays", tuple(rays["rays_d"].shape), "novel", len(novel))
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -259,6 +324,7 @@ def main():
                  max_ray_batch=4096, n_outside=0, seed=11, backward=True)
     case_network("infer_staged", n=70, steps=16, up=16, perturb=False, train=False, staged=True,
                  max_ray_batch=32, n_outside=2, seed=12, backward=False)
+    case_frontend("frontend", height=24, width=40, n=300, seed=21)
 
 
 if __name__ == "__main__":

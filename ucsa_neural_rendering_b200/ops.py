@@ -444,3 +444,51 @@ def grid_update(density_grid, fresh, decay):
 def grid_packbits(density_grid, mean_density, bitfield):
     check(lib().ucsa_grid_packbits(_ptr(density_grid, torch.float32), density_grid.numel(), float(mean_density),
                                    _ptr(bitfield, torch.int32), _stream()), "grid_packbits")
+
+
+# ---------------------------------------------------------------------------------------------- front / back ends
+def generate_rays(pose, intrinsics, height, width, inds=None, n=None):
+    """Pinhole rays of one view (ngp_utils.py:28-70, joint_train_lightning_net.py:109-151).  pose: device [4,4] f32
+    cam2world; intrinsics (fx, fy, cx, cy); inds: device int64 pixel indices (row-major) or None for pixels 0..n-1
+    (default: the whole image).  -> rays_o [N,3], rays_d [N,3], direction_norms [N]"""
+    fx, fy, cx, cy = (float(v) for v in intrinsics)
+    if inds is None:
+        n = height * width if n is None else n
+    else:
+        n = inds.numel()
+    dev = pose.device
+    rays_o = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    rays_d = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    norms = torch.empty(n, dtype=torch.float32, device=dev)
+    check(lib().ucsa_generate_rays(_ptr(pose, torch.float32, "pose"), fx, fy, cx, cy, width, height,
+                                   _ptr(inds, torch.int64, "inds"), n, _ptr(rays_o), _ptr(rays_d), _ptr(norms),
+                                   _stream()), "generate_rays")
+    return rays_o, rays_d, norms
+
+
+def gather_gt(image_h, inds, labels=None, depth=None):
+    """Ground truth of the sampled pixels (joint_train_lightning_net.py:180-187).  image_h: device fp16 [C,H,W];
+    labels: int64 [H,W] or None; depth: f32 [H,W] or None.  -> gt_rgb fp16 [N,C], labels [N] | None, depth [N] | None"""
+    c = image_h.shape[0]
+    hw = image_h[0].numel()
+    n = inds.numel()
+    dev = image_h.device
+    gt_rgb = torch.empty(n, c, dtype=torch.float16, device=dev)
+    gt_labels = torch.empty(n, dtype=torch.int64, device=dev) if labels is not None else None
+    gt_depth = torch.empty(n, dtype=torch.float32, device=dev) if depth is not None else None
+    check(lib().ucsa_gather_gt(_ptr(image_h, torch.float16, "image"), _ptr(labels, torch.int64, "labels"),
+                               _ptr(depth, torch.float32, "depth"), hw, c, _ptr(inds, torch.int64, "inds"), n,
+                               _ptr(gt_rgb), _ptr(gt_labels), _ptr(gt_depth), _stream()), "gather_gt")
+    return gt_rgb, gt_labels, gt_depth
+
+
+def label_epilogue(semantics, image=None, bgr=False, want_labels=True):
+    """Pseudo-label epilogue of rendered pixels (joint_train_lightning_net.py:246-250,755-768).  semantics [N,C] f32,
+    image [N,3] f32 or None.  -> label_u8 [N] (argmax + 1) | None, rgb_u8 [N,3] | None"""
+    n, c = semantics.shape
+    dev = semantics.device
+    labels = torch.empty(n, dtype=torch.uint8, device=dev) if want_labels else None
+    rgb = torch.empty(n, 3, dtype=torch.uint8, device=dev) if image is not None else None
+    check(lib().ucsa_label_epilogue(_ptr(image, torch.float32, "image"), _ptr(semantics, torch.float32, "semantics"),
+                                    n, c, int(bgr), _ptr(labels), _ptr(rgb), _stream()), "label_epilogue")
+    return labels, rgb
