@@ -73,6 +73,19 @@ def test_oracle_frontend_matches_reference_fixture(fx):
     assert np.array_equal(lab_u8, fx["label_u8"]) and np.array_equal(rgb_u8, fx["rgb_u8"])
 
 
+def test_front_end_ops_refuse_cpu_tensors(fx):
+    """no CPU fallback on the product path: the wrappers raise instead of computing on the host"""
+    from ucsa_neural_rendering_b200 import ops
+    from ucsa_neural_rendering_b200._lib import UcsaError
+
+    with pytest.raises(UcsaError):
+        ops.generate_rays(torch.eye(4), fx["intrinsics"], 4, 4)
+    with pytest.raises(UcsaError):
+        ops.label_epilogue(torch.rand(8, 40))
+    with pytest.raises(UcsaError):
+        ops.gather_gt(torch.rand(3, 4, 4).half(), torch.zeros(2, dtype=torch.int64))
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 def test_generate_rays_kernel(fx):
@@ -129,3 +142,21 @@ def test_label_epilogue_kernel_is_exact(fx):
     first_max = (ref == ref.max(-1, keepdim=True).values).float().argmax(-1)  # lowest index among equal maxima
     lab, _ = ops.label_epilogue(big)
     assert torch.equal(lab.long(), first_max + 1)
+
+
+@pytest.mark.gpu
+def test_view_sampler_feeds_the_engine_batch_format(fx):
+    from ucsa_neural_rendering_b200.frontend import ViewSampler
+
+    h, w = int(fx["height"]), int(fx["width"])
+    vs = ViewSampler(fx["ngp_poses"], fx["intrinsics"], h, w, images_h=fx["image_h"][None].repeat(6, 0),
+                     labels=fx["labels"][None].repeat(6, 0), depths=fx["depth"][None].repeat(6, 0))
+    g = torch.Generator(device=DEV).manual_seed(0)
+    b = vs.sample(1, 500, generator=g)
+    inds = b["inds"].cpu().numpy()
+    assert b["rays_d"].shape == (500, 3) and b["gt_rgb"].dtype == torch.float16 and b["labels"].dtype == torch.int64
+    np.testing.assert_allclose(b["rays_d"].cpu().numpy(), fx["rays_d"][1][inds], rtol=0, atol=2.5e-7)
+    assert np.array_equal(b["gt_rgb"].cpu().numpy(), fx["image_h"].reshape(3, -1).T[inds])
+    assert np.array_equal(b["depth"].cpu().numpy(), fx["depth"].reshape(-1)[inds])
+    o, d, n = vs.full_view(0)
+    assert d.shape == (h * w, 3) and torch.equal(o[0], vs.poses[0, :3, 3])
