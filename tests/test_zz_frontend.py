@@ -139,7 +139,8 @@ def test_label_epilogue_kernel_is_exact(fx):
     ref = big.clone()
     ref[ref.sum(-1) == 0] = 1
     ref = ref / ref.sum(-1, keepdim=True)
-    first_max = (ref == ref.max(-1, keepdim=True).values).float().argmax(-1)  # lowest index among equal maxima
+    is_max = ref == ref.max(-1, keepdim=True).values
+    first_max = torch.where(is_max, torch.arange(40, device=DEV).expand_as(ref), torch.full_like(ref, 99).long()).min(-1).values  # lowest index among equal maxima
     lab, _ = ops.label_epilogue(big)
     assert torch.equal(lab.long(), first_max + 1)
 
