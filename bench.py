@@ -167,7 +167,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from ucsa_neural_rendering_b200 import _lib
+    from ucsa_neural_rendering_b200 import _lib, ops
     from ucsa_neural_rendering_b200.nerf import SemanticNeRFNetwork
     from ucsa_neural_rendering_b200.scene import SyntheticScene
     from ucsa_neural_rendering_b200.engine import TrainEngine
@@ -323,7 +323,8 @@ def run_ours(args):
         e0.record()
         for _ in range(n_views):
             out = net.render(vo[None], vd[None], **render_args)
-            labels_u8 = out["semantics"].argmax(-1).to(torch.uint8)  # the label map a caller writes out
+            # the label map + u8 colours a caller writes out (pseudo-label epilogue, row f3)
+            labels_u8, rgb_u8 = ops.label_epilogue(out["semantics"][0], out["image"][0])
         e1.record()
         barrier()
     net.train()
@@ -331,7 +332,7 @@ def run_ours(args):
     render_info = {"rays_per_s": world * scene.W * scene.H / (render_ms * 1e-3), "views_per_s": world / (render_ms * 1e-3),
                    "ms_per_view": render_ms, "rays_per_view": scene.W * scene.H, "chunk": render_chunk,
                    "samples_per_ray": NUM_STEPS + UPSAMPLE_STEPS, "api": "SemanticNeRFNetwork.render(staged=True)"}
-    del labels_u8
+    del labels_u8, rgb_u8
 
     if rank != 0:
         if world > 1:
