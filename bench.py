@@ -13,8 +13,14 @@ backward + Adam, exactly the work of training_step_nerf (joint_train_lightning_n
            truth and a D2H read of the loss inside the timed region.
 `roofline`: dominant kernel (by device time inside the timed region, CUDA events on the launch stream) against
            the measured HBM peak; algorithmic bytes = 588 B/sample x samples per launch.
-`cpu_baseline`: the CPU oracle port of the reference path (oracle/live_path.py) on a bounded sample, rank 0, N=1.
-`--impl reference`: the same oracle port, K steps of a bounded sample each, on all host cores.
+`cpu_baseline`: the CPU oracle port of the reference path (oracle/live_path.py), one full 4096-ray step, rank 0, N=1.
+`--impl reference`: the same oracle port on all host cores, K timed steps of the SAME 4096-ray batch size (processed
+           in 1024-ray slices with gradient accumulation to bound memory; warm-up steps use 256 rays).
+`config1` : BASELINE.json configs[0], the 4096 x 128 x 40 dense composite (forward and backward) against the HBM
+           roofline, with the reference's run() on the host cores beside it.
+Extra keys: `render` (config 3, one 640x480 view per rank), `trained` (the headline step after 300 optimisation steps,
+           when the w > 1e-4 mask really prunes), `strong_scaling_2p16` (config 4's 2^16-ray global batch split over
+           the ranks), `exchange_check` (N > 1: fused peer exchange vs the NCCL formulation, replicas identical).
 """
 from __future__ import annotations
 
@@ -36,6 +42,7 @@ NUM_STEPS, UPSAMPLE_STEPS = 256, 256
 N_CLASSES = 40
 BOUND = 4.0
 ENCODE_BYTES_PER_SAMPLE = 588  # 12 xyz + 512 gather/scatter + 64 features
+DTYPE = "fp16 encode/MLP (fp32 accumulate), fp32 sampling/composite"
 CONFIG = {
     "workload": "semantic-nerf train step: hashgrid 16x2^19, 4096 rays/GPU, 256+256 samples/ray, "
                 "synthetic ScanNet-shaped scene 640x480",
@@ -98,20 +105,42 @@ class ClockSampler:
                                      parts[5:9]):
                     if val.lower().startswith("active"):
                         reasons.add(name)
-        if not sm:  # region shorter than the sampling period: take whatever was seen
-            sm = [float(l.split(",")[1]) for _, l in self.rows[-3:] if l.count(",") >= 8] or [0.0]
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        note = None
+        if not sm:  # region shorter than the sampling period: take the samples nearest to it
+            near = []
+            for ts, line in self.rows:
+                parts = [p.strip() for p in line.split(",")]
+                try:
+                    near.append((abs(ts - 0.5 * (t0 + t1)), float(parts[1])))
+                    smax = float(parts[2])
+                except (ValueError, IndexError):
+                    continue
+            near.sort()
+            sm = [c for _, c in near[:3]]
+            note = "no sample inside the timed region; nearest samples used"
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": smax, "reasons": ["no nvidia-smi sample parsed"], "samples": 0}
+        out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 # ------------------------------------------------------------------------------------------ CPU oracle arm
+ORACLE_SLICE = 1024  # rays per forward/backward slice of the CPU arm (bounds memory; gradients accumulate)
+ORACLE_WARMUP_RAYS = 256
+
+
 def oracle_step_rays_per_s(n_rays, steps, warmup, threads):
-    """fwd + bwd of the reference path (oracle port) on `n_rays` rays x (256+256) samples; -> (rays/s, ms/step)."""
+    """training_step_nerf of the reference on the CPU oracle port: render (256+256 samples) + losses + backward + Adam
+    on `n_rays` rays per step, processed in ORACLE_SLICE-ray slices whose gradients accumulate (same arithmetic as one
+    pass: the losses are means over the whole batch).  Warm-up steps use ORACLE_WARMUP_RAYS rays (untimed).
+    -> (rays/s, ms/step)."""
     import torch
 
     from oracle import live_path
+    from oracle.losses import nerf_losses
     from ucsa_neural_rendering_b200.scene import SyntheticScene
-    from ucsa_neural_rendering_b200.trainer import nerf_losses
 
     torch.set_num_threads(threads)
     heads = live_path.OracleHeads(bound=BOUND, num_semantic_classes=N_CLASSES, seed=1337, hash_amp=1e-4)
@@ -122,15 +151,19 @@ def oracle_step_rays_per_s(n_rays, steps, warmup, threads):
     g = torch.Generator().manual_seed(123)
     times = []
     for s in range(warmup + steps):
-        pix = torch.randint(0, scene.W * scene.H, (n_rays,), generator=g)
+        n = n_rays if s >= warmup else min(n_rays, ORACLE_WARMUP_RAYS)
+        pix = torch.randint(0, scene.W * scene.H, (n,), generator=g)
         o, d, dn = scene.rays(s % scene.n_views, pix)
         rgb, depth, label = scene.ground_truth(o, d, dn)
         t0 = time.perf_counter()
         opt.zero_grad()
-        out = live_path.run(heads, o[None], d[None], dn[None], num_steps=NUM_STEPS, upsample_steps=UPSAMPLE_STEPS,
-                            perturb=True)
-        loss, _ = nerf_losses(out, rgb[None], label[None], depth[None], scene.one_m_to_scene_uom)
-        loss.backward()
+        for lo in range(0, n, ORACLE_SLICE):
+            hi = min(lo + ORACLE_SLICE, n)
+            out = live_path.run(heads, o[None, lo:hi], d[None, lo:hi], dn[None, lo:hi], num_steps=NUM_STEPS,
+                                upsample_steps=UPSAMPLE_STEPS, perturb=True)
+            loss, _ = nerf_losses(out, rgb[None, lo:hi], label[None, lo:hi], depth[None, lo:hi],
+                                  scene.one_m_to_scene_uom, global_scale=(hi - lo) / n)
+            loss.backward()
         opt.step()
         dt = time.perf_counter() - t0
         if s >= warmup:
@@ -144,18 +177,17 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_rays = 64
-    value, ms = oracle_step_rays_per_s(n_rays, args.steps, max(args.warmup, 1), cores)
-    cfg = dict(CONFIG)
-    cfg["reference_sample"] = f"{n_rays} rays x {NUM_STEPS + UPSAMPLE_STEPS} samples per step"
+    n_rays = RAYS_PER_GPU  # the same batch as the CUDA arm
+    value, ms = oracle_step_rays_per_s(n_rays, args.steps, args.warmup, cores)
+    sample = (f"oracle/live_path.py + oracle/losses.py fwd+bwd + torch Adam, {n_rays} rays x "
+              f"{NUM_STEPS + UPSAMPLE_STEPS} samples per timed step (slices of {ORACLE_SLICE} rays, gradients "
+              f"accumulated), {args.steps} steps; {args.warmup} warm-up steps of {ORACLE_WARMUP_RAYS} rays")
     line = {
         "impl": "reference", "metric": "semantic_nerf_train_rays_per_s", "value": value, "unit": "rays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16 encode/MLP, fp32 composite",
-        "data": "synthetic", "config": cfg,
-        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"oracle/live_path.py fwd+bwd+Adam, {n_rays} rays x 512 samples per step, "
-                                   f"{args.steps} steps"},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE,
+        "data": "synthetic", "config": dict(CONFIG, parallelism=f"ray-sharded dp{args.gpus}"),
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -163,6 +195,75 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ CUDA arm
+def time_config1(dev, peak):
+    """BASELINE.json configs[0] on the GPU: dense composite of 4096 rays x 128 samples x 40 classes, forward and
+    backward (csrc/composite_dense.cu), CUDA events per launch.  The forward working set (95 MB) would fit the 126 MB
+    L2, so four independent input sets are rotated: a launch's inputs were last touched ~300 MB of traffic ago."""
+    import torch
+
+    from ucsa_neural_rendering_b200 import ops
+
+    n, t, c, sets, reps = 4096, 128, 40, 4, 5
+    g = torch.Generator(device=dev).manual_seed(1234)
+    f32 = dict(dtype=torch.float32, device=dev)
+    data = []
+    for _ in range(sets):
+        sigma = 50.0 * torch.rand(n, t, generator=g, **f32) ** 4
+        rgb = torch.rand(n, t, 3, generator=g, **f32)
+        prob = torch.softmax(torch.randn(n, t, c, generator=g, **f32), dim=-1)
+        d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g, **f32), dim=-1)
+        nears, fars = ops.near_far_from_aabb(torch.zeros(n, 3, **f32), d, torch.tensor([-BOUND] * 3 + [BOUND] * 3, **f32))
+        z = nears[:, None] + (fars - nears)[:, None] * torch.linspace(0, 1, t, **f32)[None]
+        data.append(dict(sigma=sigma, rgb=rgb, prob=prob, z=z.contiguous(), dn=torch.ones(n, **f32),
+                         w=torch.empty(n, t, **f32), depth=torch.empty(n, **f32), image=torch.empty(n, 3, **f32),
+                         sem=torch.empty(n, c, **f32), gd=torch.randn(n, generator=g, **f32),
+                         gi=torch.randn(n, 3, generator=g, **f32), gs=torch.randn(n, c, generator=g, **f32),
+                         d_sigma=torch.empty(n, t, **f32), d_rgb=torch.empty(n, t, 3, **f32),
+                         d_prob=torch.empty(n, t, c, **f32)))
+
+    def fwd(x):
+        ops.composite_dense_fwd(x["sigma"], x["z"], x["rgb"], x["prob"], x["dn"], 1.0, x["w"], x["depth"], x["image"],
+                                x["sem"])
+
+    def bwd(x):
+        ops.composite_dense_bwd(x["sigma"], x["z"], x["rgb"], x["w"], x["dn"], x["gd"], x["gi"], x["gs"], 1.0,
+                                x["d_sigma"], x["d_rgb"], x["d_prob"])
+
+    for x in data:  # warm-up (also fills the weights the backward reads)
+        fwd(x)
+        bwd(x)
+    torch.cuda.synchronize()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    t_f, t_b = [], []
+    for _ in range(reps):
+        for x in data:
+            a, b_, c_ = ev(), ev(), ev()
+            a.record()
+            fwd(x)
+            b_.record()
+            bwd(x)
+            c_.record()
+            t_f.append((a, b_))
+            t_b.append((b_, c_))
+    torch.cuda.synchronize()
+    ms_f = statistics.mean(a.elapsed_time(b_) for a, b_ in t_f)
+    ms_b = statistics.mean(a.elapsed_time(b_) for a, b_ in t_b)
+    # algorithmic bytes, SURVEY.md section 8(d): forward 180 B/sample + 180 B/ray; backward reads 180 + writes 176 per
+    # sample and reads 352 per ray
+    bytes_f = n * t * 180 + n * 180
+    bytes_b = n * t * (180 + 176) + n * 352
+    return {
+        "workload": "dense composite 4096 rays x 128 samples x 40 classes (BASELINE.json configs[0])",
+        "l2": "4 rotating input sets of 95 MB (forward) / 188 MB (backward) each: no launch finds its inputs in L2",
+        "fwd": {"ms": ms_f, "algorithmic_bytes": bytes_f, "achieved_gbs": bytes_f / ms_f / 1e6,
+                "frac_of_hbm_peak": bytes_f / ms_f / 1e6 / peak},
+        "bwd": {"ms": ms_b, "algorithmic_bytes": bytes_b, "achieved_gbs": bytes_b / ms_b / 1e6,
+                "frac_of_hbm_peak": bytes_b / ms_b / 1e6 / peak},
+        "rays_per_s_fwd": n / (ms_f * 1e-3), "rays_per_s_fwd_bwd": n / ((ms_f + ms_b) * 1e-3), "peak_gbs": peak,
+        "launches": 2 * sets * reps,
+    }
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -181,6 +282,8 @@ def run_ours(args):
                          "(use --impl reference for the CPU oracle arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    clocks = ClockSampler(local_rank)  # started early: nvidia-smi needs a moment before its first row
+    clocks.start()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
@@ -198,12 +301,17 @@ def run_ours(args):
 
     total_steps = args.warmup + args.steps
     g = torch.Generator(device=dev).manual_seed(123 + rank)
-    batches = []
-    for s in range(total_steps):
-        pix = torch.randint(0, scene.W * scene.H, (RAYS_PER_GPU,), device=dev, generator=g)
-        o, d, dn = scene.rays(s % scene.n_views, pix)
-        rgb, depth, label = scene.ground_truth(o, d, dn)
-        batches.append(tuple(x[None].contiguous() for x in (o, d, dn, rgb.half(), label, depth)))
+
+    def make_batches(count, n_rays):
+        out = []
+        for s in range(count):
+            pix = torch.randint(0, scene.W * scene.H, (n_rays,), device=dev, generator=g)
+            o, d, dn = scene.rays(s % scene.n_views, pix)
+            rgb, depth, label = scene.ground_truth(o, d, dn)
+            out.append(tuple(x[None].contiguous() for x in (o, d, dn, rgb.half(), label, depth)))
+        return out
+
+    batches = make_batches(total_steps, RAYS_PER_GPU)
     host = [tuple(x.cpu().pin_memory() for x in b) for b in batches]
     h2d_bytes = sum(x.numel() * x.element_size() for x in host[0])
 
@@ -219,37 +327,39 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def time_engine_steps(eng, data, first, last):
+        """device time (max over ranks) of eng.train_step over data[first:last], barrier + synchronize on both sides"""
+        barrier()
+        e0.record()
+        for s in range(first, last):
+            eng.train_step(*data[s % len(data)])
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
     # ---------------------------------------------------------------- value: inputs resident in HBM
     # One step = one replay of the captured CUDA graph (engine.TrainEngine): render + losses + backward + Adam.
     _lib.stats.reset()
-    engine.train_step(*batches[0])  # first call captures the graph: count the kernels of one step here
+    engine.train_step(*batches[0])  # first call captures the graph
     torch.cuda.synchronize()
     for s in range(1, args.warmup):
         engine.train_step(*batches[s])
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
-    e0.record()
-    for s in range(args.warmup, total_steps):
-        engine.train_step(*batches[s])
-    e1.record()
-    barrier()
+    ms_total = time_engine_steps(engine, batches, args.warmup, total_steps)
     t_wall1 = time.time()
-    clock_info = clocks.stop(t_wall0, t_wall1)
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
     value = world * RAYS_PER_GPU * args.steps / (ms_total * 1e-3)
 
     # per-kernel device time: the same steps once more, launched eagerly with CUDA events around the kernels
     timed = {"ucsa_density_fwd", "ucsa_density_bwd", "ucsa_heads_fwd", "ucsa_heads_bwd", "ucsa_adam_step",
-             "ucsa_adam_exchange", "ucsa_resample_merge"}
-    eager = engine  # same engine, same buffers, launched kernel by kernel instead of replaying the graph
+             "ucsa_adam_exchange", "ucsa_resample_merge", "ucsa_grad_check", "ucsa_weights_fwd", "ucsa_weights_bwd",
+             "ucsa_compact_masked"}
     was_graph, engine.use_graph = engine.use_graph, False
-    eager.train_step(*batches[0])
+    engine.train_step(*batches[0])
     torch.cuda.synchronize()
     _lib.stats.reset()
-    eager.train_step(*batches[1])
+    engine.train_step(*batches[1])
     torch.cuda.synchronize()
     per_step_launches = _lib.stats.launches  # kernels of ONE step; the graph replays exactly these
     by_name = dict(_lib.stats.by_name)
@@ -257,11 +367,45 @@ def run_ours(args):
     _lib.stats.reset()
     _lib.stats.timed = set(timed)
     for s in range(args.warmup, total_steps):
-        eager.train_step(*batches[s])
+        engine.train_step(*batches[s])
     torch.cuda.synchronize()
     kernel_ms = {k: _lib.stats.elapsed_ms(k) for k in timed}
     _lib.stats.timed = set()
     engine.use_graph = was_graph
+    k_over_s_init = float(engine.ws.ray_off[-1]) / (RAYS_PER_GPU * (NUM_STEPS + UPSAMPLE_STEPS))
+
+    # the engine fed from pinned host memory (H2D of the batch + D2H of the loss inside the timed region)
+    barrier()
+    e0.record()
+    for s in range(args.warmup, total_steps):
+        engine.load_batch(*host[s])
+        float(engine.step()[0])
+    e1.record()
+    barrier()
+    e2e_engine_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_engine_value = world * RAYS_PER_GPU * args.steps / (e2e_engine_ms * 1e-3)
+
+    # ---------------------------------------------------------------- multi-GPU: evidence for the fused exchange
+    exchange_check = engine.exchange_check() if world > 1 else None
+    exchange_mode = engine.exchange
+    multicast = bool(engine.peer is not None and engine.peer.multicast)
+
+    # ---------------------------------------------------------------- extra: the same step on a trained model
+    # at random initialisation nearly every sample passes w > 1e-4 (K/S ~ 0.93: the heads see the worst case); after a
+    # few hundred steps the mask prunes.  300 optimisation steps over the batches above, then K timed steps.
+    trained = None
+    if not args.no_extras:
+        n_train = 300
+        for s in range(n_train):
+            engine.train_step(*batches[s % len(batches)])
+        ms_tr = time_engine_steps(engine, batches, args.warmup, total_steps)
+        k_over_s = float(engine.ws.ray_off[-1]) / (RAYS_PER_GPU * (NUM_STEPS + UPSAMPLE_STEPS))
+        loss4 = [float(v) for v in engine.loss]
+        trained = {"after_steps": n_train + 2 * total_steps, "ms_per_step": ms_tr / args.steps,
+                   "rays_per_s": world * RAYS_PER_GPU * args.steps / (ms_tr * 1e-3), "k_over_s": k_over_s,
+                   "k_over_s_at_init": k_over_s_init, "loss": loss4,
+                   "skipped_steps": engine.skipped_steps}
+    engine.gather_masters()
 
     # ---------------------------------------------------------------- e2e: public API, host buffers
     opt = torch.optim.Adam([
@@ -294,46 +438,71 @@ def run_ours(args):
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * RAYS_PER_GPU * args.steps / (e2e_ms * 1e-3)
-
-    # the engine fed from pinned host memory (H2D of the batch + D2H of the loss inside the timed region)
-    barrier()
-    e0.record()
-    for s in range(args.warmup, total_steps):
-        engine.load_batch(*host[s])
-        float(engine.step()[0])
-    e1.record()
-    barrier()
-    e2e_engine_ms = max_over_ranks(e0.elapsed_time(e1))
-    e2e_engine_value = world * RAYS_PER_GPU * args.steps / (e2e_engine_ms * 1e-3)
+    del opt
+    for p_ in net.parameters():
+        p_.grad = None
 
     # ---------------------------------------------------------------- extra: full-frame rendering
-    # one 640x480 view per rank (views shard, no collective), staged in chunks, no perturbation; reported beside the
-    # headline, not part of it
-    render_chunk = 65536
-    view_pix = torch.arange(scene.W * scene.H, device=dev)
-    net.eval()
-    with torch.no_grad():
-        vo, vd, vdn = scene.rays(rank % scene.n_views, view_pix)
-        render_args = dict(direction_norms=vdn.view(1, -1, 1), staged=True, max_ray_batch=render_chunk, bg_color=None,
-                           perturb=False, seed=99)
-        for _ in range(2):
-            out = net.render(vo[None], vd[None], **render_args)
-        n_views = 3
-        barrier()
-        e0.record()
-        for _ in range(n_views):
-            out = net.render(vo[None], vd[None], **render_args)
-            # the label map + u8 colours a caller writes out (pseudo-label epilogue, row f3)
-            labels_u8, rgb_u8 = ops.label_epilogue(out["semantics"][0], out["image"][0])
-        e1.record()
-        barrier()
-    net.train()
-    render_ms = max_over_ranks(e0.elapsed_time(e1)) / n_views
-    render_info = {"rays_per_s": world * scene.W * scene.H / (render_ms * 1e-3), "views_per_s": world / (render_ms * 1e-3),
-                   "ms_per_view": render_ms, "rays_per_view": scene.W * scene.H, "chunk": render_chunk,
-                   "samples_per_ray": NUM_STEPS + UPSAMPLE_STEPS, "api": "SemanticNeRFNetwork.render(staged=True)"}
-    del labels_u8, rgb_u8
+    # one 640x480 view per rank (views shard, no collective), staged, no perturbation, with the caller's DEFAULT
+    # max_ray_batch = 4096 (joint_train_lightning_net.py:237 / renderer_semantics.py:306): the network re-chunks to
+    # 65536 rays internally; "strict_4096" forces the reference's chunking.
+    render_info = None
+    if not args.no_extras:
+        view_pix = torch.arange(scene.W * scene.H, device=dev)
+        net.eval()
+        with torch.no_grad():
+            vo, vd, vdn = scene.rays(rank % scene.n_views, view_pix)
+            render_args = dict(direction_norms=vdn.view(1, -1, 1), staged=True, bg_color=None, perturb=False, seed=99)
 
+            def time_render(n_views):
+                for _ in range(2):
+                    net.render(vo[None], vd[None], **render_args)
+                barrier()
+                e0.record()
+                for _ in range(n_views):
+                    out = net.render(vo[None], vd[None], **render_args)
+                    # the label map + u8 colours a caller writes out (pseudo-label epilogue, row f3)
+                    ops.label_epilogue(out["semantics"][0], out["image"][0])
+                e1.record()
+                barrier()
+                return max_over_ranks(e0.elapsed_time(e1)) / n_views
+
+            render_ms = time_render(3)
+            chunk_default = net.stage_chunk
+            net.stage_chunk = None
+            render_ms_strict = time_render(2)
+            net.stage_chunk = chunk_default
+        net.train()
+        rays_view = scene.W * scene.H
+        render_info = {"rays_per_s": world * rays_view / (render_ms * 1e-3), "views_per_s": world / (render_ms * 1e-3),
+                       "ms_per_view": render_ms, "rays_per_view": rays_view, "max_ray_batch": 4096,
+                       "internal_chunk": chunk_default, "samples_per_ray": NUM_STEPS + UPSAMPLE_STEPS,
+                       "api": "SemanticNeRFNetwork.render(staged=True) with the default max_ray_batch",
+                       "strict_4096": {"rays_per_s": world * rays_view / (render_ms_strict * 1e-3),
+                                       "ms_per_view": render_ms_strict}}
+
+    # ---------------------------------------------------------------- extra: config 4's 2^16-ray global batch, strong scaling
+    strong = None
+    if not args.no_extras:
+        try:
+            n_strong = 65536 // world
+            del engine
+            torch.cuda.empty_cache()
+            eng2 = TrainEngine(net, n_strong, num_steps=NUM_STEPS, upsample_steps=UPSAMPLE_STEPS,
+                               one_m_to_scene_uom=uom, use_graph=not args.no_graph, exchange=args.exchange)
+            b2 = make_batches(3, n_strong)
+            for s in range(3):
+                eng2.train_step(*b2[s])
+            k2 = max(3, args.steps // 4)
+            ms2 = time_engine_steps(eng2, b2, 0, k2)
+            strong = {"global_batch": n_strong * world, "rays_per_gpu": n_strong, "steps": k2, "ms_per_step": ms2 / k2,
+                      "rays_per_s": n_strong * world * k2 / (ms2 * 1e-3), "scaling": "strong"}
+            eng2.gather_masters()
+            del eng2
+        except Exception as exc:  # noqa: BLE001 - an extra must never take the headline down
+            strong = {"error": repr(exc)[:300]}
+
+    clock_info = clocks.stop(t_wall0, t_wall1)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -351,52 +520,64 @@ def run_ours(args):
     dur_ms = statistics.mean(kernel_ms[dominant])
     alg_bytes = ENCODE_BYTES_PER_SAMPLE * samples_per_launch[dominant]
     achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
-    traffic, traffic_src = None, None
-    try:  # DRAM bytes per launch of the same kernel from the committed ncu capture (scripts/summarize_ncu.py traffic)
+    kname = dominant.replace("ucsa_", "") + "_tc_kernel"
+    traffic, traffic_src, counters = None, None, None
+    try:  # per-launch ncu counters of the same kernel from the committed capture (scripts/summarize_ncu.py traffic)
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             tj = json.load(fh)
-        traffic = tj["bytes_per_launch"].get(dominant.replace("ucsa_", "") + "_tc_kernel")
+        traffic = tj["bytes_per_launch"].get(kname)
         traffic_src = tj["source"]
+        counters = tj.get("l2_requests_per_launch", {}).get(kname)
     except (OSError, ValueError, KeyError):
         pass
     compulsory = 76 * samples_per_launch[dominant] + 13_074_912 * (2 if dominant == "ucsa_density_fwd" else 4)
     roofline = {
-        "bound": "hbm", "kernel": dominant.replace("ucsa_", "") + "_tc_kernel", "achieved": achieved, "peak": peak,
+        "bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": dur_ms,
         "hbm_compulsory": {"bytes_per_launch": compulsory, "achieved": compulsory / (dur_ms * 1e-3) / 1e9,
                            "note": "76 B/sample (xyz, features, saved activations) + the table once (SURVEY 8d)"},
-        # what actually binds the density kernels: the L2 request rate (scripts/gather_probe.cu, measured on B200:
-        # 285 G 16-byte gathers/s, 192 G reductions/s whatever their width); operation counts per sample from
-        # DESIGN.md section 5 (forward: 12 hashed levels x 4 corner pairs x 1.25; backward: ~68 after run-merging)
-        "l2_request_roofline": {
-            "ops_per_launch_est": (60 if dominant == "ucsa_density_fwd" else 68) * samples_per_launch[dominant],
-            "peak_gops": 285.0 if dominant == "ucsa_density_fwd" else 192.0,
-            "achieved_gops": (60 if dominant == "ucsa_density_fwd" else 68) * samples_per_launch[dominant]
-            / (dur_ms * 1e-3) / 1e9,
-            "frac": (60 if dominant == "ucsa_density_fwd" else 68) * samples_per_launch[dominant]
-            / (dur_ms * 1e-3) / 1e9 / (285.0 if dominant == "ucsa_density_fwd" else 192.0),
-            "note": "operation counts are analytic estimates; peaks measured by scripts/gather_probe.cu"},
         "note": "588 B/sample counts the 512 B of table gathers/scatters, which hit the L2-resident table rather "
                 "than HBM (traffic = measured DRAM bytes of the launch); the kernel is bound by L2 reduction / L1 "
                 "gather throughput, see DESIGN.md sections 5 and 9",
         "kernel_ms_per_step": {k.replace("ucsa_", ""): totals[k] / args.steps for k in totals},
     }
+    if counters:
+        # what actually binds the density kernels: the L2 request rate (scripts/gather_probe.cu, measured on B200:
+        # 285 G 16-byte gathers/s, 192 G reductions/s whatever their width).  Request counts are ncu counters of the
+        # committed capture (lts__t_requests_srcunit_tex_op_red / _op_read), not estimates.
+        op = "red" if dominant == "ucsa_density_bwd" else "read"
+        peak_g = 192.0 if op == "red" else 285.0
+        reqs = counters.get("lts_requests_" + op)
+        if reqs:
+            roofline["l2_request_roofline"] = {
+                "op": op, "requests_per_launch": reqs, "peak_greq_s": peak_g,
+                "achieved_greq_s": reqs / (dur_ms * 1e-3) / 1e9, "frac": reqs / (dur_ms * 1e-3) / 1e9 / peak_g,
+                "source": traffic_src, "counters": counters}
 
+    config1 = time_config1(dev, peak) if not args.no_extras else None
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_cpu = 64
-        v, ms = oracle_step_rays_per_s(n_cpu, 3, 1, cores)
+        v, ms = oracle_step_rays_per_s(RAYS_PER_GPU, 1, 1, cores)
         cpu = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-               "sample": f"oracle/live_path.py fwd+bwd+Adam on {n_cpu} rays x 512 samples, 3 steps after 1 warm-up "
+               "sample": f"oracle/live_path.py fwd+bwd+Adam, ONE step of {RAYS_PER_GPU} rays x 512 samples (the GPU "
+                         f"arm's batch; slices of {ORACLE_SLICE} rays) after one {ORACLE_WARMUP_RAYS}-ray warm-up step "
                          f"({ms:.0f} ms/step)"}
+        if config1 is not None:
+            from oracle import config1 as oracle_config1
+
+            c1 = oracle_config1.time_cpu(threads=cores, repeats=3, warmup=1)
+            config1["cpu_reference"] = dict(c1, kind="port", what="oracle/config1.py: live_path.run(num_steps=128, "
+                                            "upsample_steps=0) with synthetic heads, best of 3 (renderer_semantics.py:"
+                                            "123-299 on the host cores)")
+            config1["cpu_reference"]["rays_per_s_fwd"] = 4096 / (c1["fwd_ms"] * 1e-3)
 
     line = {
         "metric": "semantic_nerf_train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "fp16 encode/MLP (fp32 accumulate), fp32 sampling/composite", "data": "synthetic",
+        "dtype": DTYPE, "data": "synthetic",
         "config": dict(CONFIG, parallelism=f"ray-sharded dp{world}"),
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps,
@@ -406,11 +587,12 @@ def run_ours(args):
                            "api": "TrainEngine.load_batch(pinned host) + step() + loss readback"}},
         "gpu_launches": launches, "gpu_launches_per_step": by_name,
         "step_impl": "cuda-graph replay of %d kernels" % per_step_launches if not args.no_graph else "eager kernel chain",
-        "render": render_info,
+        "render": render_info, "trained": trained, "strong_scaling_2p16": strong, "config1": config1,
         "gradient_exchange": {"none": "single GPU", "nccl": "NCCL all-reduce + replicated Adam",
                               "peer": "ucsa_adam_exchange over symmetric memory (%s)" % (
-                                  "multimem.ld_reduce / multimem.st via NVSwitch" if engine.peer is not None
-                                  and engine.peer.multicast else "peer loads / stores")}[engine.exchange],
+                                  "multimem.ld_reduce / multimem.st via NVSwitch" if multicast
+                                  else "peer loads / stores")}[exchange_mode],
+        "exchange_check": exchange_check,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info,
     }
     emit(line)
@@ -450,6 +632,8 @@ def main():
     ap.add_argument("--exchange", choices=["peer", "nccl"], default=None,
                     help="multi-GPU gradient exchange (default: peer memory when available)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra measurements (render, trained model, strong scaling, config 1)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

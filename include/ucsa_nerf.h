@@ -43,6 +43,7 @@ extern "C" {
 #define UCSA_SIGMA_PARAMS 3072  /* 32->64->16            network_tcnn_semantics.py:48-58  */
 #define UCSA_COLOR_PARAMS 7168  /* 32->64->64->16        network_tcnn_semantics.py:74-84  */
 #define UCSA_MAX_CLASSES 48     /* semantics 16->64->pad16(C)  network_tcnn_semantics.py:90-100 */
+#define UCSA_LOSS_SCRATCH_BYTES 1024 /* ucsa_nerf_loss: per-CTA partial sums + done counter */
 #define UCSA_MAX_PEERS 16       /* ranks of one NVLink domain in ucsa_adam_exchange */
 #define UCSA_TILE_ROWS(rows) (((rows) + 127u) / 128u * 128u) /* rows of a tile-layout activation buffer */
 
@@ -266,11 +267,20 @@ UCSA_API int ucsa_mlp_bwd_simt(const void* x_h, uint32_t n, const void* w_h, con
                                void* dx_h, float* grad_w, void* stream);
 
 /* ---- parameter plumbing: fp32 master -> fp16 working copy; fused Adam (row f1:
- * joint_train_lightning_net.py:897-919: lr, betas (0.9,0.99), eps 1e-15, weight_decay on the MLPs). */
+ * joint_train_lightning_net.py:897-919: lr, betas (0.9,0.99), eps 1e-15, weight_decay on the MLPs).  lr and the
+ * betas are doubles: torch.optim.Adam forms 1 - beta, the bias corrections and the step size in Python doubles and
+ * rounds once, and the kernel does the same so that it tracks torch to the last bits. */
 UCSA_API int ucsa_cast_f32_to_f16(const float* src, uint64_t n, void* dst_h, void* stream);
 UCSA_API int ucsa_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_h,
-                   uint64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   uint64_t n, double lr, double beta1, double beta2, float eps, float weight_decay,
                    float grad_scale_inv, const float* found_inf, uint32_t step, const int32_t* step_dev,
+                   const int32_t* skipped_dev, void* stream);
+/* GradScaler's overflow check (joint_train_lightning_net.py:46,509-513; torch.amp.GradScaler.unscale_ / step): one
+ * pass over a gradient buffer.  found_inf[0] = 1 if any entry is inf / NaN else 0; when it is 1 and skipped_dev is
+ * given, skipped_dev[0] += 1 (ucsa_adam_step / ucsa_adam_exchange then skip the update, and Adam's step count is
+ * step_dev[0] - skipped_dev[0]).  scratch2: two zero-initialised uint32 words owned by the caller (re-armed by the
+ * kernel, so the launch can be replayed from a CUDA graph). */
+UCSA_API int ucsa_grad_check(const float* grad, uint64_t n, float* found_inf, int32_t* skipped_dev, uint32_t* scratch2,
                    void* stream);
 
 /* ---- (e)+f1. gradient exchange fused into Adam over peer memory (the reference: DDP all-reduce inside Lightning,
@@ -279,21 +289,29 @@ UCSA_API int ucsa_adam_step(float* param, const float* grad, float* exp_avg, flo
  * multicast addresses (NVLS; all three or all null -> plain peer loads / stores).  The calling rank owns parameters
  * [begin, end): it sums the gradients of all ranks, applies Adam (moments exp_avg / exp_avg_sq hold end-begin
  * entries; weight decay applies to parameters >= wd_begin) and writes the new values into every rank's buffers.
+ * found_inf_ptrs_host (optional): `world` addresses of the ranks' overflow flags (ucsa_grad_check, in symmetric
+ * memory): when any is set the update is skipped on every rank and skipped_dev[0] += 1 on the caller.
+ * broadcast_masters = 0 keeps the fp32 masters of a slice on its owner only (param_ptrs_host[rank] is then the only
+ * master address used; mc_param may be null): peers receive just the fp16 working copy the kernels read, and a
+ * checkpoint gathers the owned slices explicitly.
  * Bracket the launch with cross-rank barriers: gradients complete before, parameters visible after. */
 UCSA_API int ucsa_adam_exchange(const uint64_t* grad_ptrs_host, const uint64_t* param_ptrs_host,
                    const uint64_t* param_h_ptrs_host, const float* mc_grad, float* mc_param, void* mc_param_h,
                    uint32_t world, uint32_t rank, uint64_t begin, uint64_t end, uint64_t wd_begin, float* exp_avg,
-                   float* exp_avg_sq, float lr, float beta1, float beta2, float eps, float weight_decay,
-                   uint32_t step, const int32_t* step_dev, void* stream);
+                   float* exp_avg_sq, double lr, double beta1, double beta2, float eps, float weight_decay,
+                   uint32_t step, const int32_t* step_dev, const uint64_t* found_inf_ptrs_host, int32_t* skipped_dev,
+                   int broadcast_masters, void* stream);
 
 /* ---- f2. losses of forward_nerf_train (joint_train_lightning_net.py:199-221,503-507) and their gradients w.r.t.
  * image / depth / semantics in one kernel.  gt_rgb as fp16 [N,3] (batch["img_fp16"]) or fp32; labels int64 with -1 =
- * ignore; loss4 = (total, colour, semantics, depth).  total is multiplied by global_scale (1/world for sharded rays). */
+ * ignore; loss4 = (total, colour, semantics, depth).  total is multiplied by global_scale (1/world for sharded rays).
+ * scratch: UCSA_LOSS_SCRATCH_BYTES of device memory owned by the caller, zero-filled once (the kernel re-arms it);
+ * one block per engine / stream, so concurrent launches never share partial sums. */
 UCSA_API int ucsa_nerf_loss(const float* image, const float* depth, const float* semantics, const void* gt_rgb_h,
                    const float* gt_rgb_f, const int64_t* labels, const float* gt_depth, uint32_t n_rays,
                    uint32_t n_classes, float one_m_to_scene_uom, float weight_semantics, float weight_depth,
                    float global_scale, float* loss4, float* g_image, float* g_depth, float* g_semantics,
-                   void* stream);
+                   void* scratch, void* stream);
 
 /* ---- f2 (front). pinhole rays of the pixels `inds` [N] (row-major, may repeat; null = pixels 0..N-1) of one view:
  * dataset/ngp_utils.py:28-70 (get_rays), lightning/joint_train_lightning_net.py:109-151 (get_rays_train).

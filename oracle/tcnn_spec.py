@@ -140,21 +140,68 @@ def _round_h(t: torch.Tensor) -> torch.Tensor:
     return _RoundH.apply(t)
 
 
+class _HashGridFn(torch.autograd.Function):
+    """All-torch gather / scatter of the grid (no numpy round-trips): per level one [S,8] index block, one gather and
+    -- backward -- one index_add_ into the level's slice of the gradient.  Same arithmetic and summation order
+    (corner 0..7, fp32) as the numpy helpers above, which stay the bit-exact index contract."""
+
+    @staticmethod
+    def forward(ctx, x01, params, table):
+        xs = x01.detach().to(torch.float32).cpu()
+        tab_h = params.detach().half().float().view(-1, N_FEATURES)
+        s = xs.shape[0]
+        out = torch.empty(s, N_LEVELS * N_FEATURES, dtype=torch.float32)
+        saved_idx, saved_w = [], []
+        m32 = 0xFFFFFFFF
+        for lvl in range(N_LEVELS):
+            scale = float(table["scale"][lvl])
+            pos = (xs.double() * scale + 0.5).float()  # float32 fma: the product is exact in float64
+            cell_f = torch.floor(pos)
+            frac = pos - cell_f
+            cell = cell_f.long() & m32
+            n = int(table["entries"][lvl])
+            r = int(table["res"][lvl])
+            idx = torch.empty(s, 8, dtype=torch.int64)
+            w = torch.empty(s, 8, dtype=torch.float32)
+            for c in range(8):
+                cx = (cell[:, 0] + (c & 1)) & m32
+                cy = (cell[:, 1] + ((c >> 1) & 1)) & m32
+                cz = (cell[:, 2] + ((c >> 2) & 1)) & m32
+                if table["hashed"][lvl]:
+                    i = cx ^ ((cy * int(PRIME_Y)) & m32) ^ ((cz * int(PRIME_Z)) & m32)
+                else:
+                    i = (cx + ((cy * r) & m32) + ((cz * ((r * r) & m32)) & m32)) & m32
+                idx[:, c] = i % n + int(table["offset"][lvl])
+                wc = torch.ones(s, dtype=torch.float32)
+                for d in range(3):
+                    f = frac[:, d]
+                    wc = wc * (f if (c >> d) & 1 else (1.0 - f))
+                w[:, c] = wc
+            vals = tab_h[idx.view(-1)].view(s, 8, N_FEATURES)
+            acc = torch.zeros(s, N_FEATURES, dtype=torch.float32)
+            for c in range(8):
+                acc = acc + w[:, c:c + 1] * vals[:, c]
+            out[:, lvl * N_FEATURES:(lvl + 1) * N_FEATURES] = acc
+            saved_idx.append(idx)
+            saved_w.append(w)
+        ctx.saved_idx, ctx.saved_w, ctx.n_params = saved_idx, saved_w, params.numel()
+        return out.half().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        grad = torch.zeros(ctx.n_params // N_FEATURES, N_FEATURES, dtype=torch.float32)
+        for lvl in range(N_LEVELS):
+            gl = g[:, lvl * N_FEATURES:(lvl + 1) * N_FEATURES]
+            contrib = (ctx.saved_w[lvl].unsqueeze(2) * gl.unsqueeze(1)).reshape(-1, N_FEATURES)
+            grad.index_add_(0, ctx.saved_idx[lvl].view(-1), contrib)
+        return None, grad.view(-1), None
+
+
 def hashgrid_forward(x01: torch.Tensor, params: torch.Tensor, table) -> torch.Tensor:
     """x01 [S,3] f32 in [0,1]; params [total*2] f32 master.  Returns [S,32] f32 holding
-    fp16-representable values (level-major feature order l0f0,l0f1,l1f0,...)."""
-    xs = x01.detach().cpu().numpy().astype(np.float32)
-    tab_h = _round_h(params).view(-1, N_FEATURES)
-    feats = []
-    for lvl in range(N_LEVELS):
-        cell, frac = grid_cells(xs, table, lvl)
-        acc = torch.zeros(xs.shape[0], N_FEATURES, dtype=torch.float32)
-        for c in range(8):
-            idx = corner_index(cell, table, lvl, c).astype(np.int64) + int(table["offset"][lvl])
-            w = torch.from_numpy(corner_weight(frac, c)).unsqueeze(1)
-            acc = acc + w * tab_h[torch.from_numpy(idx)]
-        feats.append(acc)
-    return _round_h(torch.cat(feats, dim=1))
+    fp16-representable values (level-major feature order l0f0,l0f1,l1f0,...).  Both roundings (table -> fp16,
+    output -> fp16) are straight-through for the gradient, like _round_h."""
+    return _HashGridFn.apply(x01, params, table)
 
 
 def sh4_forward(d01: torch.Tensor) -> torch.Tensor:

@@ -80,14 +80,23 @@ def full(src, dst):
 
 
 def traffic(src, dst):
-    """DRAM bytes (read + write) per launch of every profiled kernel -> JSON that bench.py reports as roofline.traffic"""
+    """Per launch of every profiled kernel: DRAM bytes (read + write) -> bench.py's roofline.traffic, and the L2 request
+    counters (reductions / reads issued by the SMs) -> bench.py's l2_request_roofline."""
     import json
 
     raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    acc = {}
+    req_metrics = {
+        "lts_requests_red": "lts__t_requests_srcunit_tex_op_red.sum",
+        "lts_requests_read": "lts__t_requests_srcunit_tex_op_read.sum",
+        "l1_requests_red": "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum",
+        "l1_requests_ld": "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+        "lts_sectors_red": "lts__t_sectors_op_red.sum",
+        "lts_hit_rate_pct": "lts__t_sector_hit_rate.pct",
+    }
+    acc, reqs = {}, {}
     for row in rows[2:]:
         name = row[hdr.index("Kernel Name")].split("(")[0].split("::")[-1].split("<")[0]
         total = 0.0
@@ -95,8 +104,16 @@ def traffic(src, dst):
             i = hdr.index(m)
             total += float(row[i].replace(",", "")) * scale[units[i]]
         acc.setdefault(name, []).append(total)
+        for key, m in req_metrics.items():
+            if m in hdr:
+                try:
+                    reqs.setdefault(name, {}).setdefault(key, []).append(float(row[hdr.index(m)].replace(",", "")))
+                except ValueError:
+                    pass
     out = {"source": src, "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full), mean over "
-           "the profiled launches", "bytes_per_launch": {k: sum(v) / len(v) for k, v in acc.items()}}
+           "the profiled launches; l2_requests_per_launch: ncu request counters, same launches",
+           "bytes_per_launch": {k: sum(v) / len(v) for k, v in acc.items()},
+           "l2_requests_per_launch": {k: {m: sum(x) / len(x) for m, x in v.items()} for k, v in reqs.items()}}
     with open(dst, "w") as fh:
         json.dump(out, fh, indent=1)
     print(json.dumps(out, indent=1))

@@ -82,11 +82,17 @@ def test_host_side_argument_checks_run_before_any_launch(handle):
     # the fused exchange: slice bounds in whole float4 groups, rank inside the world
     arr = (ctypes.c_uint64 * 2)(16, 16)
     rc = handle.ucsa_adam_exchange(arr, arr, arr, None, None, None, 2, 0, 2, 8, 0, one, one, 1e-2, 0.9, 0.99, 1e-15,
-                                   0.0, 1, None, None)
+                                   0.0, 1, None, None, None, 1, None)
     assert rc == -1 and b"multiples of 4" in handle.ucsa_last_error_string()
     rc = handle.ucsa_adam_exchange(arr, arr, arr, None, None, None, 2, 2, 0, 8, 0, one, one, 1e-2, 0.9, 0.99, 1e-15,
-                                   0.0, 1, None, None)
+                                   0.0, 1, None, None, None, 1, None)
     assert rc == -1 and b"rank < world" in handle.ucsa_last_error_string()
+    # the optimizer's overflow check and the loss kernel refuse missing scratch blocks instead of sharing globals
+    rc = handle.ucsa_grad_check(one, 16, one, None, None, None)
+    assert rc == -1 and b"null" in handle.ucsa_last_error_string()
+    rc = handle.ucsa_nerf_loss(one, one, one, one, None, one, one, 4, 40, 1.0, 0.04, 0.1, 1.0, one, one, one, one, None,
+                               None)
+    assert rc == -1 and b"null" in handle.ucsa_last_error_string()
 
 
 def test_tile_layout_helpers_and_launch_accounting():

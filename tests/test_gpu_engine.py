@@ -43,13 +43,15 @@ def test_loss_kernel_matches_reference_losses():
     sem[0, :5] = 0  # rays without any semantic mass: "invalid" -> ignored
     sem = sem.to(DEV).requires_grad_()
     _, _, _, rgb, labels, gt_depth = _batch(n, c, 3)
-    total, (lc, ls, ld) = nerf_losses({"image": image, "semantics": sem, "depth": depth}, rgb, labels, gt_depth, 0.6,
-                                      global_scale=0.5, fused=False)  # the reference's torch expression
+    from oracle.losses import nerf_losses as oracle_losses  # the reference's torch expression
+
+    total, (lc, ls, ld) = oracle_losses({"image": image, "semantics": sem, "depth": depth}, rgb, labels, gt_depth, 0.6,
+                                        global_scale=0.5)
     total.backward()
     loss4 = torch.zeros(4, device=DEV)
     gi, gd, gs = torch.empty(n, 3, device=DEV), torch.empty(n, device=DEV), torch.empty(n, c, device=DEV)
     ops.nerf_loss(image.detach().view(n, 3), depth.detach().view(n), sem.detach().view(n, c), rgb.view(n, 3),
-                  labels.view(n), gt_depth.view(n), 0.6, 0.04, 0.1, 0.5, loss4, gi, gd, gs)
+                  labels.view(n), gt_depth.view(n), 0.6, 0.04, 0.1, 0.5, loss4, gi, gd, gs, ops.loss_scratch(DEV))
     torch.testing.assert_close(loss4, torch.stack([total.detach(), lc.detach(), ls.detach(), ld.detach()]), rtol=1e-5,
                                atol=1e-6)
     torch.testing.assert_close(gi, image.grad.view(n, 3), rtol=1e-5, atol=1e-9)
@@ -151,3 +153,77 @@ def test_adam_exchange_kernel_equals_adam_step_on_one_rank():
     assert torch.equal(p[begin:end], ref_p[begin:end]) and torch.equal(h[begin:end], ref_h[begin:end])
     assert torch.equal(m, m_ref[begin:end]) and torch.equal(v, v_ref[begin:end])
     assert torch.equal(p[:begin], p0[:begin]) and torch.equal(p[end:], p0[end:])  # outside the owned slice: untouched
+
+
+def test_adam_step_matches_torch_adam_under_gradscaler():
+    """ucsa_grad_check + ucsa_adam_step against torch.optim.Adam driven by torch.amp.GradScaler, the optimizer of
+    joint_train_lightning_net.py:46,509-513,897-919: lr 1e-2, betas (0.9, 0.99), eps 1e-15, two groups with weight
+    decay 1e-6 on the MLP group only; 10 steps, one of which carries an inf gradient and must be skipped (no moment /
+    parameter change, no bias-correction advance), after which GradScaler halves its scale."""
+    from ucsa_neural_rendering_b200 import ops
+
+    g = torch.Generator().manual_seed(11)
+    sizes = (100_003, 14_336)  # "encoding" (odd length: exercises the scalar tail), "net"
+    wds = (0.0, 1e-6)
+    p0 = [(torch.rand(sizes[0], generator=g) * 2e-4 - 1e-4), torch.randn(sizes[1], generator=g) * 0.3]
+    ref_p = [torch.nn.Parameter(p.clone().to(DEV)) for p in p0]
+    opt = torch.optim.Adam([{"params": [ref_p[0]]}, {"params": [ref_p[1]], "weight_decay": wds[1]}], lr=1e-2,
+                           betas=(0.9, 0.99), eps=1e-15)
+    scaler = torch.amp.GradScaler("cuda", init_scale=128.0, growth_interval=10_000)
+    our_p = [p.clone().to(DEV) for p in p0]
+    our_h = [torch.empty(n, dtype=torch.float16, device=DEV) for n in sizes]
+    our_m = [torch.zeros(n, device=DEV) for n in sizes]
+    our_v = [torch.zeros(n, device=DEV) for n in sizes]
+    # one flat gradient buffer like the engine's; views must stay 16-byte aligned -> pad the first group
+    pad0 = (sizes[0] + 3) // 4 * 4
+    flat = torch.zeros(pad0 + sizes[1], device=DEV)
+    views = [flat[:sizes[0]], flat[pad0:pad0 + sizes[1]]]
+    step_dev = torch.zeros(1, dtype=torch.int32, device=DEV)
+    skipped = torch.zeros(1, dtype=torch.int32, device=DEV)
+    found = torch.zeros(1, device=DEV)
+    scratch = torch.zeros(2, dtype=torch.int32, device=DEV)
+    inf_step = 4
+    for it in range(10):
+        scale = float(scaler.get_scale())
+        true_g = [torch.randn(n, generator=g) * (10.0 ** float(torch.randint(-6, 1, (1,), generator=g))) for n in sizes]
+        true_g[0][::7] = 0.0  # untouched hash entries
+        scaled = [(t * scale).to(DEV) for t in true_g]
+        if it == inf_step:
+            scaled[0][12345] = float("inf")
+        # reference: GradScaler.unscale_ + step + update
+        scaler.scale(torch.zeros(1, device=DEV))  # initialises the scaler's state like a scaled backward would
+        for p, sg in zip(ref_p, scaled):
+            p.grad = sg.clone()
+        scaler.step(opt)
+        scaler.update()
+        # ours
+        flat.zero_()
+        for v, sg in zip(views, scaled):
+            v.copy_(sg)
+        step_dev.add_(1)
+        before = [t.clone() for t in our_p + our_m + our_v]
+        ops.grad_check(flat, found, scratch, skipped_dev=skipped)
+        for i in range(2):
+            ops.adam_step(our_p[i], views[i], our_m[i], our_v[i], our_h[i], lr=1e-2, beta1=0.9, beta2=0.99, eps=1e-15,
+                          weight_decay=wds[i], grad_scale_inv=1.0 / scale, found_inf=found, step=1, step_dev=step_dev,
+                          skipped_dev=skipped)
+        torch.cuda.synchronize()
+        if it == inf_step:
+            assert float(found) == 1.0 and int(skipped) == 1
+            for a, b in zip(before, our_p + our_m + our_v):
+                assert torch.equal(a, b), "a skipped step must not touch parameters or moments"
+            assert float(scaler.get_scale()) == scale * 0.5  # the reference backed off
+        else:
+            assert float(found) == 0.0
+        assert int(scratch[0]) == 0 and int(scratch[1]) == 0, "the check re-arms its scratch"
+    assert int(step_dev) - int(skipped) == 9
+    for i in range(2):
+        ref = ref_p[i].detach()
+        st = opt.state[ref_p[i]]
+        assert int(st["step"]) == 9
+        rel = ((our_p[i] - ref).abs() / ref.abs().clamp_min(1e-12))
+        # the same float operations in the same order; what is left is fused-multiply-add contraction in either code
+        torch.testing.assert_close(our_p[i], ref, rtol=1e-6, atol=1e-9, msg=lambda m: f"group {i}: {m}; max rel {float(rel.max()):.3e}")
+        torch.testing.assert_close(our_m[i], st["exp_avg"], rtol=1e-6, atol=1e-12)
+        torch.testing.assert_close(our_v[i], st["exp_avg_sq"], rtol=1e-6, atol=1e-20)
+        assert torch.equal(our_h[i], our_p[i].half()), "fp16 working copy = rounded master"

@@ -79,13 +79,19 @@ def test_infer_staged_golden(golden_dir):
     n, steps, up = [int(v) for v in g["cfg"][:3]]
     net = _net_from_oracle(_oracle_heads(g))
     net.eval()
+    args = dict(direction_norms=_t(g["direction_norms"]).to(DEV), staged=True, max_ray_batch=int(g["cfg"][6]),
+                bg_color=1, perturb=False, num_steps=steps, upsample_steps=up, u=_t(g["u"]).to(DEV))
+    net.stage_chunk = None  # the reference's chunk loop exactly: max_ray_batch rays per pass, ragged tail
     with torch.no_grad():
-        out = net.render(_t(g["rays_o"]).to(DEV), _t(g["rays_d"]).to(DEV),
-                         direction_norms=_t(g["direction_norms"]).to(DEV), staged=True,
-                         max_ray_batch=int(g["cfg"][6]), bg_color=1, perturb=False, num_steps=steps,
-                         upsample_steps=up, u=_t(g["u"]).to(DEV))
+        out = net.render(_t(g["rays_o"]).to(DEV), _t(g["rays_d"]).to(DEV), **args)
     for k in ("depth", "image", "semantics"):
         _close(k, out[k].cpu().numpy(), g[k], rtol=4e-3, atol_rel=2e-3)
+    # default: without gradients the network re-chunks to >= 65536 rays; the result does not depend on the chunking
+    net.stage_chunk = 65536
+    with torch.no_grad():
+        out2 = net.render(_t(g["rays_o"]).to(DEV), _t(g["rays_d"]).to(DEV), **args)
+    for k in out:
+        torch.testing.assert_close(out2[k], out[k], rtol=1e-5, atol=1e-6)
 
 
 def test_fused_equals_generic_path_at_reference_sizes():
@@ -334,3 +340,108 @@ def test_config2_full_size_properties():
     bad = (g_mix - want).abs() > 3e-2 * want.abs() + 1e-2 * scale
     assert float(bad.float().mean()) < 1e-5, float(bad.float().mean())
     assert float(g_img.abs().max()) > 0 and float(g_dep.abs().max()) > 0
+
+
+def _scene_batch(n, seed, view=3):
+    from ucsa_neural_rendering_b200.scene import SyntheticScene
+
+    scene = SyntheticScene(seed=0)
+    g = torch.Generator().manual_seed(seed)
+    pix = torch.randint(0, scene.W * scene.H, (n,), generator=g)
+    o, d, dn = scene.rays(view, pix)
+    rgb, depth, label = scene.ground_truth(o, d, dn)
+    return scene, g, o, d, dn, rgb, depth, label
+
+
+def test_oracle_at_reference_sample_counts_render_and_engine():
+    """256 + 256 samples per ray (renderer_semantics.py:127-128), rays of the benchmark's synthetic scene: the fused
+    render() AND the TrainEngine's forward/backward (the path bench.py times) against the CPU oracle, outputs at 2e-3,
+    gradients at 3e-2 (fp16 backward chain)."""
+    from oracle.losses import nerf_losses as oracle_losses
+    from ucsa_neural_rendering_b200.engine import TrainEngine
+
+    n, steps, up = 96, 256, 256
+    scene, g, o, d, dn, rgb, depth, label = _scene_batch(n, 21)
+    heads = live_path.OracleHeads(bound=4, num_semantic_classes=40, seed=41, hash_amp=0.3)
+    net = _net_from_oracle(heads)
+    net.train()
+    t_rand = torch.rand(n, steps, generator=g)
+    u = torch.rand(n, up, generator=g)
+    ref = live_path.run(heads, o[None], d[None], dn[None], num_steps=steps, upsample_steps=up, perturb=True,
+                        t_rand=t_rand, u=u)
+    ref_total, ref_parts = oracle_losses(ref, rgb[None], label[None], depth[None], scene.one_m_to_scene_uom)
+    ref_total.backward()
+    ref_grads = [heads.encoder.grad, heads.sigma_net.grad, heads.color_net.grad, heads.semantics_net.grad]
+
+    # (1) the drop-in API
+    out = net.render(o[None].to(DEV), d[None].to(DEV), direction_norms=dn[None].to(DEV), staged=False, perturb=True,
+                     t_rand=t_rand.to(DEV), u=u.to(DEV))
+    for k in ("depth", "image", "semantics"):
+        _close(k, out[k].detach().cpu().numpy(), ref[k].detach().numpy(), rtol=4e-3, atol_rel=2e-3)
+
+    # (2) the engine: same kernels on a static workspace + fused loss kernel, gradients in one flat buffer
+    eng = TrainEngine(net, n, num_steps=steps, upsample_steps=up, one_m_to_scene_uom=scene.one_m_to_scene_uom,
+                      use_graph=False)
+    eng.t_rand, eng.u = t_rand.to(DEV), u.to(DEV)
+    eng.load_batch(o.to(DEV), d.to(DEV), dn.to(DEV), rgb.half().to(DEV), label.to(DEV), depth.to(DEV))
+    eng._forward_backward()
+    torch.cuda.synchronize()
+    for k, got in (("depth", eng.ws.depth), ("image", eng.ws.image), ("semantics", eng.ws.semantics)):
+        _close("engine_" + k, got.cpu().numpy(), ref[k].detach().numpy()[0], rtol=4e-3, atol_rel=2e-3)
+    loss = eng.loss.cpu().numpy()
+    # gt colours are fp16 on the engine side (batch["img_fp16"]): 5e-4 of slack on the colour term
+    np.testing.assert_allclose(loss[0], float(ref_total), rtol=4e-3)
+    np.testing.assert_allclose(loss[1:], [float(x) for x in ref_parts], rtol=4e-3, atol=1e-5)
+    for name, got, want in zip(("hash", "sigma", "color", "sem"), eng.grads, ref_grads):
+        _close("engine_grad_" + name, got.cpu().numpy(), want.numpy(), rtol=3e-2, atol_rel=1e-2)
+
+
+def test_fused_compositing_isolated_to_1e5():
+    """The compositing fused into the heads kernels, isolated from the fp16 MLP error: at config-2 size (4096 rays x
+    256+256 samples) the kernel's own per-row colours / logits / weights are re-summed in float64 and compared with the
+    kernel's image / semantics / depth at 1e-5 (renderer_semantics.py:269-285); likewise dL/dw of the backward."""
+    from ucsa_neural_rendering_b200 import ops, pipeline
+
+    n, tc, tf, c = 4096, 256, 256, 40
+    scene, g, o, d, dn, *_ = _scene_batch(n, 5)
+    heads = live_path.OracleHeads(bound=4, num_semantic_classes=c, seed=13, hash_amp=0.3)
+    net = _net_from_oracle(heads)
+    net.train()
+    o, d, dn = o.to(DEV), d.to(DEV), dn.view(-1).to(DEV)
+    ws = pipeline.RenderWorkspace(n, tc, tf, c, DEV, need_grad=True)
+    pipeline.forward_chain(net, ws, o, d, dn, net.aabb_train, perturb=True, seed=3)
+    torch.cuda.synchronize()
+    off = ws.ray_off.long()
+    k = int(off[-1])
+    counts = off[1:] - off[:-1]
+    assert 0.2 * n * (tc + tf) < k <= n * (tc + tf)
+    ray = torch.repeat_interleave(torch.arange(n, device=DEV), counts)
+    # the same kernels once more, this time also writing the per-row logits
+    logits = torch.zeros(ws.k_max, 48, dtype=torch.float16, device=DEV)
+    rgb = torch.zeros(ws.k_max, 3, device=DEV)
+    image, sem = torch.zeros(n, 3, device=DEV), torch.zeros(n, c, device=DEV)
+    ops.heads_fwd(ws.sel, ws.ray_off, n, tc + tf, ws.k_max, d, ws.h, net.color_net.half_params(),
+                  net.semantics_net.half_params(), c, rgb, logits, ws.hc1, ws.hc2, ws.hs, w_sel=ws.w_sel, image=image,
+                  semantics=sem)
+    torch.cuda.synchronize()
+    assert torch.equal(rgb[:k], ws.rgb[:k])
+    w = ws.w_sel[:k].double()
+    assert float(w.min()) > 1e-4  # only masked-in samples were compacted (renderer_semantics.py:249-250)
+    f64 = dict(dtype=torch.float64, device=DEV)
+    image_ref = torch.zeros(n, 3, **f64).index_add_(0, ray, w[:, None] * rgb[:k].double())
+    prob = torch.softmax(logits[:k, :c].double(), dim=-1)
+    sem_ref = torch.zeros(n, c, **f64).index_add_(0, ray, w[:, None] * prob)
+    depth_ref = torch.zeros(n, **f64).index_add_(0, ray, w * ws.z_sel[:k].double()) / dn.double()
+    for name, got, want in (("image", image, image_ref), ("semantics", sem, sem_ref), ("depth", ws.depth, depth_ref),
+                            ("image(chain)", ws.image, image_ref), ("semantics(chain)", ws.semantics, sem_ref)):
+        torch.testing.assert_close(got.double(), want, rtol=1e-5, atol=1e-7, msg=lambda m, name=name: f"{name}: {m}")
+    # backward: dL/dw_k = g_image . rgb_k + g_depth * z_k / norm  (semantic weights are detached, :270)
+    gi, gd, gs = (torch.randn(n, 3, generator=g).to(DEV), torch.randn(n, generator=g).to(DEV),
+                  torch.randn(n, c, generator=g).to(DEV))
+    gc, gsw = torch.zeros(ops.COLOR_PARAMS, device=DEV), torch.zeros(ops.SEM_PARAMS, device=DEV)
+    ops.heads_bwd(ws.sel, ws.ray_off, n, tc + tf, ws.k_max, d, ws.h, net.color_net.half_params(),
+                  net.semantics_net.half_params(), c, ws.rgb, ws.hc1, ws.hc2, ws.hs, ws.w_sel, ws.z_sel, gi, gd, gs, dn,
+                  128.0, ws.dh, ws.d_w_sel, gc, gsw)
+    torch.cuda.synchronize()
+    dw_ref = (gi.double()[ray] * rgb[:k].double()).sum(-1) + gd.double()[ray] * ws.z_sel[:k].double() / dn.double()[ray]
+    torch.testing.assert_close(ws.d_w_sel[:k].double(), dw_ref, rtol=1e-5, atol=1e-5 * float(dw_ref.abs().max()) * 0.1)

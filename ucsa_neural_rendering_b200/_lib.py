@@ -38,6 +38,7 @@ class UcsaError(RuntimeError):
 _SCALARS = {
     "int": ctypes.c_int,
     "float": ctypes.c_float,
+    "double": ctypes.c_double,
     "uint32_t": ctypes.c_uint32,
     "uint64_t": ctypes.c_uint64,
     "int32_t": ctypes.c_int32,

@@ -25,6 +25,19 @@ int check_launch(const char* what) {
   return UCSA_OK;
 }
 
+int set_max_dyn_smem(const void* fn, size_t bytes, const char* what) {
+  if (bytes > 227 * 1024) {
+    set_error("%s: needs %zu bytes of shared memory per CTA (limit 227 KB)", what, bytes);
+    return UCSA_ERR_UNSUPPORTED;
+  }
+  const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(%zu bytes): %s", what, bytes, cudaGetErrorString(e));
+    return UCSA_ERR_CUDA;
+  }
+  return UCSA_OK;
+}
+
 }  // namespace ucsa
 
 extern "C" {

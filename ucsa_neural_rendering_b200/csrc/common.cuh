@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/ucsa_nerf.h"
 
 namespace ucsa {
@@ -16,6 +18,9 @@ constexpr float kTransEps = 1e-15f;      // renderer_semantics.py:193,244
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
+// Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device (the attribute is per device / context);
+// checked, and rejected above the 227 KB a CTA can have.
+int set_max_dyn_smem(const void* fn, size_t bytes, const char* what);
 
 #define UCSA_REQUIRE(cond, ...)                 \
   do {                                          \

@@ -230,7 +230,7 @@ static int dense_smem(const void* fn, size_t bytes) {
       set_error("composite_dense: T too large for shared-memory staging");
       return UCSA_ERR_UNSUPPORTED;
     }
-    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    return set_max_dyn_smem(fn, bytes, "composite_dense");
   }
   return UCSA_OK;
 }

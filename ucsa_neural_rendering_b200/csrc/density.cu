@@ -212,10 +212,14 @@ extern "C" int ucsa_density_fwd_simt(const float* xyz, const float* rays_o, cons
   UCSA_REQUIRE(table_h && w_sigma_h && sigma && h, "density_fwd: null table/weights/outputs");
   UCSA_REQUIRE((reinterpret_cast<uintptr_t>(table_h) & 15u) == 0, "density_fwd_simt: the fp16 table must be 16-byte aligned");
   if (a.n_samples == 0) return UCSA_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(density_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
-    attr_set = true;
+  {
+    static std::atomic<uint64_t> smem_devices{0};  // per device: the attribute belongs to the context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(smem_devices.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
+      if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(density_fwd_kernel), kFwdSmem, "density_fwd_kernel")) return rc;
+      smem_devices.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
   }
   density_fwd_kernel<<<persistent_grid(a.n_samples, 4), kTileRows, kFwdSmem, as_stream(stream)>>>(
       a, static_cast<const __half2*>(table_h), static_cast<const __half*>(w_sigma_h), sigma,
@@ -234,10 +238,14 @@ extern "C" int ucsa_density_bwd_simt(const float* xyz, const float* rays_o, cons
   UCSA_REQUIRE(w_sigma_h && h && enc && hid && grad_w_sigma, "density_bwd: null saved tensors / outputs");
   UCSA_REQUIRE(loss_scale > 0.f, "density_bwd: loss_scale must be positive");
   if (a.n_samples == 0) return UCSA_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(density_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
-    attr_set = true;
+  {
+    static std::atomic<uint64_t> smem_devices{0};  // per device: the attribute belongs to the context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(smem_devices.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
+      if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(density_bwd_kernel), kBwdSmem, "density_bwd_kernel")) return rc;
+      smem_devices.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
   }
   density_bwd_kernel<<<persistent_grid(a.n_samples, 3), kTileRows, kBwdSmem, as_stream(stream)>>>(
       a, static_cast<const __half*>(w_sigma_h), static_cast<const __half*>(h), static_cast<const __half*>(enc),

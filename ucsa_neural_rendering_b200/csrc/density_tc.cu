@@ -385,11 +385,15 @@ extern "C" int ucsa_density_fwd(const float* xyz, const float* rays_o, const flo
   UCSA_REQUIRE((reinterpret_cast<uintptr_t>(table_h) & 15u) == 0, "density_fwd: the fp16 table must be 16-byte aligned");
   if (a.n_samples == 0) return UCSA_OK;
   if (int rc = check_tiled(a, tiled, "density_fwd")) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(density_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
-    cudaFuncSetAttribute(density_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
-    attr_set = true;
+  {
+    static std::atomic<uint64_t> smem_devices{0};  // per device: the attribute belongs to the context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(smem_devices.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
+      if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(density_fwd_tc_kernel<false>), kFwdSmem, "density_fwd_tc_kernel")) return rc;
+      if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(density_fwd_tc_kernel<true>), kFwdSmem, "density_fwd_tc_kernel")) return rc;
+      smem_devices.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
   }
   static int ctas_per_sm = 0;
   if (ctas_per_sm == 0) {  // tuning knob (bring-up): UCSA_DFWD_CTAS overrides the resident CTAs per SM
@@ -416,11 +420,15 @@ extern "C" int ucsa_density_bwd(const float* xyz, const float* rays_o, const flo
   UCSA_REQUIRE(loss_scale > 0.f, "density_bwd: loss_scale must be positive");
   if (a.n_samples == 0) return UCSA_OK;
   if (int rc = check_tiled(a, tiled, "density_bwd")) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(density_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
-    cudaFuncSetAttribute(density_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
-    attr_set = true;
+  {
+    static std::atomic<uint64_t> smem_devices{0};  // per device: the attribute belongs to the context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(smem_devices.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
+      if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(density_bwd_tc_kernel<false>), kBwdSmem, "density_bwd_tc_kernel")) return rc;
+      if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(density_bwd_tc_kernel<true>), kBwdSmem, "density_bwd_tc_kernel")) return rc;
+      smem_devices.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
   }
   static uint32_t run_max_res = 0;
   if (run_max_res == 0) {  // tuning knob (bring-up): finest resolution that still merges same-cell runs per warp

@@ -258,10 +258,14 @@ extern "C" int ucsa_heads_fwd_simt(const int32_t* sel, const int32_t* ray_off, u
   UCSA_REQUIRE(sel && ray_off && rays_d && h && w_color_h && w_sem_h && rgb && logits, "heads_fwd: null pointer");
   UCSA_REQUIRE(n_classes >= 1 && n_classes <= UCSA_MAX_CLASSES, "heads_fwd: 1 <= classes <= %d", UCSA_MAX_CLASSES);
   if (k_max == 0) return UCSA_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadsFwdSmem);
-    attr_set = true;
+  {
+    static std::atomic<uint64_t> smem_devices{0};  // per device: the attribute belongs to the context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(smem_devices.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
+      if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(heads_fwd_kernel), kHeadsFwdSmem, "heads_fwd_kernel")) return rc;
+      smem_devices.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
   }
   heads_fwd_kernel<<<heads_grid(k_max, 2), kTileRows, kHeadsFwdSmem, as_stream(stream)>>>(
       sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h),
@@ -281,10 +285,14 @@ extern "C" int ucsa_heads_bwd_simt(const int32_t* sel, const int32_t* ray_off, u
   UCSA_REQUIRE(n_classes >= 1 && n_classes <= UCSA_MAX_CLASSES, "heads_bwd: 1 <= classes <= %d", UCSA_MAX_CLASSES);
   UCSA_REQUIRE(loss_scale > 0.f, "heads_bwd: loss_scale must be positive");
   if (k_max == 0) return UCSA_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(heads_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadsBwdSmem);
-    attr_set = true;
+  {
+    static std::atomic<uint64_t> smem_devices{0};  // per device: the attribute belongs to the context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(smem_devices.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
+      if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(heads_bwd_kernel), kHeadsBwdSmem, "heads_bwd_kernel")) return rc;
+      smem_devices.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
   }
   heads_bwd_kernel<<<heads_grid(k_max, 1), kTileRows, kHeadsBwdSmem, as_stream(stream)>>>(
       sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h),

@@ -798,11 +798,15 @@ extern "C" int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32
                "heads_fwd: fused compositing needs w_sel, image and semantics together");
   UCSA_REQUIRE(n_classes >= 1 && n_classes <= UCSA_MAX_CLASSES, "heads_fwd: 1 <= classes <= %d", UCSA_MAX_CLASSES);
   if (k_max == 0) return UCSA_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(heads_fwd_color_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdColorSmem);
-    cudaFuncSetAttribute(heads_fwd_sem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSemSmem);
-    attr_set = true;
+  {
+    static std::atomic<uint64_t> smem_devices{0};  // per device: the attribute belongs to the context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(smem_devices.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
+      if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(heads_fwd_color_kernel), kFwdColorSmem, "heads_fwd_color_kernel")) return rc;
+      if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(heads_fwd_sem_kernel), kFwdSemSmem, "heads_fwd_sem_kernel")) return rc;
+      smem_devices.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
   }
   cudaStream_t st = as_stream(stream);
   heads_fwd_color_kernel<<<heads_grid(k_max, kFwdColorCtas), 128, kFwdColorSmem, st>>>(
@@ -828,11 +832,15 @@ extern "C" int ucsa_heads_bwd(const int32_t* sel, const int32_t* ray_off, uint32
   UCSA_REQUIRE(n_classes >= 1 && n_classes <= UCSA_MAX_CLASSES, "heads_bwd: 1 <= classes <= %d", UCSA_MAX_CLASSES);
   UCSA_REQUIRE(loss_scale > 0.f, "heads_bwd: loss_scale must be positive");
   if (k_max == 0) return UCSA_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(heads_bwd_color_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdColorSmem);
-    cudaFuncSetAttribute(heads_bwd_sem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSemSmem);
-    attr_set = true;
+  {
+    static std::atomic<uint64_t> smem_devices{0};  // per device: the attribute belongs to the context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(smem_devices.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
+      if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(heads_bwd_color_kernel), kBwdColorSmem, "heads_bwd_color_kernel")) return rc;
+      if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(heads_bwd_sem_kernel), kBwdSemSmem, "heads_bwd_sem_kernel")) return rc;
+      smem_devices.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
   }
   cudaStream_t st = as_stream(stream);
   heads_bwd_color_kernel<<<heads_grid(k_max, kBwdColorCtas), 128, kBwdColorSmem, st>>>(

@@ -9,15 +9,15 @@
 // Outputs: loss[4] = (total, color, sem, depth) and d total / d image, d depth, d semantics.
 // One warp per ray (coalesced over the class axis), kLossCtas CTAs; every CTA recounts the valid depths (N reads out of
 // L2), the last CTA to finish adds the per-CTA partial sums in a fixed order, so the losses are deterministic.
-// The partial-sum scratch is a static device array: calls must not overlap on different streams of one process.
+// The partial sums and the done-counter live in a caller-owned scratch block (UCSA_LOSS_SCRATCH_BYTES, zero-filled
+// once; the kernel re-arms it), so launches of different engines / streams never share state.
 #include "common.cuh"
 
 namespace ucsa {
 namespace {
 
 constexpr int kLossCtas = 64, kLossThreads = 256;
-__device__ float g_loss_partial[kLossCtas][3];
-__device__ unsigned int g_loss_done = 0;
+static_assert(UCSA_LOSS_SCRATCH_BYTES >= (kLossCtas * 3 + 1) * 4, "loss scratch too small");
 
 __device__ __forceinline__ float block_sum(float v, float* scratch) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -40,7 +40,8 @@ nerf_loss_kernel(const float* __restrict__ image, const float* __restrict__ dept
                  const __half* __restrict__ gt_rgb_h, const float* __restrict__ gt_rgb_f,
                  const int64_t* __restrict__ labels, const float* __restrict__ gt_depth, uint32_t n, uint32_t c,
                  float uom, float w_sem, float w_depth, float global_scale, float* __restrict__ loss,
-                 float* __restrict__ g_image, float* __restrict__ g_depth, float* __restrict__ g_sem) {
+                 float* __restrict__ g_image, float* __restrict__ g_depth, float* __restrict__ g_sem,
+                 float* __restrict__ g_loss_partial, unsigned int* __restrict__ g_loss_done) {
   __shared__ float scratch[32];
   __shared__ bool is_last;
   float cnt = 0.f;
@@ -89,18 +90,18 @@ nerf_loss_kernel(const float* __restrict__ image, const float* __restrict__ dept
   const float t_sem = block_sum(s_sem, scratch);
   const float t_depth = block_sum(s_depth, scratch);
   if (threadIdx.x == 0) {
-    g_loss_partial[blockIdx.x][0] = t_color;
-    g_loss_partial[blockIdx.x][1] = t_sem;
-    g_loss_partial[blockIdx.x][2] = t_depth;
+    g_loss_partial[blockIdx.x * 3 + 0] = t_color;
+    g_loss_partial[blockIdx.x * 3 + 1] = t_sem;
+    g_loss_partial[blockIdx.x * 3 + 2] = t_depth;
     __threadfence();
-    is_last = atomicAdd(&g_loss_done, 1u) == gridDim.x - 1;
+    is_last = atomicAdd(g_loss_done, 1u) == gridDim.x - 1;
   }
   __syncthreads();
   if (!is_last) return;
   __threadfence();
   float sums[3] = {0.f, 0.f, 0.f};
   if (threadIdx.x < 3) {
-    const volatile float* part = &g_loss_partial[0][0];
+    const volatile float* part = g_loss_partial;
     for (uint32_t b = 0; b < gridDim.x; ++b) sums[threadIdx.x] += part[b * 3 + threadIdx.x];
     scratch[threadIdx.x] = sums[threadIdx.x];
   }
@@ -113,7 +114,7 @@ nerf_loss_kernel(const float* __restrict__ image, const float* __restrict__ dept
     loss[1] = l_color;
     loss[2] = l_sem;
     loss[3] = l_depth;
-    g_loss_done = 0;  // re-arm for the next launch
+    *g_loss_done = 0;  // re-arm for the next launch
   }
 }
 
@@ -126,14 +127,18 @@ extern "C" int ucsa_nerf_loss(const float* image, const float* depth, const floa
                               const float* gt_rgb_f, const int64_t* labels, const float* gt_depth, uint32_t n_rays,
                               uint32_t n_classes, float one_m_to_scene_uom, float weight_semantics,
                               float weight_depth, float global_scale, float* loss4, float* g_image, float* g_depth,
-                              float* g_semantics, void* stream) {
-  UCSA_REQUIRE(image && depth && semantics && labels && gt_depth && loss4 && g_image && g_depth && g_semantics,
+                              float* g_semantics, void* scratch, void* stream) {
+  UCSA_REQUIRE(image && depth && semantics && labels && gt_depth && loss4 && g_image && g_depth && g_semantics &&
+                   scratch,
                "nerf_loss: null pointer");
   UCSA_REQUIRE((gt_rgb_h != nullptr) != (gt_rgb_f != nullptr), "nerf_loss: give gt_rgb as fp16 or as fp32");
   UCSA_REQUIRE(n_rays >= 1 && n_classes >= 1 && one_m_to_scene_uom > 0.f, "nerf_loss: bad sizes");
   nerf_loss_kernel<<<kLossCtas, kLossThreads, 0, as_stream(stream)>>>(image, depth, semantics, static_cast<const __half*>(gt_rgb_h),
                                                       gt_rgb_f, labels, gt_depth, n_rays, n_classes,
                                                       one_m_to_scene_uom, weight_semantics, weight_depth, global_scale,
-                                                      loss4, g_image, g_depth, g_semantics);
+                                                      loss4, g_image, g_depth, g_semantics,
+                                                      static_cast<float*>(scratch),
+                                                      reinterpret_cast<unsigned int*>(static_cast<float*>(scratch) +
+                                                                                      kLossCtas * 3));
   return check_launch("nerf_loss");
 }

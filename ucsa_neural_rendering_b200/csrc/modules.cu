@@ -209,8 +209,7 @@ uint32_t mlp_grid(uint32_t n, int per_sm) {
 template <int D0, int D1, int D2, int D3>
 int launch_mlp_fwd(const void* x, uint32_t n, const void* w, void* y, void* acts, cudaStream_t st) {
   using S = MlpShape<D0, D1, D2, D3>;
-  cudaFuncSetAttribute(mlp_fwd_kernel<D0, D1, D2, D3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)S::kFwdSmem);
+  if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(mlp_fwd_kernel<D0, D1, D2, D3>), S::kFwdSmem, "mlp_fwd_kernel")) return rc;
   mlp_fwd_kernel<D0, D1, D2, D3><<<mlp_grid(n, 2), kTileRows, S::kFwdSmem, st>>>(
       static_cast<const __half*>(x), n, static_cast<const __half*>(w), static_cast<__half*>(y),
       static_cast<__half*>(acts));
@@ -220,8 +219,7 @@ template <int D0, int D1, int D2, int D3>
 int launch_mlp_bwd(const void* x, uint32_t n, const void* w, const void* acts, const void* dy, float inv_scale,
                    void* dx, float* grad_w, cudaStream_t st) {
   using S = MlpShape<D0, D1, D2, D3>;
-  cudaFuncSetAttribute(mlp_bwd_kernel<D0, D1, D2, D3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)S::kBwdSmem);
+  if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(mlp_bwd_kernel<D0, D1, D2, D3>), S::kBwdSmem, "mlp_bwd_kernel")) return rc;
   mlp_bwd_kernel<D0, D1, D2, D3><<<mlp_grid(n, 1), kTileRows, S::kBwdSmem, st>>>(
       static_cast<const __half*>(x), n, static_cast<const __half*>(w), static_cast<const __half*>(acts),
       static_cast<const __half*>(dy), inv_scale, static_cast<__half*>(dx), grad_w);

@@ -20,39 +20,51 @@ __global__ void cast_kernel(const float* __restrict__ src, uint64_t n, __half* _
   }
 }
 
-// torch.optim.Adam semantics (L2 weight decay added to the gradient, bias-corrected moments).
+// torch.optim.Adam semantics (L2 weight decay added to the gradient, bias-corrected moments), operation by operation
+// as torch/optim/adam.py writes them: exp_avg.lerp_(grad, 1 - beta1); exp_avg_sq.mul_(beta2).addcmul_(grad, grad,
+// value = 1 - beta2); denom = exp_avg_sq.sqrt() / sqrt(bias_correction2) + eps; param.addcdiv_(exp_avg, denom,
+// value = -lr / bias_correction1).  The scalars (1 - beta, bias corrections, step size) are formed in double like
+// Python does and rounded once to float.
 struct AdamCoef {
-  float lr_over_bc1, b1, b2, eps, wd, ginv, bc2_sqrt;
+  float step_size, b1, one_minus_b1, b2, one_minus_b2, eps, wd, ginv, bc2_sqrt;
 };
+
+// the per-launch scalars, from the (device-side) step count; thread 0 of a CTA
+__device__ __forceinline__ void adam_scalars(double lr, double b1, double b2, int step, float* out_step_size,
+                                             float* out_bc2_sqrt) {
+  const double bc1 = 1.0 - pow(b1, static_cast<double>(step));
+  const double bc2 = 1.0 - pow(b2, static_cast<double>(step));
+  *out_step_size = static_cast<float>(lr / bc1);
+  *out_bc2_sqrt = static_cast<float>(sqrt(bc2));
+}
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamCoef& c) {
   float grad = g * c.ginv;
-  if (c.wd != 0.f) grad = fmaf(c.wd, p, grad);
-  m = fmaf(c.b1, m, (1.0f - c.b1) * grad);
-  v = fmaf(c.b2, v, (1.0f - c.b2) * grad * grad);
+  if (c.wd != 0.f) grad = grad + c.wd * p;
+  m = m + c.one_minus_b1 * (grad - m);
+  v = v * c.b2;
+  v = v + c.one_minus_b2 * grad * grad;
   const float denom = sqrtf(v) / c.bc2_sqrt + c.eps;
-  p = p - c.lr_over_bc1 * (m / denom);
+  p = p - c.step_size * (m / denom);
 }
 
 // Four parameters per thread (16-byte accesses); the bias corrections are formed once per CTA, because with the
-// step count on the device (CUDA-graph replay) they cost two powf per evaluation.
+// step count on the device (CUDA-graph replay) they cost two pow per evaluation.
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-            __half* __restrict__ p_h, uint64_t n, float lr, float b1, float b2, float eps, float wd, float ginv,
-            const float* __restrict__ found_inf, float bc1, float bc2_sqrt, const int32_t* __restrict__ step_dev) {
+            __half* __restrict__ p_h, uint64_t n, double lr, double b1, double b2, float eps, float wd, float ginv,
+            const float* __restrict__ found_inf, int step, const int32_t* __restrict__ step_dev,
+            const int32_t* __restrict__ skipped_dev) {
   if (found_inf != nullptr && *found_inf != 0.f) return;  // GradScaler: skip the step on overflow
   __shared__ float bc[2];
   if (threadIdx.x == 0) {
-    if (step_dev != nullptr) {  // step count lives on the device: bias corrections from it
-      const float st = static_cast<float>(*step_dev);
-      bc1 = 1.0f - powf(b1, st);
-      bc2_sqrt = sqrtf(1.0f - powf(b2, st));
-    }
-    bc[0] = bc1;
-    bc[1] = bc2_sqrt;
+    // step count on the device (CUDA-graph replay); skipped steps do not advance it (GradScaler.step + Adam)
+    if (step_dev != nullptr) step = *step_dev - (skipped_dev != nullptr ? *skipped_dev : 0);
+    adam_scalars(lr, b1, b2, step, &bc[0], &bc[1]);
   }
   __syncthreads();
-  const AdamCoef c{lr / bc[0], b1, b2, eps, wd, ginv, bc[1]};
+  const AdamCoef c{bc[0], static_cast<float>(b1), static_cast<float>(1.0 - b1), static_cast<float>(b2),
+                   static_cast<float>(1.0 - b2), eps, wd, ginv, bc[1]};
   const uint64_t i = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     float4 pp = *reinterpret_cast<const float4*>(p + i);
@@ -86,6 +98,39 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 }
 
 
+// GradScaler's inf check (joint_train_lightning_net.py:46,509-513 -> torch.amp.GradScaler.unscale_/step): one pass
+// over the flat gradient buffer; found_inf = 1 when any entry is inf / NaN.  The last CTA to finish publishes the
+// flag, bumps the skipped-step counter and re-arms the scratch words, so the launch is graph-replayable.
+__global__ void __launch_bounds__(256)
+grad_check_kernel(const float* __restrict__ g, uint64_t n, float* __restrict__ found_inf,
+                  int32_t* __restrict__ skipped_dev, uint32_t* __restrict__ scratch) {
+  const uint64_t n4 = n / 4;
+  bool bad = false;
+  const uint4* g4 = reinterpret_cast<const uint4*>(g);
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint4 q = g4[i];
+    // exponent all ones <=> inf or NaN
+    bad |= ((q.x & 0x7f800000u) == 0x7f800000u) | ((q.y & 0x7f800000u) == 0x7f800000u) |
+           ((q.z & 0x7f800000u) == 0x7f800000u) | ((q.w & 0x7f800000u) == 0x7f800000u);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3u))
+    bad |= (__float_as_uint(g[n4 * 4 + threadIdx.x]) & 0x7f800000u) == 0x7f800000u;
+  const int any = __syncthreads_or(bad ? 1 : 0);
+  if (threadIdx.x == 0) {
+    if (any) atomicOr(&scratch[1], 1u);
+    __threadfence();
+    const uint32_t ticket = atomicAdd(&scratch[0], 1u);
+    if (ticket == gridDim.x - 1) {
+      __threadfence();
+      const uint32_t flag = atomicExch(&scratch[1], 0u);
+      *found_inf = flag ? 1.0f : 0.0f;
+      if (flag && skipped_dev != nullptr) *skipped_dev += 1;
+      scratch[0] = 0u;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Gradient exchange fused into the optimizer, over NVLink / NVSwitch peer memory (row (e) of SURVEY.md section 8).
 // Every rank holds the full parameters (fp32 masters + fp16 working copy) and a full gradient buffer in SYMMETRIC
@@ -104,6 +149,7 @@ struct PeerPtrs {
   float* grad[kMaxPeers];
   float* param[kMaxPeers];
   __half* param_h[kMaxPeers];
+  const float* found_inf[kMaxPeers];  // per-rank overflow flags (ucsa_grad_check), or all null
 };
 
 __device__ __forceinline__ float4 mc_ld_reduce_add(const float* mc) {
@@ -127,17 +173,23 @@ template <bool MC_LOAD, bool MC_STORE>
 __global__ void __launch_bounds__(256)
 adam_exchange_kernel(const PeerPtrs peers, const float* __restrict__ mc_grad, float* __restrict__ mc_param,
                      __half* __restrict__ mc_param_h, uint32_t world, uint32_t rank, uint64_t begin, uint64_t end,
-                     uint64_t wd_begin, float* __restrict__ m, float* __restrict__ v, float lr, float b1, float b2,
-                     float eps, float wd, float bc1, float bc2_sqrt, const int32_t* __restrict__ step_dev) {
+                     uint64_t wd_begin, float* __restrict__ m, float* __restrict__ v, double lr, double b1, double b2,
+                     float eps, float wd, int step, const int32_t* __restrict__ step_dev,
+                     int32_t* __restrict__ skipped_dev, int broadcast_masters) {
+  // GradScaler semantics across the job: an overflow on ANY rank skips the step on every rank (each rank reads all
+  // the flags, so no extra collective is needed); skipped steps do not advance Adam's step count.
+  if (peers.found_inf[0] != nullptr) {
+    bool any = false;
+    for (uint32_t r = 0; r < world; ++r) any |= *peers.found_inf[r] != 0.f;
+    if (any) {
+      if (blockIdx.x == 0 && threadIdx.x == 0 && skipped_dev != nullptr) *skipped_dev += 1;
+      return;
+    }
+  }
   __shared__ float bc[2];
   if (threadIdx.x == 0) {
-    if (step_dev != nullptr) {
-      const float st = static_cast<float>(*step_dev);
-      bc1 = 1.0f - powf(b1, st);
-      bc2_sqrt = sqrtf(1.0f - powf(b2, st));
-    }
-    bc[0] = bc1;
-    bc[1] = bc2_sqrt;
+    if (step_dev != nullptr) step = *step_dev - (skipped_dev != nullptr ? *skipped_dev : 0);
+    adam_scalars(lr, b1, b2, step, &bc[0], &bc[1]);
   }
   __syncthreads();
   // kUnroll float4 groups per thread and iteration, all remote gradient loads issued before the first use: the
@@ -172,7 +224,8 @@ adam_exchange_kernel(const PeerPtrs peers, const float* __restrict__ mc_grad, fl
     for (int u = 0; u < kUnroll; ++u) {
       const uint64_t i = idx[u];
       if (i >= end) continue;
-      const AdamCoef c{lr / bc[0], b1, b2, eps, i >= wd_begin ? wd : 0.f, 1.0f, bc[1]};
+      const AdamCoef c{bc[0], static_cast<float>(b1), static_cast<float>(1.0 - b1), static_cast<float>(b2),
+                       static_cast<float>(1.0 - b2), eps, i >= wd_begin ? wd : 0.f, 1.0f, bc[1]};
       float4 pp = *reinterpret_cast<const float4*>(peers.param[rank] + i);
       const uint64_t k = i - begin;
       float4 mm = *reinterpret_cast<const float4*>(m + k);
@@ -185,12 +238,16 @@ adam_exchange_kernel(const PeerPtrs peers, const float* __restrict__ mc_grad, fl
       *reinterpret_cast<float4*>(v + k) = vv;
       const __half2 lo = __floats2half2_rn(pp.x, pp.y), hi = __floats2half2_rn(pp.z, pp.w);
       const uint32_t lo_b = *reinterpret_cast<const uint32_t*>(&lo), hi_b = *reinterpret_cast<const uint32_t*>(&hi);
+      // broadcast_masters == 0: the fp32 masters of a slice live on its owner only (one third of the store traffic);
+      // every rank still receives the fp16 working copy the kernels read
       if (MC_STORE) {
-        mc_st_f32x4(mc_param + i, pp);
+        if (broadcast_masters) mc_st_f32x4(mc_param + i, pp);
+        else *reinterpret_cast<float4*>(peers.param[rank] + i) = pp;
         mc_st_f16x4(mc_param_h + i, lo_b, hi_b);
       } else {
+        if (!broadcast_masters) *reinterpret_cast<float4*>(peers.param[rank] + i) = pp;
         for (uint32_t r = 0; r < world; ++r) {
-          *reinterpret_cast<float4*>(peers.param[r] + i) = pp;
+          if (broadcast_masters) *reinterpret_cast<float4*>(peers.param[r] + i) = pp;
           *reinterpret_cast<uint2*>(peers.param_h[r] + i) = make_uint2(lo_b, hi_b);
         }
       }
@@ -213,9 +270,9 @@ extern "C" int ucsa_cast_f32_to_f16(const float* src, uint64_t n, void* dst_h, v
 }
 
 extern "C" int ucsa_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_h,
-                              uint64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                              uint64_t n, double lr, double beta1, double beta2, float eps, float weight_decay,
                               float grad_scale_inv, const float* found_inf, uint32_t step, const int32_t* step_dev,
-                              void* stream) {
+                              const int32_t* skipped_dev, void* stream) {
   UCSA_REQUIRE(param && grad && exp_avg && exp_avg_sq, "adam_step: null pointer");
   UCSA_REQUIRE(step >= 1 || step_dev != nullptr, "adam_step: step counts from 1");
   UCSA_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
@@ -223,20 +280,30 @@ extern "C" int ucsa_adam_step(float* param, const float* grad, float* exp_avg, f
                    (reinterpret_cast<uintptr_t>(param_h) & 7u) == 0,
                "adam_step: buffers must be 16-byte aligned (fp16 copy: 8-byte)");
   if (n == 0) return UCSA_OK;
-  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
-  const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
   adam_kernel<<<ceil_div((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq,
                                                                static_cast<__half*>(param_h), n, lr, beta1, beta2,
-                                                               eps, weight_decay, grad_scale_inv, found_inf, bc1,
-                                                               sqrtf(bc2), step_dev);
+                                                               eps, weight_decay, grad_scale_inv, found_inf,
+                                                               static_cast<int>(step), step_dev, skipped_dev);
   return check_launch("adam_step");
+}
+
+extern "C" int ucsa_grad_check(const float* grad, uint64_t n, float* found_inf, int32_t* skipped_dev,
+                               uint32_t* scratch2, void* stream) {
+  UCSA_REQUIRE(grad && found_inf && scratch2, "grad_check: null pointer");
+  UCSA_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15u) == 0, "grad_check: grad must be 16-byte aligned");
+  const uint64_t n4 = n / 4;
+  uint32_t blocks = ceil_div(n4 > 0 ? n4 : 1, 256 * 8);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  grad_check_kernel<<<blocks, 256, 0, as_stream(stream)>>>(grad, n, found_inf, skipped_dev, scratch2);
+  return check_launch("grad_check");
 }
 
 extern "C" int ucsa_adam_exchange(const uint64_t* grad_ptrs_host, const uint64_t* param_ptrs_host,
                                   const uint64_t* param_h_ptrs_host, const float* mc_grad, float* mc_param,
                                   void* mc_param_h, uint32_t world, uint32_t rank, uint64_t begin, uint64_t end,
-                                  uint64_t wd_begin, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
-                                  float beta2, float eps, float weight_decay, uint32_t step, const int32_t* step_dev,
+                                  uint64_t wd_begin, float* exp_avg, float* exp_avg_sq, double lr, double beta1,
+                                  double beta2, float eps, float weight_decay, uint32_t step, const int32_t* step_dev,
+                                  const uint64_t* found_inf_ptrs_host, int32_t* skipped_dev, int broadcast_masters,
                                   void* stream) {
   UCSA_REQUIRE(grad_ptrs_host && param_ptrs_host && param_h_ptrs_host && exp_avg && exp_avg_sq,
                "adam_exchange: null pointer");
@@ -246,23 +313,26 @@ extern "C" int ucsa_adam_exchange(const uint64_t* grad_ptrs_host, const uint64_t
                "adam_exchange: slice bounds must be multiples of 4 parameters");
   UCSA_REQUIRE(step >= 1 || step_dev != nullptr, "adam_exchange: step counts from 1");
   const bool multicast = mc_grad != nullptr;
-  UCSA_REQUIRE(!multicast || (mc_param && mc_param_h), "adam_exchange: give all three multicast addresses or none");
+  UCSA_REQUIRE(!multicast || (mc_param_h && (mc_param || !broadcast_masters)),
+               "adam_exchange: give the multicast addresses of every buffer that is broadcast, or none");
   if (begin == end) return UCSA_OK;
   PeerPtrs peers{};
   for (uint32_t r = 0; r < world; ++r) {
     peers.grad[r] = reinterpret_cast<float*>(grad_ptrs_host[r]);
     peers.param[r] = reinterpret_cast<float*>(param_ptrs_host[r]);
     peers.param_h[r] = reinterpret_cast<__half*>(param_h_ptrs_host[r]);
-    UCSA_REQUIRE(peers.grad[r] && peers.param[r] && peers.param_h[r], "adam_exchange: null peer pointer");
+    peers.found_inf[r] = found_inf_ptrs_host ? reinterpret_cast<const float*>(found_inf_ptrs_host[r]) : nullptr;
+    UCSA_REQUIRE(peers.grad[r] && peers.param_h[r] && (peers.param[r] || (!broadcast_masters && r != rank)),
+                 "adam_exchange: null peer pointer");
+    UCSA_REQUIRE(!found_inf_ptrs_host || peers.found_inf[r], "adam_exchange: null found_inf pointer");
   }
-  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
-  const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
   const uint64_t tiles = ((end - begin) + 256 * 4 * 4 - 1) / (256 * 4 * 4);  // 256 threads x float4 x kUnroll
   const uint32_t cap = kNumSMs * 8;
   const uint32_t blocks = static_cast<uint32_t>(tiles < cap ? tiles : cap);
   auto kernel = multicast ? adam_exchange_kernel<true, true> : adam_exchange_kernel<false, false>;
   kernel<<<blocks, 256, 0, as_stream(stream)>>>(peers, mc_grad, mc_param, static_cast<__half*>(mc_param_h), world, rank,
                                                begin, end, wd_begin, exp_avg, exp_avg_sq, lr, beta1, beta2, eps,
-                                               weight_decay, bc1, sqrtf(bc2), step_dev);
+                                               weight_decay, static_cast<int>(step), step_dev, skipped_dev,
+                                               broadcast_masters);
   return check_launch("adam_exchange");
 }

@@ -275,11 +275,8 @@ extern "C" int ucsa_resample_merge(const float* sigma, float* z_cat, const float
   uint32_t warps = static_cast<uint32_t>((32u * 1024u) / warp_bytes);  // rays per CTA (one wave at 4096 rays)
   warps = warps > 8 ? 8 : (warps < 1 ? 1 : warps);
   const size_t smem = warps * warp_bytes;
-  static size_t smem_set = 48 * 1024;
-  if (smem > smem_set) {
-    cudaFuncSetAttribute(resample_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    smem_set = smem;
-  }
+  if (smem > 48 * 1024)  // size depends on the call: set every time (per device, checked)
+    if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(resample_merge_kernel), smem, "resample_merge")) return rc;
   resample_merge_kernel<<<ceil_div(n_rays, warps), 32 * warps, smem, as_stream(stream)>>>(
       sigma, z_cat, u, seed, step_dev, ray_base, tc, tf, density_scale, order, n_rays, warp_floats);
   return check_launch("resample_merge");

@@ -179,7 +179,7 @@ int set_smem(const void* fn, size_t bytes) {
       set_error("samples per ray too large for the shared-memory staging (%zu bytes)", bytes);
       return UCSA_ERR_UNSUPPORTED;
     }
-    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    return set_max_dyn_smem(fn, bytes, "weights");
   }
   return UCSA_OK;
 }

@@ -219,12 +219,12 @@ class _FusedRender(torch.autograd.Function):
     @staticmethod
     def forward(ctx, enc_params, sigma_params, color_params, sem_params, rays_o, rays_d, dnorm, net, cfg):
         need = any(ctx.needs_input_grad[:4])  # (grad mode is off inside forward)
-        ws = pipeline.RenderWorkspace(rays_o.shape[0], cfg["num_steps"], cfg["upsample_steps"],
-                                      net.num_semantic_classes, rays_o.device, need)
+        ws, token = pipeline.cached_workspace(net, rays_o.shape[0], cfg["num_steps"], cfg["upsample_steps"],
+                                              net.num_semantic_classes, rays_o.device, need)
         pipeline.forward_chain(net, ws, rays_o, rays_d, dnorm, cfg["aabb"], perturb=cfg["perturb"],
                                t_rand=cfg["t_rand"], u=cfg["u"], seed=cfg["seed"], ray_base=cfg["ray_base"])
         if need:
-            ctx.net, ctx.ws, ctx.aabb = net, ws, cfg["aabb"]
+            ctx.net, ctx.ws, ctx.aabb, ctx.token = net, ws, cfg["aabb"], token  # token: the workspace stays ours
             ctx.save_for_backward(rays_o, rays_d, dnorm)
         return ws.depth, ws.image, ws.semantics
 
@@ -233,14 +233,15 @@ class _FusedRender(torch.autograd.Function):
     def backward(ctx, g_depth, g_image, g_sem):
         net, ws = ctx.net, ctx.ws
         rays_o, rays_d, dnorm = ctx.saved_tensors
-        f32 = dict(dtype=torch.float32, device=rays_o.device)
-        g_table = torch.zeros(net.encoder.params.numel(), **f32)
-        g_sig = torch.zeros(ops.SIGMA_PARAMS, **f32)
-        g_col = torch.zeros(ops.COLOR_PARAMS, **f32)
-        g_semw = torch.zeros(ops.SEM_PARAMS, **f32)
+        if ws is None:
+            raise RuntimeError("the fused render node was already differentiated (its workspace has been released)")
+        n_table = net.encoder.params.numel()
+        sizes = (n_table, ops.SIGMA_PARAMS, ops.COLOR_PARAMS, ops.SEM_PARAMS)
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=rays_o.device)  # one allocation, one memset
+        g_table, g_sig, g_col, g_semw = torch.split(flat, sizes)
         pipeline.backward_chain(net, ws, rays_o, rays_d, dnorm, ctx.aabb, g_image.float().contiguous(),
                                 g_depth.float().contiguous(), g_sem.float().contiguous(), g_table, g_sig, g_col, g_semw)
-        ctx.ws = None
+        ctx.ws = ctx.token = None  # the workspace may be handed out again
         return g_table, g_sig, g_col, g_semw, None, None, None, None, None
 
 
@@ -288,6 +289,10 @@ class SemanticNeRFNetwork(SemanticNeRFRenderer):
         self.in_dim_semantics = self.geo_feat_dim
         self.semantics_net = FusedMLP(self.in_dim_semantics, num_semantic_classes, num_layers_semantics - 1,
                                       hidden_dim_semantics, seed=1340, out_pad=ops.MAX_CLASSES)
+        # render(staged=True) without gradients re-chunks to at least this many rays whatever max_ray_batch says
+        # (the caller's default of 4096 means 75 launches of every kernel per 640x480 frame): random numbers are keyed
+        # by the global ray index, so the result does not depend on the chunking
+        self.stage_chunk = 65536
 
     # ------------------------------------------------------------------ module-level API of the reference
     def forward(self, x, d):

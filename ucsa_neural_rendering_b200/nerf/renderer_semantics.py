@@ -364,6 +364,11 @@ class SemanticNeRFRenderer(nn.Module):
             semantics = torch.empty((B, N, self.num_semantic_classes), device=device)
             t_rand, u = kwargs.pop("t_rand", None), kwargs.pop("u", None)
             seed = kwargs.pop("seed", None) or self._next_seed()
+            # max_ray_batch bounds the reference's memory; a subclass whose run() is chunk-invariant (random numbers
+            # keyed by ray index) may ask for larger chunks when no graph is recorded (self.stage_chunk)
+            stage_chunk = getattr(self, "stage_chunk", None)
+            if stage_chunk and not torch.is_grad_enabled():
+                max_ray_batch = max(int(max_ray_batch), int(stage_chunk))
             for b in range(B):
                 head = 0
                 while head < N:

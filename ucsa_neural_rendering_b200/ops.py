@@ -330,17 +330,29 @@ def cast_f32_to_f16(src, dst):
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, param_h, *, lr, beta1, beta2, eps, weight_decay, grad_scale_inv,
-              found_inf, step, step_dev=None):
+              found_inf, step, step_dev=None, skipped_dev=None):
+    """torch.optim.Adam (L2 weight decay) with GradScaler semantics: gradients are multiplied by grad_scale_inv; when
+    found_inf[0] != 0 nothing is written.  With step_dev, Adam's step count is step_dev[0] - skipped_dev[0]."""
     check(lib().ucsa_adam_step(_ptr(param, torch.float32), _ptr(grad, torch.float32), _ptr(exp_avg, torch.float32),
                                _ptr(exp_avg_sq, torch.float32), _ptr(param_h, torch.float16), param.numel(), float(lr),
                                float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale_inv),
-                               _ptr(found_inf, torch.float32), int(step), _ptr(step_dev, torch.int32), _stream()),
-          "adam_step")
+                               _ptr(found_inf, torch.float32), int(step), _ptr(step_dev, torch.int32),
+                               _ptr(skipped_dev, torch.int32), _stream()), "adam_step")
 
 
-def adam_exchange(peer, exp_avg, exp_avg_sq, *, wd_begin, lr, beta1, beta2, eps, weight_decay, step, step_dev=None):
+def grad_check(grad, found_inf, scratch2, skipped_dev=None):
+    """found_inf[0] = 1.0 if grad holds an inf / NaN else 0.0 (GradScaler's check); bumps skipped_dev[0] when set.
+    scratch2: two zero-initialised int32 words owned by the caller."""
+    check(lib().ucsa_grad_check(_ptr(grad, torch.float32, "grad"), grad.numel(), _ptr(found_inf, torch.float32),
+                                _ptr(skipped_dev, torch.int32), _ptr(scratch2, torch.int32, "scratch2"), _stream()),
+          "grad_check")
+
+
+def adam_exchange(peer, exp_avg, exp_avg_sq, *, wd_begin, lr, beta1, beta2, eps, weight_decay, step, step_dev=None,
+                  found_inf_ptrs=None, skipped_dev=None, broadcast_masters=True):
     """Fused reduce-scatter + Adam + all-gather over peer memory; `peer` is a parallel.PeerExchange.  The caller puts a
-    cross-rank barrier before (gradients complete) and after (parameters visible)."""
+    cross-rank barrier before (gradients complete) and after (parameters visible).  found_inf_ptrs: the ranks'
+    overflow flags (any set -> every rank skips); broadcast_masters=False keeps fp32 masters on the owner."""
     arr = ctypes.c_uint64 * peer.world
     mc = peer.multicast
     check(lib().ucsa_adam_exchange(arr(*peer.grad_ptrs), arr(*peer.param_ptrs), arr(*peer.param_h_ptrs),
@@ -348,11 +360,22 @@ def adam_exchange(peer, exp_avg, exp_avg_sq, *, wd_begin, lr, beta1, beta2, eps,
                                    peer.mc_param_h if mc else None, peer.world, peer.rank, peer.begin, peer.end,
                                    int(wd_begin), _ptr(exp_avg, torch.float32), _ptr(exp_avg_sq, torch.float32),
                                    float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
-                                   _ptr(step_dev, torch.int32), _stream()), "adam_exchange")
+                                   _ptr(step_dev, torch.int32),
+                                   arr(*found_inf_ptrs) if found_inf_ptrs is not None else None,
+                                   _ptr(skipped_dev, torch.int32), int(bool(broadcast_masters)), _stream()),
+          "adam_exchange")
+
+
+LOSS_SCRATCH_BYTES = 1024  # UCSA_LOSS_SCRATCH_BYTES
+
+
+def loss_scratch(device):
+    """Zero-filled scratch block of ucsa_nerf_loss; allocate one per engine / workspace (never shared across streams)."""
+    return torch.zeros(LOSS_SCRATCH_BYTES // 4, dtype=torch.float32, device=device)
 
 
 def nerf_loss(image, depth, semantics, gt_rgb, labels, gt_depth, uom, w_sem, w_depth, global_scale, loss4, g_image,
-              g_depth, g_semantics):
+              g_depth, g_semantics, scratch):
     n, c = semantics.shape
     half = gt_rgb.dtype == torch.float16
     check(lib().ucsa_nerf_loss(_ptr(image, torch.float32), _ptr(depth, torch.float32), _ptr(semantics, torch.float32),
@@ -360,7 +383,8 @@ def nerf_loss(image, depth, semantics, gt_rgb, labels, gt_depth, uom, w_sem, w_d
                                None if half else _ptr(gt_rgb, torch.float32), _ptr(labels, torch.int64, "labels"),
                                _ptr(gt_depth, torch.float32, "gt_depth"), n, c, float(uom), float(w_sem), float(w_depth),
                                float(global_scale), _ptr(loss4, torch.float32), _ptr(g_image, torch.float32),
-                               _ptr(g_depth, torch.float32), _ptr(g_semantics, torch.float32), _stream()), "nerf_loss")
+                               _ptr(g_depth, torch.float32), _ptr(g_semantics, torch.float32),
+                               _ptr(scratch, torch.float32, "scratch"), _stream()), "nerf_loss")
 
 
 # ---------------------------------------------------------------------------------------------- occupancy-grid path

@@ -83,13 +83,20 @@ class PeerExchange:
         self.param = symm.empty(n_params, dtype=torch.float32, device=device)
         self.param_h = symm.empty(n_params, dtype=torch.float16, device=device)
         self.grad.zero_()
-        self._handles = [symm.rendezvous(t, dist.group.WORLD) for t in (self.grad, self.param, self.param_h)]
+        # per-rank overflow flag of the step (ucsa_grad_check writes it, every rank's ucsa_adam_exchange reads all)
+        self.flag = symm.empty(4, dtype=torch.float32, device=device)
+        self.flag.zero_()
+        self._handles = [symm.rendezvous(t, dist.group.WORLD) for t in (self.grad, self.param, self.param_h, self.flag)]
+        self.flag_ptrs, _ = self._addresses(self.flag, self._handles[3])
         self.grad_ptrs, self.mc_grad = self._addresses(self.grad, self._handles[0])
         self.param_ptrs, self.mc_param = self._addresses(self.param, self._handles[1])
         self.param_h_ptrs, self.mc_param_h = self._addresses(self.param_h, self._handles[2])
         # multimem through the NVSwitch pays off from about 8 ranks on (see csrc/optim.cu); below that plain peer
         # loads / stores are faster.  UCSA_PEER_MULTICAST=0/1 overrides.
         have_mc = bool(self.mc_grad and self.mc_param and self.mc_param_h)
+        # fp32 masters of a slice stay on its owner (peers only need the fp16 working copy the kernels read): one third
+        # of the store traffic of the exchange.  UCSA_PEER_BROADCAST_MASTERS=1 replicates the masters as well.
+        self.broadcast_masters = os.environ.get("UCSA_PEER_BROADCAST_MASTERS", "0") == "1"
         want = os.environ.get("UCSA_PEER_MULTICAST", "auto")
         self.multicast = have_mc and (want == "1" or (want != "0" and self.world > 4))
         self.begin, self.end = owner_slice(n_params, self.rank, self.world)
@@ -101,6 +108,16 @@ class PeerExchange:
             raise RuntimeError("symmetric tensor lies outside its rendezvoused buffer")
         mc = int(handle.multicast_ptr) if handle.multicast_ptr else 0
         return [p + delta for p in ptrs], (mc + delta if mc else 0)
+
+    def gather_masters(self):
+        """Make every rank's fp32 masters complete (collective; only needed when broadcast_masters is off, before a
+        checkpoint / state_dict): each owner broadcasts its slice."""
+        if self.broadcast_masters:
+            return
+        for r in range(self.world):
+            lo, hi = owner_slice(self.n, r, self.world)
+            if hi > lo:
+                dist.broadcast(self.param[lo:hi], src=r)
 
     def barrier(self, channel: int):
         """Device-side barrier over all ranks on the current stream (CUDA-graph capturable)."""

@@ -11,6 +11,8 @@ Kernel sequence, forward:  near_far -> sample_coarse -> density (coarse) -> resa
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import ops
@@ -57,6 +59,47 @@ class RenderWorkspace:
             self.d_sigma = torch.empty(n, t, **f32)
         else:
             self.enc = self.hid = self.hc1 = self.hc2 = self.hs = None
+        self._token = None  # weak reference to the autograd node that still needs this workspace (cached_workspace)
+
+    def fresh_outputs(self):
+        """New depth / image / semantics tensors (the ones a caller keeps); everything else is scratch."""
+        f32 = dict(dtype=torch.float32, device=self.z_cat.device)
+        self.depth = torch.empty(self.n, **f32)
+        self.image = torch.empty(self.n, 3, **f32)
+        self.semantics = torch.empty(self.n, self.c, **f32)
+
+
+# Workspaces of the autograd path, per network and shape: render() is called with the same (rays, samples) shape every
+# step, and a workspace is ~25 allocations / ~1 GB at 4096 rays.  A workspace whose backward is still pending (its
+# autograd node is alive) is never handed out again; a second one is allocated instead.
+_WS_CACHE = weakref.WeakKeyDictionary()
+_WS_CACHE_MAX = 4
+
+
+class WorkspaceToken:
+    """Lifetime marker held by the autograd node that owns a cached workspace."""
+
+
+def cached_workspace(net, n, tc, tf, c, device, need_grad):
+    """-> (workspace, token or None).  The caller keeps `token` alive for as long as it needs the scratch contents
+    (i.e. until its backward has run); outputs are always fresh tensors."""
+    per_net = _WS_CACHE.setdefault(net, {})
+    key = (n, tc, tf, c, str(device), bool(need_grad))
+    ws = per_net.get(key)
+    if ws is None or (ws._token is not None and ws._token() is not None):
+        fresh = RenderWorkspace(n, tc, tf, c, device, need_grad)
+        if ws is None:
+            while len(per_net) >= _WS_CACHE_MAX:
+                per_net.pop(next(iter(per_net)))
+            per_net[key] = fresh
+        ws = fresh
+    else:
+        ws.fresh_outputs()
+    token = None
+    if need_grad:
+        token = WorkspaceToken()
+        ws._token = weakref.ref(token)
+    return ws, token
 
 
 def forward_chain(net, ws, rays_o, rays_d, dnorm, aabb, *, perturb, t_rand=None, u=None, seed=0, ray_base=0,

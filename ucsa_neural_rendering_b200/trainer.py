@@ -8,13 +8,18 @@ losses, backward, Adam (two groups, weight decay on the MLPs only).  The optimiz
 
 Multi-GPU: one process per GPU, each rank renders its own slice of the ray batch; after backward one NCCL
 all-reduce(sum) over a single flat gradient buffer; every rank then applies the same Adam update, so no
-parameter broadcast is needed.  Losses are means over the *global* ray count."""
+parameter broadcast is needed.  The colour and semantic losses are means over the *global* ray count.  The depth
+loss is a mean over valid (gt_depth != 0) rays: each rank normalises by its own valid count and the 1/world factor
+averages the per-rank means, which equals the global mean only when the ranks hold equally many valid depths (rays of
+a batch are drawn from the same views, so the counts differ by sampling noise only; the single-GPU objective and
+the reference's are unchanged)."""
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
 
 from . import ops, parallel
+from ._lib import UcsaError
 
 
 class _FusedLosses(torch.autograd.Function):
@@ -27,9 +32,10 @@ class _FusedLosses(torch.autograd.Function):
         dev = image.device
         loss4 = torch.empty(4, dtype=torch.float32, device=dev)
         grads = torch.empty(n * (4 + c), dtype=torch.float32, device=dev)
+        scratch = ops.loss_scratch(dev)  # per call: never shared with another stream's launch
         g_image, g_depth, g_sem = grads[:3 * n].view(n, 3), grads[3 * n:4 * n], grads[4 * n:].view(n, c)
         ops.nerf_loss(image, depth, semantics, gt_rgb, labels, gt_depth, uom, w_sem, w_depth, global_scale, loss4,
-                      g_image, g_depth, g_sem)
+                      g_image, g_depth, g_sem, scratch)
         ctx.save_for_backward(grads)
         ctx.n, ctx.c = n, c
         parts = loss4[1:]
@@ -45,37 +51,24 @@ class _FusedLosses(torch.autograd.Function):
 
 
 def nerf_losses(outputs, gt_rgb, labels, gt_depth, one_m_to_scene_uom, weight_depth=0.1, weight_semantics=0.04,
-                global_scale=1.0, fused=None):
+                global_scale=1.0):
     """joint_train_lightning_net.py:199-221 and :503-507.  Shapes [B,N,...] as rendered.
-    On CUDA tensors the losses and their gradients come from one kernel (fused=None: automatic); fused=False keeps the
-    reference's torch expression (also the CPU path of the host-logic tests)."""
+    The three losses and their gradients come from one kernel (ucsa_nerf_loss); CUDA tensors only."""
     pred_rgb, semantics, pred_depth = outputs["image"], outputs["semantics"], outputs["depth"]
-    if fused is None:
-        fused = pred_rgb.is_cuda and semantics.shape[-1] <= ops.MAX_CLASSES
-    if fused:
-        c = semantics.shape[-1]
-        rgb = gt_rgb.reshape(-1, 3)
-        if rgb.dtype not in (torch.float16, torch.float32):
-            rgb = rgb.float()
-        total, parts = _FusedLosses.apply(
-            pred_rgb.reshape(-1, 3).float().contiguous(), pred_depth.reshape(-1).float().contiguous(),
-            semantics.reshape(-1, c).float().contiguous(), rgb.contiguous(), labels.reshape(-1).long().contiguous(),
-            gt_depth.reshape(-1).float().contiguous(), float(one_m_to_scene_uom), float(weight_semantics),
-            float(weight_depth), float(global_scale))
-        return total, (parts[0], parts[1], parts[2])
-    labels = labels.clone()
-    invalid = torch.sum(semantics, dim=-1) == 0
-    semantics = torch.where(invalid.unsqueeze(-1), torch.ones_like(semantics), semantics)
-    semantics = semantics / torch.sum(semantics, dim=-1, keepdim=True)
-    labels[invalid] = -1
-    loss_color = torch.nn.functional.mse_loss(pred_rgb, gt_rgb.float(), reduction="none").mean()
-    logp = torch.log(semantics + 1e-15).permute(0, 2, 1)
-    loss_sem = torch.nn.functional.nll_loss(logp, labels, ignore_index=-1, reduction="none").mean()
-    valid = gt_depth != 0
-    loss_depth = torch.nn.functional.l1_loss(pred_depth[valid] / one_m_to_scene_uom, gt_depth[valid],
-                                             reduction="none").mean(-1)
-    total = loss_color + loss_sem * weight_semantics + loss_depth * weight_depth
-    return total * global_scale, (loss_color, loss_sem, loss_depth)
+    c = semantics.shape[-1]
+    if not pred_rgb.is_cuda:
+        raise UcsaError("nerf_losses needs CUDA tensors (the rendering path has no CPU fallback)")
+    if c > ops.MAX_CLASSES:
+        raise NotImplementedError(f"nerf_losses: at most {ops.MAX_CLASSES} classes")
+    rgb = gt_rgb.reshape(-1, 3)
+    if rgb.dtype not in (torch.float16, torch.float32):
+        rgb = rgb.float()
+    total, parts = _FusedLosses.apply(
+        pred_rgb.reshape(-1, 3).float().contiguous(), pred_depth.reshape(-1).float().contiguous(),
+        semantics.reshape(-1, c).float().contiguous(), rgb.contiguous(), labels.reshape(-1).long().contiguous(),
+        gt_depth.reshape(-1).float().contiguous(), float(one_m_to_scene_uom), float(weight_semantics),
+        float(weight_depth), float(global_scale))
+    return total, (parts[0], parts[1], parts[2])
 
 
 class NerfTrainer:
@@ -104,16 +97,25 @@ class NerfTrainer:
         for (m, _), g in zip(self.groups, self.grad_views):
             m.params.grad = g  # autograd accumulates straight into the flat all-reduce buffer
             m.half_params()
+        # GradScaler-style overflow handling on the device (joint_train_lightning_net.py:46,509-513)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.skipped_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.found_inf = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._check_scratch = torch.zeros(2, dtype=torch.int32, device=dev)
 
     def zero_grad(self):
         self.flat_grad.zero_()
 
     def optimizer_step(self):
+        """Adam on the (already all-reduced) flat gradient; a step whose gradient holds inf / NaN is skipped."""
         self.step += 1
+        self.step_dev.add_(1)
+        ops.grad_check(self.flat_grad, self.found_inf, self._check_scratch, skipped_dev=self.skipped_dev)
         for (m, wd), g, ea, eas in zip(self.groups, self.grad_views, self.exp_avg, self.exp_avg_sq):
             half = m.half_params()
             ops.adam_step(m.params.data, g, ea, eas, half, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1],
-                          eps=self.eps, weight_decay=wd, grad_scale_inv=1.0, found_inf=None, step=self.step)
+                          eps=self.eps, weight_decay=wd, grad_scale_inv=1.0, found_inf=self.found_inf, step=1,
+                          step_dev=self.step_dev, skipped_dev=self.skipped_dev)
 
     def train_step(self, rays_o, rays_d, direction_norms, gt_rgb, labels, gt_depth, one_m_to_scene_uom, seed=None,
                    ray_base=0):
