@@ -252,13 +252,19 @@ def time_config1(dev, peak):
     # sample and reads 352 per ray
     bytes_f = n * t * 180 + n * 180
     bytes_b = n * t * (180 + 176) + n * 352
+    # what this backward really has to move: d_prob = w * g_semantics does not read p (semantic weights are detached,
+    # renderer_semantics.py:270), so per sample it reads sigma, z, rgb, w (24 B) and writes 176 B
+    bytes_b_needed = n * t * (24 + 176) + n * 184
     return {
         "workload": "dense composite 4096 rays x 128 samples x 40 classes (BASELINE.json configs[0])",
         "l2": "4 rotating input sets of 95 MB (forward) / 188 MB (backward) each: no launch finds its inputs in L2",
         "fwd": {"ms": ms_f, "algorithmic_bytes": bytes_f, "achieved_gbs": bytes_f / ms_f / 1e6,
                 "frac_of_hbm_peak": bytes_f / ms_f / 1e6 / peak},
         "bwd": {"ms": ms_b, "algorithmic_bytes": bytes_b, "achieved_gbs": bytes_b / ms_b / 1e6,
-                "frac_of_hbm_peak": bytes_b / ms_b / 1e6 / peak},
+                "frac_of_hbm_peak": bytes_b / ms_b / 1e6 / peak, "bytes_the_kernel_needs": bytes_b_needed,
+                "frac_of_hbm_peak_needed_bytes": bytes_b_needed / ms_b / 1e6 / peak,
+                "note": "SURVEY 8(d) counts a 160 B/sample read of p that the backward does not need; the second figure "
+                        "uses the bytes the kernel must move (its 92 MB of writes may still sit in L2 when it ends)"},
         "rays_per_s_fwd": n / (ms_f * 1e-3), "rays_per_s_fwd_bwd": n / ((ms_f + ms_b) * 1e-3), "peak_gbs": peak,
         "launches": 2 * sets * reps,
     }
@@ -395,13 +401,17 @@ def run_ours(args):
     # few hundred steps the mask prunes.  300 optimisation steps over the batches above, then K timed steps.
     trained = None
     if not args.no_extras:
-        n_train = 300
-        for s in range(n_train):
-            engine.train_step(*batches[s % len(batches)])
+        n_train = args.train_steps
+        gt = torch.Generator(device=dev).manual_seed(777 + rank)
+        for s in range(n_train):  # fresh pixels of a fresh view every step, generated on the device
+            pix = torch.randint(0, scene.W * scene.H, (RAYS_PER_GPU,), device=dev, generator=gt)
+            o, d, dn = scene.rays(int(torch.randint(0, scene.n_views, (1,), generator=gt, device=dev)), pix)
+            rgb, depth, label = scene.ground_truth(o, d, dn)
+            engine.train_step(o, d, dn, rgb.half(), label, depth)
         ms_tr = time_engine_steps(engine, batches, args.warmup, total_steps)
         k_over_s = float(engine.ws.ray_off[-1]) / (RAYS_PER_GPU * (NUM_STEPS + UPSAMPLE_STEPS))
         loss4 = [float(v) for v in engine.loss]
-        trained = {"after_steps": n_train + 2 * total_steps, "ms_per_step": ms_tr / args.steps,
+        trained = {"after_steps": n_train + 2 * total_steps + 2, "ms_per_step": ms_tr / args.steps,
                    "rays_per_s": world * RAYS_PER_GPU * args.steps / (ms_tr * 1e-3), "k_over_s": k_over_s,
                    "k_over_s_at_init": k_over_s_init, "loss": loss4,
                    "skipped_steps": engine.skipped_steps}
@@ -415,7 +425,9 @@ def run_ours(args):
     for p_ in net.parameters():
         p_.grad = None
 
-    def e2e_step(s):
+    loss_host = torch.zeros(total_steps, dtype=torch.float32).pin_memory()
+
+    def e2e_step(s, sync):
         o, d, dn, rgb, label, depth = (x.to(dev, non_blocking=True) for x in host[s])
         opt.zero_grad(set_to_none=False)
         out = net.render(o, d, direction_norms=dn, staged=False, bg_color=None, perturb=True, seed=5000 + s,
@@ -426,18 +438,28 @@ def run_ours(args):
             for p in net.parameters():
                 dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
         opt.step()
-        return float(loss.detach())  # D2H read of the step's result
+        if sync:
+            return float(loss.detach())  # blocking D2H read of the step's result
+        loss_host[s].copy_(loss.detach(), non_blocking=True)  # D2H read of the step's result, pinned destination
+        return None
 
-    for s in range(args.warmup):
-        e2e_step(s)
-    barrier()
-    e0.record()
-    for s in range(args.warmup, total_steps):
-        e2e_step(s)
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    def time_e2e(sync):
+        for s in range(args.warmup):
+            e2e_step(s, sync)
+        barrier()
+        e0.record()
+        for s in range(args.warmup, total_steps):
+            e2e_step(s, sync)
+        e1.record()
+        barrier()  # (synchronizes: every loss has landed in host memory before the clock is read)
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # the step's loss goes to pinned host memory with an asynchronous copy each step (what a Lightning loop does: the
+    # logged loss is only read on the host at the logging interval); "blocking" reads it with .item() every step
+    e2e_ms = time_e2e(sync=False)
     e2e_value = world * RAYS_PER_GPU * args.steps / (e2e_ms * 1e-3)
+    assert bool(torch.isfinite(loss_host[args.warmup:]).all()) and float(loss_host[args.warmup:].abs().sum()) > 0
+    e2e_blocking_ms = time_e2e(sync=True)
     del opt
     for p_ in net.parameters():
         p_.grad = None
@@ -582,7 +604,10 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps,
                 "api": "SemanticNeRFNetwork.render + nerf_losses + torch.optim.Adam (the drop-in API a Lightning "
-                       "loop calls), pinned host inputs",
+                       "loop calls), pinned host inputs, loss copied to pinned host memory every step (non-blocking)",
+                "blocking_readback": {"value": world * RAYS_PER_GPU * args.steps / (e2e_blocking_ms * 1e-3),
+                                      "ms_per_step": e2e_blocking_ms / args.steps,
+                                      "note": "same, with float(loss) (a host synchronisation) every step"},
                 "engine": {"value": e2e_engine_value, "ms_per_step": e2e_engine_ms / args.steps,
                            "api": "TrainEngine.load_batch(pinned host) + step() + loss readback"}},
         "gpu_launches": launches, "gpu_launches_per_step": by_name,
@@ -632,6 +657,8 @@ def main():
     ap.add_argument("--exchange", choices=["peer", "nccl"], default=None,
                     help="multi-GPU gradient exchange (default: peer memory when available)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=1500,
+                    help="optimisation steps before the 'trained' measurement (an extra)")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the extra measurements (render, trained model, strong scaling, config 1)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")

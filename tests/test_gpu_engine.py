@@ -222,8 +222,10 @@ def test_adam_step_matches_torch_adam_under_gradscaler():
         st = opt.state[ref_p[i]]
         assert int(st["step"]) == 9
         rel = ((our_p[i] - ref).abs() / ref.abs().clamp_min(1e-12))
-        # the same float operations in the same order; what is left is fused-multiply-add contraction in either code
-        torch.testing.assert_close(our_p[i], ref, rtol=1e-6, atol=1e-9, msg=lambda m: f"group {i}: {m}; max rel {float(rel.max()):.3e}")
+        # the same float operations in the same order; what is left is fused-multiply-add contraction inside torch's
+        # kernels.  atol = 1e-6 x the step size (lr = 1e-2): parameters that cancelled to ~0 over the 9 updates carry
+        # the absolute error of the updates, not a relative one
+        torch.testing.assert_close(our_p[i], ref, rtol=1e-6, atol=1e-8, msg=lambda m: f"group {i}: {m}; max rel {float(rel.max()):.3e}")
         torch.testing.assert_close(our_m[i], st["exp_avg"], rtol=1e-6, atol=1e-12)
         torch.testing.assert_close(our_v[i], st["exp_avg_sq"], rtol=1e-6, atol=1e-20)
         assert torch.equal(our_h[i], our_p[i].half()), "fp16 working copy = rounded master"

@@ -255,8 +255,10 @@ def test_against_compiled_reference_kernels(ops):
 
 @pytest.mark.parametrize("perturb", [0, 3])
 def test_inference_wavefront_against_compiled_reference(ops, perturb):
-    """march_rays / composite_rays / compact_rays (raymarching.cu:528-643, :645-720, :837-864, bound at
-    bindings.cpp:15-17) against the reference's own kernels: three wavefront rounds on the same alive list."""
+    """march_rays (raymarching.cu:528-643) and compact_rays (:837-864), the two inference kernels the reference binds
+    (bindings.cpp:15,17), against the reference's own compiled kernels over three wavefront rounds.  (The reference's
+    composite_rays is not bound -- bindings.cpp:16 is commented out -- so the rounds are advanced by ours, which
+    test_inference_wavefront_kernels holds to the C restatement of :645-729.)"""
     ref = build_oracle.load_reference()
     if ref is None:
         pytest.skip("oracle/_ref not built (reference sources were not mounted at build time)")
@@ -268,60 +270,41 @@ def test_inference_wavefront_against_compiled_reference(ops, perturb):
     n_alive = 1111
     alive = torch.randperm(n, device=DEV, generator=g)[:n_alive].int().contiguous()
     rays_t = nears[alive.long()].clone()
-    st = {k: (torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), torch.zeros(n, 3, device=DEV)) for k in "ab"}
-    alive_a, t_a = alive.clone(), rays_t.clone()
-    alive_b, t_b = alive.clone(), rays_t.clone()
+    ws, dp, im = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), torch.zeros(n, 3, device=DEV)
     died_total = 0
     for rnd in range(3):
         m = n_alive * n_step
         x1, d1, e1 = torch.zeros(m, 3, device=DEV), torch.zeros(m, 3, device=DEV), torch.zeros(m, 2, device=DEV)
-        ref.march_rays(n_alive, n_step, alive_a, t_a, o, d, 4.0, 1 / 128, 3, 128, grid, 0.5, nears, fars, x1, d1, e1,
+        # the reference seeds its jitter by the position in the alive list: both sides get the SAME list
+        ref.march_rays(n_alive, n_step, alive, rays_t, o, d, 4.0, 1 / 128, 3, 128, grid, 0.5, nears, fars, x1, d1, e1,
                        perturb)
-        x2, d2, e2 = ops.march_rays(n_alive, n_step, alive_b, t_b, o, d, 4.0, 1 / 128, grid, None, 0.5, nears, fars, m,
+        x2, d2, e2 = ops.march_rays(n_alive, n_step, alive, rays_t, o, d, 4.0, 1 / 128, grid, None, 0.5, nears, fars, m,
                                     perturb)
-        # the two alive lists hold the same rays, possibly in a different order (the reference compacts with atomics)
-        pa, pb = torch.argsort(alive_a[:n_alive]), torch.argsort(alive_b[:n_alive])
-        assert torch.equal(alive_a[:n_alive][pa], alive_b[:n_alive][pb])
-        assert torch.equal(t_a[:n_alive][pa], t_b[:n_alive][pb])
-        rows = lambda t, p: t.view(n_alive, n_step, -1)[p]
-        assert torch.equal(rows(x1, pa), rows(x2, pb)), "sample positions must be bit-exact"
-        assert torch.equal(rows(e1, pa), rows(e2, pb)), "step sizes must be bit-exact"
-        assert torch.equal(rows(d1, pa), rows(d2, pb))
+        assert torch.equal(x1, x2), "sample positions must be bit-exact"
+        assert torch.equal(e1, e2), "step sizes must be bit-exact"
+        assert torch.equal(d1, d2)
         assert int((e1[:, 0] > 0).sum()) > 0
-        # the same per-sample sigma / rgb for both (keyed by ray and step so the orders do not matter)
-        key = (alive_a[:n_alive].long()[:, None] * 131 + torch.arange(n_step, device=DEV)[None] + 7 * rnd).float()
-        sig_a = 25 * (torch.sin(key * 12.9898) * 0.5 + 0.5) ** 2
-        rgb_a = torch.stack([torch.sin(key * k) * 0.5 + 0.5 for k in (1.1, 2.3, 3.7)], -1)
-        inv = torch.empty_like(pb)
-        inv[pb] = torch.arange(n_alive, device=DEV)
-        perm_ab = pa[inv]  # row i of b corresponds to row perm_ab[i] of a
-        sig_b, rgb_b = sig_a[perm_ab].contiguous(), rgb_a[perm_ab].contiguous()
-        ref.composite_rays(n_alive, n_step, alive_a, t_a, sig_a.view(-1).contiguous(), rgb_a.view(-1, 3).contiguous(),
-                           e1, *st["a"])
-        ops.composite_rays(n_alive, n_step, alive_b, t_b, sig_b.view(-1), rgb_b.view(-1, 3), None, e2, 0, *st["b"],
-                           None)
-        assert torch.equal(t_a[:n_alive][pa] < 0, t_b[:n_alive][pb] < 0), "the same rays terminate"
-        torch.testing.assert_close(t_a[:n_alive][pa], t_b[:n_alive][pb], rtol=1e-6, atol=0)
-        for qa, qb in zip(st["a"], st["b"]):
-            torch.testing.assert_close(qa, qb, rtol=1e-5, atol=1e-6)
-        # compaction
-        na_a, nt_a = torch.zeros_like(alive_a), torch.zeros_like(t_a)
-        na_b, nt_b = torch.zeros_like(alive_b), torch.zeros_like(t_b)
+        sig = 25 * torch.rand(m, device=DEV, generator=g) ** 2
+        rgb = torch.rand(m, 3, device=DEV, generator=g)
+        ops.composite_rays(n_alive, n_step, alive, rays_t, sig, rgb, None, e2, 0, ws, dp, im, None)
+        # compaction of the rays that survived (rays_t >= 0)
+        na_a, nt_a = torch.zeros_like(alive), torch.zeros_like(rays_t)
+        na_b, nt_b = torch.zeros_like(alive), torch.zeros_like(rays_t)
         cnt_a = torch.zeros(1, dtype=torch.int32, device=DEV)
         cnt_b = torch.zeros(1, dtype=torch.int32, device=DEV)
-        ref.compact_rays(n_alive, na_a, alive_a, nt_a, t_a, cnt_a)
-        ops.compact_rays(n_alive, na_b, alive_b, nt_b, t_b, cnt_b)
+        ref.compact_rays(n_alive, na_a, alive, nt_a, rays_t, cnt_a)
+        ops.compact_rays(n_alive, na_b, alive, nt_b, rays_t, cnt_b)
         assert int(cnt_a) == int(cnt_b)
         new_alive = int(cnt_a)
         died_total += n_alive - new_alive
-        # ours is order-preserving (a scan), the reference's order is whatever its atomics produced
-        keep = t_b[:n_alive] >= 0
-        assert torch.equal(na_b[:new_alive], alive_b[:n_alive][keep]) and torch.equal(nt_b[:new_alive], t_b[:n_alive][keep])
+        # ours preserves the order (a scan); the reference's order is whatever its atomics produced
+        keep = rays_t[:n_alive] >= 0
+        assert torch.equal(na_b[:new_alive], alive[:n_alive][keep])
+        assert torch.equal(nt_b[:new_alive], rays_t[:n_alive][keep])
         sa, sb = torch.argsort(na_a[:new_alive]), torch.argsort(na_b[:new_alive])
         assert torch.equal(na_a[:new_alive][sa], na_b[:new_alive][sb])
-        torch.testing.assert_close(nt_a[:new_alive][sa], nt_b[:new_alive][sb], rtol=1e-6, atol=0)
-        # next round from identical lists: the reference seeds its jitter by the position in the alive list
-        alive_a, t_a, alive_b, t_b, n_alive = na_b.clone(), nt_b.clone(), na_b, nt_b, new_alive
+        assert torch.equal(nt_a[:new_alive][sa], nt_b[:new_alive][sb])
+        alive, rays_t, n_alive = na_b, nt_b, new_alive
         if n_alive == 0:
             break
     assert died_total > 0, "the case must exercise termination + compaction"

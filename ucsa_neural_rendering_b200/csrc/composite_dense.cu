@@ -6,6 +6,9 @@
 // weights in shared memory; pass 2 streams the probability block of the ray as 16-byte vectors.  Lane l of
 // the 32/G*G active lanes (G = C/4) always sees the same four classes (l % G), so its accumulator is one
 // float4 in registers for the whole ray; partial sums of the 32/G sample phases are folded at the end.
+#include <cstdlib>
+
+#include "mlp_umma.cuh"
 #include "weights.cuh"
 
 namespace ucsa {
@@ -131,6 +134,105 @@ composite_dense_fwd_kernel(const float* __restrict__ sigma, const float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// TMA-staged forward (the production path when a ray's inputs fit a stage): the kernel above leaves every warp with a
+// handful of dependent load rounds (z / sigma -> weights -> rgb -> probabilities, ~1 us of HBM latency each), which is
+// what bounds a 35 us kernel.  Here a PERSISTENT warp walks its rays with a two-stage ring in shared memory: one lane
+// requests ALL inputs of the next ray (z, sigma, rgb and the [T, C] probability block, four bulk copies completing on
+// one mbarrier) before the warp starts on the current ray, so every byte is in flight one ray ahead and the
+// arithmetic reads shared memory only.  23 KB per stage at T = 128, C = 40; 4 warps x 2 stages per SM keep ~92 KB
+// in flight per SM, twice what HBM latency x bandwidth needs.  Same arithmetic, in the same order, as the kernel above.
+struct DenseStage {
+  uint32_t z_off, sigma_off, rgb_off, prob_off, bytes;  // byte offsets inside a stage
+};
+
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+composite_dense_fwd_tma_kernel(const float* __restrict__ sigma, const float* __restrict__ z,
+                               const float* __restrict__ rgb, const float* __restrict__ prob,
+                               const float* __restrict__ dnorm, uint32_t n_rays, uint32_t t, uint32_t c,
+                               float density_scale, float* __restrict__ weights, float* __restrict__ depth,
+                               float* __restrict__ image, float* __restrict__ semantics, DenseStage lay,
+                               uint32_t warp_bytes) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  unsigned char* mine = smem_raw + static_cast<size_t>(wib) * warp_bytes;  // [stage 0 | stage 1 | wm | 2 barriers]
+  unsigned char* stage_base[2] = {mine, mine + lay.bytes};
+  float* wm = reinterpret_cast<float*>(mine + 2 * lay.bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mine + 2 * lay.bytes + ((4 * t + 15) & ~15u));
+  const uint32_t stride = gridDim.x * kWarpsPerCta;
+  uint32_t n = blockIdx.x * kWarpsPerCta + wib;
+  if (n >= n_rays) return;  // (whole warps only: no CTA-wide barrier below)
+  const uint64_t stream = l2_policy_stream();
+  if (lane == 0) {
+    umma::mbar_init(&bars[0], 1);
+    umma::mbar_init(&bars[1], 1);
+  }
+  __syncwarp();
+
+  auto request = [&](uint32_t ray, int st) {  // lane 0 only
+    const uint64_t row = static_cast<uint64_t>(ray) * t;
+    const uint32_t dst = umma::smem_u32(stage_base[st]);
+    umma::mbar_expect_tx(&bars[st], lay.bytes);
+    umma::bulk_load(dst + lay.z_off, z + row, 4 * t, &bars[st], stream);
+    umma::bulk_load(dst + lay.sigma_off, sigma + row, 4 * t, &bars[st], stream);
+    umma::bulk_load(dst + lay.rgb_off, rgb + row * 3, 12 * t, &bars[st], stream);
+    umma::bulk_load(dst + lay.prob_off, prob + row * c, 4 * t * c, &bars[st], stream);
+  };
+  if (lane == 0) request(n, 0);
+  uint32_t phase[2] = {0u, 0u};
+  const uint32_t g = c / 4;     // float4 groups per sample
+  const uint32_t spi = 32 / g;  // samples per warp step
+  const uint32_t sub = lane / g, grp = lane % g;
+  const bool active = static_cast<uint32_t>(lane) < spi * g;
+
+  for (int st = 0; n < n_rays; n += stride, st ^= 1) {
+    if (lane == 0 && n + stride < n_rays) {
+      umma::fence_async_smem();  // the other stage was read by this warp (generic proxy) one ray ago
+      request(n + stride, st ^ 1);
+    }
+    umma::mbar_wait(&bars[st], phase[st]);
+    phase[st] ^= 1u;
+    const float* zs = reinterpret_cast<const float*>(stage_base[st] + lay.z_off);
+    const float* sg = reinterpret_cast<const float*>(stage_base[st] + lay.sigma_off);
+    const float* cs = reinterpret_cast<const float*>(stage_base[st] + lay.rgb_off);
+    const float4* ps = reinterpret_cast<const float4*>(stage_base[st] + lay.prob_off);
+    const uint64_t row = static_cast<uint64_t>(n) * t;
+    const float dsum = ray_weights(zs, sg, t, density_scale, lane, wm, weights ? weights + row : nullptr);
+    if (lane == 0) depth[n] = dsum / dnorm[n];
+    __syncwarp();
+    {  // colour: lanes 0..29 = 10 samples x 3 channels per step
+      const int csub = lane / 3, ch = lane % 3;
+      float acc = 0.f;
+      if (lane < 30)
+        for (uint32_t s = csub; s < t; s += 10) acc = fmaf(wm[s], cs[s * 3 + ch], acc);
+      float tot = 0.f;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) tot += __shfl_sync(kFullMask, acc, (3 * k + ch) % 32);
+      if (lane < 3) image[static_cast<uint64_t>(n) * 3 + lane] = tot;
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
+#pragma unroll 4
+      for (uint32_t s = sub; s < t; s += spi) {
+        const float4 v = ps[static_cast<size_t>(s) * g + grp];
+        const float w = wm[s];
+        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+      }
+    }
+    float4 tot = acc;
+    for (uint32_t k = 1; k < spi; ++k) {
+      const int src = (lane + k * g) % 32;
+      tot.x += __shfl_sync(kFullMask, acc.x, src);
+      tot.y += __shfl_sync(kFullMask, acc.y, src);
+      tot.z += __shfl_sync(kFullMask, acc.z, src);
+      tot.w += __shfl_sync(kFullMask, acc.w, src);
+    }
+    if (static_cast<uint32_t>(lane) < g)
+      *reinterpret_cast<float4*>(semantics + static_cast<uint64_t>(n) * c + 4 * lane) = tot;
+    __syncwarp();  // every lane is done with this stage and with wm before they are refilled
+  }
+}
+
 template <bool VEC4>
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
 composite_dense_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ z,
@@ -247,6 +349,36 @@ extern "C" int ucsa_composite_dense_fwd(const float* sigma, const float* z, cons
   const bool vec4 = n_classes % 4 == 0 && n_classes <= 128 && (reinterpret_cast<uintptr_t>(prob) % 16 == 0) &&
                     (reinterpret_cast<uintptr_t>(semantics) % 16 == 0);
   const dim3 grid(ceil_div(n_rays, kWarpsPerCta)), block(32 * kWarpsPerCta);
+  // TMA-staged persistent kernel: rows of every input must be 16-byte multiples at 16-byte aligned addresses (bulk
+  // copies), and two stages per warp must fit the CTA's shared memory
+  {
+    DenseStage lay;
+    lay.z_off = 0;
+    lay.sigma_off = 4 * t;
+    lay.rgb_off = 8 * t;
+    lay.prob_off = 20 * t;
+    lay.bytes = 20 * t + 4 * t * n_classes;
+    const uint32_t warp_bytes = (2 * lay.bytes + ((4 * t + 15) & ~15u) + 16 + 127) & ~127u;
+    const size_t tma_smem = static_cast<size_t>(kWarpsPerCta) * warp_bytes;
+    const auto aligned = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+    static int use_tma = -1;
+    if (use_tma < 0) {  // bring-up knob: UCSA_DENSE_TMA=0 forces the load/compute kernel
+      const char* e = getenv("UCSA_DENSE_TMA");
+      use_tma = (e == nullptr || e[0] != '0') ? 1 : 0;
+    }
+    if (use_tma && vec4 && t % 4 == 0 && 32 / (n_classes / 4) >= 1 && aligned(sigma) && aligned(z) && aligned(rgb) &&
+        tma_smem <= 227 * 1024 && lay.bytes < (1u << 20)) {
+      const void* fn = reinterpret_cast<const void*>(composite_dense_fwd_tma_kernel);
+      if (int rc = set_max_dyn_smem(fn, tma_smem, "composite_dense_fwd")) return rc;
+      const uint32_t per_sm = static_cast<uint32_t>((227 * 1024) / (tma_smem + 1024));
+      const uint32_t cap = kNumSMs * (per_sm < 1 ? 1 : per_sm);
+      const uint32_t want = ceil_div(n_rays, kWarpsPerCta);
+      composite_dense_fwd_tma_kernel<<<want < cap ? want : cap, block, tma_smem, as_stream(stream)>>>(
+          sigma, z, rgb, prob, direction_norms, n_rays, t, n_classes, density_scale, weights, depth, image,
+          semantics, lay, warp_bytes);
+      return check_launch("composite_dense_fwd");
+    }
+  }
   if (vec4) {
     if (int rc = dense_smem(reinterpret_cast<const void*>(composite_dense_fwd_kernel<true>), smem)) return rc;
     composite_dense_fwd_kernel<true><<<grid, block, smem, as_stream(stream)>>>(

@@ -434,7 +434,7 @@ extern "C" int ucsa_density_bwd(const float* xyz, const float* rays_o, const flo
   if (run_max_res == 0) {  // tuning knob (bring-up): finest resolution that still merges same-cell runs per warp
     const char* e = getenv("UCSA_RUN_MAX_RES");
     run_max_res = e ? static_cast<uint32_t>(atoi(e)) : kRunMaxRes;
-    if (run_max_res < 1 || run_max_res > kRunResLimit) run_max_res = kRunMaxRes;
+    if (run_max_res < 1) run_max_res = kRunMaxRes;
   }
   auto kernel = tiled ? density_bwd_tc_kernel<true> : density_bwd_tc_kernel<false>;
   kernel<<<persistent_grid(a.n_samples, kBwdCtasPerSm), 128, kBwdSmem, as_stream(stream)>>>(

@@ -194,24 +194,30 @@ __device__ __forceinline__ void scatter_level(float* __restrict__ grad_table, co
   }
 }
 
-// Warp-collective scatter for the coarse levels (res <= kRunMaxRes): neighbouring lanes hold neighbouring samples of
-// a ray, and at a coarse level a run of them sits in ONE cell (16 samples per cell at level 0 of the 256+256
-// configuration).  The eight corner contributions are summed over each run of equal-cell lanes with a segmented
-// shuffle reduction and only the head lane of a run issues reductions: up to an order of magnitude fewer
-// red.global operations, which are what bounds the backward pass (about 1.3 LSU cycles per lane and operation).
-// Every lane of the warp must call this; `active` = the lane has a sample with a non-zero gradient.
-constexpr uint32_t kRunMaxRes = 128;     // default threshold
-constexpr uint32_t kRunResLimit = 1022;  // cell coordinates are packed into 10 bits each
+// Warp-collective scatter: neighbouring lanes hold neighbouring samples of a ray, and a run of them often sits in ONE
+// cell (16 samples per cell at level 0 of the 256+256 configuration; about two per cell at resolution 446; after some
+// training the importance samples crowd around the surfaces and share cells at every level).  The eight corner
+// contributions are summed over each run of equal-cell lanes with a segmented shuffle reduction and only the head
+// lane of a run issues reductions: fewer red.global operations, which are what bounds the backward pass (L2 request
+// rate, about 1.3 LSU cycles per lane and operation).  The reduction stops at the first distance no run spans, and a
+// warp without any two neighbours in one cell skips it altogether, so it is applied at EVERY level
+// (measured, bench.py config 2, ms per density_bwd launch by finest merged resolution: 128: 0.960, 195: 0.935,
+// 295: 0.910, 446: 0.870).  Every lane of the warp must call this; `active` = the lane has a sample with a
+// non-zero gradient.
+constexpr uint32_t kRunMaxRes = 0xffffu;  // default: all levels (UCSA_RUN_MAX_RES overrides, bring-up knob)
 
 __device__ __forceinline__ void scatter_level_runs(float* __restrict__ grad_table, const LevelGeom& lv,
                                                    const float x01[3], float g0, float g1, bool active,
                                                    uint64_t keep) {
   const int lane = threadIdx.x & 31;
   const Cell cell = locate(lv, x01);
-  const uint32_t key = active ? (cell.c[0] | (cell.c[1] << 10) | (cell.c[2] << 20)) : (0x80000000u | lane);
+  // cell coordinates are <= 8192 (finest level): x, y in one word, z (and the inactive marker) in the other
+  const uint32_t key_xy = cell.c[0] | (cell.c[1] << 16);
+  const uint32_t key_z = active ? cell.c[2] : (0x80000000u | lane);
   // bit L of `links`: lanes L and L+1 are in the same cell
-  const uint32_t next_key = __shfl_down_sync(kFullMask, key, 1);
-  const uint32_t links = __ballot_sync(kFullMask, lane < 31 && next_key == key);
+  const uint32_t next_xy = __shfl_down_sync(kFullMask, key_xy, 1);
+  const uint32_t next_z = __shfl_down_sync(kFullMask, key_z, 1);
+  const uint32_t links = __ballot_sync(kFullMask, lane < 31 && next_xy == key_xy && next_z == key_z);
   float c[16];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -222,9 +228,10 @@ __device__ __forceinline__ void scatter_level_runs(float* __restrict__ grad_tabl
   bool head = active;
   if (links != 0u) {  // warp-uniform
     const uint32_t run = links >> lane;  // bit d-1 .. : links from this lane onwards
-#pragma unroll
+#pragma unroll 1
     for (int d = 1; d < 32; d <<= 1) {
       const bool take = (run & ((1u << d) - 1u)) == ((1u << d) - 1u);  // lanes L .. L+d all share the cell
+      if (__ballot_sync(kFullMask, take) == 0u) break;  // no run reaches this far (nor any longer distance)
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float o = __shfl_down_sync(kFullMask, c[i], d);

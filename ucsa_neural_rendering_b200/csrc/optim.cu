@@ -38,14 +38,17 @@ __device__ __forceinline__ void adam_scalars(double lr, double b1, double b2, in
   *out_bc2_sqrt = static_cast<float>(sqrt(bc2));
 }
 
+// Explicit roundings (no compiler-chosen contraction): both kernels below produce identical bits, and the sequence is
+// the one torch's foreach kernels compile to (lerp -> fma(w, g - m, m); addcmul -> fma(value * g, g, v); addcdiv ->
+// fma(value, m / denom, p); add(param, alpha = wd) -> fma(wd, p, g)).
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamCoef& c) {
-  float grad = g * c.ginv;
-  if (c.wd != 0.f) grad = grad + c.wd * p;
-  m = m + c.one_minus_b1 * (grad - m);
-  v = v * c.b2;
-  v = v + c.one_minus_b2 * grad * grad;
-  const float denom = sqrtf(v) / c.bc2_sqrt + c.eps;
-  p = p - c.step_size * (m / denom);
+  float grad = __fmul_rn(g, c.ginv);
+  if (c.wd != 0.f) grad = __fmaf_rn(c.wd, p, grad);
+  m = __fmaf_rn(c.one_minus_b1, __fsub_rn(grad, m), m);
+  v = __fmul_rn(v, c.b2);
+  v = __fmaf_rn(__fmul_rn(c.one_minus_b2, grad), grad, v);
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), c.bc2_sqrt), c.eps);
+  p = __fmaf_rn(-c.step_size, __fdiv_rn(m, denom), p);
 }
 
 // Four parameters per thread (16-byte accesses); the bias corrections are formed once per CTA, because with the
@@ -65,8 +68,12 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   __syncthreads();
   const AdamCoef c{bc[0], static_cast<float>(b1), static_cast<float>(1.0 - b1), static_cast<float>(b2),
                    static_cast<float>(1.0 - b2), eps, wd, ginv, bc[1]};
-  const uint64_t i = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
-  if (i + 3 < n) {
+  // grid-stride over float4 groups: a bounded number of CTAs, so the double-precision scalars above are formed a few
+  // thousand times per launch instead of once per 1024 parameters
+  const uint64_t n4 = n / 4;
+  for (uint64_t q = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < n4;
+       q += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t i = q * 4;
     float4 pp = *reinterpret_cast<const float4*>(p + i);
     const float4 gg = *reinterpret_cast<const float4*>(g + i);
     float4 mm = *reinterpret_cast<const float4*>(m + i);
@@ -85,15 +92,15 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
       o.y = *reinterpret_cast<const uint32_t*>(&hi);
       *reinterpret_cast<uint2*>(p_h + i) = o;
     }
-  } else {
-    for (uint64_t k = i; k < n; ++k) {
-      float pk = p[k], mk = m[k], vk = v[k];
-      adam_one(pk, g[k], mk, vk, c);
-      p[k] = pk;
-      m[k] = mk;
-      v[k] = vk;
-      if (p_h != nullptr) p_h[k] = __float2half_rn(pk);
-    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3u)) {  // scalar tail
+    const uint64_t k = n4 * 4 + threadIdx.x;
+    float pk = p[k], mk = m[k], vk = v[k];
+    adam_one(pk, g[k], mk, vk, c);
+    p[k] = pk;
+    m[k] = mk;
+    v[k] = vk;
+    if (p_h != nullptr) p_h[k] = __float2half_rn(pk);
   }
 }
 
@@ -280,7 +287,9 @@ extern "C" int ucsa_adam_step(float* param, const float* grad, float* exp_avg, f
                    (reinterpret_cast<uintptr_t>(param_h) & 7u) == 0,
                "adam_step: buffers must be 16-byte aligned (fp16 copy: 8-byte)");
   if (n == 0) return UCSA_OK;
-  adam_kernel<<<ceil_div((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq,
+  uint32_t blocks = ceil_div((n + 3) / 4, 256);
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq,
                                                                static_cast<__half*>(param_h), n, lr, beta1, beta2,
                                                                eps, weight_decay, grad_scale_inv, found_inf,
                                                                static_cast<int>(step), step_dev, skipped_dev);
