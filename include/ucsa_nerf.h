@@ -223,6 +223,18 @@ UCSA_API int ucsa_compact_rays(uint32_t n_alive, int32_t* rays_alive, const int3
 UCSA_API int ucsa_grid_update(float* density_grid, const float* fresh, uint64_t n_cells, float decay, void* stream);
 UCSA_API int ucsa_grid_packbits(const float* density_grid, uint64_t n_cells, float mean_density, uint32_t* bitfield,
                        void* stream);
+/* The whole grid refresh as a kernel chain (the reference allocates density_grid, renderer_semantics.py:89-103, but
+ * ships no update; rule after torch-ngp, which it is adapted from):
+ * ucsa_grid_density: sigma of ONE jittered point per cell of the [cascades, H, H, H] grid (cell order of
+ *   raymarching.cu:204) -- hash-grid encode + sigma MLP + trunc_exp in the density kernel, the points are generated
+ *   on the fly (seed = counter-based stream), nothing but the [cascades*H^3] sigmas touches memory;
+ * ucsa_grid_update_pack: grid = max(grid*decay, fresh*fresh_scale), mean_density_dev[0] = mean(max(grid,0)),
+ *   bitfield bit i = grid[i] > min(0.01, mean).  sum_scratch: one double owned by the caller. */
+UCSA_API int ucsa_grid_density(const void* table_h, const ucsa_grid_desc* grid_host, const void* w_sigma_h, float bound,
+                       uint32_t cascades, uint32_t grid_h, uint64_t seed, float* sigma_cells, void* stream);
+UCSA_API int ucsa_grid_update_pack(float* density_grid, const float* fresh, uint64_t n_cells, float decay,
+                       float fresh_scale, double* sum_scratch, float* mean_density_dev, uint32_t* bitfield,
+                       void* stream);
 
 /* ---- stand-alone encoders / MLP, the module-level API the reference network exposes
  * (self.encoder, self.encoder_dir, tcnn.Network; network_tcnn_semantics.py:108,117,121,125). */

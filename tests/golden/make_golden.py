@@ -314,6 +314,125 @@ def case_frontend(name, *, height, width, n, seed):
     print(name, "rays", tuple(rays["rays_d"].shape), "novel", len(novel))
 
 
+def install_lightning_stubs():
+    """What joint_train_lightning_net.py imports besides torch / torchvision / cv2 / PIL, none of it on the NeRF path:
+    pytorch_lightning (absent; LightningModule -> nn.Module), the DeepLab wrapper, the metric and visualizer helpers
+    (Lightning / matplotlib / imageio dependent).  nr4seg.dataset.ngp_utils is the reference's own file, loaded by
+    path because the package __init__ imports the dataset classes."""
+    import importlib.util
+
+    pl = types.ModuleType("pytorch_lightning")
+
+    class LightningModule(torch.nn.Module):
+        current_epoch = 0
+
+    pl.LightningModule = LightningModule
+    sys.modules["pytorch_lightning"] = pl
+    for name, attrs in (("nr4seg.network", ["DeepLabV3"]), ("nr4seg.utils", []), ("nr4seg.utils.metrics", ["SemanticsMeter"]),
+                        ("nr4seg.visualizer", ["Visualizer"]), ("nr4seg.dataset", [])):
+        mod = types.ModuleType(name)
+        for a in attrs:
+            setattr(mod, a, type(a, (), {"__init__": lambda self, *args, **kw: None}))
+        sys.modules[name] = mod
+    spec_ = importlib.util.spec_from_file_location("nr4seg.dataset.ngp_utils",
+                                                   "/root/reference/nr4seg/dataset/ngp_utils.py")
+    ngp_utils = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(ngp_utils)
+    sys.modules["nr4seg.dataset.ngp_utils"] = ngp_utils
+    return ngp_utils
+
+
+def case_lightning(name, *, height, width, seed):
+    """The CONSUMER side of the boundary: the reference's unmodified JointTrainLightningNet.forward_nerf_train and
+    forward_nerf_test (joint_train_lightning_net.py:167-257) drive the reference network (tcnn stubbed as above) on a
+    small view; the batch, the pixels they sampled and what they returned are frozen.  tests/test_gpu_boundary.py
+    replays the same calls on the drop-in module under CUDA autocast."""
+    ngp_utils = install_lightning_stubs()
+    import importlib.util
+
+    # the module file itself, unmodified; loaded by path because nr4seg/lightning/__init__.py imports the data modules
+    spec_pl = importlib.util.spec_from_file_location(
+        "ref_joint_train_lightning_net", "/root/reference/nr4seg/lightning/joint_train_lightning_net.py")
+    ref_pl = importlib.util.module_from_spec(spec_pl)
+    spec_pl.loader.exec_module(ref_pl)
+    from nr4seg.nerf import activation as ref_act
+    from nr4seg.nerf import network_tcnn_semantics as ref_net
+
+    ref_net.trunc_exp = lambda x: ref_act.trunc_exp(x.float())
+    _Network._count = 0
+    nerf = ref_net.SemanticNeRFNetwork(encoding="hashgrid", bound=4, cuda_ray=False, density_scale=1,
+                                       num_semantic_classes=40)
+    mod = ref_pl.JointTrainLightningNet.__new__(ref_pl.JointTrainLightningNet)
+    torch.nn.Module.__init__(mod)
+    mod.num_classes = 40
+    mod.nerf_model = nerf
+    mod.criterion_nerf_rgb = torch.nn.MSELoss(reduction="none")
+    mod.criterion_nerf_semantics = torch.nn.NLLLoss(ignore_index=-1, reduction="none")
+    mod.criterion_nerf_depth = torch.nn.L1Loss(reduction="none")
+    mod._default_H = mod._default_W = None
+
+    g = torch.Generator().manual_seed(seed)
+    n_pix = height * width
+    # camera inside the box, looking around: nerf_matrix_to_ngp convention is whatever the caller hands over
+    from scipy.spatial.transform import Rotation
+
+    pose = np.eye(4, dtype=np.float32)
+    pose[:3, :3] = Rotation.from_euler("xyz", [0.3, -0.5, 0.2]).as_matrix()
+    pose[:3, 3] = [0.4, -0.3, 0.2]
+    intr = np.array([0.9 * width, 0.95 * width, width / 2 - 0.3, height / 2 + 0.7], dtype=np.float64)
+    img = torch.rand(1, 3, height, width, generator=g)
+    depth = torch.rand(1, height, width, generator=g) * 3
+    depth[0, ::5, ::3] = 0  # invalid depth readings
+    seg = torch.randint(0, 40, (1, height, width), generator=g)
+    uom = 0.6
+    batch = {"pose": torch.from_numpy(pose)[None], "intrinsics": [tuple(float(v) for v in intr)], "H": [height],
+             "W": [width], "img_fp16": img.half().float(), "img": img, "depth": depth, "one_m_to_scene_uom": [uom]}
+    # (img_fp16 is handed over as fp32 HOLDING fp16 values: under CUDA autocast mse_loss runs in fp32 on the promoted
+    # fp16 pixels, and the CUDA-autocast decorators of the reference do nothing on this CPU-only build machine)
+    steps = up = 256  # the defaults of render() -> run() (renderer_semantics.py:127-128)
+    n_rays = min(4096, n_pix)
+    t_rand = spec.splitmix_uniform(n_rays * steps, 901, 0.0, 1.0).view(n_rays, steps)
+    u_train = spec.splitmix_uniform(n_rays * up, 902, 0.0, 1.0).view(n_rays, up)
+    u_test = spec.splitmix_uniform(n_pix * up, 903, 0.0, 1.0).view(n_pix, up)
+
+    captured = {}
+    orig_rays = mod.get_rays_train
+
+    def capture(batch_, bs_, N=4096):
+        out = orig_rays(batch_, bs_, N)
+        captured["inds"] = out[3].clone()
+        return out
+
+    mod.get_rays_train = capture
+    torch.manual_seed(seed)
+    nerf.train()
+    with RandQueue([t_rand, u_train]):
+        l_color, l_sem, l_depth = mod.forward_nerf_train(batch, {"seg_semantics": seg}, 0)
+    total = l_color + l_sem * 0.04 + l_depth * 0.1  # training_step_nerf, :503-507
+    (total * LOSS_SCALE).backward()
+    grads = {k: (getattr(nerf, k).params.grad / LOSS_SCALE) for k in ("sigma_net", "color_net", "semantics_net")}
+    # full frame, the pseudo-label pass (:225-257); rays as the DataLoader builds them (ngp_utils.get_rays)
+    rays = ngp_utils.get_rays(torch.from_numpy(pose)[None], intr, height, width)
+    tbatch = {"rays_o": rays["rays_o"], "rays_d": rays["rays_d"], "direction_norms": rays["direction_norms"],
+              "viewpoint_is_novel": [False], "img": img}
+    nerf.eval()
+    with torch.no_grad(), RandQueue([u_test]):
+        test_out = mod.forward_nerf_test(tbatch)
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"), height=height, width=width, pose=pose, intrinsics=intr,
+        img=img.numpy(), depth=depth.numpy(), seg=seg.numpy(), uom=np.float32(uom), inds=captured["inds"].numpy(),
+        losses=np.array([float(l_color), float(l_sem), float(l_depth), float(total)], dtype=np.float64),
+        grad_sigma_net=grads["sigma_net"].numpy(), grad_color_net=grads["color_net"].numpy(),
+        grad_semantics_net=grads["semantics_net"].numpy(),
+        test_rays_o=rays["rays_o"].numpy(), test_rays_d=rays["rays_d"].numpy(),
+        test_norms=rays["direction_norms"].numpy(), nerf_rgb=test_out["nerf_rgb"].numpy(),
+        nerf_semantics=test_out["nerf_semantics"].numpy().astype(np.int64),
+        nerf_semantics_raw=test_out["nerf_semantics_raw"].numpy().astype(np.float32),
+        cfg=np.array([steps, up, 40, STATE["seed"], 901, 902, 903], dtype=np.int64), hash_amp=np.float32(STATE["hash_amp"]))
+    print(name, "losses", float(l_color), float(l_sem), float(l_depth), "rays", n_rays, "frame", test_out["nerf_rgb"].shape)
+
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -325,6 +444,7 @@ def main():
     case_network("infer_staged", n=70, steps=16, up=16, perturb=False, train=False, staged=True,
                  max_ray_batch=32, n_outside=2, seed=12, backward=False)
     case_frontend("frontend", height=24, width=40, n=300, seed=21)
+    case_lightning("lightning_step", height=20, width=32, seed=31)
 
 
 if __name__ == "__main__":

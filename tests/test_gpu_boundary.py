@@ -1,0 +1,127 @@
+"""Consumer-side test of the drop-in boundary.
+
+tests/golden/lightning_step.npz was produced by the reference's UNMODIFIED JointTrainLightningNet.forward_nerf_train
+and forward_nerf_test (joint_train_lightning_net.py:167-257) driving the reference network (tests/golden/
+make_golden.py: case_lightning).  The reference tree does not exist on the GPU box, so the caller is replayed here
+call for call -- same batch dictionary, same pixels, `torch.autocast("cuda")`, `img_fp16`, `render(...,
+staged=False, bg_color=None, perturb=True, epoch=...)` for training and `render(..., staged=True, bg_color=1,
+perturb=False)` with the default max_ray_batch for the pseudo-label pass -- on the drop-in SemanticNeRFNetwork, and
+held to what the reference computed."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import live_path, tcnn_spec as spec
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _fixture(golden_dir):
+    return {k: v for k, v in np.load(os.path.join(golden_dir, "lightning_step.npz")).items()}
+
+
+def _draws(g, n_train, n_pix):
+    steps, up = int(g["cfg"][0]), int(g["cfg"][1])
+    s1, s2, s3 = (int(v) for v in g["cfg"][4:7])
+    t_rand = spec.splitmix_uniform(n_train * steps, s1, 0.0, 1.0).view(n_train, steps)
+    u_train = spec.splitmix_uniform(n_train * up, s2, 0.0, 1.0).view(n_train, up)
+    u_test = spec.splitmix_uniform(n_pix * up, s3, 0.0, 1.0).view(n_pix, up)
+    return t_rand, u_train, u_test
+
+
+def _net(g):
+    from ucsa_neural_rendering_b200 import build
+    from ucsa_neural_rendering_b200.nerf import SemanticNeRFNetwork
+
+    build.build_library()
+    heads = live_path.OracleHeads(bound=4, num_semantic_classes=int(g["cfg"][2]), seed=int(g["cfg"][3]),
+                                  hash_amp=float(g["hash_amp"]))
+    net = SemanticNeRFNetwork(encoding="hashgrid", bound=4, cuda_ray=False, density_scale=1,
+                              num_semantic_classes=int(g["cfg"][2]))  # joint_train_lightning_net.py:29-35
+    with torch.no_grad():
+        net.encoder.params.copy_(heads.encoder)
+        net.sigma_net.params.copy_(heads.sigma_net)
+        net.color_net.params.copy_(heads.color_net)
+        net.semantics_net.params.copy_(heads.semantics_net)
+    return net.to(DEV)
+
+
+def test_forward_nerf_train_contract(golden_dir):
+    """training_step_nerf's forward (:167-223) + the scaled backward (:509-513) through the public API."""
+    from ucsa_neural_rendering_b200 import ops
+
+    g = _fixture(golden_dir)
+    h, w = int(g["height"]), int(g["width"])
+    net = _net(g).train()
+    inds = torch.from_numpy(g["inds"]).to(DEV)  # [B, N] pixels get_rays_train drew
+    n = inds.shape[1]
+    t_rand, u_train, _ = _draws(g, n, h * w)
+    batch = {"pose": torch.from_numpy(g["pose"])[None].to(DEV), "img_fp16": torch.from_numpy(g["img"]).half().to(DEV),
+             "depth": torch.from_numpy(g["depth"]).to(DEV), "one_m_to_scene_uom": [float(g["uom"])]}
+    seg = torch.from_numpy(g["seg"]).to(DEV)
+    # get_rays_train (:108-157) on the device: the product's ray generator (row f2)
+    rays_o, rays_d, norms = ops.generate_rays(batch["pose"][0].contiguous(), g["intrinsics"], h, w, inds=inds[0])
+    rays_o, rays_d, direction_norms = rays_o[None], rays_d[None], norms[None, :, None]
+    scaler = torch.amp.GradScaler("cuda", enabled=True)  # self.nerf_scaler (:46)
+    with torch.autocast("cuda", enabled=True):  # the decorator at :167
+        images = batch["img_fp16"]
+        b, c = images.shape[:2]
+        gt_rgb = torch.gather(images.reshape(b, c, -1).permute(0, 2, 1), 1, torch.stack(c * [inds], -1))
+        labels = torch.gather(seg.view(b, -1), 1, inds)
+        gt_depth = torch.gather(batch["depth"].view(b, -1), 1, inds)
+        outputs = net.render(rays_o, rays_d, direction_norms=direction_norms, staged=False, bg_color=None,
+                             perturb=True, epoch=0, t_rand=t_rand.to(DEV), u=u_train.to(DEV))
+        pred_rgb, semantics, pred_depth = outputs["image"], outputs["semantics"], outputs["depth"]
+        assert pred_rgb.dtype == semantics.dtype == pred_depth.dtype == torch.float32  # renderer_semantics.py:291-299
+        invalid = torch.sum(semantics, dim=-1) == 0
+        semantics[invalid] = 1  # in place on the module's output, as the reference does (:202)
+        semantics = semantics / torch.sum(semantics, dim=-1, keepdim=True)
+        labels[invalid] = -1
+        loss_color = torch.nn.MSELoss(reduction="none")(pred_rgb, gt_rgb).mean()
+        logp = torch.log(semantics + 1e-15).permute(0, 2, 1)
+        loss_sem = torch.nn.NLLLoss(ignore_index=-1, reduction="none")(logp, labels).mean()
+        uom = batch["one_m_to_scene_uom"][0]
+        loss_depth = torch.nn.L1Loss(reduction="none")(pred_depth[gt_depth != 0] / uom, gt_depth[gt_depth != 0]).mean(-1)
+    got = np.array([float(loss_color), float(loss_sem), float(loss_depth)])
+    # fp16 encoding / MLPs: 2e-3 on the rendered quantities, hence on their means
+    np.testing.assert_allclose(got, g["losses"][:3], rtol=4e-3, atol=1e-4)
+    total = loss_color + loss_sem * 0.04 + loss_depth * 0.1
+    scaler.scale(total).backward()
+    inv = 1.0 / float(scaler.get_scale())
+    for name, mod in (("sigma_net", net.sigma_net), ("color_net", net.color_net), ("semantics_net", net.semantics_net)):
+        ref = g["grad_" + name]
+        np.testing.assert_allclose(mod.params.grad.cpu().numpy() * inv, ref, rtol=3e-2, atol=1e-2 * np.abs(ref).max(),
+                                   err_msg=name)
+    assert torch.isfinite(net.encoder.params.grad).all() and float(net.encoder.params.grad.abs().sum()) > 0
+
+
+def test_forward_nerf_test_contract(golden_dir):
+    """The pseudo-label pass (:225-257): full frame, staged=True with the caller's default max_ray_batch, bg_color=1."""
+    g = _fixture(golden_dir)
+    h, w = int(g["height"]), int(g["width"])
+    c = int(g["cfg"][2])
+    net = _net(g).eval()
+    _, _, u_test = _draws(g, g["inds"].shape[1], h * w)
+    batch = {"rays_o": torch.from_numpy(g["test_rays_o"]).to(DEV), "rays_d": torch.from_numpy(g["test_rays_d"]).to(DEV),
+             "direction_norms": torch.from_numpy(g["test_norms"]).to(DEV)}
+    with torch.no_grad(), torch.autocast("cuda", enabled=True):
+        outputs = net.render(batch["rays_o"], batch["rays_d"], direction_norms=batch["direction_norms"], staged=True,
+                             bg_color=1, perturb=False, u=u_test.to(DEV))
+        pred_rgb = outputs["image"].reshape(1, h, w, 3)
+        semantics = outputs["semantics"].reshape(1, h, w, c)
+        invalid = torch.sum(semantics, dim=-1) == 0
+        semantics[invalid] = 1
+        semantics = semantics / torch.sum(semantics, dim=-1, keepdim=True)
+        pred_semantics = torch.argmax(semantics, dim=-1)
+    rgb = pred_rgb.permute(0, 3, 1, 2).cpu().numpy()
+    np.testing.assert_allclose(rgb, g["nerf_rgb"], rtol=4e-3, atol=2e-3)
+    np.testing.assert_allclose(semantics.cpu().numpy(), g["nerf_semantics_raw"], rtol=4e-3, atol=2e-3)
+    # pseudo labels: identical wherever the reference's top two classes are further apart than the fp16 tolerance
+    ref_raw = torch.from_numpy(g["nerf_semantics_raw"])
+    top2 = torch.topk(ref_raw, 2, dim=-1).values
+    clear = (top2[..., 0] - top2[..., 1]) > 4e-3
+    same = pred_semantics.cpu() == torch.from_numpy(g["nerf_semantics"])
+    assert bool(same[clear].all()) and float(clear.float().mean()) > 0.5

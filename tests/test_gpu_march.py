@@ -339,3 +339,41 @@ def test_run_cuda_end_to_end():
     # same samples, same weights up to the wavefront's early termination (T < 1e-4)
     torch.testing.assert_close(out2["image"], out["image"].detach(), rtol=5e-3, atol=5e-3)
     torch.testing.assert_close(out2["semantics"], out["semantics"].detach(), rtol=5e-3, atol=5e-3)
+
+
+def test_grid_refresh_kernel_chain_matches_eager_definition(ops):
+    """Row a20 (defined by this repo after torch-ngp; the reference ships no update): the three-launch refresh of
+    SemanticNeRFNetwork.update_extra_state against the eager definition in SemanticNeRFRenderer -- same cells, same
+    EMA-max rule, same bitfield rule.  The two draw different jitter inside a cell, so densities are compared on a
+    smooth field where the jitter matters little, and the bookkeeping (decay, mean, bits) exactly."""
+    from ucsa_neural_rendering_b200.nerf import SemanticNeRFNetwork
+    from ucsa_neural_rendering_b200.nerf.renderer_semantics import SemanticNeRFRenderer
+
+    net = SemanticNeRFNetwork(encoding="hashgrid", bound=4, cuda_ray=True, density_scale=1,
+                              num_semantic_classes=40).to(DEV)
+    with torch.no_grad():  # a smooth field: only the two coarsest levels carry signal
+        net.encoder.params.zero_()
+        n01 = 2 * int(net.encoder.grid.offset[2])
+        net.encoder.params[:n01].uniform_(-1.0, 1.0)
+    net.update_extra_state()
+    g1, bits1, mean1 = net.density_grid.clone(), net.density_bitfield.clone(), net.mean_density
+    assert mean1 > 0 and abs(mean1 - float(g1.clamp(min=0).mean())) < 1e-5 * mean1
+    ref_bits = torch.zeros_like(bits1)
+    ops.grid_packbits(g1, mean1, ref_bits)
+    assert torch.equal(bits1, ref_bits)
+    # eager definition on a second module with the same parameters
+    net2 = SemanticNeRFNetwork(encoding="hashgrid", bound=4, cuda_ray=True, density_scale=1,
+                               num_semantic_classes=40).to(DEV)
+    net2.load_state_dict(net.state_dict(), strict=False)
+    net2.density_grid.zero_()
+    SemanticNeRFRenderer.update_extra_state(net2)
+    g2 = net2.density_grid
+    rel = (g1 - g2).abs() / (g2.abs() + 1e-3)
+    assert float(rel.mean()) < 0.05, float(rel.mean())  # same field, different jitter inside each cell
+    assert abs(net2.mean_density - mean1) < 0.02 * mean1
+    # second refresh: EMA-max against the decayed previous grid
+    before = net.density_grid.clone()
+    net.update_extra_state(decay=0.5)
+    assert bool((net.density_grid >= before * 0.5 - 1e-7).all())
+    # all cells of a cascade are visited: no cell keeps the initial zero when the field is positive everywhere
+    assert float((net.density_grid <= 0).float().mean()) == 0.0

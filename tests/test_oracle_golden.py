@@ -133,3 +133,39 @@ def test_c_oracle_march_properties():
     empty = np.zeros_like(full)
     _, _, _, rays0, cnt0 = raymarch.march_rays_train(o, d, empty, 1.0, 4.0, 1 / 128, nears, fars, n * 1024, 0)
     assert cnt0[0] == 0 and (rays0[:, 2] == 0).all()
+
+
+def test_oracle_reproduces_the_unmodified_lightning_step(golden_dir):
+    """tests/golden/lightning_step.npz: losses and pseudo labels the reference's own forward_nerf_train /
+    forward_nerf_test (joint_train_lightning_net.py:167-257) returned; the oracle (ray generation, live path, losses)
+    must reproduce them -- this pins oracle/frontend.py + live_path.py + losses.py to the consumer of the path."""
+    from oracle import frontend
+    from oracle.losses import nerf_losses
+
+    g = {k: v for k, v in np.load(os.path.join(golden_dir, "lightning_step.npz")).items()}
+    h, w = int(g["height"]), int(g["width"])
+    steps, up, c, seed = (int(v) for v in g["cfg"][:4])
+    s1, s2, s3 = (int(v) for v in g["cfg"][4:7])
+    heads = live_path.OracleHeads(bound=4, num_semantic_classes=c, seed=seed, hash_amp=float(g["hash_amp"]))
+    inds = torch.from_numpy(g["inds"])[0]
+    n = inds.numel()
+    o, d, dn = frontend.get_rays(g["pose"], g["intrinsics"], h, w, inds=inds)
+    img16 = torch.from_numpy(g["img"]).half().float()[0]
+    gt_rgb, labels, gt_depth = frontend.gather_gt(img16, g["seg"][0], g["depth"][0], inds)
+    t_rand = spec.splitmix_uniform(n * steps, s1, 0.0, 1.0).view(n, steps)
+    u = spec.splitmix_uniform(n * up, s2, 0.0, 1.0).view(n, up)
+    out = live_path.run(heads, o[None], d[None], dn[None, :, None], num_steps=steps, upsample_steps=up, perturb=True,
+                        t_rand=t_rand, u=u)
+    total, parts = nerf_losses(out, gt_rgb[None], labels[None], gt_depth[None], float(g["uom"]))
+    got = np.array([float(p) for p in parts] + [float(total)])
+    np.testing.assert_allclose(got, g["losses"], rtol=2e-5, atol=1e-7)
+    # full-frame pseudo labels
+    u_test = spec.splitmix_uniform(h * w * up, s3, 0.0, 1.0).view(h * w, up)
+    with torch.no_grad():
+        full = live_path.render(heads, torch.from_numpy(g["test_rays_o"]), torch.from_numpy(g["test_rays_d"]),
+                                torch.from_numpy(g["test_norms"]), staged=True, num_steps=steps, upsample_steps=up,
+                                perturb=False, u=u_test)
+    np.testing.assert_allclose(full["image"].reshape(1, h, w, 3).permute(0, 3, 1, 2).numpy(), g["nerf_rgb"], rtol=2e-5,
+                               atol=1e-6)
+    label_u8, _ = frontend.label_epilogue(full["semantics"][0].numpy(), full["image"][0].numpy())
+    assert (label_u8.reshape(h, w).astype(np.int64) - 1 == g["nerf_semantics"][0]).mean() > 0.999

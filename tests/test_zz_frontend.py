@@ -161,3 +161,37 @@ def test_view_sampler_feeds_the_engine_batch_format(fx):
     assert np.array_equal(b["depth"].cpu().numpy(), fx["depth"].reshape(-1)[inds])
     o, d, n = vs.full_view(0)
     assert d.shape == (h * w, 3) and torch.equal(o[0], vs.poses[0, :3, 3])
+
+
+@pytest.mark.gpu
+def test_pseudo_label_writer_async_png(golden_dir, tmp_path):
+    """row f3, second half: label map / colour image / colour visualisation leave the device as u8, are copied
+    asynchronously and PNG-encoded by worker threads; what lands on disk is what the reference's predict step writes
+    (joint_train_lightning_net.py:755-782)."""
+    import cv2
+
+    from oracle import frontend as oracle_frontend
+    from ucsa_neural_rendering_b200.labels import PseudoLabelWriter, default_palette
+
+    h, w, c = 48, 64, 40
+    g = torch.Generator().manual_seed(3)
+    views = []
+    with PseudoLabelWriter(str(tmp_path), h, w, workers=3, slots=2) as wr:  # fewer slots than views: back-pressure
+        for v in range(5):
+            sem = torch.rand(h * w, c, generator=g) ** 3
+            sem[::11] = 0  # pixels without semantic mass -> uniform -> label 1
+            rgb = torch.rand(h * w, 3, generator=g)
+            views.append((sem, rgb))
+            wr.submit(sem.cuda(), rgb.cuda(), f"{v:04d}", subfolder="novel_viewpoints" if v == 4 else "")
+    assert wr.submitted == 5
+    pal = default_palette()
+    for v, (sem, rgb) in enumerate(views):
+        sub = "novel_viewpoints" if v == 4 else ""
+        label_ref, rgb_ref = oracle_frontend.label_epilogue(sem.numpy(), rgb.numpy())
+        label = cv2.imread(str(tmp_path / sub / "nerf_label" / f"{v:04d}.png"), cv2.IMREAD_UNCHANGED)
+        assert label.dtype == np.uint8 and label.shape == (h, w)
+        assert np.array_equal(label, label_ref.reshape(h, w))
+        img = cv2.imread(str(tmp_path / sub / "nerf_image" / f"{v:04d}.png"), cv2.IMREAD_COLOR)
+        assert np.array_equal(img[..., ::-1], rgb_ref.reshape(h, w, 3))  # cv2 reads BGR back
+        vis = cv2.imread(str(tmp_path / sub / "nerf_label_vis" / f"{v:04d}.png"), cv2.IMREAD_COLOR)
+        assert np.array_equal(vis[..., ::-1], pal[label_ref.reshape(h, w)])

@@ -135,101 +135,110 @@ composite_dense_fwd_kernel(const float* __restrict__ sigma, const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// TMA-staged forward (the production path when a ray's inputs fit a stage): the kernel above leaves every warp with a
-// handful of dependent load rounds (z / sigma -> weights -> rgb -> probabilities, ~1 us of HBM latency each), which is
-// what bounds a 35 us kernel.  Here a PERSISTENT warp walks its rays with a two-stage ring in shared memory: one lane
-// requests ALL inputs of the next ray (z, sigma, rgb and the [T, C] probability block, four bulk copies completing on
-// one mbarrier) before the warp starts on the current ray, so every byte is in flight one ray ahead and the
-// arithmetic reads shared memory only.  23 KB per stage at T = 128, C = 40; 4 warps x 2 stages per SM keep ~92 KB
-// in flight per SM, twice what HBM latency x bandwidth needs.  Same arithmetic, in the same order, as the kernel above.
+// TMA-staged forward (the production path when a ray's inputs fit shared memory).  The kernel above leaves every
+// warp with a chain of dependent load rounds (z / sigma -> weights -> rgb -> probabilities, ~1.5 us of HBM latency
+// each under load): 30-34 us for a 95 MB problem.  Here ONE CTA of 128 threads owns one ray: one thread requests ALL
+// inputs of the ray (z, sigma, rgb and the [T, C] probability block: four bulk copies completing on one mbarrier,
+// 23 KB at T = 128, C = 40), nine such CTAs are resident per SM (so ~200 KB are in flight per SM while other CTAs
+// compute), and the arithmetic reads shared memory only: thread = sample for the weights (block-wide product scan),
+// thread = (class group, sample phase) for the probability sums.  (A first version with one persistent WARP per ray
+// and a two-stage ring ran at one warp per scheduler: 7.5 cycles per instruction, 39 us.)
 struct DenseStage {
-  uint32_t z_off, sigma_off, rgb_off, prob_off, bytes;  // byte offsets inside a stage
+  uint32_t z_off, sigma_off, rgb_off, prob_off, bytes;  // byte offsets inside the stage
 };
+constexpr int kTmaThreads = 128;
 
-__global__ void __launch_bounds__(32 * kWarpsPerCta)
+__global__ void __launch_bounds__(kTmaThreads)
 composite_dense_fwd_tma_kernel(const float* __restrict__ sigma, const float* __restrict__ z,
                                const float* __restrict__ rgb, const float* __restrict__ prob,
-                               const float* __restrict__ dnorm, uint32_t n_rays, uint32_t t, uint32_t c,
-                               float density_scale, float* __restrict__ weights, float* __restrict__ depth,
-                               float* __restrict__ image, float* __restrict__ semantics, DenseStage lay,
-                               uint32_t warp_bytes) {
+                               const float* __restrict__ dnorm, uint32_t t, uint32_t c, float density_scale,
+                               float* __restrict__ weights, float* __restrict__ depth, float* __restrict__ image,
+                               float* __restrict__ semantics, DenseStage lay) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  unsigned char* mine = smem_raw + static_cast<size_t>(wib) * warp_bytes;  // [stage 0 | stage 1 | wm | 2 barriers]
-  unsigned char* stage_base[2] = {mine, mine + lay.bytes};
-  float* wm = reinterpret_cast<float*>(mine + 2 * lay.bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(mine + 2 * lay.bytes + ((4 * t + 15) & ~15u));
-  const uint32_t stride = gridDim.x * kWarpsPerCta;
-  uint32_t n = blockIdx.x * kWarpsPerCta + wib;
-  if (n >= n_rays) return;  // (whole warps only: no CTA-wide barrier below)
-  const uint64_t stream = l2_policy_stream();
-  if (lane == 0) {
-    umma::mbar_init(&bars[0], 1);
-    umma::mbar_init(&bars[1], 1);
+  // [stage | wm[t] | part: float4[subs][g] | warp_prod[4] red[4] | barrier]
+  float* wm = reinterpret_cast<float*>(smem_raw + lay.bytes);
+  const uint32_t g = c / 4;                 // float4 groups per sample
+  const uint32_t subs = kTmaThreads / g;    // sample phases of the probability sums
+  float4* part = reinterpret_cast<float4*>(smem_raw + lay.bytes + ((4 * t + 15) & ~15u));
+  float* warp_prod = reinterpret_cast<float*>(part + subs * g);
+  float* red = warp_prod + 4;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 4);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t n = blockIdx.x;
+  const uint64_t row = static_cast<uint64_t>(n) * t;
+  if (tid == 0) {
+    umma::mbar_init(bar, 1);
+    const uint64_t stream = l2_policy_stream();
+    const uint32_t dst = umma::smem_u32(smem_raw);
+    umma::mbar_expect_tx(bar, lay.bytes);
+    umma::bulk_load(dst + lay.z_off, z + row, 4 * t, bar, stream);
+    umma::bulk_load(dst + lay.sigma_off, sigma + row, 4 * t, bar, stream);
+    umma::bulk_load(dst + lay.rgb_off, rgb + row * 3, 12 * t, bar, stream);
+    umma::bulk_load(dst + lay.prob_off, prob + row * c, 4 * t * c, bar, stream);
   }
-  __syncwarp();
+  __syncthreads();  // the barrier is initialised before anybody polls it
+  umma::mbar_wait(bar, 0);
+  const float* zs = reinterpret_cast<const float*>(smem_raw + lay.z_off);
+  const float* sg = reinterpret_cast<const float*>(smem_raw + lay.sigma_off);
+  const float* cs = reinterpret_cast<const float*>(smem_raw + lay.rgb_off);
+  const float4* ps = reinterpret_cast<const float4*>(smem_raw + lay.prob_off);
 
-  auto request = [&](uint32_t ray, int st) {  // lane 0 only
-    const uint64_t row = static_cast<uint64_t>(ray) * t;
-    const uint32_t dst = umma::smem_u32(stage_base[st]);
-    umma::mbar_expect_tx(&bars[st], lay.bytes);
-    umma::bulk_load(dst + lay.z_off, z + row, 4 * t, &bars[st], stream);
-    umma::bulk_load(dst + lay.sigma_off, sigma + row, 4 * t, &bars[st], stream);
-    umma::bulk_load(dst + lay.rgb_off, rgb + row * 3, 12 * t, &bars[st], stream);
-    umma::bulk_load(dst + lay.prob_off, prob + row * c, 4 * t * c, &bars[st], stream);
-  };
-  if (lane == 0) request(n, 0);
-  uint32_t phase[2] = {0u, 0u};
-  const uint32_t g = c / 4;     // float4 groups per sample
-  const uint32_t spi = 32 / g;  // samples per warp step
-  const uint32_t sub = lane / g, grp = lane % g;
-  const bool active = static_cast<uint32_t>(lane) < spi * g;
+  // weights: thread = sample of a 128-sample chunk; transmittance by a block-wide product scan with the same
+  // multiplication order as chunk_transmittance (prefix of earlier chunks, then earlier warps, then the warp scan)
+  float carry = 1.0f, dsum = 0.f;
+  for (uint32_t base = 0; base < t; base += kTmaThreads) {
+    const uint32_t s = base + tid;
+    const bool valid = s < t;
+    SampleTerms st{1.f, 0.f, 1.f, 0.f};
+    if (valid) st = sample_terms(zs, sg, s, t, density_scale);
+    const float incl = warp_scan_mul(valid ? st.keep : 1.0f, lane);
+    if (lane == 31) warp_prod[wid] = incl;
+    __syncthreads();
+    float prefix = carry;
+    for (int w = 0; w < wid; ++w) prefix *= warp_prod[w];
+    float excl = __shfl_up_sync(kFullMask, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    const float w_s = st.alpha * (prefix * excl);
+    for (int w = 0; w < 4; ++w) carry *= warp_prod[w];
+    if (valid) {
+      const bool keep = w_s > kMaskThreshold;
+      wm[s] = keep ? w_s : 0.f;
+      if (weights != nullptr) weights[row + s] = w_s;
+      if (keep) dsum += w_s * zs[s];
+    }
+    __syncthreads();  // warp_prod is rewritten by the next chunk; wm is complete after the last one
+  }
+  dsum = warp_sum(dsum);
+  if (lane == 0) red[wid] = dsum;
 
-  for (int st = 0; n < n_rays; n += stride, st ^= 1) {
-    if (lane == 0 && n + stride < n_rays) {
-      umma::fence_async_smem();  // the other stage was read by this warp (generic proxy) one ray ago
-      request(n + stride, st ^ 1);
-    }
-    umma::mbar_wait(&bars[st], phase[st]);
-    phase[st] ^= 1u;
-    const float* zs = reinterpret_cast<const float*>(stage_base[st] + lay.z_off);
-    const float* sg = reinterpret_cast<const float*>(stage_base[st] + lay.sigma_off);
-    const float* cs = reinterpret_cast<const float*>(stage_base[st] + lay.rgb_off);
-    const float4* ps = reinterpret_cast<const float4*>(stage_base[st] + lay.prob_off);
-    const uint64_t row = static_cast<uint64_t>(n) * t;
-    const float dsum = ray_weights(zs, sg, t, density_scale, lane, wm, weights ? weights + row : nullptr);
-    if (lane == 0) depth[n] = dsum / dnorm[n];
-    __syncwarp();
-    {  // colour: lanes 0..29 = 10 samples x 3 channels per step
-      const int csub = lane / 3, ch = lane % 3;
-      float acc = 0.f;
-      if (lane < 30)
-        for (uint32_t s = csub; s < t; s += 10) acc = fmaf(wm[s], cs[s * 3 + ch], acc);
-      float tot = 0.f;
-#pragma unroll
-      for (int k = 0; k < 10; ++k) tot += __shfl_sync(kFullMask, acc, (3 * k + ch) % 32);
-      if (lane < 3) image[static_cast<uint64_t>(n) * 3 + lane] = tot;
-    }
+  // colour: warp ch < 3 sums channel ch over all samples
+  if (wid < 3) {
+    float acc = 0.f;
+    for (uint32_t s = lane; s < t; s += 32) acc = fmaf(wm[s], cs[s * 3 + wid], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) image[static_cast<uint64_t>(n) * 3 + wid] = acc;
+  }
+  // probabilities: thread = (sample phase, class group); consecutive threads read consecutive 16-byte vectors
+  {
+    const uint32_t sub = tid / g, grp = tid % g;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active) {
+    if (static_cast<uint32_t>(tid) < subs * g) {
 #pragma unroll 4
-      for (uint32_t s = sub; s < t; s += spi) {
+      for (uint32_t s = sub; s < t; s += subs) {
         const float4 v = ps[static_cast<size_t>(s) * g + grp];
         const float w = wm[s];
         acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
       }
+      part[sub * g + grp] = acc;
     }
-    float4 tot = acc;
-    for (uint32_t k = 1; k < spi; ++k) {
-      const int src = (lane + k * g) % 32;
-      tot.x += __shfl_sync(kFullMask, acc.x, src);
-      tot.y += __shfl_sync(kFullMask, acc.y, src);
-      tot.z += __shfl_sync(kFullMask, acc.z, src);
-      tot.w += __shfl_sync(kFullMask, acc.w, src);
-    }
-    if (static_cast<uint32_t>(lane) < g)
-      *reinterpret_cast<float4*>(semantics + static_cast<uint64_t>(n) * c + 4 * lane) = tot;
-    __syncwarp();  // every lane is done with this stage and with wm before they are refilled
+  }
+  __syncthreads();
+  if (tid == 0) depth[n] = (red[0] + red[1] + red[2] + red[3]) / dnorm[n];
+  if (static_cast<uint32_t>(tid) < c) {  // class tid: fold the sample phases in a fixed order
+    const float* pf = reinterpret_cast<const float*>(part);
+    float tot = 0.f;
+    for (uint32_t k = 0; k < subs; ++k) tot += pf[(k * g) * 4 + tid];
+    semantics[static_cast<uint64_t>(n) * c + tid] = tot;
   }
 }
 
@@ -349,8 +358,8 @@ extern "C" int ucsa_composite_dense_fwd(const float* sigma, const float* z, cons
   const bool vec4 = n_classes % 4 == 0 && n_classes <= 128 && (reinterpret_cast<uintptr_t>(prob) % 16 == 0) &&
                     (reinterpret_cast<uintptr_t>(semantics) % 16 == 0);
   const dim3 grid(ceil_div(n_rays, kWarpsPerCta)), block(32 * kWarpsPerCta);
-  // TMA-staged persistent kernel: rows of every input must be 16-byte multiples at 16-byte aligned addresses (bulk
-  // copies), and two stages per warp must fit the CTA's shared memory
+  // TMA-staged kernel (one CTA per ray): rows of every input must be 16-byte multiples at 16-byte aligned addresses
+  // (bulk copies), and the ray's stage must fit the CTA's shared memory
   {
     DenseStage lay;
     lay.z_off = 0;
@@ -358,24 +367,20 @@ extern "C" int ucsa_composite_dense_fwd(const float* sigma, const float* z, cons
     lay.rgb_off = 8 * t;
     lay.prob_off = 20 * t;
     lay.bytes = 20 * t + 4 * t * n_classes;
-    const uint32_t warp_bytes = (2 * lay.bytes + ((4 * t + 15) & ~15u) + 16 + 127) & ~127u;
-    const size_t tma_smem = static_cast<size_t>(kWarpsPerCta) * warp_bytes;
+    const uint32_t g4 = n_classes / 4;
+    const size_t tma_smem = lay.bytes + ((4 * t + 15) & ~15u) + (g4 ? (kTmaThreads / g4) * g4 * 16 : 0) + 32 + 16;
     const auto aligned = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
     static int use_tma = -1;
     if (use_tma < 0) {  // bring-up knob: UCSA_DENSE_TMA=0 forces the load/compute kernel
       const char* e = getenv("UCSA_DENSE_TMA");
       use_tma = (e == nullptr || e[0] != '0') ? 1 : 0;
     }
-    if (use_tma && vec4 && t % 4 == 0 && 32 / (n_classes / 4) >= 1 && aligned(sigma) && aligned(z) && aligned(rgb) &&
-        tma_smem <= 227 * 1024 && lay.bytes < (1u << 20)) {
+    if (use_tma && vec4 && t % 4 == 0 && g4 >= 1 && g4 <= 32 && n_classes <= kTmaThreads && aligned(sigma) &&
+        aligned(z) && aligned(rgb) && tma_smem <= 200 * 1024 && lay.bytes < (1u << 20)) {
       const void* fn = reinterpret_cast<const void*>(composite_dense_fwd_tma_kernel);
       if (int rc = set_max_dyn_smem(fn, tma_smem, "composite_dense_fwd")) return rc;
-      const uint32_t per_sm = static_cast<uint32_t>((227 * 1024) / (tma_smem + 1024));
-      const uint32_t cap = kNumSMs * (per_sm < 1 ? 1 : per_sm);
-      const uint32_t want = ceil_div(n_rays, kWarpsPerCta);
-      composite_dense_fwd_tma_kernel<<<want < cap ? want : cap, block, tma_smem, as_stream(stream)>>>(
-          sigma, z, rgb, prob, direction_norms, n_rays, t, n_classes, density_scale, weights, depth, image,
-          semantics, lay, warp_bytes);
+      composite_dense_fwd_tma_kernel<<<n_rays, kTmaThreads, tma_smem, as_stream(stream)>>>(
+          sigma, z, rgb, prob, direction_norms, t, n_classes, density_scale, weights, depth, image, semantics, lay);
       return check_launch("composite_dense_fwd");
     }
   }

@@ -34,9 +34,31 @@ struct DensityArgs {
   uint64_t n_samples;            // n_rays*span
   float bound;
   ucsa_grid_desc grid;
+  // occupancy-grid mode (ucsa_grid_density): sample s = cell s of a [cascades, H, H, H] grid, jittered inside the cell
+  uint32_t cell_h;  // 0 = off
+  uint64_t cell_seed;
 };
 
 __device__ __forceinline__ uint64_t locate_sample(const DensityArgs& a, uint64_t s, float x01[3]) {
+  if (a.cell_h != 0u) {
+    // cell (cas, x, y, z) in the marching kernels' order (raymarching.cu:204: index = cas*H^3 + x*H^2 + y*H + z); point =
+    // cell centre of cascade cas (half extent min(2^cas, bound)) + uniform jitter of one cell (torch-ngp's update rule)
+    const uint32_t hh = a.cell_h;
+    const uint64_t cube = static_cast<uint64_t>(hh) * hh * hh;
+    const uint32_t cas = static_cast<uint32_t>(s / cube);
+    const uint32_t idx = static_cast<uint32_t>(s % cube);
+    const uint32_t c3[3] = {idx / (hh * hh), (idx / hh) % hh, idx % hh};
+    const float cas_bound = fminf(exp2f(static_cast<float>(cas)), a.bound);
+    const float half = cas_bound / static_cast<float>(hh);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float centre = 2.0f * static_cast<float>(c3[d]) / static_cast<float>(hh - 1) - 1.0f;
+      const float jitter = uniform01(a.cell_seed, static_cast<uint32_t>(s), static_cast<uint32_t>(s >> 32) * 4u + d, 7u);
+      const float p = centre * (cas_bound - half) + (2.0f * jitter - 1.0f) * half;
+      x01[d] = __fdiv_rn(__fadd_rn(p, a.bound), 2.0f * a.bound);
+    }
+    return s;
+  }
   if (a.xyz != nullptr) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) x01[d] = __fdiv_rn(__fadd_rn(a.xyz[3 * s + d], a.bound), 2.0f * a.bound);
@@ -53,7 +75,7 @@ __device__ __forceinline__ uint64_t locate_sample(const DensityArgs& a, uint64_t
 // k0, span and t to be multiples of 128 in ray mode (checked on the host), so that a tile never straddles rays or
 // passes and the coarse pass, the fine pass and the backward pass agree on the block of every sample.
 __device__ __forceinline__ uint64_t saved_block(const DensityArgs& a, uint64_t s0) {
-  if (a.xyz != nullptr) return s0 / 128;
+  if (a.xyz != nullptr || a.cell_h != 0u) return s0 / 128;
   const uint64_t n = s0 / a.span;
   return (n * a.t + a.k0 + (s0 % a.span)) / 128;
 }
@@ -156,8 +178,10 @@ density_fwd_tc_kernel(const DensityArgs a, const __half2* __restrict__ table, co
         lo.h[i] = __float2half_rn(v[i]);
         hi.h[i] = __float2half_rn(v[8 + i]);
       }
-      st_stream(h + flat * 16, lo.v, stream);
-      st_stream(h + flat * 16 + 8, hi.v, stream);
+      if (h != nullptr) {
+        st_stream(h + flat * 16, lo.v, stream);
+        st_stream(h + flat * 16 + 8, hi.v, stream);
+      }
       st_stream_f32(sigma + flat, expf(__half2float(lo.h[0])), stream);  // trunc_exp forward, fp32
     }
   }
@@ -345,13 +369,13 @@ int fill_args(DensityArgs& a, const float* xyz, const float* rays_o, const float
   UCSA_REQUIRE_GRID(grid, "density");
   UCSA_REQUIRE(bound > 0.f, "density: bound must be positive");
   if (xyz != nullptr) {
-    a = DensityArgs{xyz, nullptr, nullptr, nullptr, nullptr, n_rays, 1u, 0u, 1u, n_rays, bound, *grid};
+    a = DensityArgs{xyz, nullptr, nullptr, nullptr, nullptr, n_rays, 1u, 0u, 1u, n_rays, bound, *grid, 0u, 0ull};
     return UCSA_OK;
   }
   UCSA_REQUIRE(rays_o && rays_d && aabb6 && z_cat, "density: rays_o/rays_d/aabb/z_cat required without xyz");
   UCSA_REQUIRE(k0 < k1 && k1 <= t, "density: bad slot range [%u,%u) of %u", k0, k1, t);
   a = DensityArgs{nullptr, rays_o, rays_d, aabb6, z_cat, n_rays, t, k0, k1 - k0,
-                  static_cast<uint64_t>(n_rays) * (k1 - k0), bound, *grid};
+                  static_cast<uint64_t>(n_rays) * (k1 - k0), bound, *grid, 0u, 0ull};
   return UCSA_OK;
 }
 
@@ -406,6 +430,25 @@ extern "C" int ucsa_density_fwd(const float* xyz, const float* rays_o, const flo
       a, static_cast<const __half2*>(table_h), static_cast<const __half*>(w_sigma_h), sigma,
       static_cast<__half*>(h), static_cast<__half*>(enc), static_cast<__half*>(hid));
   return check_launch("density_fwd");
+}
+
+extern "C" int ucsa_grid_density(const void* table_h, const ucsa_grid_desc* grid_host, const void* w_sigma_h,
+                                 float bound, uint32_t cascades, uint32_t grid_h, uint64_t seed, float* sigma_cells,
+                                 void* stream) {
+  UCSA_REQUIRE_GRID(grid_host, "grid_density");
+  UCSA_REQUIRE(table_h && w_sigma_h && sigma_cells, "grid_density: null pointer");
+  UCSA_REQUIRE((reinterpret_cast<uintptr_t>(table_h) & 15u) == 0, "grid_density: the fp16 table must be 16-byte aligned");
+  UCSA_REQUIRE(bound > 0.f && cascades >= 1 && cascades <= 16 && grid_h >= 2 && grid_h <= 1024,
+               "grid_density: bad occupancy-grid geometry");
+  DensityArgs a{nullptr, nullptr, nullptr, nullptr, nullptr, 0u, 1u, 0u, 1u,
+                static_cast<uint64_t>(cascades) * grid_h * grid_h * grid_h, bound, *grid_host, grid_h, seed};
+  if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(density_fwd_tc_kernel<false>), kFwdSmem,
+                                "density_fwd_tc_kernel"))
+    return rc;
+  density_fwd_tc_kernel<false><<<persistent_grid(a.n_samples, kFwdCtasPerSm), 128, kFwdSmem, as_stream(stream)>>>(
+      a, static_cast<const __half2*>(table_h), static_cast<const __half*>(w_sigma_h), sigma_cells, nullptr, nullptr,
+      nullptr);
+  return check_launch("grid_density");
 }
 
 extern "C" int ucsa_density_bwd(const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,

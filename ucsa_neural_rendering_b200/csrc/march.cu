@@ -431,6 +431,44 @@ __global__ void grid_update_kernel(float* __restrict__ grid, const float* __rest
   const float f = fresh[i];
   if (f >= 0.f) grid[i] = fmaxf(grid[i] * decay, f);
 }
+// The same update with the bookkeeping that follows it fused in: fresh is scaled by density_scale, and the sum of
+// max(grid, 0) over all cells (for mean_density) is accumulated in double (per-CTA partial sums, one atomic each).
+__global__ void __launch_bounds__(256)
+grid_update_sum_kernel(float* __restrict__ grid, const float* __restrict__ fresh, uint64_t n, float decay,
+                       float fresh_scale, double* __restrict__ sum) {
+  __shared__ double part[8];
+  double acc = 0.0;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    float gval = grid[i];
+    const float f = fresh[i] * fresh_scale;
+    if (f >= 0.f) {
+      gval = fmaxf(gval * decay, f);
+      grid[i] = gval;
+    }
+    acc += static_cast<double>(fmaxf(gval, 0.f));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullMask, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += part[w];
+    atomicAdd(sum, tot);
+  }
+}
+// bitfield with the threshold min(0.01, mean) taken from the device-side sum
+__global__ void grid_packbits_dev_kernel(const float* __restrict__ grid, uint64_t n, const double* __restrict__ sum,
+                                         uint32_t* __restrict__ bits, float* __restrict__ mean_out) {
+  const float mean = static_cast<float>(*sum / static_cast<double>(n));
+  const float thresh = fminf(kDensityThresh, mean);
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i == 0 && mean_out != nullptr) *mean_out = mean;
+  const bool occ = i < n && grid[i] > thresh;
+  const unsigned word = __ballot_sync(kFullMask, occ);
+  if ((threadIdx.x & 31) == 0 && i < n) bits[i >> 5] = word;
+}
 // bit i = grid[i] > thresh, 32 cells per thread-word via ballot
 __global__ void grid_packbits_kernel(const float* __restrict__ grid, uint64_t n, float thresh, uint32_t* __restrict__ bits) {
   const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -555,6 +593,19 @@ extern "C" int ucsa_grid_update(float* density_grid, const float* fresh, uint64_
   if (n_cells == 0) return UCSA_OK;
   grid_update_kernel<<<ceil_div(n_cells, 256), 256, 0, as_stream(stream)>>>(density_grid, fresh, n_cells, decay);
   return check_launch("grid_update");
+}
+
+extern "C" int ucsa_grid_update_pack(float* density_grid, const float* fresh, uint64_t n_cells, float decay,
+                                     float fresh_scale, double* sum_scratch, float* mean_density_dev,
+                                     uint32_t* bitfield, void* stream) {
+  UCSA_REQUIRE(density_grid && fresh && sum_scratch && mean_density_dev && bitfield, "grid_update_pack: null pointer");
+  UCSA_REQUIRE(n_cells % 32 == 0 && n_cells > 0, "grid_update_pack: cell count must be a positive multiple of 32");
+  if (cudaMemsetAsync(sum_scratch, 0, sizeof(double), as_stream(stream)) != cudaSuccess) return check_launch("grid_update_pack");
+  grid_update_sum_kernel<<<kNumSMs * 8, 256, 0, as_stream(stream)>>>(density_grid, fresh, n_cells, decay, fresh_scale,
+                                                                     sum_scratch);
+  grid_packbits_dev_kernel<<<ceil_div(n_cells, 256), 256, 0, as_stream(stream)>>>(density_grid, n_cells, sum_scratch,
+                                                                                  bitfield, mean_density_dev);
+  return check_launch("grid_update_pack");
 }
 
 extern "C" int ucsa_grid_packbits(const float* density_grid, uint64_t n_cells, float mean_density, uint32_t* bitfield,

@@ -345,6 +345,37 @@ class SemanticNeRFNetwork(SemanticNeRFRenderer):
             semantics = F.softmax(h.float(), dim=-1)
         return semantics
 
+    # ------------------------------------------------------------------ occupancy grid (cuda_ray=True)
+    @torch.no_grad()
+    def update_extra_state(self, decay=0.95, S=128):
+        """Refresh the occupancy grid from the current density field (call every ~16 training steps): three launches
+        -- ucsa_grid_density (one jittered point per cell through the fused encode + sigma-MLP kernel, points generated
+        on the fly), ucsa_grid_update_pack (EMA-max + mean, then the bitfield) -- and ONE host read (mean_density is a
+        Python float in the reference's interface).  The generic eager form lives in SemanticNeRFRenderer."""
+        if not self.cuda_ray:
+            return
+        grid = self.density_grid
+        dev = grid.device
+        h = grid.shape[1]
+        st = getattr(self, "_grid_state", None)
+        if st is None or st["fresh"].device != dev or st["fresh"].numel() != grid.numel():
+            st = {"fresh": torch.empty(grid.numel(), dtype=torch.float32, device=dev),
+                  "sum": torch.zeros(1, dtype=torch.float64, device=dev),
+                  "mean": torch.zeros(1, dtype=torch.float32, device=dev)}
+            self._grid_state = st
+        if getattr(self, "density_bitfield", None) is None or self.density_bitfield.device != dev:
+            self.density_bitfield = torch.zeros(grid.numel() // 32, dtype=torch.int32, device=dev)
+        ops.grid_density(self.encoder.grid, self.encoder.half_params(), self.sigma_net.half_params(), self.bound,
+                         self.cascade, h, self._next_seed(), st["fresh"])
+        ops.grid_update_pack(grid, st["fresh"], decay, float(self.density_scale), st["sum"], st["mean"],
+                             self.density_bitfield)
+        self.mean_density = float(st["mean"])  # the one host read
+        self.iter_density += 1
+        total_step = min(16, self.local_step)
+        if total_step > 0:
+            self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
+        self.local_step = 0
+
     # ------------------------------------------------------------------ fused rendering
     def run(self, rays_o, rays_d, direction_norms, num_steps=256, upsample_steps=256, bg_color=None,
             perturb=False, epoch=None, **kwargs):

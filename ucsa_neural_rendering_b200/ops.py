@@ -470,6 +470,22 @@ def grid_packbits(density_grid, mean_density, bitfield):
                                    _ptr(bitfield, torch.int32), _stream()), "grid_packbits")
 
 
+def grid_density(grid, table_h, w_sigma_h, bound, cascades, grid_h, seed, sigma_cells):
+    """sigma at one jittered point per occupancy-grid cell ([cascades, H, H, H], marching order)"""
+    check(lib().ucsa_grid_density(_ptr(table_h, torch.float16, "table_h"), ctypes.byref(grid),
+                                  _ptr(w_sigma_h, torch.float16, "w_sigma_h"), float(bound), int(cascades), int(grid_h),
+                                  int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(sigma_cells, torch.float32, "sigma_cells"),
+                                  _stream()), "grid_density")
+
+
+def grid_update_pack(density_grid, fresh, decay, fresh_scale, sum_scratch, mean_dev, bitfield):
+    check(lib().ucsa_grid_update_pack(_ptr(density_grid, torch.float32), _ptr(fresh, torch.float32),
+                                      density_grid.numel(), float(decay), float(fresh_scale),
+                                      _ptr(sum_scratch, torch.float64, "sum_scratch"),
+                                      _ptr(mean_dev, torch.float32, "mean_dev"), _ptr(bitfield, torch.int32),
+                                      _stream()), "grid_update_pack")
+
+
 # ---------------------------------------------------------------------------------------------- front / back ends
 def generate_rays(pose, intrinsics, height, width, inds=None, n=None):
     """Pinhole rays of one view (ngp_utils.py:28-70, joint_train_lightning_net.py:109-151).  pose: device [4,4] f32
@@ -504,6 +520,14 @@ def gather_gt(image_h, inds, labels=None, depth=None):
                                _ptr(depth, torch.float32, "depth"), hw, c, _ptr(inds, torch.int64, "inds"), n,
                                _ptr(gt_rgb), _ptr(gt_labels), _ptr(gt_depth), _stream()), "gather_gt")
     return gt_rgb, gt_labels, gt_depth
+
+
+def label_epilogue_into(semantics, image, labels, rgb, bgr=False):
+    """ucsa_label_epilogue into caller-owned u8 buffers (labels [N] | None, rgb [N,3] | None)"""
+    n, c = semantics.shape
+    check(lib().ucsa_label_epilogue(_ptr(image, torch.float32, "image"), _ptr(semantics, torch.float32, "semantics"),
+                                    n, c, int(bgr), _ptr(labels, torch.uint8), _ptr(rgb, torch.uint8), _stream()),
+          "label_epilogue")
 
 
 def label_epilogue(semantics, image=None, bgr=False, want_labels=True):
