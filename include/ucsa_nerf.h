@@ -43,7 +43,7 @@ extern "C" {
 #define UCSA_SIGMA_PARAMS 3072  /* 32->64->16            network_tcnn_semantics.py:48-58  */
 #define UCSA_COLOR_PARAMS 7168  /* 32->64->64->16        network_tcnn_semantics.py:74-84  */
 #define UCSA_MAX_CLASSES 48     /* semantics 16->64->pad16(C)  network_tcnn_semantics.py:90-100 */
-#define UCSA_LOSS_SCRATCH_BYTES 1024 /* ucsa_nerf_loss: per-CTA partial sums + done counter */
+#define UCSA_LOSS_SCRATCH_BYTES 2048 /* ucsa_nerf_loss: per-CTA partial sums + done counter */
 #define UCSA_MAX_PEERS 16       /* ranks of one NVLink domain in ucsa_adam_exchange */
 #define UCSA_TILE_ROWS(rows) (((rows) + 127u) / 128u * 128u) /* rows of a tile-layout activation buffer */
 

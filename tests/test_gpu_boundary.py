@@ -119,9 +119,13 @@ def test_forward_nerf_test_contract(golden_dir):
     rgb = pred_rgb.permute(0, 3, 1, 2).cpu().numpy()
     np.testing.assert_allclose(rgb, g["nerf_rgb"], rtol=4e-3, atol=2e-3)
     np.testing.assert_allclose(semantics.cpu().numpy(), g["nerf_semantics_raw"], rtol=4e-3, atol=2e-3)
-    # pseudo labels: identical wherever the reference's top two classes are further apart than the fp16 tolerance
+    # pseudo labels (argmax): a random-init semantic head is nearly uniform over the 40 classes, so the top two classes
+    # of a pixel may be closer than the fp16 error; labels must agree wherever the reference's margin exceeds twice
+    # the largest deviation observed above, and on the vast majority of pixels overall
     ref_raw = torch.from_numpy(g["nerf_semantics_raw"])
+    dev_max = float((semantics.cpu() - ref_raw).abs().max())
     top2 = torch.topk(ref_raw, 2, dim=-1).values
-    clear = (top2[..., 0] - top2[..., 1]) > 4e-3
+    clear = (top2[..., 0] - top2[..., 1]) > 2 * dev_max
     same = pred_semantics.cpu() == torch.from_numpy(g["nerf_semantics"])
-    assert bool(same[clear].all()) and float(clear.float().mean()) > 0.5
+    assert bool(same[clear].all())
+    assert float(same.float().mean()) > 0.9, (float(same.float().mean()), dev_max)

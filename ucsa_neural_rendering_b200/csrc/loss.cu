@@ -16,7 +16,7 @@
 namespace ucsa {
 namespace {
 
-constexpr int kLossCtas = 64, kLossThreads = 256;
+constexpr int kLossCtas = 148, kLossThreads = 512;  // one CTA per SM: 2368 warps, <= 2 rays each at 4096 rays
 static_assert(UCSA_LOSS_SCRATCH_BYTES >= (kLossCtas * 3 + 1) * 4, "loss scratch too small");
 
 __device__ __forceinline__ float block_sum(float v, float* scratch) {

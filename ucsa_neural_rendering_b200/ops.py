@@ -366,7 +366,7 @@ def adam_exchange(peer, exp_avg, exp_avg_sq, *, wd_begin, lr, beta1, beta2, eps,
           "adam_exchange")
 
 
-LOSS_SCRATCH_BYTES = 1024  # UCSA_LOSS_SCRATCH_BYTES
+LOSS_SCRATCH_BYTES = 2048  # UCSA_LOSS_SCRATCH_BYTES
 
 
 def loss_scratch(device):
