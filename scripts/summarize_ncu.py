@@ -84,7 +84,10 @@ def traffic(src, dst):
     counters (reductions / reads issued by the SMs) -> bench.py's l2_request_roofline."""
     import json
 
-    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if src.endswith(".csv"):  # `ncu -i rep --page raw --csv` already run on the GPU box (reports can exceed the 64 MiB limit)
+        raw = open(src).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}

@@ -13,7 +13,8 @@ import threading
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(PKG_DIR), "include", "ucsa_nerf.h")
-LIB_PATH = os.path.join(PKG_DIR, "csrc", "libucsa_nerf.so")
+# UCSA_LIB: development override (A/B runs of two builds of the same ABI); the default is the in-tree build
+LIB_PATH = os.environ.get("UCSA_LIB") or os.path.join(PKG_DIR, "csrc", "libucsa_nerf.so")
 
 GRID_LEVELS = 16
 

@@ -424,6 +424,16 @@ extern "C" int ucsa_density_fwd(const float* xyz, const float* rays_o, const flo
     const char* e = getenv("UCSA_DFWD_CTAS");
     ctas_per_sm = e ? atoi(e) : kFwdCtasPerSm;
     if (ctas_per_sm < 1 || ctas_per_sm > 8) ctas_per_sm = kFwdCtasPerSm;
+    // tuning knob (bring-up): UCSA_DFWD_CARVEOUT = shared-memory carve-out in percent of the SM's 228 KB; what is left
+    // is L1, which serves the gathers of the coarse levels (measured: 8 KB more shared memory per CTA, i.e. the next
+    // carve-out step, cost 55 % of this kernel's speed)
+    if (const char* c = getenv("UCSA_DFWD_CARVEOUT")) {
+      const int pct = atoi(c);
+      if (pct >= 0 && pct <= 100) {
+        cudaFuncSetAttribute(density_fwd_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(density_fwd_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      }
+    }
   }
   auto kernel = tiled ? density_fwd_tc_kernel<true> : density_fwd_tc_kernel<false>;
   kernel<<<persistent_grid(a.n_samples, ctas_per_sm), 128, kFwdSmem, as_stream(stream)>>>(

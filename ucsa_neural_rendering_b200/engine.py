@@ -155,8 +155,8 @@ class TrainEngine:
 
     def _capture(self):
         side = torch.cuda.Stream(device=self.device)
+        state = self._snapshot()  # (before the side stream is forked: the clones must not race the warm-up steps)
         side.wait_stream(torch.cuda.current_stream())
-        state = self._snapshot()
         with torch.cuda.stream(side):  # warm-up outside capture (lazy attribute set-up, allocator)
             for _ in range(2):
                 self._forward_backward()
