@@ -503,6 +503,105 @@ def run_ours(args):
                        "strict_4096": {"rays_per_s": world * rays_view / (render_ms_strict * 1e-3),
                                        "ms_per_view": render_ms_strict}}
 
+    # ---------------------------------------------------------------- extra: GPU stand-in for the tcnn path
+    # tiny-cuda-nn cannot be installed here, so BASELINE.json's "10x the reference GPU path" has no measurable
+    # denominator.  Stand-in, clearly labelled: the same step with the network heads in eager PyTorch (index gathers +
+    # fp16 cuBLAS matmuls + autograd, baseline/eager_torch_heads.py) through the reference-shaped run(); rank 0 only.
+    stand_in = None
+    if not args.no_extras and rank == 0:
+        try:
+            from baseline.eager_torch_heads import EagerTorchNetwork
+
+            ref_net = EagerTorchNetwork(bound=BOUND, num_semantic_classes=N_CLASSES).to(dev).train()
+            ref_opt = torch.optim.Adam([{"params": [ref_net.table]},
+                                        {"params": [p for n_, p in ref_net.named_parameters() if n_ != "table"],
+                                         "weight_decay": 1e-6}], lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+            scaler = torch.amp.GradScaler("cuda")
+
+            def ref_step(s):
+                o, d, dn, rgb, label, depth = batches[s % len(batches)]
+                ref_opt.zero_grad(set_to_none=True)
+                out = ref_net.render(o, d, direction_norms=dn, staged=False, bg_color=None, perturb=True, seed=7000 + s)
+                loss, _ = nerf_losses(out, rgb, label, depth, uom)
+                scaler.scale(loss).backward()
+                scaler.step(ref_opt)
+                scaler.update()
+
+            for s in range(2):
+                ref_step(s)
+            torch.cuda.synchronize()
+            k_ref = 5
+            e0.record()
+            for s in range(k_ref):
+                ref_step(2 + s)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_ref = e0.elapsed_time(e1) / k_ref
+            stand_in = {"what": "STAND-IN, not tiny-cuda-nn: reference-shaped run() with eager-PyTorch heads (hash-grid "
+                                "as index gathers, fp16 cuBLAS MLPs, autograd) + GradScaler + torch Adam on this GPU",
+                        "ms_per_step": ms_ref, "rays_per_s": RAYS_PER_GPU / (ms_ref * 1e-3), "steps": k_ref,
+                        "rays_per_step": RAYS_PER_GPU}
+            del ref_net, ref_opt
+            torch.cuda.empty_cache()
+        except Exception as exc:  # noqa: BLE001 - an extra must never take the headline down
+            stand_in = {"error": repr(exc)[:300]}
+
+    # ---------------------------------------------------------------- extra: the occupancy-grid path (rows a16-a20)
+    # dormant in the reference (cuda_ray=False is hard-coded by its only caller); measured here so that it has
+    # numbers: grid refresh (3 launches + 1 host read), one training render (march + heads + ragged composite,
+    # forward + backward) of 4096 rays, and the inference wavefront over one 640x480 view.  Parameters of the trained
+    # network above; rank 0 only.
+    occupancy = None
+    if not args.no_extras and rank == 0:
+        try:
+            occ_net = SemanticNeRFNetwork(encoding="hashgrid", bound=BOUND, cuda_ray=True, density_scale=1,
+                                          num_semantic_classes=N_CLASSES).to(dev)
+            with torch.no_grad():
+                for dst, src in ((occ_net.encoder, net.encoder), (occ_net.sigma_net, net.sigma_net),
+                                 (occ_net.color_net, net.color_net), (occ_net.semantics_net, net.semantics_net)):
+                    dst.params.copy_(src.params)
+            occ_net.train()
+
+            def timed_ms(fn, reps):
+                fn()
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / reps
+
+            ms_refresh = timed_ms(occ_net.update_extra_state, 5)
+            o, d, dn = batches[0][:3]
+
+            def occ_train():
+                for p_ in occ_net.parameters():
+                    p_.grad = None
+                out = occ_net.render(o, d, direction_norms=dn, staged=False, perturb=True, dt_gamma=1 / 128,
+                                     force_all_rays=True)
+                (out["image"].sum() + out["depth"].sum() + out["semantics"].sum()).backward()
+
+            ms_train = timed_ms(occ_train, 5)
+            samples = int(occ_net.step_counter[(occ_net.local_step - 1) % 16, 0])
+            occ_net.eval()
+            with torch.no_grad():
+                vo, vd, vdn = scene.rays(0, torch.arange(scene.W * scene.H, device=dev))
+                ms_view = timed_ms(lambda: occ_net.render(vo[None], vd[None], direction_norms=vdn.view(1, -1, 1),
+                                                          staged=True, perturb=False, dt_gamma=1 / 128), 2)
+            occupancy = {"grid_refresh_ms": ms_refresh, "cells": int(occ_net.density_grid.numel()),
+                         "mean_density": float(occ_net.mean_density),
+                         "occupied_fraction": float((occ_net.density_grid > min(0.01, occ_net.mean_density)).float().mean()),
+                         "train_render_fwd_bwd_ms": ms_train, "train_rays": RAYS_PER_GPU, "train_samples": samples,
+                         "train_rays_per_s": RAYS_PER_GPU / (ms_train * 1e-3),
+                         "infer_view_ms": ms_view, "infer_rays_per_s": scene.W * scene.H / (ms_view * 1e-3),
+                         "note": "module-level (eager) heads between the marching / compositing kernels; forward + "
+                                 "backward of the training render, no optimizer"}
+            del occ_net
+            torch.cuda.empty_cache()
+        except Exception as exc:  # noqa: BLE001 - an extra must never take the headline down
+            occupancy = {"error": repr(exc)[:300]}
+
     # ---------------------------------------------------------------- extra: config 4's 2^16-ray global batch, strong scaling
     strong = None
     if not args.no_extras:
@@ -613,6 +712,7 @@ def run_ours(args):
         "gpu_launches": launches, "gpu_launches_per_step": by_name,
         "step_impl": "cuda-graph replay of %d kernels" % per_step_launches if not args.no_graph else "eager kernel chain",
         "render": render_info, "trained": trained, "strong_scaling_2p16": strong, "config1": config1,
+        "stand_in": stand_in, "occupancy_path": occupancy,
         "gradient_exchange": {"none": "single GPU", "nccl": "NCCL all-reduce + replicated Adam",
                               "peer": "ucsa_adam_exchange over symmetric memory (%s)" % (
                                   "multimem.ld_reduce / multimem.st via NVSwitch" if multicast
