@@ -11,6 +11,8 @@
 // The hidden activations saved for the backward pass (hc1, hc2, hs) are tile-layout buffers (mlp_umma.cuh): tile i
 // of the compact row list is one contiguous 16 KB block, written and read back with single bulk copies.  The
 // logits are not saved at all: the semantic backward kernel recomputes them from hs with one extra product.
+#include <cstdlib>
+
 #include "mlp_umma.cuh"
 #include "sh4.cuh"
 
@@ -289,6 +291,198 @@ heads_fwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
   umma::ctx_free(ctx, kFwdTmemCols);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-specialised form of the colour forward kernel: 4 worker warps (thread = row = TMEM lane) + 1 driver warp, TWO
+// tiles in flight per CTA (slots A / B with their own tiles and 64 TMEM columns each).  The workers alternate between
+// the slots in program order -- inputs A, inputs B, epilogue-1 A, epilogue-1 B, ... -- and one lane of the driver warp
+// issues every MMA, commit and bulk store, so while the tensor core (and the commit -> mbarrier round trip, and the
+// bulk store's read of a tile) work on one slot the workers compute on the other, with no CTA-wide barrier in the
+// loop.  Hand-offs are mbarriers: in_full[s] (128 worker arrivals: "the operand tile of slot s is written"),
+// acc_full[s] (tcgen05.commit: "the accumulator of slot s is complete"), st_done[s] (driver: "the bulk store has read
+// the tile").  The single-tile kernel above overlaps stages only across CTAs (5 per SM) and stalls all 128 threads on
+// thread 0's MMA issue / store wait; here 3 CTAs = 6 tiles are in flight per SM.
+constexpr int kWsThreads = 160, kWsCtas = 3;
+constexpr uint32_t kWsSlotBytes = Tile<32>::kBytes + Tile<64>::kBytes + 128 * 4 * sizeof(float) + 128 * sizeof(int) + 128;
+constexpr uint32_t kFwdColorWsSmem = kColorWeightBytesFwd + 2 * kWsSlotBytes + 6 * 8 + 16;
+static_assert(kWsCtas * (kFwdColorWsSmem + 1024) <= 227 * 1024, "colour forward (warp-specialised): shared memory");
+
+__global__ void __launch_bounds__(kWsThreads, kWsCtas)
+heads_fwd_color_ws_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__ k_ptr, uint32_t t,
+                          const float* __restrict__ rays_d, const __half* __restrict__ h,
+                          const __half* __restrict__ w_color, const float* __restrict__ w_sel,
+                          float* __restrict__ rgb, __half* __restrict__ hc1, __half* __restrict__ hc2,
+                          float* __restrict__ image) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* wc1 = smem;
+  unsigned char* wc2 = wc1 + kWc1;
+  unsigned char* wc3 = wc2 + kWc2;
+  unsigned char* slots = wc3 + kWc3;
+  unsigned char* tail = slots + 2 * kWsSlotBytes;
+  uint64_t* in_full = reinterpret_cast<uint64_t*>(tail);  // [2]
+  uint64_t* acc_full = in_full + 2;                        // [2]
+  uint64_t* st_done = acc_full + 2;                        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(st_done + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  umma::load_weight_tile<32>(wc1, w_color + kColorW1, 64);
+  umma::load_weight_tile<64>(wc2, w_color + kColorW2, 64);
+  umma::load_weight_tile<64>(wc3, w_color + kColorW3, 16);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      umma::mbar_init(&in_full[s], 128);
+      umma::mbar_init(&acc_full[s], 1);
+      umma::mbar_init(&st_done[s], 1);
+    }
+  }
+  if (warp == 4) umma::tmem_alloc(tmem_slot, 128);
+  umma::fence_async_smem();  // the weight tiles are read by the tensor core (async proxy)
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const bool save = hc1 != nullptr;
+  const uint32_t k_rows = static_cast<uint32_t>(*k_ptr);
+  const uint32_t n_tiles = (k_rows + 127) / 128;
+  const uint32_t n_pairs = (n_tiles + 1) / 2;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ driver: MMA issue, commits, bulk stores
+    if (lane == 0) {
+      const uint32_t b1 = umma::smem_u32(wc1), b2 = umma::smem_u32(wc2), b3 = umma::smem_u32(wc3);
+      const uint64_t stream = l2_policy_stream();
+      uint32_t ph_in[2] = {0u, 0u};
+      for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+#pragma unroll
+        for (int stage = 0; stage < 3; ++stage) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const uint32_t tile = 2 * pair + s;
+            unsigned char* base = slots + s * kWsSlotBytes;
+            const uint32_t s_in_c = umma::smem_u32(base), s_h = umma::smem_u32(base + Tile<32>::kBytes);
+            umma::mbar_wait(&in_full[s], ph_in[s]);
+            ph_in[s] ^= 1u;
+            umma::tc_fence_after();
+            if (stage == 0) umma::issue_fwd<32, 64>(tmem + 64 * s, s_in_c, b1);
+            else if (stage == 1) umma::issue_fwd<64, 64>(tmem + 64 * s, s_h, b2);
+            else umma::issue_fwd<64, 16>(tmem + 64 * s, s_h, b3);
+            if (save && stage > 0) {  // one bulk group per slot (empty for a tile past the end)
+              if (tile < n_tiles)
+                umma::bulk_store(umma::tile_block<64>(stage == 1 ? hc1 : hc2, tile), s_h, Tile<64>::kBytes, stream);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            umma::commit(&acc_full[s]);
+          }
+          if (save && stage > 0) {  // both slots' products are issued: now wait for the stores to have read their tiles
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            umma::mbar_arrive(&st_done[0]);
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            umma::mbar_arrive(&st_done[1]);
+          }
+        }
+      }
+      if (save) umma::bulk_store_fence_reads();
+    }
+  } else {
+    // ------------------------------------------------------------ workers: rows of both slots
+    const uint64_t stream = l2_policy_stream();
+    (void)stream;
+    const bool fuse_composite = image != nullptr;
+    uint32_t ph_acc[2] = {0u, 0u}, ph_st[2] = {0u, 0u};
+    bool st_pending[2] = {false, false};  // the hc2 store of the previous pair may still be reading t_h
+    // tile index of (pair, slot) -> flat sample index of this thread's row; inputs one pair ahead, sel two pairs ahead
+    auto flat_at = [&](uint32_t pair_, int s_) { return flat_of(sel, 2 * pair_ + s_, n_tiles, k_rows); };
+    uint32_t flat[2], flat_next[2];
+    RowInputs in_cur[2], in_next[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      flat[s] = flat_at(blockIdx.x, s);
+      flat_next[s] = flat_at(blockIdx.x + gridDim.x, s);
+      const uint32_t tile = 2 * blockIdx.x + s;
+      load_row_inputs(in_cur[s], rays_d, h, flat[s], t, tile < n_tiles && tile * 128 + threadIdx.x < k_rows, true);
+    }
+    for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      bool valid[2];
+      float w_row[2];
+      uint32_t r[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {  // stage 0 operands
+        const uint32_t tile = 2 * pair + s;
+        r[s] = tile * 128 + threadIdx.x;
+        valid[s] = tile < n_tiles && r[s] < k_rows;
+        w_row[s] = (valid[s] && fuse_composite) ? w_sel[r[s]] : 0.f;
+        write_inputs(in_cur[s], valid[s], slots + s * kWsSlotBytes, nullptr);
+        umma::fence_async_smem();
+        umma::tc_fence_before();
+        umma::mbar_arrive(&in_full[s]);
+      }
+      uint32_t flat_next2[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {  // the next pair's loads, after this pair's values were consumed
+        const uint32_t tile_next = 2 * (pair + gridDim.x) + s;
+        load_row_inputs(in_next[s], rays_d, h, flat_next[s], t,
+                        tile_next < n_tiles && tile_next * 128 + threadIdx.x < k_rows, true);
+        flat_next2[s] = flat_at(pair + 2 * gridDim.x, s);
+      }
+#pragma unroll
+      for (int stage = 0; stage < 2; ++stage) {  // hidden layers: accumulator -> ReLU -> fp16 tile of the next product
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          unsigned char* t_h = slots + s * kWsSlotBytes + Tile<32>::kBytes;
+          umma::mbar_wait(&acc_full[s], ph_acc[s]);
+          ph_acc[s] ^= 1u;
+          if (st_pending[s]) {  // t_h is rewritten below: the store that was issued from it has to have read it
+            umma::mbar_wait(&st_done[s], ph_st[s]);
+            ph_st[s] ^= 1u;
+          }
+          st_pending[s] = save;  // this stage's product is followed by a store of the tile written now
+          umma::tc_fence_after();
+          umma::Ctx ctx{tmem + 64u * s, nullptr, 0u};
+#pragma unroll
+          for (int c0 = 0; c0 < 64; c0 += 16) umma::acc_to_tile16<64, true>(ctx, c0, t_h, c0);
+          umma::fence_async_smem();
+          umma::tc_fence_before();
+          umma::mbar_arrive(&in_full[s]);
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {  // output layer + compositing
+        unsigned char* base = slots + s * kWsSlotBytes;
+        float* part = reinterpret_cast<float*>(base + Tile<32>::kBytes + Tile<64>::kBytes);
+        int* ray_of_row = reinterpret_cast<int*>(part + 128 * 4);
+        uint32_t* heads = reinterpret_cast<uint32_t*>(ray_of_row + 128);
+        umma::mbar_wait(&acc_full[s], ph_acc[s]);
+        ph_acc[s] ^= 1u;
+        umma::tc_fence_after();
+        umma::Ctx ctx{tmem + 64u * s, nullptr, 0u};
+        float v[16];
+        umma::tmem_ld16(ctx.lane_addr(0), v);
+        umma::tc_fence_before();
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float x = round_h(v[c]);
+          const float col = round_h(1.0f / (1.0f + expf(-x)));  // fp16 sigmoid under autocast
+          if (valid[s]) rgb[static_cast<uint64_t>(r[s]) * 3 + c] = col;
+          if (fuse_composite) part[threadIdx.x * 4 + c] = w_row[s] * col;
+        }
+        if (fuse_composite) {
+          publish_runs(sel, r[s], k_rows, t, valid[s] ? static_cast<int>(flat[s] / t) : -1, ray_of_row, heads);
+          umma::named_barrier(1, 128);
+          composite_flush(part, 4, ray_of_row, heads, 3, image, 3);
+          // part / ray_of_row of this slot are rewritten one pair later, after three hand-offs that need all workers
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        in_cur[s] = in_next[s];
+        flat[s] = flat_next[s];
+        flat_next[s] = flat_next2[s];
+      }
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) umma::tmem_dealloc(tmem, 128);
+}
+
 __global__ void __launch_bounds__(128, kFwdSemCtas)
 heads_fwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__ k_ptr, uint32_t t,
                      const __half* __restrict__ h, const __half* __restrict__ w_sem, int n_classes,
@@ -404,7 +598,10 @@ heads_fwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
   umma::ctx_free(ctx, kFwdTmemCols);
 }
 
-template <int N, bool TRANSPOSED>
+// HI: the accumulator was placed at TMEM lane offset 16 (rows m at lanes 16 + m % 16 + 32 * (m / 16)): an M = 64
+// product accepts that address, so two weight-gradient accumulators share the same columns (scripts/dev/
+// tmem_lane_probe.cu is the experiment that established it on B200).
+template <int N, bool TRANSPOSED, bool HI = false>
 __device__ __forceinline__ void flush_wgrad(const umma::Ctx& ctx, uint32_t col0, float* __restrict__ grad, int ld,
                                             float scale) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -412,8 +609,8 @@ __device__ __forceinline__ void flush_wgrad(const umma::Ctx& ctx, uint32_t col0,
   for (int c0 = 0; c0 < N; c0 += 16) {
     float v[16];
     umma::tmem_ld16(ctx.lane_addr(col0 + c0), v);
-    if (lane < 16) {
-      const int m = warp * 16 + lane;
+    if (HI ? lane >= 16 : lane < 16) {
+      const int m = warp * 16 + (lane & 15);
 #pragma unroll
       for (int i = 0; i < 16; ++i)
         atomicAdd(grad + (TRANSPOSED ? (c0 + i) * ld + m : m * ld + c0 + i), v[i] * scale);
@@ -423,14 +620,17 @@ __device__ __forceinline__ void flush_wgrad(const umma::Ctx& ctx, uint32_t col0,
 
 // ---------------------------------------------------------------------------------------------- backward
 // Two kernels, colour first, then semantics, so that each fits several CTAs per SM:
-//   colour   : tiles in_c, h1, h2, dpre, dh2, dh1 (76 KB) + colour weights; TMEM 176 -> 256 columns; 2 CTAs / SM
+//   colour   : tiles in_c, h1, h2 (dh2 in place), dh1, dpre (60 KB) + colour weights; TMEM 128 columns (the three
+//              weight-gradient accumulators share 64 columns: dWc2 on the low, dWc1 | dWc3 on the high 16 lanes of
+//              every 32-lane quadrant);                                                                3 CTAs / SM
 //   semantics: tiles hs, dhs, dlog (in_s re-uses dlog) (44 KB) + weights;   TMEM 128 columns;        4 CTAs / SM
 // The colour kernel writes its share of dL/dgeo_feat into dh and the semantic kernel adds its own.
-constexpr uint32_t kBwdColorCols = 256, kBwdSemCols = 128;
-constexpr int kBwdColorCtas = 2, kBwdSemCtas = 4;
+constexpr uint32_t kBwdColorCols = 128, kBwdSemCols = 128;
+constexpr int kBwdColorCtas = 3, kBwdSemCtas = 4;
 constexpr uint32_t kColorWeightBytes = kWc1 + kWc2 + kWc3;
 constexpr uint32_t kSemWeightBytes = kWs1 + kWs2;
-constexpr uint32_t kBwdColorSmem = kColorWeightBytes + Tile<32>::kBytes + 4 * Tile<64>::kBytes + Tile<16>::kBytes + 64;
+constexpr uint32_t kBwdColorSmem = kColorWeightBytes + Tile<32>::kBytes + 3 * Tile<64>::kBytes + Tile<16>::kBytes + 64;
+static_assert(kBwdColorCtas * (kBwdColorSmem + 1024) <= 227 * 1024, "colour backward: shared memory of the resident CTAs");
 constexpr uint32_t kBwdSemSmem = kSemWeightBytes + 2 * Tile<64>::kBytes + Tile<kSemOut>::kBytes + 64;
 static_assert(kBwdSemCtas * (kBwdSemSmem + 1024) <= 227 * 1024, "semantic backward: shared memory of the resident CTAs");
 
@@ -451,8 +651,9 @@ heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
   unsigned char* t_h1 = t_in_c + Tile<32>::kBytes;
   unsigned char* t_h2 = t_h1 + Tile<64>::kBytes;
   unsigned char* t_dh1 = t_h2 + Tile<64>::kBytes;
-  unsigned char* t_dh2 = t_dh1 + Tile<64>::kBytes;
-  unsigned char* t_dpre = t_dh2 + Tile<64>::kBytes;
+  unsigned char* t_dh2 = t_h2;  // in place: every thread turns its own h2 chunks into dh2 chunks once the products
+                                // reading h2 (the Wc3 weight gradient) are covered by the commit it waited for
+  unsigned char* t_dpre = t_dh1 + Tile<64>::kBytes;
   unsigned char* tail = t_dpre + Tile<16>::kBytes;
   uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* ld_bar = reinterpret_cast<uint64_t*>(tail + 8);  // completion of the bulk loads of the saved tiles
@@ -465,7 +666,9 @@ heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
   const uint32_t s_in_c = umma::smem_u32(t_in_c), s_h1 = umma::smem_u32(t_h1), s_h2 = umma::smem_u32(t_h2),
                  s_dh1 = umma::smem_u32(t_dh1), s_dh2 = umma::smem_u32(t_dh2), s_dpre = umma::smem_u32(t_dpre),
                  b1 = umma::smem_u32(wc1), b2 = umma::smem_u32(wc2), b3 = umma::smem_u32(wc3);
-  constexpr uint32_t kAcc = 0, kGc1 = 64, kGc2 = 96, kGc3 = 160;
+  // TMEM columns: scratch 0..63 | dWc2 64..127 on lanes 0-15 (+32 i) | dWc1 64..95 and dWc3 96..111 on lanes 16-31 (+32 i)
+  constexpr uint32_t kHi = 16u << 16;  // TMEM address: lane offset 16
+  constexpr uint32_t kAcc = 0, kGc2 = 64, kGc1 = 64, kGc3 = 96;
   const uint64_t stream = l2_policy_stream();
   uint32_t ld_phase = 0;
 
@@ -543,8 +746,8 @@ heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
     if (threadIdx.x == 0) {
       umma::tc_fence_after();
       umma::issue_dgrad<16, 64>(ctx.tmem + kAcc, s_dpre, b3);
-      umma::commit(ctx.bar);
-      umma::issue_wgrad<16>(ctx.tmem + kGc3, s_h2, s_dpre, first);  // d(Wc3)^T = h2^T . dpre
+      umma::issue_wgrad<16>(ctx.tmem + kGc3 + kHi, s_h2, s_dpre, first);  // d(Wc3)^T = h2^T . dpre
+      umma::commit(ctx.bar);  // covers the weight gradient too: the epilogue below overwrites h2 in place
     }
     ctx.wait();
 #pragma unroll
@@ -564,7 +767,7 @@ heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
       umma::tc_fence_after();
       umma::issue_dgrad<64, 32>(ctx.tmem + kAcc, s_dh1, b1);
       umma::commit(ctx.bar);
-      umma::issue_wgrad<32>(ctx.tmem + kGc1, s_dh1, s_in_c, first);  // d(Wc1) = dh1^T . in_c
+      umma::issue_wgrad<32>(ctx.tmem + kGc1 + kHi, s_dh1, s_in_c, first);  // d(Wc1) = dh1^T . in_c
     }
     ctx.wait();
     float d_in_c[16];
@@ -593,9 +796,9 @@ heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
   }
   if (!first) {
     ctx.wait();
-    flush_wgrad<32, false>(ctx, kGc1, grad_w_color + kColorW1, 32, inv_scale);
+    flush_wgrad<32, false, true>(ctx, kGc1, grad_w_color + kColorW1, 32, inv_scale);
     flush_wgrad<64, false>(ctx, kGc2, grad_w_color + kColorW2, 64, inv_scale);
-    flush_wgrad<16, true>(ctx, kGc3, grad_w_color + kColorW3, 64, inv_scale);
+    flush_wgrad<16, true, true>(ctx, kGc3, grad_w_color + kColorW3, 64, inv_scale);
   }
   umma::ctx_free(ctx, kBwdColorCols);
 }
@@ -809,6 +1012,19 @@ extern "C" int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32
     }
   }
   cudaStream_t st = as_stream(stream);
+  static int use_ws = -1;
+  if (use_ws < 0) {  // bring-up knob: UCSA_HEADS_WS=1 selects the warp-specialised two-slot colour kernel
+    const char* e = getenv("UCSA_HEADS_WS");
+    use_ws = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  if (use_ws) {
+    if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(heads_fwd_color_ws_kernel), kFwdColorWsSmem, "heads_fwd_color_ws_kernel")) return rc;
+    const uint32_t pairs = ((k_max + 127) / 128 + 1) / 2;
+    const uint32_t cap = kNumSMs * kWsCtas;
+    heads_fwd_color_ws_kernel<<<pairs < cap ? pairs : cap, kWsThreads, kFwdColorWsSmem, st>>>(
+        sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h), w_sel,
+        rgb, static_cast<__half*>(hc1), static_cast<__half*>(hc2), image);
+  } else
   heads_fwd_color_kernel<<<heads_grid(k_max, kFwdColorCtas), 128, kFwdColorSmem, st>>>(
       sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h), w_sel,
       rgb, static_cast<__half*>(hc1), static_cast<__half*>(hc2), image);
