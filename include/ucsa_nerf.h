@@ -101,9 +101,9 @@ UCSA_API int ucsa_density_fwd(const float* xyz, const float* rays_o, const float
 UCSA_API int ucsa_density_bwd(const float* xyz, const float* rays_o, const float* rays_d, const float* aabb6,
                      const float* z_cat, uint32_t n_rays, uint32_t t, uint32_t k0, uint32_t k1, float bound,
                      const ucsa_grid_desc* grid_host, const void* w_sigma_h, const void* h, const void* enc,
-                     const void* hid, int tiled, const float* d_sigma, const void* dh, const uint8_t* use_geo,
-                     float loss_scale, float* grad_table, float* grad_replicas, uint32_t n_replicas,
-                     float* grad_w_sigma, void* stream);
+                     const void* hid, int tiled, const float* d_sigma, const void* dh, const void* dh2,
+                     const uint8_t* use_geo, float loss_scale, float* grad_table, float* grad_replicas,
+                     uint32_t n_replicas, float* grad_w_sigma, void* stream);
 /* grad_table[dense part] += sum of the replicas; the replicas are zero again on return. */
 UCSA_API int ucsa_reduce_grad_replicas(float* grad_replicas, uint32_t n_replicas, const ucsa_grid_desc* grid_host,
                               float* grad_table, void* stream);
@@ -139,7 +139,11 @@ UCSA_API int ucsa_compact_masked(const float* w_sorted, const float* z_cat, cons
  * logits fp16 [K,48] row-major, optional (may be null: the backward pass recomputes them).
  * hc1, hc2, hs (all three or none): hidden activations saved for ucsa_heads_bwd, OPAQUE tile-layout buffers of
  * UCSA_TILE_ROWS(k_max) * 64 halves each - 128-row tiles stored as contiguous 16 KB blocks in the tensor-core
- * operand layout (csrc/mlp_umma.cuh), moved with one bulk copy per tile. */
+ * operand layout (csrc/mlp_umma.cuh), moved with one bulk copy per tile.
+ * Two kernels (colour, semantics) that run concurrently: the second is launched on a library-owned helper stream
+ * forked from and joined back to `stream` with events, so for the caller everything is ordered on `stream` and the
+ * call can be captured into a CUDA graph (make the first call on a device outside a capture: it creates the helper
+ * stream). */
 UCSA_API int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32_t n_rays, uint32_t t, uint32_t k_max,
                    const float* rays_d, const void* h, const void* w_color_h, const void* w_sem_h,
                    uint32_t n_classes, const float* w_sel, float* rgb, void* logits, void* hc1, void* hc2, void* hs,
@@ -149,13 +153,17 @@ UCSA_API int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32_t
  * dL/drgb, dL/dlogits (soft-max backward; semantic weights are detached, renderer_semantics.py:270) per row on the
  * fly, writes d_w_sel [K] = dL/dw of every masked-in sample (for ucsa_weights_bwd), dh[sel][1..15] =
  * loss_scale * dL/dgeo_feat (fp16), and accumulates grad_w_color [7168], grad_w_sem [4096] (fp32, unscaled).
- * hc1, hc2, hs are the tile-layout buffers ucsa_heads_fwd filled.  Two kernels: colour, then semantics. */
+ * hc1, hc2, hs are the tile-layout buffers ucsa_heads_fwd filled.  Two kernels, colour and semantics.  dh_sem
+ * (optional, same shape as dh): the semantic kernel writes its share of dL/dgeo_feat there instead of adding it
+ * to dh, which makes the two kernels independent -- they then run concurrently (helper stream, see ucsa_heads_fwd) --
+ * and ucsa_density_bwd takes the second share as `dh2`.  With dh_sem = null the kernels run one after the other
+ * and dh holds the sum.  Both forms give bit-identical gradients. */
 UCSA_API int ucsa_heads_bwd(const int32_t* sel, const int32_t* ray_off, uint32_t n_rays, uint32_t t, uint32_t k_max,
                    const float* rays_d, const void* h, const void* w_color_h, const void* w_sem_h,
                    uint32_t n_classes, const float* rgb, const void* hc1, const void* hc2,
                    const void* hs, const float* w_sel, const float* z_sel, const float* g_image,
                    const float* g_depth, const float* g_semantics, const float* direction_norms, float loss_scale,
-                   void* dh, float* d_w_sel, float* grad_w_color, float* grad_w_sem, void* stream);
+                   void* dh, void* dh_sem, float* d_w_sel, float* grad_w_color, float* grad_w_sem, void* stream);
 
 /* ---- a14, stand-alone form over the compact rows (renderer_semantics.py:279-285): image = sum w*rgb,
  * semantics = sum w*softmax(logits).  One pass, fp32.  The rendering pipeline uses the fused form inside

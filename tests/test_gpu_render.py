@@ -292,6 +292,19 @@ def test_fused_heads_match_cuda_core_heads_plus_composite_kernels(n, t):
     # for that row: tolerate a 1e-5 fraction of such elements, hold everything else to the tolerance
     bad = (a - b).abs() > 2e-2 * b.abs() + 1e-2 * float(b.abs().max())
     assert float(bad.float().mean()) < 1e-5, float(bad.float().mean())
+    # concurrent form: the semantic kernel writes its share of dL/dgeo_feat to its own buffer and the two kernels run
+    # side by side; half(colour + semantic) must reproduce the in-place sum bit for bit, everything else as before
+    dh3, dhs = torch.zeros(n, t, 16, **f16), torch.zeros(n, t, 16, **f16)
+    dw3 = torch.zeros(k_max, **f32)
+    gc3, gs3 = torch.zeros(ops.COLOR_PARAMS, **f32), torch.zeros(ops.SEM_PARAMS, **f32)
+    ops.heads_bwd(sel, off, n, t, k_max, d, h, w_col, w_sem, c, rgb1, a1, a2, a3, w_sel, z_sel, gi, gd, gs, dn,
+                  scale, dh3, dw3, gc3, gs3, dh_sem=dhs)
+    torch.cuda.synchronize()
+    summed = (dh3.float() + dhs.float()).half()
+    assert torch.equal(summed.view(-1, 16)[m], dh1.view(-1, 16)[m])
+    assert torch.equal(dw3[:k], dw1[:k])
+    torch.testing.assert_close(gc3, gc1, rtol=1e-4, atol=1e-5 * float(gc1.abs().max()))
+    torch.testing.assert_close(gs3, gs1, rtol=1e-4, atol=1e-5 * float(gs1.abs().max()))
 
 
 def test_config2_full_size_properties():

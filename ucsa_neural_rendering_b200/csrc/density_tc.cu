@@ -210,7 +210,7 @@ template <bool TILED>
 __global__ void __launch_bounds__(128)
 density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, const __half* __restrict__ h,
                       const __half* __restrict__ enc, const __half* __restrict__ hid,
-                      const float* __restrict__ d_sigma, const __half* __restrict__ dh,
+                      const float* __restrict__ d_sigma, const __half* __restrict__ dh, const __half* __restrict__ dh2,
                       const uint8_t* __restrict__ use_geo, float loss_scale, float* __restrict__ grad_table,
                       float* __restrict__ grad_replicas, uint32_t n_replicas, float* __restrict__ grad_w,
                       uint32_t run_max_res) {
@@ -264,6 +264,16 @@ density_bwd_tc_kernel(const DensityArgs a, const __half* __restrict__ w_sigma, c
       if (use_geo != nullptr && dh != nullptr && use_geo[flat]) {
         lo.v = ld_stream(dh + flat * 16, stream);
         hi.v = ld_stream(dh + flat * 16 + 8, stream);
+        if (dh2 != nullptr) {  // second share of dL/dgeo_feat (the semantic head's), summed like the in-place form did
+          H8 lo2, hi2;
+          lo2.v = ld_stream(dh2 + flat * 16, stream);
+          hi2.v = ld_stream(dh2 + flat * 16 + 8, stream);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            lo.h[i] = __float2half_rn(__half2float(lo.h[i]) + __half2float(lo2.h[i]));
+            hi.h[i] = __float2half_rn(__half2float(hi.h[i]) + __half2float(hi2.h[i]));
+          }
+        }
       } else {
         lo.v = make_uint4(0, 0, 0, 0);
         hi.v = make_uint4(0, 0, 0, 0);
@@ -465,7 +475,7 @@ extern "C" int ucsa_density_bwd(const float* xyz, const float* rays_o, const flo
                                 const float* z_cat, uint32_t n_rays, uint32_t t, uint32_t k0, uint32_t k1,
                                 float bound, const ucsa_grid_desc* grid_host, const void* w_sigma_h,
                                 const void* h, const void* enc, const void* hid, int tiled, const float* d_sigma,
-                                const void* dh, const uint8_t* use_geo, float loss_scale, float* grad_table,
+                                const void* dh, const void* dh2, const uint8_t* use_geo, float loss_scale, float* grad_table,
                                 float* grad_replicas, uint32_t n_replicas, float* grad_w_sigma, void* stream) {
   DensityArgs a;
   if (int rc = fill_args(a, xyz, rays_o, rays_d, aabb6, z_cat, n_rays, t, k0, k1, bound, grid_host)) return rc;
@@ -492,7 +502,8 @@ extern "C" int ucsa_density_bwd(const float* xyz, const float* rays_o, const flo
   auto kernel = tiled ? density_bwd_tc_kernel<true> : density_bwd_tc_kernel<false>;
   kernel<<<persistent_grid(a.n_samples, kBwdCtasPerSm), 128, kBwdSmem, as_stream(stream)>>>(
       a, static_cast<const __half*>(w_sigma_h), static_cast<const __half*>(h), static_cast<const __half*>(enc),
-      static_cast<const __half*>(hid), d_sigma, static_cast<const __half*>(dh), use_geo, loss_scale, grad_table,
+      static_cast<const __half*>(hid), d_sigma, static_cast<const __half*>(dh), static_cast<const __half*>(dh2), use_geo,
+      loss_scale, grad_table,
       grad_replicas, n_replicas, grad_w_sigma, run_max_res);
   return check_launch("density_bwd");
 }

@@ -12,6 +12,7 @@
 // of the compact row list is one contiguous 16 KB block, written and read back with single bulk copies.  The
 // logits are not saved at all: the semantic backward kernel recomputes them from hs with one extra product.
 #include <cstdlib>
+#include <mutex>
 
 #include "mlp_umma.cuh"
 #include "sh4.cuh"
@@ -808,7 +809,7 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
                      const float* __restrict__ rays_d, const __half* __restrict__ h, const __half* __restrict__ w_sem,
                      int n_classes, const __half* __restrict__ hs,
                      const float* __restrict__ w_sel, const float* __restrict__ g_sem, float loss_scale,
-                     __half* __restrict__ dh, float* __restrict__ grad_w_sem) {
+                     __half* __restrict__ dh, __half* __restrict__ dh_sem, float* __restrict__ grad_w_sem) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* ws1 = smem;
   unsigned char* ws2 = ws1 + kWs1;
@@ -917,7 +918,7 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
     RowInputs in_row;
     load_row_inputs(in_row, nullptr, h, flat, t, valid, false);
     uint4 dh_lo = make_uint4(0, 0, 0, 0), dh_hi = make_uint4(0, 0, 0, 0);
-    if (valid) {
+    if (valid && dh_sem == nullptr) {  // (with dh_sem the semantic share goes to its own buffer: nothing to read)
       dh_lo = reinterpret_cast<const uint4*>(dh + static_cast<uint64_t>(flat) * 16)[0];
       dh_hi = reinterpret_cast<const uint4*>(dh + static_cast<uint64_t>(flat) * 16)[1];
     }
@@ -958,8 +959,10 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
       for (int i = 0; i < 7; ++i) lo.h[i + 1] = __float2half_rn(__half2float(lo.h[i + 1]) + round_h(d_in_s[i]));
 #pragma unroll
       for (int i = 0; i < 8; ++i) hi.h[i] = __float2half_rn(__half2float(hi.h[i]) + round_h(d_in_s[7 + i]));
-      reinterpret_cast<uint4*>(dh + static_cast<uint64_t>(flat) * 16)[0] = lo.v;
-      reinterpret_cast<uint4*>(dh + static_cast<uint64_t>(flat) * 16)[1] = hi.v;
+      // (dh_sem: 0 + round_h(x) is exact, so density_bwd's half(colour + semantic) reproduces the in-place sum bit for bit)
+      __half* out = dh_sem != nullptr ? dh_sem : dh;
+      reinterpret_cast<uint4*>(out + static_cast<uint64_t>(flat) * 16)[0] = lo.v;
+      reinterpret_cast<uint4*>(out + static_cast<uint64_t>(flat) * 16)[1] = hi.v;
     }
     ctx.publish();
     if (threadIdx.x == 0) {
@@ -977,6 +980,38 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
     flush_wgrad<kSemOut, true>(ctx, kGs2, grad_w_sem + kSemW2, 64, inv_scale);
   }
   umma::ctx_free(ctx, kBwdSemCols);
+}
+
+// Library-owned helper stream per device for the kernel pairs that run concurrently: forked from and joined back to the
+// caller's stream with events, so everything stays ordered on the caller's stream and is capturable into a CUDA graph.
+std::mutex g_side_mutex;
+cudaStream_t g_side[64] = {};
+cudaEvent_t g_ev_fork[64] = {}, g_ev_join[64] = {};
+
+int fork_side_stream(cudaStream_t st, cudaStream_t* side_out, int* dev_out) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (g_side[dev] == nullptr) {  // first call on this device (never inside a stream capture: engines warm up first)
+    std::lock_guard<std::mutex> lock(g_side_mutex);
+    if (g_side[dev] == nullptr) {
+      cudaStream_t s_new;
+      if (cudaStreamCreateWithFlags(&s_new, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&g_ev_fork[dev], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&g_ev_join[dev], cudaEventDisableTiming) != cudaSuccess)
+        return check_launch("helper stream");
+      g_side[dev] = s_new;
+    }
+  }
+  cudaEventRecord(g_ev_fork[dev], st);
+  cudaStreamWaitEvent(g_side[dev], g_ev_fork[dev], 0);
+  *side_out = g_side[dev];
+  *dev_out = dev;
+  return UCSA_OK;
+}
+void join_side_stream(cudaStream_t st, int dev) {
+  cudaEventRecord(g_ev_join[dev], g_side[dev]);
+  cudaStreamWaitEvent(st, g_ev_join[dev], 0);
 }
 
 uint32_t heads_grid(uint32_t k_max, int ctas_per_sm) {
@@ -1024,13 +1059,39 @@ extern "C" int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32
     heads_fwd_color_ws_kernel<<<pairs < cap ? pairs : cap, kWsThreads, kFwdColorWsSmem, st>>>(
         sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h), w_sel,
         rgb, static_cast<__half*>(hc1), static_cast<__half*>(hc2), image);
-  } else
-  heads_fwd_color_kernel<<<heads_grid(k_max, kFwdColorCtas), 128, kFwdColorSmem, st>>>(
-      sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h), w_sel,
-      rgb, static_cast<__half*>(hc1), static_cast<__half*>(hc2), image);
-  heads_fwd_sem_kernel<<<heads_grid(k_max, kFwdSemCtas), 128, kFwdSemSmem, st>>>(
-      sel, ray_off + n_rays, t, static_cast<const __half*>(h), static_cast<const __half*>(w_sem_h),
-      static_cast<int>(n_classes), w_sel, static_cast<__half*>(logits), static_cast<__half*>(hs), semantics);
+  } else {
+    // The two kernels run CONCURRENTLY: the semantic kernel goes to a helper stream forked from / joined to `st` with
+    // events (capturable), and each kernel's persistent grid is sized so that both fit an SM at once (2 colour + 3
+    // semantic CTAs: 187 KB of shared memory, 320 TMEM columns).  In training the colour kernel is bound by the HBM
+    // writes of its saved activations (64 % of peak) and the semantic kernel by instruction issue (58 %), so together
+    // they take 0.275 ms instead of 0.316 ms one after the other (bench.py, config 2; (2,4) 0.279, (3,3) 0.283,
+    // (2,2) 0.348).  UCSA_FWD_OVERLAP=0 restores the sequential launch; UCSA_FWD_COLOR_CTAS / UCSA_FWD_SEM_CTAS
+    // override the grid sizes (bring-up knobs).
+    static int overlap = -1, color_ctas = 0, sem_ctas = 0;
+    if (overlap < 0) {
+      std::lock_guard<std::mutex> lock(g_side_mutex);
+      const char* e = getenv("UCSA_FWD_OVERLAP");
+      const int ov = (e != nullptr && e[0] == '0') ? 0 : 1;
+      color_ctas = ov ? 2 : kFwdColorCtas;
+      sem_ctas = ov ? 3 : kFwdSemCtas;
+      if (const char* c = getenv("UCSA_FWD_COLOR_CTAS")) color_ctas = atoi(c) >= 1 && atoi(c) <= 5 ? atoi(c) : color_ctas;
+      if (const char* c = getenv("UCSA_FWD_SEM_CTAS")) sem_ctas = atoi(c) >= 1 && atoi(c) <= 5 ? atoi(c) : sem_ctas;
+      overlap = ov;
+    }
+    cudaStream_t st_sem = st;
+    int dev = 0;
+    if (overlap) {
+      if (int rc = fork_side_stream(st, &st_sem, &dev)) return rc;
+    }
+    heads_fwd_color_kernel<<<heads_grid(k_max, color_ctas), 128, kFwdColorSmem, st>>>(
+        sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h), w_sel,
+        rgb, static_cast<__half*>(hc1), static_cast<__half*>(hc2), image);
+    heads_fwd_sem_kernel<<<heads_grid(k_max, sem_ctas), 128, kFwdSemSmem, st_sem>>>(
+        sel, ray_off + n_rays, t, static_cast<const __half*>(h), static_cast<const __half*>(w_sem_h),
+        static_cast<int>(n_classes), w_sel, static_cast<__half*>(logits), static_cast<__half*>(hs), semantics);
+    if (overlap) join_side_stream(st, dev);
+    return check_launch("heads_fwd");
+  }
   return check_launch("heads_fwd");
 }
 
@@ -1040,7 +1101,7 @@ extern "C" int ucsa_heads_bwd(const int32_t* sel, const int32_t* ray_off, uint32
                               const void* hc1, const void* hc2, const void* hs, const float* w_sel,
                               const float* z_sel, const float* g_image, const float* g_depth,
                               const float* g_semantics, const float* direction_norms, float loss_scale, void* dh,
-                              float* d_w_sel, float* grad_w_color, float* grad_w_sem, void* stream) {
+                              void* dh_sem, float* d_w_sel, float* grad_w_color, float* grad_w_sem, void* stream) {
   UCSA_REQUIRE(sel && ray_off && rays_d && h && w_color_h && w_sem_h && rgb && hc1 && hc2 && hs && w_sel &&
                    z_sel && g_image && g_depth && g_semantics && direction_norms && dh && d_w_sel && grad_w_color &&
                    grad_w_sem,
@@ -1059,13 +1120,36 @@ extern "C" int ucsa_heads_bwd(const int32_t* sel, const int32_t* ray_off, uint32
     }
   }
   cudaStream_t st = as_stream(stream);
-  heads_bwd_color_kernel<<<heads_grid(k_max, kBwdColorCtas), 128, kBwdColorSmem, st>>>(
+  // With dh_sem the two kernels are independent (each writes its own share of dL/dgeo_feat) and CAN run concurrently,
+  // the semantic one on the helper stream (see ucsa_heads_fwd).  Measured (bench.py, config 2, ms for both kernels;
+  // colour:semantic CTAs per SM): sequential 0.450 | 1:2 0.445 | 1:4 0.484 | 1:3 0.515 | 2:2 0.619 | 2:1 0.707 --
+  // unlike the forward pair, both backward kernels are bound by the same thing (latency at low occupancy), so
+  // sharing the SM buys nothing: the default stays sequential at full occupancy, UCSA_BWD_OVERLAP=1 opts in.
+  static int color_ctas = 0, sem_ctas = 0, overlap = -1;
+  if (overlap < 0) {
+    std::lock_guard<std::mutex> lock(g_side_mutex);
+    const char* e = getenv("UCSA_BWD_OVERLAP");
+    const int ov = (e != nullptr && e[0] == '1') ? 1 : 0;
+    color_ctas = ov ? 1 : kBwdColorCtas;
+    sem_ctas = ov ? 2 : kBwdSemCtas;
+    if (const char* c = getenv("UCSA_BWD_COLOR_CTAS")) color_ctas = atoi(c) >= 1 && atoi(c) <= kBwdColorCtas ? atoi(c) : color_ctas;
+    if (const char* c = getenv("UCSA_BWD_SEM_CTAS")) sem_ctas = atoi(c) >= 1 && atoi(c) <= kBwdSemCtas ? atoi(c) : sem_ctas;
+    overlap = ov;
+  }
+  const bool concurrent = overlap && dh_sem != nullptr;
+  cudaStream_t st_sem = st;
+  int dev = 0;
+  if (concurrent) {
+    if (int rc = fork_side_stream(st, &st_sem, &dev)) return rc;
+  }
+  heads_bwd_color_kernel<<<heads_grid(k_max, concurrent ? color_ctas : kBwdColorCtas), 128, kBwdColorSmem, st>>>(
       sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h), rgb,
       static_cast<const __half*>(hc1), static_cast<const __half*>(hc2), w_sel, z_sel, g_image, g_depth,
       direction_norms, loss_scale, static_cast<__half*>(dh), d_w_sel, grad_w_color);
-  heads_bwd_sem_kernel<<<heads_grid(k_max, kBwdSemCtas), 128, kBwdSemSmem, st>>>(
+  heads_bwd_sem_kernel<<<heads_grid(k_max, concurrent ? sem_ctas : kBwdSemCtas), 128, kBwdSemSmem, st_sem>>>(
       sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_sem_h),
       static_cast<int>(n_classes), static_cast<const __half*>(hs), w_sel,
-      g_semantics, loss_scale, static_cast<__half*>(dh), grad_w_sem);
+      g_semantics, loss_scale, static_cast<__half*>(dh), static_cast<__half*>(dh_sem), grad_w_sem);
+  if (concurrent) join_side_stream(st, dev);
   return check_launch("heads_bwd");
 }

@@ -114,7 +114,7 @@ def density_tiled(tc, tf):
 
 def density_bwd(grid, w_sigma_h, bound, *, xyz=None, rays_o=None, rays_d=None, aabb=None, z_cat=None, k0=0, k1=1,
                 h, enc, hid, d_sigma, dh, use_geo, loss_scale, grad_table, grad_w_sigma, simt=False, replicas=None,
-                tiled=False):
+                tiled=False, dh2=None):
     """replicas: zero-filled fp32 [R, 2*dense_entries] (see grad_replicas()); folded into grad_table before returning"""
     if xyz is not None:
         n, t = xyz.shape[0], 1
@@ -127,10 +127,11 @@ def density_bwd(grid, w_sigma_h, bound, *, xyz=None, rays_o=None, rays_d=None, a
            float(loss_scale), _ptr(grad_table, torch.float32, "grad_table"))
     tail = (_ptr(grad_w_sigma, torch.float32, "grad_w_sigma"), _stream())
     if simt:
-        if tiled:
-            raise ValueError("the CUDA-core density kernels use row-major enc / hid")
+        if tiled or dh2 is not None:
+            raise ValueError("the CUDA-core density kernels use row-major enc / hid and a single dh")
         check(lib().ucsa_density_bwd_simt(*head, *mid, *tail), "density_bwd_simt")
         return
+    mid = (mid[0], mid[1], _ptr(dh2, torch.float16, "dh2")) + mid[2:]
     if tiled:
         _check_tiled(n * t, 32, enc=enc)
         _check_tiled(n * t, 64, hid=hid)
@@ -198,7 +199,9 @@ def heads_fwd(sel, ray_off, n_rays, t, k_max, rays_d, h, w_color_h, w_sem_h, n_c
 
 def heads_bwd(sel, ray_off, n_rays, t, k_max, rays_d, h, w_color_h, w_sem_h, n_classes, rgb, hc1, hc2, hs,
               w_sel, z_sel, g_image, g_depth, g_semantics, direction_norms, loss_scale, dh, d_w_sel, grad_w_color,
-              grad_w_sem):
+              grad_w_sem, dh_sem=None):
+    """dh_sem: optional second buffer for the semantic head's share of dL/dgeo_feat (the two kernels then run
+    concurrently; pass it to density_bwd as dh2)"""
     _check_tiled(k_max, 64, hc1=hc1, hc2=hc2, hs=hs)
     check(lib().ucsa_heads_bwd(_ptr(sel, torch.int32), _ptr(ray_off, torch.int32), n_rays, t, k_max,
                                _ptr(rays_d, torch.float32), _ptr(h, torch.float16), _ptr(w_color_h, torch.float16),
@@ -207,8 +210,9 @@ def heads_bwd(sel, ray_off, n_rays, t, k_max, rays_d, h, w_color_h, w_sem_h, n_c
                                _ptr(hs, torch.float16), _ptr(w_sel, torch.float32), _ptr(z_sel, torch.float32),
                                _ptr(g_image, torch.float32, "g_image"), _ptr(g_depth, torch.float32, "g_depth"),
                                _ptr(g_semantics, torch.float32, "g_semantics"), _ptr(direction_norms, torch.float32),
-                               float(loss_scale), _ptr(dh, torch.float16), _ptr(d_w_sel, torch.float32),
-                               _ptr(grad_w_color, torch.float32), _ptr(grad_w_sem, torch.float32), _stream()),
+                               float(loss_scale), _ptr(dh, torch.float16), _ptr(dh_sem, torch.float16, "dh_sem"),
+                               _ptr(d_w_sel, torch.float32), _ptr(grad_w_color, torch.float32),
+                               _ptr(grad_w_sem, torch.float32), _stream()),
           "heads_bwd")
 
 
