@@ -111,7 +111,9 @@ def test_resample_merge(ops, tc, tf):
     # ulp of difference in the pdf normaliser (torch.sum is pairwise, the kernel sums in order) moves the sample
     # by a visible fraction of that bin; the same holds for the rounding order of the cdf (the kernel uses warp scans,
     # torch on the CPU a sequential cumsum: a few ulps of a cdf near 1 against a bin mass of 1e-5).  Such samples are
-    # rare and carry no weight: demand 1e-5-level agreement for 97 % and agreement within a fraction of a bin for all.
+    # rare and carry no weight: demand 1e-5-level agreement for 97 % and agreement within a fraction of a bin for all
+    # (tests/test_gpu_render.py::test_oracle_at_reference_sample_counts_render_and_engine checks that the rays which
+    # contain such samples still render within tolerance).
     err = (got_new - z_new).abs() / z_new.abs().clamp_min(1e-3)
     assert (err < 2e-5).float().mean() > 0.97, float((err < 2e-5).float().mean())
     bin_width = (z[:, 1:] - z[:, :-1]).max(dim=1, keepdim=True).values

@@ -381,7 +381,8 @@ def test_oracle_at_reference_sample_counts_render_and_engine():
     t_rand = torch.rand(n, steps, generator=g)
     u = torch.rand(n, up, generator=g)
     ref = live_path.run(heads, o[None], d[None], dn[None], num_steps=steps, upsample_steps=up, perturb=True,
-                        t_rand=t_rand, u=u)
+                        t_rand=t_rand, u=u, return_aux=True)
+    ref_aux = ref.pop("aux")
     ref_total, ref_parts = oracle_losses(ref, rgb[None], label[None], depth[None], scene.one_m_to_scene_uom)
     ref_total.backward()
     ref_grads = [heads.encoder.grad, heads.sigma_net.grad, heads.color_net.grad, heads.semantics_net.grad]
@@ -407,6 +408,19 @@ def test_oracle_at_reference_sample_counts_render_and_engine():
     np.testing.assert_allclose(loss[1:], [float(x) for x in ref_parts], rtol=4e-3, atol=1e-5)
     for name, got, want in zip(("hash", "sigma", "color", "sem"), eng.grads, ref_grads):
         _close("engine_grad_" + name, got.cpu().numpy(), want.numpy(), rtol=3e-2, atol_rel=1e-2)
+    # Importance samples: inverse-CDF sampling is ill-conditioned inside near-empty bins, where the kernel and torch may
+    # place a sample a fraction of a bin apart (tests/test_gpu_kernels.py::test_resample_merge allows 3 % of them).  The
+    # rays that contain such samples must still render within tolerance -- checked here on exactly those rays.
+    z_fine = eng.ws.z_cat[:, steps:].cpu()
+    z_ref = torch.sort(ref_aux["z_new"], dim=1).values
+    off = ((z_fine - z_ref).abs() / z_ref.abs().clamp_min(1e-3)) > 2e-5
+    assert float(off.float().mean()) < 0.03
+    rays_off = off.any(dim=1)
+    if bool(rays_off.any()):
+        for k, got in (("depth", eng.ws.depth), ("image", eng.ws.image), ("semantics", eng.ws.semantics)):
+            a, b = got.cpu().numpy()[rays_off.numpy()], ref[k].detach().numpy()[0][rays_off.numpy()]
+            np.testing.assert_allclose(a, b, rtol=4e-3, atol=2e-3 * max(np.abs(ref[k].detach().numpy()).max(), 1e-12),
+                                       err_msg="rays with displaced importance samples: " + k)
 
 
 def test_fused_compositing_isolated_to_1e5():

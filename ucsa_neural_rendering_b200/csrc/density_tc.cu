@@ -499,8 +499,14 @@ extern "C" int ucsa_density_bwd(const float* xyz, const float* rays_o, const flo
     run_max_res = e ? static_cast<uint32_t>(atoi(e)) : kRunMaxRes;
     if (run_max_res < 1) run_max_res = kRunMaxRes;
   }
+  static int bwd_ctas = 0;
+  if (bwd_ctas == 0) {  // tuning knob (bring-up): UCSA_DBWD_CTAS caps the resident CTAs per SM (grid size)
+    const char* e = getenv("UCSA_DBWD_CTAS");
+    bwd_ctas = e ? atoi(e) : kBwdCtasPerSm;
+    if (bwd_ctas < 1 || bwd_ctas > kBwdCtasPerSm) bwd_ctas = kBwdCtasPerSm;
+  }
   auto kernel = tiled ? density_bwd_tc_kernel<true> : density_bwd_tc_kernel<false>;
-  kernel<<<persistent_grid(a.n_samples, kBwdCtasPerSm), 128, kBwdSmem, as_stream(stream)>>>(
+  kernel<<<persistent_grid(a.n_samples, bwd_ctas), 128, kBwdSmem, as_stream(stream)>>>(
       a, static_cast<const __half*>(w_sigma_h), static_cast<const __half*>(h), static_cast<const __half*>(enc),
       static_cast<const __half*>(hid), d_sigma, static_cast<const __half*>(dh), static_cast<const __half*>(dh2), use_geo,
       loss_scale, grad_table,
