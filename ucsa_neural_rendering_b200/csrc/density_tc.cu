@@ -64,8 +64,15 @@ __device__ __forceinline__ uint64_t locate_sample(const DensityArgs& a, uint64_t
     for (int d = 0; d < 3; ++d) x01[d] = __fdiv_rn(__fadd_rn(a.xyz[3 * s + d], a.bound), 2.0f * a.bound);
     return s;
   }
-  const uint32_t n = static_cast<uint32_t>(s / a.span);
-  const uint32_t k = a.k0 + static_cast<uint32_t>(s % a.span);
+  uint32_t n, k;
+  if ((a.n_samples >> 32) == 0) {  // (kernel-uniform) 32-bit division: the 64-bit form is a ~100-instruction routine
+    const uint32_t s32 = static_cast<uint32_t>(s);
+    n = s32 / a.span;
+    k = a.k0 + (s32 - n * a.span);
+  } else {
+    n = static_cast<uint32_t>(s / a.span);
+    k = a.k0 + static_cast<uint32_t>(s % a.span);
+  }
   const uint64_t flat = static_cast<uint64_t>(n) * a.t + k;
   sample_x01(a.rays_o, a.rays_d, a.aabb, a.z_cat[flat], n, a.bound, x01);
   return flat;

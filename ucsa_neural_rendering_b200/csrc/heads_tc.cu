@@ -22,6 +22,12 @@ namespace {
 
 using umma::Tile;
 
+__device__ __forceinline__ float exp2f_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr int kSemOut = UCSA_MAX_CLASSES;  // semantic output layer is always 48 wide (pad16 of 33..48 classes)
 constexpr int kColorW1 = 0, kColorW2 = 64 * 32, kColorW3 = kColorW2 + 64 * 64;  // offsets in w_color
 constexpr int kSemW1 = 0, kSemW2 = 64 * 16;                                      // offsets in w_sem
@@ -484,11 +490,15 @@ heads_fwd_color_ws_kernel(const int32_t* __restrict__ sel, const int32_t* __rest
   if (warp == 4) umma::tmem_dealloc(tmem, 128);
 }
 
+// NC: the class count as a compile-time constant (40 = the reference's configuration: the soft-max / staging loops
+// lose their per-column predicates and the 8 padded columns altogether), 0 = read n_classes_rt at run time
+template <int NC>
 __global__ void __launch_bounds__(128, kFwdSemCtas)
 heads_fwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__ k_ptr, uint32_t t,
-                     const __half* __restrict__ h, const __half* __restrict__ w_sem, int n_classes,
+                     const __half* __restrict__ h, const __half* __restrict__ w_sem, int n_classes_rt,
                      const float* __restrict__ w_sel, __half* __restrict__ logits, __half* __restrict__ hs,
                      float* __restrict__ semantics) {
+  const int n_classes = NC > 0 ? NC : n_classes_rt;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* ws1 = smem;
   unsigned char* ws2 = ws1 + kWs1;
@@ -575,7 +585,7 @@ heads_fwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
 #pragma unroll
         for (int c = 0; c < kSemOut; ++c) {
           if (c < n_classes) {  // (uniform) columns past the class count are never staged nor read
-            lg[c] = __expf(lg[c] - m);
+            lg[c] = exp2f_approx((lg[c] - m) * 1.4426950408889634f);  // = __expf(lg - m): one multiply + ex2.approx
             sum += lg[c];
           }
         }
@@ -804,12 +814,14 @@ heads_bwd_color_kernel(const int32_t* __restrict__ sel, const int32_t* __restric
   umma::ctx_free(ctx, kBwdColorCols);
 }
 
+template <int NC>
 __global__ void __launch_bounds__(128, kBwdSemCtas)
 heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict__ k_ptr, uint32_t t,
                      const float* __restrict__ rays_d, const __half* __restrict__ h, const __half* __restrict__ w_sem,
-                     int n_classes, const __half* __restrict__ hs,
+                     int n_classes_rt, const __half* __restrict__ hs,
                      const float* __restrict__ w_sel, const float* __restrict__ g_sem, float loss_scale,
                      __half* __restrict__ dh, __half* __restrict__ dh_sem, float* __restrict__ grad_w_sem) {
+  const int n_classes = NC > 0 ? NC : n_classes_rt;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* ws1 = smem;
   unsigned char* ws2 = ws1 + kWs1;
@@ -886,17 +898,29 @@ heads_bwd_sem_kernel(const int32_t* __restrict__ sel, const int32_t* __restrict_
         float sum = 0.f;
 #pragma unroll
         for (int c = 0; c < kSemOut; ++c) {
-          p[c] = c < n_classes ? __expf(p[c] - m) : 0.f;  // same soft-max arithmetic as the forward kernel
+          // same soft-max arithmetic as the forward kernel
+          p[c] = c < n_classes ? exp2f_approx((p[c] - m) * 1.4426950408889634f) : 0.f;
           sum += p[c];
         }
         const float inv = 1.0f / sum;
         float dot = 0.f;
         float q[kSemOut];
         const float* g_row = g_sem + static_cast<uint64_t>(flat / t) * n_classes;
+        if (NC > 0 && NC % 4 == 0) {  // the ray's dL/dsemantics row as 16-byte loads (rows are 16-byte aligned)
+#pragma unroll
+          for (int c = 0; c < NC; c += 4) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(g_row + c));
+            q[c] = w_row * g4.x, q[c + 1] = w_row * g4.y, q[c + 2] = w_row * g4.z, q[c + 3] = w_row * g4.w;
+          }
+#pragma unroll
+          for (int c = NC; c < kSemOut; ++c) q[c] = 0.f;
+        } else {
+#pragma unroll
+          for (int c = 0; c < kSemOut; ++c) q[c] = c < n_classes ? w_row * __ldg(g_row + c) : 0.f;
+        }
 #pragma unroll
         for (int c = 0; c < kSemOut; ++c) {
           p[c] *= inv;
-          q[c] = c < n_classes ? w_row * __ldg(g_row + c) : 0.f;
           dot = fmaf(q[c], p[c], dot);
         }
 #pragma unroll
@@ -1042,7 +1066,8 @@ extern "C" int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32
     cudaGetDevice(&dev);
     if (!(smem_devices.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
       if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(heads_fwd_color_kernel), kFwdColorSmem, "heads_fwd_color_kernel")) return rc;
-      if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(heads_fwd_sem_kernel), kFwdSemSmem, "heads_fwd_sem_kernel")) return rc;
+      if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(heads_fwd_sem_kernel<0>), kFwdSemSmem, "heads_fwd_sem_kernel")) return rc;
+      if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(heads_fwd_sem_kernel<40>), kFwdSemSmem, "heads_fwd_sem_kernel")) return rc;
       smem_devices.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
   }
@@ -1086,7 +1111,8 @@ extern "C" int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32
     heads_fwd_color_kernel<<<heads_grid(k_max, color_ctas), 128, kFwdColorSmem, st>>>(
         sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h), w_sel,
         rgb, static_cast<__half*>(hc1), static_cast<__half*>(hc2), image);
-    heads_fwd_sem_kernel<<<heads_grid(k_max, sem_ctas), 128, kFwdSemSmem, st_sem>>>(
+    auto sem_kernel = n_classes == 40 ? heads_fwd_sem_kernel<40> : heads_fwd_sem_kernel<0>;
+    sem_kernel<<<heads_grid(k_max, sem_ctas), 128, kFwdSemSmem, st_sem>>>(
         sel, ray_off + n_rays, t, static_cast<const __half*>(h), static_cast<const __half*>(w_sem_h),
         static_cast<int>(n_classes), w_sel, static_cast<__half*>(logits), static_cast<__half*>(hs), semantics);
     if (overlap) join_side_stream(st, dev);
@@ -1115,7 +1141,8 @@ extern "C" int ucsa_heads_bwd(const int32_t* sel, const int32_t* ray_off, uint32
     cudaGetDevice(&dev);
     if (!(smem_devices.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
       if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(heads_bwd_color_kernel), kBwdColorSmem, "heads_bwd_color_kernel")) return rc;
-      if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(heads_bwd_sem_kernel), kBwdSemSmem, "heads_bwd_sem_kernel")) return rc;
+      if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(heads_bwd_sem_kernel<0>), kBwdSemSmem, "heads_bwd_sem_kernel")) return rc;
+      if (int rc = set_max_dyn_smem(reinterpret_cast<const void*>(heads_bwd_sem_kernel<40>), kBwdSemSmem, "heads_bwd_sem_kernel")) return rc;
       smem_devices.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
   }
@@ -1146,7 +1173,9 @@ extern "C" int ucsa_heads_bwd(const int32_t* sel, const int32_t* ray_off, uint32
       sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h), rgb,
       static_cast<const __half*>(hc1), static_cast<const __half*>(hc2), w_sel, z_sel, g_image, g_depth,
       direction_norms, loss_scale, static_cast<__half*>(dh), d_w_sel, grad_w_color);
-  heads_bwd_sem_kernel<<<heads_grid(k_max, concurrent ? sem_ctas : kBwdSemCtas), 128, kBwdSemSmem, st_sem>>>(
+  auto sem_kernel = (n_classes == 40 && reinterpret_cast<uintptr_t>(g_semantics) % 16 == 0) ? heads_bwd_sem_kernel<40>
+                                                                                          : heads_bwd_sem_kernel<0>;
+  sem_kernel<<<heads_grid(k_max, concurrent ? sem_ctas : kBwdSemCtas), 128, kBwdSemSmem, st_sem>>>(
       sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_sem_h),
       static_cast<int>(n_classes), static_cast<const __half*>(hs), w_sel,
       g_semantics, loss_scale, static_cast<__half*>(dh), static_cast<__half*>(dh_sem), grad_w_sem);
