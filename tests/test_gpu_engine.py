@@ -142,6 +142,12 @@ def test_adam_exchange_kernel_equals_adam_step_on_one_rank():
     for lo, hi, wd in ((0, wd_begin, 0.0), (wd_begin, n, 1e-3)):
         ops.adam_step(ref_p[lo:hi], grad[lo:hi], m_ref[lo:hi], v_ref[lo:hi], ref_h[lo:hi], weight_decay=wd,
                       grad_scale_inv=1.0, found_inf=None, step=1, step_dev=step_dev, **hyper)
+    # the same two groups as ONE launch over the flat buffer (weight decay from wd_begin on): what TrainEngine issues
+    one_p, one_h = p0.clone(), torch.empty(n, dtype=torch.float16, device=DEV)
+    one_m, one_v = m0.clone(), v0.clone()
+    ops.adam_step(one_p, grad, one_m, one_v, one_h, weight_decay=1e-3, wd_begin=wd_begin, grad_scale_inv=1.0,
+                  found_inf=None, step=1, step_dev=step_dev, **hyper)
+    assert torch.equal(one_p, ref_p) and torch.equal(one_h, ref_h) and torch.equal(one_m, m_ref) and torch.equal(one_v, v_ref)
     # fused exchange on the slice [8000, 36000) of a one-rank "world"
     begin, end = 8000, 36000
     p, h = p0.clone(), torch.zeros(n, dtype=torch.float16, device=DEV)

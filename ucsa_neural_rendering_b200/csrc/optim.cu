@@ -55,9 +55,9 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 // step count on the device (CUDA-graph replay) they cost two pow per evaluation.
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-            __half* __restrict__ p_h, uint64_t n, double lr, double b1, double b2, float eps, float wd, float ginv,
-            const float* __restrict__ found_inf, int step, const int32_t* __restrict__ step_dev,
-            const int32_t* __restrict__ skipped_dev) {
+            __half* __restrict__ p_h, uint64_t n, double lr, double b1, double b2, float eps, float wd,
+            uint64_t wd_begin, float ginv, const float* __restrict__ found_inf, int step,
+            const int32_t* __restrict__ step_dev, const int32_t* __restrict__ skipped_dev) {
   if (found_inf != nullptr && *found_inf != 0.f) return;  // GradScaler: skip the step on overflow
   __shared__ float bc[2];
   if (threadIdx.x == 0) {
@@ -66,14 +66,15 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     adam_scalars(lr, b1, b2, step, &bc[0], &bc[1]);
   }
   __syncthreads();
-  const AdamCoef c{bc[0], static_cast<float>(b1), static_cast<float>(1.0 - b1), static_cast<float>(b2),
-                   static_cast<float>(1.0 - b2), eps, wd, ginv, bc[1]};
+  AdamCoef c{bc[0], static_cast<float>(b1), static_cast<float>(1.0 - b1), static_cast<float>(b2),
+             static_cast<float>(1.0 - b2), eps, wd, ginv, bc[1]};
   // grid-stride over float4 groups: a bounded number of CTAs, so the double-precision scalars above are formed a few
   // thousand times per launch instead of once per 1024 parameters
   const uint64_t n4 = n / 4;
   for (uint64_t q = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < n4;
        q += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
     const uint64_t i = q * 4;
+    c.wd = i >= wd_begin ? wd : 0.f;  // weight decay applies from parameter wd_begin on (a multiple of 4)
     float4 pp = *reinterpret_cast<const float4*>(p + i);
     const float4 gg = *reinterpret_cast<const float4*>(g + i);
     float4 mm = *reinterpret_cast<const float4*>(m + i);
@@ -95,6 +96,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3u)) {  // scalar tail
     const uint64_t k = n4 * 4 + threadIdx.x;
+    c.wd = k >= wd_begin ? wd : 0.f;
     float pk = p[k], mk = m[k], vk = v[k];
     adam_one(pk, g[k], mk, vk, c);
     p[k] = pk;
@@ -278,10 +280,11 @@ extern "C" int ucsa_cast_f32_to_f16(const float* src, uint64_t n, void* dst_h, v
 
 extern "C" int ucsa_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_h,
                               uint64_t n, double lr, double beta1, double beta2, float eps, float weight_decay,
-                              float grad_scale_inv, const float* found_inf, uint32_t step, const int32_t* step_dev,
-                              const int32_t* skipped_dev, void* stream) {
+                              uint64_t wd_begin, float grad_scale_inv, const float* found_inf, uint32_t step,
+                              const int32_t* step_dev, const int32_t* skipped_dev, void* stream) {
   UCSA_REQUIRE(param && grad && exp_avg && exp_avg_sq, "adam_step: null pointer");
   UCSA_REQUIRE(step >= 1 || step_dev != nullptr, "adam_step: step counts from 1");
+  UCSA_REQUIRE(wd_begin % 4 == 0, "adam_step: wd_begin must be a multiple of 4 parameters");
   UCSA_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
                  reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15u) == 0 &&
                    (reinterpret_cast<uintptr_t>(param_h) & 7u) == 0,
@@ -291,7 +294,7 @@ extern "C" int ucsa_adam_step(float* param, const float* grad, float* exp_avg, f
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
   adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq,
                                                                static_cast<__half*>(param_h), n, lr, beta1, beta2,
-                                                               eps, weight_decay, grad_scale_inv, found_inf,
+                                                               eps, weight_decay, wd_begin, grad_scale_inv, found_inf,
                                                                static_cast<int>(step), step_dev, skipped_dev);
   return check_launch("adam_step");
 }

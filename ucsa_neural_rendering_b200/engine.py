@@ -104,9 +104,23 @@ class TrainEngine:
             self.exp_avg = [torch.zeros(n_own, **f32)]
             self.exp_avg_sq = [torch.zeros(n_own, **f32)]
         else:
-            self.flat_grad = torch.zeros(sum(sizes), **f32)
-            self.exp_avg = [torch.zeros_like(m.params) for m, _ in self.groups]
-            self.exp_avg_sq = [torch.zeros_like(m.params) for m, _ in self.groups]
+            # one flat parameter space here too (masters, fp16 copies, moments, gradients): the optimizer is ONE launch
+            # over it, weight decay from the first MLP parameter on
+            total = sum(sizes)
+            self.flat_grad = torch.zeros(total, **f32)
+            self.flat_param = torch.empty(total, **f32)
+            self.flat_half = torch.empty(total, dtype=torch.float16, device=dev)
+            off = 0
+            with torch.no_grad():
+                for (m, _), s in zip(self.groups, sizes):
+                    view = self.flat_param[off:off + s]
+                    view.copy_(m.params.data.reshape(-1))
+                    m.params.data = view.view(m.params.shape)
+                    m._half = self.flat_half[off:off + s].view(m.params.shape)
+                    m._half_key = None
+                    off += s
+            self.exp_avg = [torch.zeros(total, **f32)]
+            self.exp_avg_sq = [torch.zeros(total, **f32)]
         self.grads, off = [], 0
         for s in sizes:
             self.grads.append(self.flat_grad[off:off + s])
@@ -148,10 +162,12 @@ class TrainEngine:
             return
         # (exchange == "nccl": the all-reduce already spread any inf / NaN to every rank's copy)
         ops.grad_check(self.flat_grad, self.found_inf, self._check_scratch, skipped_dev=self.skipped_dev)
-        for (m, wd), g, ea, eas in zip(self.groups, self.grads, self.exp_avg, self.exp_avg_sq):
-            ops.adam_step(m.params.data, g, ea, eas, m.half_params(), lr=self.lr, beta1=self.betas[0],
-                          beta2=self.betas[1], eps=self.eps, weight_decay=wd, grad_scale_inv=1.0,
-                          found_inf=self.found_inf, step=1, step_dev=self.step_dev, skipped_dev=self.skipped_dev)
+        for m, _ in self.groups:  # (masters changed from outside: version check + recast, no launch otherwise)
+            m.half_params()
+        ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg[0], self.exp_avg_sq[0], self.flat_half, lr=self.lr,
+                      beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.wd_net,
+                      wd_begin=self.groups[0][0].params.numel(), grad_scale_inv=1.0, found_inf=self.found_inf, step=1,
+                      step_dev=self.step_dev, skipped_dev=self.skipped_dev)
 
     def _capture(self):
         side = torch.cuda.Stream(device=self.device)
