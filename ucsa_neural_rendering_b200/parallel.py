@@ -91,14 +91,15 @@ class PeerExchange:
         self.grad_ptrs, self.mc_grad = self._addresses(self.grad, self._handles[0])
         self.param_ptrs, self.mc_param = self._addresses(self.param, self._handles[1])
         self.param_h_ptrs, self.mc_param_h = self._addresses(self.param_h, self._handles[2])
-        # multimem through the NVSwitch pays off from about 8 ranks on (see csrc/optim.cu); below that plain peer
-        # loads / stores are faster.  UCSA_PEER_MULTICAST=0/1 overrides.
+        # multimem through the NVSwitch pays off from 4 ranks on (ucsa_adam_exchange, 13.1 M parameters: 0.113 ms vs
+        # 0.127 ms with peer loads at 4 ranks, 0.113 ms at 8); at 2 ranks plain peer loads / stores are faster
+        # (0.078 ms vs 0.19 ms).  UCSA_PEER_MULTICAST=0/1 overrides.
         have_mc = bool(self.mc_grad and self.mc_param and self.mc_param_h)
         # fp32 masters of a slice stay on its owner (peers only need the fp16 working copy the kernels read): one third
         # of the store traffic of the exchange.  UCSA_PEER_BROADCAST_MASTERS=1 replicates the masters as well.
         self.broadcast_masters = os.environ.get("UCSA_PEER_BROADCAST_MASTERS", "0") == "1"
         want = os.environ.get("UCSA_PEER_MULTICAST", "auto")
-        self.multicast = have_mc and (want == "1" or (want != "0" and self.world > 4))
+        self.multicast = have_mc and (want == "1" or (want != "0" and self.world >= 4))
         self.begin, self.end = owner_slice(n_params, self.rank, self.world)
 
     def _addresses(self, tensor, handle):
