@@ -149,3 +149,21 @@ def test_engine_skips_a_step_whose_gradient_overflows():
     assert torch.isfinite(loss[0]) and float(eng.found_inf) == 0.0
     assert int(eng.step_dev) == 4 and eng.skipped_steps == 1  # Adam has taken 3 steps
     assert not torch.equal(before[0], eng.groups[0][0].params.detach())
+
+
+def test_opt_in_kernel_variants_pass_the_heads_parity_test():
+    """The bring-up variants that stay in the library behind environment knobs (warp-specialised two-slot colour
+    forward kernel, concurrent backward heads kernels, sequential forward heads kernels) must keep passing the heads
+    parity test; the knobs are read once per process, hence a subprocess per variant."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for env in ({"UCSA_HEADS_WS": "1"}, {"UCSA_BWD_OVERLAP": "1"}, {"UCSA_FWD_OVERLAP": "0"}):
+        res = subprocess.run(
+            [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider",
+             os.path.join(root, "tests", "test_gpu_render.py"), "-k",
+             "fused_heads_match_cuda_core or train_small_golden or fused_compositing_isolated"],
+            env=dict(os.environ, **env), capture_output=True, text=True, timeout=600, cwd=root)
+        assert res.returncode == 0, (env, res.stdout[-1500:], res.stderr[-500:])
