@@ -220,12 +220,16 @@ UCSA_API int ucsa_composite_rays_train_backward(const float* grad_weights_sum, c
                                        float* grad_sigmas, float* grad_rgbs, float* grad_local_semantics,
                                        void* stream);
 /* inference wavefront: raymarching.cu:647-729 (+ semantics), order-preserving compaction for :837-855 */
+/* semantic input: class probabilities local_semantics [M,C] f32, OR the semantic head's fp16 logits [M,logits_ld]
+ * (the soft-max over the first C columns is then taken inside the kernel), or neither (rgb + depth only). */
 UCSA_API int ucsa_composite_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, float* rays_t,
-                        const float* sigmas, const float* rgbs, const float* local_semantics, const float* deltas,
-                        uint32_t n_classes, float* weights_sum, float* depth, float* image, float* semantics,
-                        void* stream);
+                        const float* sigmas, const float* rgbs, const float* local_semantics, const void* logits_h,
+                        uint32_t logits_ld, const float* deltas, uint32_t n_classes, float* weights_sum, float* depth,
+                        float* image, float* semantics, void* stream);
+/* scratch (optional): ceil(n_alive / 1024) ints; with it a long list is compacted by many CTAs (count, scan, write)
+ * instead of one CTA walking it -- the result is the same order-preserving list. */
 UCSA_API int ucsa_compact_rays(uint32_t n_alive, int32_t* rays_alive, const int32_t* rays_alive_old, float* rays_t,
-                      const float* rays_t_old, int32_t* alive_counter, void* stream);
+                      const float* rays_t_old, int32_t* alive_counter, int32_t* scratch, void* stream);
 /* occupancy grid maintenance (not in the reference; torch-ngp's rule): grid = max(grid*decay, fresh) where fresh >= 0;
  * bitfield bit i = grid[i] > min(0.01, mean_density). */
 UCSA_API int ucsa_grid_update(float* density_grid, const float* fresh, uint64_t n_cells, float decay, void* stream);

@@ -377,3 +377,31 @@ def test_grid_refresh_kernel_chain_matches_eager_definition(ops):
     assert bool((net.density_grid >= before * 0.5 - 1e-7).all())
     # all cells of a cascade are visited: no cell keeps the initial zero when the field is positive everywhere
     assert float((net.density_grid <= 0).float().mean()) == 0.0
+
+
+def test_wavefront_composite_takes_logits_or_probabilities(ops):
+    """ucsa_composite_rays with the semantic head's fp16 logits (soft-max inside the kernel) must equal the same call
+    with the probabilities computed beforehand"""
+    g = torch.Generator().manual_seed(17)
+    n, n_alive, n_step, c = 400, 300, 4, 40
+    alive = torch.randperm(n, generator=g)[:n_alive].int().to(DEV)
+    m = n_alive * n_step
+    sig = (30 * torch.rand(m, generator=g) ** 2).to(DEV)
+    rgb = torch.rand(m, 3, generator=g).to(DEV)
+    deltas = torch.stack([0.01 + 0.05 * torch.rand(m, generator=g), 0.01 + 0.06 * torch.rand(m, generator=g)], 1).to(DEV)
+    deltas[5 * n_step + 2] = 0  # a ray that ends early (delta == 0 terminates it)
+    logits = (torch.randn(m, 48, generator=g) * 2).half().to(DEV)
+    prob = torch.softmax(logits[:, :c].float(), dim=-1).contiguous()
+    outs = []
+    for mode in ("prob", "logits"):
+        rt = torch.rand(n_alive, generator=torch.Generator().manual_seed(3)).to(DEV)
+        ws, dp, im = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), torch.zeros(n, 3, device=DEV)
+        sem = torch.zeros(n, c, device=DEV)
+        if mode == "prob":
+            ops.composite_rays(n_alive, n_step, alive, rt, sig, rgb, prob, deltas, c, ws, dp, im, sem)
+        else:
+            ops.composite_rays(n_alive, n_step, alive, rt, sig, rgb, None, deltas, c, ws, dp, im, sem, logits=logits)
+        outs.append((rt, ws, dp, im, sem))
+    for a, b in zip(*outs):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+    assert float(outs[0][4].sum()) > 0

@@ -340,6 +340,7 @@ __global__ void composite_train_bwd_kernel(const float* __restrict__ grad_ws, co
 __global__ void composite_rays_kernel(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays_alive,
                                       float* __restrict__ rays_t, const float* __restrict__ sigmas,
                                       const float* __restrict__ rgbs, const float* __restrict__ sem,
+                                      const __half* __restrict__ logits, uint32_t logits_ld,
                                       const float* __restrict__ deltas, uint32_t C, float* __restrict__ weights_sum,
                                       float* __restrict__ depth, float* __restrict__ image,
                                       float* __restrict__ semantics) {
@@ -351,7 +352,8 @@ __global__ void composite_rays_kernel(uint32_t n_alive, uint32_t n_step, const i
   float ws = weights_sum[index], d = depth[index];
   float r = image[3 * index], g = image[3 * index + 1], b = image[3 * index + 2];
   float acc0 = 0.f, acc1 = 0.f;
-  if (sem != nullptr) {
+  const bool with_sem = sem != nullptr || logits != nullptr;
+  if (with_sem) {
     if (static_cast<uint32_t>(lane) < C) acc0 = semantics[static_cast<uint64_t>(index) * C + lane];
     if (static_cast<uint32_t>(lane) + 32 < C) acc1 = semantics[static_cast<uint64_t>(index) * C + lane + 32];
   }
@@ -371,6 +373,18 @@ __global__ void composite_rays_kernel(uint32_t n_alive, uint32_t n_step, const i
     if (sem != nullptr) {
       if (static_cast<uint32_t>(lane) < C) acc0 += w * sem[static_cast<uint64_t>(i) * C + lane];
       if (static_cast<uint32_t>(lane) + 32 < C) acc1 += w * sem[static_cast<uint64_t>(i) * C + lane + 32];
+    } else if (logits != nullptr) {
+      // class probabilities from the fp16 logits of the semantic head, soft-max across the warp's lanes (the loop is
+      // warp-uniform: every lane follows the same ray): saves the [M,C] probability tensor and two passes over it
+      const __half* lg = logits + static_cast<uint64_t>(i) * logits_ld;
+      const float l0 = static_cast<uint32_t>(lane) < C ? __half2float(lg[lane]) : -INFINITY;
+      const float l1 = static_cast<uint32_t>(lane) + 32 < C ? __half2float(lg[lane + 32]) : -INFINITY;
+      const float m = warp_max(fmaxf(l0, l1));
+      const float e0 = static_cast<uint32_t>(lane) < C ? __expf(l0 - m) : 0.f;
+      const float e1 = static_cast<uint32_t>(lane) + 32 < C ? __expf(l1 - m) : 0.f;
+      const float scale = w / warp_sum(e0 + e1);
+      acc0 += scale * e0;
+      acc1 += scale * e1;
     }
     if (T < 1e-4) break;
     ++step;
@@ -382,7 +396,7 @@ __global__ void composite_rays_kernel(uint32_t n_alive, uint32_t n_step, const i
     depth[index] = d;
     image[3 * index] = r, image[3 * index + 1] = g, image[3 * index + 2] = b;
   }
-  if (sem != nullptr) {
+  if (with_sem) {
     if (static_cast<uint32_t>(lane) < C) semantics[static_cast<uint64_t>(index) * C + lane] = acc0;
     if (static_cast<uint32_t>(lane) + 32 < C) semantics[static_cast<uint64_t>(index) * C + lane + 32] = acc1;
   }
@@ -421,6 +435,75 @@ compact_rays_kernel(uint32_t n_alive, int32_t* __restrict__ rays_alive, const in
     __syncthreads();
   }
   if (threadIdx.x == 0) alive_counter[0] = carry_s;
+}
+
+// The same compaction for many rays, three launches instead of one CTA walking the whole list (a 640x480 wavefront is
+// 300 serial 1024-ray chunks: 0.35 ms per round, the largest item of the inference path): per-CTA counts -> scan of
+// the <= 1024 counts -> order-preserving writes at the scanned offsets.  `scratch` holds one int per 1024-ray chunk.
+__global__ void __launch_bounds__(1024)
+compact_count_kernel(uint32_t n_alive, const float* __restrict__ rays_t_old, int32_t* __restrict__ scratch) {
+  __shared__ int warp_total[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t n = blockIdx.x * 1024u + threadIdx.x;
+  const bool keep = n < n_alive && rays_t_old[n] >= 0;
+  const unsigned ballot = __ballot_sync(kFullMask, keep);
+  if (lane == 0) warp_total[wid] = __popc(ballot);
+  __syncthreads();
+  if (wid == 0) {
+    int tot = warp_total[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(kFullMask, tot, o);
+    if (lane == 0) scratch[blockIdx.x] = tot;
+  }
+}
+__global__ void __launch_bounds__(1024)
+compact_scan_kernel(uint32_t n_blocks, int32_t* __restrict__ scratch, int32_t* __restrict__ alive_counter) {
+  __shared__ int warp_total[32];
+  __shared__ int carry_s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = alive_counter[0];
+  __syncthreads();
+  for (uint32_t base = 0; base < n_blocks; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const int v = i < n_blocks ? scratch[i] : 0;
+    const int incl = warp_iscan(v, lane);
+    if (lane == 31) warp_total[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const int tot = warp_total[lane];
+      warp_total[lane] = warp_iscan(tot, lane) - tot;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    if (i < n_blocks) scratch[i] = carry + warp_total[wid] + incl - v;  // first output slot of chunk i
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_total[wid] + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) alive_counter[0] = carry_s;
+}
+__global__ void __launch_bounds__(1024)
+compact_write_kernel(uint32_t n_alive, int32_t* __restrict__ rays_alive, const int32_t* __restrict__ rays_alive_old,
+                     float* __restrict__ rays_t, const float* __restrict__ rays_t_old,
+                     const int32_t* __restrict__ scratch) {
+  __shared__ int warp_total[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t n = blockIdx.x * 1024u + threadIdx.x;
+  const float t_old = n < n_alive ? rays_t_old[n] : -1.0f;
+  const bool keep = n < n_alive && t_old >= 0;
+  const unsigned ballot = __ballot_sync(kFullMask, keep);
+  if (lane == 0) warp_total[wid] = __popc(ballot);
+  __syncthreads();
+  if (wid == 0) {
+    const int tot = warp_total[lane];
+    warp_total[lane] = warp_iscan(tot, lane) - tot;
+  }
+  __syncthreads();
+  if (keep) {
+    const int dst = scratch[blockIdx.x] + warp_total[wid] + __popc(ballot & ((1u << lane) - 1u));
+    rays_alive[dst] = rays_alive_old[n];
+    rays_t[dst] = t_old;
+  }
 }
 
 // ------------------------------------------------------------------ occupancy grid maintenance (row a20)
@@ -568,23 +651,34 @@ extern "C" int ucsa_composite_rays_train_backward(const float* grad_weights_sum,
 
 extern "C" int ucsa_composite_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, float* rays_t,
                                    const float* sigmas, const float* rgbs, const float* local_semantics,
-                                   const float* deltas, uint32_t n_classes, float* weights_sum, float* depth,
-                                   float* image, float* semantics, void* stream) {
+                                   const void* logits_h, uint32_t logits_ld, const float* deltas, uint32_t n_classes,
+                                   float* weights_sum, float* depth, float* image, float* semantics, void* stream) {
   UCSA_REQUIRE(rays_alive && rays_t && sigmas && rgbs && deltas && weights_sum && depth && image, "composite_rays: null pointer");
-  UCSA_REQUIRE((local_semantics == nullptr) == (semantics == nullptr), "composite_rays: semantics in/out mismatch");
+  UCSA_REQUIRE(!(local_semantics && logits_h), "composite_rays: give probabilities or logits, not both");
+  UCSA_REQUIRE((local_semantics == nullptr && logits_h == nullptr) == (semantics == nullptr),
+               "composite_rays: semantics in/out mismatch");
+  UCSA_REQUIRE(logits_h == nullptr || logits_ld >= n_classes, "composite_rays: logits row stride < classes");
   UCSA_REQUIRE(n_classes <= 64, "composite_rays: at most 64 classes");
   if (n_alive == 0) return UCSA_OK;
   composite_rays_kernel<<<ceil_div(static_cast<uint64_t>(n_alive) * 32, 128), 128, 0, as_stream(stream)>>>(
-      n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, local_semantics, deltas, n_classes, weights_sum, depth, image,
-      semantics);
+      n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, local_semantics, static_cast<const __half*>(logits_h), logits_ld,
+      deltas, n_classes, weights_sum, depth, image, semantics);
   return check_launch("composite_rays");
 }
 
 extern "C" int ucsa_compact_rays(uint32_t n_alive, int32_t* rays_alive, const int32_t* rays_alive_old, float* rays_t,
-                                 const float* rays_t_old, int32_t* alive_counter, void* stream) {
+                                 const float* rays_t_old, int32_t* alive_counter, int32_t* scratch, void* stream) {
   UCSA_REQUIRE(rays_alive && rays_alive_old && rays_t && rays_t_old && alive_counter, "compact_rays: null pointer");
-  compact_rays_kernel<<<1, 1024, 0, as_stream(stream)>>>(n_alive, rays_alive, rays_alive_old, rays_t, rays_t_old,
-                                                         alive_counter);
+  if (scratch == nullptr || n_alive <= 4096) {  // a few chunks: one CTA is the shortest path
+    compact_rays_kernel<<<1, 1024, 0, as_stream(stream)>>>(n_alive, rays_alive, rays_alive_old, rays_t, rays_t_old,
+                                                           alive_counter);
+    return check_launch("compact_rays");
+  }
+  const uint32_t n_blocks = ceil_div(n_alive, 1024);
+  compact_count_kernel<<<n_blocks, 1024, 0, as_stream(stream)>>>(n_alive, rays_t_old, scratch);
+  compact_scan_kernel<<<1, 1024, 0, as_stream(stream)>>>(n_blocks, scratch, alive_counter);
+  compact_write_kernel<<<n_blocks, 1024, 0, as_stream(stream)>>>(n_alive, rays_alive, rays_alive_old, rays_t, rays_t_old,
+                                                                 scratch);
   return check_launch("compact_rays");
 }
 

@@ -312,6 +312,37 @@ class SemanticNeRFNetwork(SemanticNeRFRenderer):
         sigma, geo_feat = _DensityFn.apply(x, self.encoder.params, self.sigma_net.params, self)
         return {"sigma": sigma, "geo_feat": geo_feat}
 
+    @torch.no_grad()
+    def forward_packed(self, x, d, want_logits=False):
+        """forward(x, d) for a packed stream of points without autograd (the inference wavefront of run_cuda): the fused
+        density kernel, then the two tensor-core heads kernels on ALL points (identity row list, one direction per
+        point), then the soft-max -- 3 kernels + 1 torch op instead of the 9 launches of the module-by-module forward.
+        -> sigma [M] f32, colour [M,3] f32, class probabilities [M,C] f32 (want_logits: the fp16 logits [M,48])"""
+        x = x.detach().float().contiguous()
+        d = d.detach().float().contiguous()
+        m = x.shape[0]
+        dev = x.device
+        c = self.num_semantic_classes
+        sigma = torch.empty(m, dtype=torch.float32, device=dev)
+        rgb = torch.empty(m, 3, dtype=torch.float32, device=dev)
+        if m == 0:
+            empty = torch.empty(0, ops.MAX_CLASSES, dtype=torch.float16, device=dev)
+            return sigma, rgb, (empty if want_logits else empty[:, :c].float())
+        st = getattr(self, "_packed_state", None)
+        if st is None or st["sel"].device != dev or st["sel"].numel() < m:
+            cap = max(m, 1 << 16)
+            st = {"sel": torch.arange(cap, dtype=torch.int32, device=dev),
+                  "off": torch.zeros(2, dtype=torch.int32, device=dev)}
+            self._packed_state = st
+        st["off"][1] = m  # one "ray" that owns all rows: the heads kernels read K from the device
+        h = torch.empty(m, 16, dtype=torch.float16, device=dev)
+        logits = torch.empty(m, ops.MAX_CLASSES, dtype=torch.float16, device=dev)
+        ops.density_fwd(self.encoder.grid, self.encoder.half_params(), self.sigma_net.half_params(), self.bound, xyz=x,
+                        sigma=sigma, h=h)
+        ops.heads_fwd(st["sel"], st["off"], 1, 1, m, d, h, self.color_net.half_params(),
+                      self.semantics_net.half_params(), c, rgb, logits)
+        return sigma, rgb, (logits if want_logits else F.softmax(logits[:, :c].float(), dim=-1))
+
     def color(self, x, d, mask=None, geo_feat=None, **kwargs):
         # masked evaluation, network_tcnn_semantics.py:147-178
         if mask is not None:

@@ -145,10 +145,12 @@ def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, we
 
 
 def composite_rays_semantics(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, local_semantics, deltas, weights_sum,
-                             depth, image, semantics):
-    """raymarching.py:507-558; as composite_rays plus the in-place [N,C] semantic accumulator."""
-    ops.composite_rays(n_alive, n_step, rays_alive, rays_t, _f32(sigmas), _f32(rgbs), _f32(local_semantics),
-                       _f32(deltas), semantics.shape[-1], weights_sum, depth, image, semantics)
+                             depth, image, semantics, logits=None):
+    """raymarching.py:507-558; as composite_rays plus the in-place [N,C] semantic accumulator.  `logits` (fp16
+    [M, >= C], contiguous) may replace `local_semantics`: the soft-max is then taken inside the kernel."""
+    ops.composite_rays(n_alive, n_step, rays_alive, rays_t, _f32(sigmas), _f32(rgbs),
+                       None if logits is not None else _f32(local_semantics), _f32(deltas), semantics.shape[-1],
+                       weights_sum, depth, image, semantics, logits=logits)
     return tuple()
 
 

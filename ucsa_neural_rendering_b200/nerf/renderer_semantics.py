@@ -294,11 +294,20 @@ class SemanticNeRFRenderer(nn.Module):
                 xyzs, dirs, deltas = raymarching.march_rays(n_alive, n_step, rays_alive[i % 2], rays_t[i % 2], rays_o,
                                                             rays_d, self.bound, self.density_grid, self.mean_density,
                                                             nears, fars, 128, perturb, dt_gamma, bitfield=bits)
-                sigmas, rgbs, sems = self(xyzs, dirs)
-                sigmas = self.density_scale * sigmas
-                raymarching.composite_rays_semantics(n_alive, n_step, rays_alive[i % 2], rays_t[i % 2], sigmas,
-                                                     rgbs.float(), sems.float(), deltas, weights_sum, depth, image,
-                                                     semantics)
+                # a subclass may offer the three heads on packed points as one kernel chain (no autograd: inference),
+                # handing over the semantic LOGITS: the soft-max is then taken inside the compositing kernel
+                heads = getattr(self, "forward_packed", None) if not torch.is_grad_enabled() else None
+                if heads is not None:
+                    sigmas, rgbs, logits = heads(xyzs, dirs, want_logits=True)
+                    raymarching.composite_rays_semantics(n_alive, n_step, rays_alive[i % 2], rays_t[i % 2],
+                                                         self.density_scale * sigmas, rgbs, None, deltas, weights_sum,
+                                                         depth, image, semantics, logits=logits)
+                else:
+                    sigmas, rgbs, sems = self(xyzs, dirs)
+                    sigmas = self.density_scale * sigmas
+                    raymarching.composite_rays_semantics(n_alive, n_step, rays_alive[i % 2], rays_t[i % 2], sigmas,
+                                                         rgbs.float(), sems.float(), deltas, weights_sum, depth, image,
+                                                         semantics)
                 step += n_step
                 i += 1
         depth = depth / direction_norms

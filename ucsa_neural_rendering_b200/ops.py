@@ -450,19 +450,25 @@ def composite_rays_train_backward(grad_ws, grad_image, grad_sem, sigmas, rgbs, d
 
 
 def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, local_semantics, deltas, n_classes, weights_sum,
-                   depth, image, semantics):
+                   depth, image, semantics, logits=None):
+    """logits: fp16 [M, ld] of the semantic head instead of probabilities (soft-max inside the kernel)"""
     check(lib().ucsa_composite_rays(n_alive, n_step, _ptr(rays_alive, torch.int32), _ptr(rays_t, torch.float32),
                                     _ptr(sigmas, torch.float32), _ptr(rgbs, torch.float32),
-                                    _ptr(local_semantics, torch.float32), _ptr(deltas, torch.float32), n_classes,
+                                    _ptr(local_semantics, torch.float32), _ptr(logits, torch.float16, "logits"),
+                                    0 if logits is None else logits.shape[-1], _ptr(deltas, torch.float32), n_classes,
                                     _ptr(weights_sum, torch.float32), _ptr(depth, torch.float32),
                                     _ptr(image, torch.float32), _ptr(semantics, torch.float32), _stream()),
           "composite_rays")
 
 
-def compact_rays(n_alive, rays_alive, rays_alive_old, rays_t, rays_t_old, alive_counter):
+def compact_rays(n_alive, rays_alive, rays_alive_old, rays_t, rays_t_old, alive_counter, scratch=None):
+    """scratch: optional int32 [ceil(n_alive / 1024)] for the many-CTA form (allocated here when the list is long)"""
+    if scratch is None and n_alive > 4096:
+        scratch = torch.empty((n_alive + 1023) // 1024, dtype=torch.int32, device=rays_alive.device)
     check(lib().ucsa_compact_rays(n_alive, _ptr(rays_alive, torch.int32), _ptr(rays_alive_old, torch.int32),
                                   _ptr(rays_t, torch.float32), _ptr(rays_t_old, torch.float32),
-                                  _ptr(alive_counter, torch.int32), _stream()), "compact_rays")
+                                  _ptr(alive_counter, torch.int32), _ptr(scratch, torch.int32), _stream()),
+          "compact_rays")
 
 
 def grid_update(density_grid, fresh, decay):
