@@ -9,8 +9,9 @@ synthetic ScanNet-shaped scene with 640x480 views.  One step = render (perturb=T
 backward + Adam, exactly the work of training_step_nerf (joint_train_lightning_net.py:473-513).
 
 `value`  : rays/s with every step's rays and ground truth already resident in HBM.
-`e2e`    : the same step through the public API with HOST (pinned) inputs: H2D copy of the step's rays + ground
-           truth and a D2H read of the loss inside the timed region.
+`e2e`    : the same step through the public drop-in API (SemanticNeRFNetwork.render + nerf_losses + backward +
+           FusedAdam.step in the caller's own loop) with HOST (pinned) inputs: H2D copy of the step's rays + ground
+           truth and a D2H read of the loss inside the timed region; `e2e.torch_adam` keeps the caller's optimizer.
 `roofline`: dominant kernel (by device time inside the timed region, CUDA events on the launch stream) against
            the measured HBM peak; algorithmic bytes = 588 B/sample x samples per launch.
 `cpu_baseline`: the CPU oracle port of the reference path (oracle/live_path.py), one full 4096-ray step, rank 0, N=1.
@@ -427,10 +428,17 @@ def run_ours(args):
     engine.gather_masters()
 
     # ---------------------------------------------------------------- e2e: public API, host buffers
-    opt = torch.optim.Adam([
-        {"name": "encoding", "params": list(net.encoder.parameters())},
-        {"name": "net", "params": list(net.sigma_net.parameters()) + list(net.color_net.parameters())
-         + list(net.semantics_net.parameters()), "weight_decay": 1e-6}], lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    def param_groups():
+        return [{"name": "encoding", "params": list(net.encoder.parameters())},
+                {"name": "net", "params": list(net.sigma_net.parameters()) + list(net.color_net.parameters())
+                 + list(net.semantics_net.parameters()), "weight_decay": 1e-6}]
+
+    # The drop-in configuration INTEGRATION.md describes: the network module and the optimizer class come from this
+    # package (two changed lines in the caller), everything else is the caller's loop: render(), the three losses,
+    # backward(), optimizer.step().  FusedAdam = torch.optim.Adam's numbers behind torch.optim's interface.
+    from ucsa_neural_rendering_b200.optim import FusedAdam
+
+    opt = FusedAdam(param_groups(), lr=1e-2, betas=(0.9, 0.99), eps=1e-15, network=net)
     for p_ in net.parameters():
         p_.grad = None
 
@@ -469,7 +477,12 @@ def run_ours(args):
     e2e_value = world * RAYS_PER_GPU * args.steps / (e2e_ms * 1e-3)
     assert bool(torch.isfinite(loss_host[args.warmup:]).all()) and float(loss_host[args.warmup:].abs().sum()) > 0
     e2e_blocking_ms = time_e2e(sync=True)
-    del opt
+    # the same loop with the caller's optimizer left untouched (torch.optim.Adam, ~10 foreach passes over the table)
+    for p_ in net.parameters():
+        p_.grad = None
+    opt = torch.optim.Adam(param_groups(), lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    e2e_torch_adam_ms = time_e2e(sync=False)
+    opt = None
     for p_ in net.parameters():
         p_.grad = None
 
@@ -712,8 +725,12 @@ def run_ours(args):
         "config": dict(CONFIG, parallelism=f"ray-sharded dp{world}"),
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps,
-                "api": "SemanticNeRFNetwork.render + nerf_losses + torch.optim.Adam (the drop-in API a Lightning "
-                       "loop calls), pinned host inputs, loss copied to pinned host memory every step (non-blocking)",
+                "api": "SemanticNeRFNetwork.render + nerf_losses + backward + FusedAdam.step (the drop-in modules of "
+                       "INTEGRATION.md inside the caller's own loop), pinned host inputs, loss copied to pinned host "
+                       "memory every step (non-blocking)",
+                "torch_adam": {"value": world * RAYS_PER_GPU * args.steps / (e2e_torch_adam_ms * 1e-3),
+                               "ms_per_step": e2e_torch_adam_ms / args.steps,
+                               "note": "same loop with the caller's torch.optim.Adam left in place"},
                 "blocking_readback": {"value": world * RAYS_PER_GPU * args.steps / (e2e_blocking_ms * 1e-3),
                                       "ms_per_step": e2e_blocking_ms / args.steps,
                                       "note": "same, with float(loss) (a host synchronisation) every step"},

@@ -295,12 +295,13 @@ UCSA_API int ucsa_mlp_bwd_simt(const void* x_h, uint32_t n, const void* w_h, con
  * betas are doubles: torch.optim.Adam forms 1 - beta, the bias corrections and the step size in Python doubles and
  * rounds once, and the kernel does the same so that it tracks torch to the last bits.  weight_decay applies to the
  * parameters with index >= wd_begin (a multiple of 4): one launch covers the "encoding" group (no decay) followed by
- * the "net" group of a flat parameter buffer. */
+ * the "net" group of a flat parameter buffer.  Gradients are multiplied by grad_scale_inv and, when grad_scale_dev
+ * is given (torch.amp.GradScaler keeps its scale on the device), by 1 / grad_scale_dev[0]. */
 UCSA_API int ucsa_cast_f32_to_f16(const float* src, uint64_t n, void* dst_h, void* stream);
 UCSA_API int ucsa_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_h,
                    uint64_t n, double lr, double beta1, double beta2, float eps, float weight_decay,
-                   uint64_t wd_begin, float grad_scale_inv, const float* found_inf, uint32_t step,
-                   const int32_t* step_dev, const int32_t* skipped_dev, void* stream);
+                   uint64_t wd_begin, float grad_scale_inv, const float* grad_scale_dev, const float* found_inf,
+                   uint32_t step, const int32_t* step_dev, const int32_t* skipped_dev, void* stream);
 /* GradScaler's overflow check (joint_train_lightning_net.py:46,509-513; torch.amp.GradScaler.unscale_ / step): one
  * pass over a gradient buffer.  found_inf[0] = 1 if any entry is inf / NaN else 0; when it is 1 and skipped_dev is
  * given, skipped_dev[0] += 1 (ucsa_adam_step / ucsa_adam_exchange then skip the update, and Adam's step count is

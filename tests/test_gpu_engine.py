@@ -235,3 +235,53 @@ def test_adam_step_matches_torch_adam_under_gradscaler():
         torch.testing.assert_close(our_m[i], st["exp_avg"], rtol=1e-6, atol=1e-12)
         torch.testing.assert_close(our_v[i], st["exp_avg_sq"], rtol=1e-6, atol=1e-20)
         assert torch.equal(our_h[i], our_p[i].half()), "fp16 working copy = rounded master"
+
+
+def test_fused_adam_optimizer_is_torch_adam_under_gradscaler():
+    """ucsa_neural_rendering_b200.optim.FusedAdam (torch.optim interface, `_step_supports_amp_scaling`) against
+    torch.optim.Adam, both driven by torch.amp.GradScaler exactly like training_step_nerf does
+    (joint_train_lightning_net.py:509-513): scale(loss).backward(); scaler.step(opt); scaler.update().  Eight steps on
+    the real network, one of them with a poisoned target (inf loss -> skipped by both)."""
+    import copy
+
+    from ucsa_neural_rendering_b200.optim import FusedAdam
+
+    net_a = _net()
+    net_b = copy.deepcopy(net_a)
+
+    def groups(net):
+        return [{"name": "encoding", "params": list(net.encoder.parameters())},
+                {"name": "net", "params": list(net.sigma_net.parameters()) + list(net.color_net.parameters())
+                 + list(net.semantics_net.parameters()), "weight_decay": 1e-6}]
+
+    opt_a = torch.optim.Adam(groups(net_a), lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    opt_b = FusedAdam(groups(net_b), lr=1e-2, betas=(0.9, 0.99), eps=1e-15, network=net_b)
+    scal_a, scal_b = torch.amp.GradScaler("cuda", init_scale=1024.0), torch.amp.GradScaler("cuda", init_scale=1024.0)
+    n = 128
+    o, d, dn, rgb, labels, depth = _batch(n, 40, 21)
+    for it in range(8):
+        target = rgb.float().clone()
+        if it == 3:
+            target[0, 0, 0] = float("inf")
+        # one backward pass (network A); network B receives the very same scaled gradients, so that only the optimizers
+        # differ (two backward passes would differ in the order of their atomics, which Adam with eps = 1e-15 amplifies)
+        opt_a.zero_grad()
+        with torch.autocast("cuda", enabled=True):
+            out = net_a.render(o, d, direction_norms=dn, perturb=True, num_steps=32, upsample_steps=32, seed=100 + it)
+            loss = ((out["image"] - target) ** 2).mean() + 0.1 * out["depth"].mean()
+        scal_a.scale(loss).backward()
+        scal_b.scale(torch.zeros(1, device=DEV))  # initialises scaler B like a scaled backward would
+        for pa, pb in zip(net_a.parameters(), net_b.parameters()):
+            pb.grad = pa.grad.clone()
+        scal_a.step(opt_a)
+        scal_a.update()
+        scal_b.step(opt_b)
+        scal_b.update()
+    assert float(scal_a.get_scale()) == float(scal_b.get_scale()) == 512.0  # both backed off once
+    assert int(opt_b.state[net_b.encoder.params]["step"]) == 7 == int(opt_a.state[net_a.encoder.params]["step"])
+    for (name, pa), (_, pb) in zip(net_a.named_parameters(), net_b.named_parameters()):
+        # same gradients, same operations in the same order: torch's own kernels may contract differently (fma)
+        torch.testing.assert_close(pb.detach(), pa.detach(), rtol=1e-6, atol=1e-8, msg=lambda m, name=name: f"{name}: {m}")
+    # the fp16 working copies follow the masters without a separate cast
+    for m in (net_b.encoder, net_b.sigma_net, net_b.color_net, net_b.semantics_net):
+        assert torch.equal(m.half_params(), m.params.detach().half())

@@ -56,18 +56,21 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             __half* __restrict__ p_h, uint64_t n, double lr, double b1, double b2, float eps, float wd,
-            uint64_t wd_begin, float ginv, const float* __restrict__ found_inf, int step,
-            const int32_t* __restrict__ step_dev, const int32_t* __restrict__ skipped_dev) {
+            uint64_t wd_begin, float ginv, const float* __restrict__ grad_scale_dev,
+            const float* __restrict__ found_inf, int step, const int32_t* __restrict__ step_dev,
+            const int32_t* __restrict__ skipped_dev) {
   if (found_inf != nullptr && *found_inf != 0.f) return;  // GradScaler: skip the step on overflow
-  __shared__ float bc[2];
+  __shared__ float bc[3];
   if (threadIdx.x == 0) {
     // step count on the device (CUDA-graph replay); skipped steps do not advance it (GradScaler.step + Adam)
     if (step_dev != nullptr) step = *step_dev - (skipped_dev != nullptr ? *skipped_dev : 0);
     adam_scalars(lr, b1, b2, step, &bc[0], &bc[1]);
+    // GradScaler hands its scale over as a device tensor: unscale by its reciprocal, formed like torch does (in double)
+    bc[2] = grad_scale_dev != nullptr ? ginv * static_cast<float>(1.0 / static_cast<double>(*grad_scale_dev)) : ginv;
   }
   __syncthreads();
   AdamCoef c{bc[0], static_cast<float>(b1), static_cast<float>(1.0 - b1), static_cast<float>(b2),
-             static_cast<float>(1.0 - b2), eps, wd, ginv, bc[1]};
+             static_cast<float>(1.0 - b2), eps, wd, bc[2], bc[1]};
   // grid-stride over float4 groups: a bounded number of CTAs, so the double-precision scalars above are formed a few
   // thousand times per launch instead of once per 1024 parameters
   const uint64_t n4 = n / 4;
@@ -280,8 +283,9 @@ extern "C" int ucsa_cast_f32_to_f16(const float* src, uint64_t n, void* dst_h, v
 
 extern "C" int ucsa_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_h,
                               uint64_t n, double lr, double beta1, double beta2, float eps, float weight_decay,
-                              uint64_t wd_begin, float grad_scale_inv, const float* found_inf, uint32_t step,
-                              const int32_t* step_dev, const int32_t* skipped_dev, void* stream) {
+                              uint64_t wd_begin, float grad_scale_inv, const float* grad_scale_dev,
+                              const float* found_inf, uint32_t step, const int32_t* step_dev,
+                              const int32_t* skipped_dev, void* stream) {
   UCSA_REQUIRE(param && grad && exp_avg && exp_avg_sq, "adam_step: null pointer");
   UCSA_REQUIRE(step >= 1 || step_dev != nullptr, "adam_step: step counts from 1");
   UCSA_REQUIRE(wd_begin % 4 == 0, "adam_step: wd_begin must be a multiple of 4 parameters");
@@ -294,8 +298,8 @@ extern "C" int ucsa_adam_step(float* param, const float* grad, float* exp_avg, f
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
   adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq,
                                                                static_cast<__half*>(param_h), n, lr, beta1, beta2,
-                                                               eps, weight_decay, wd_begin, grad_scale_inv, found_inf,
-                                                               static_cast<int>(step), step_dev, skipped_dev);
+                                                               eps, weight_decay, wd_begin, grad_scale_inv, grad_scale_dev,
+                                                               found_inf, static_cast<int>(step), step_dev, skipped_dev);
   return check_launch("adam_step");
 }
 

@@ -334,14 +334,15 @@ def cast_f32_to_f16(src, dst):
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, param_h, *, lr, beta1, beta2, eps, weight_decay, grad_scale_inv,
-              found_inf, step, step_dev=None, skipped_dev=None, wd_begin=0):
+              found_inf, step, step_dev=None, skipped_dev=None, wd_begin=0, grad_scale_dev=None):
     """torch.optim.Adam (L2 weight decay) with GradScaler semantics: gradients are multiplied by grad_scale_inv; when
     found_inf[0] != 0 nothing is written.  With step_dev, Adam's step count is step_dev[0] - skipped_dev[0].
     weight_decay applies to parameters with index >= wd_begin."""
     check(lib().ucsa_adam_step(_ptr(param, torch.float32), _ptr(grad, torch.float32), _ptr(exp_avg, torch.float32),
                                _ptr(exp_avg_sq, torch.float32), _ptr(param_h, torch.float16), param.numel(), float(lr),
                                float(beta1), float(beta2), float(eps), float(weight_decay), int(wd_begin),
-                               float(grad_scale_inv), _ptr(found_inf, torch.float32), int(step),
+                               float(grad_scale_inv), _ptr(grad_scale_dev, torch.float32, "grad_scale"),
+                               _ptr(found_inf, torch.float32), int(step),
                                _ptr(step_dev, torch.int32), _ptr(skipped_dev, torch.int32), _stream()), "adam_step")
 
 
