@@ -1084,6 +1084,11 @@ extern "C" int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32
     heads_fwd_color_ws_kernel<<<pairs < cap ? pairs : cap, kWsThreads, kFwdColorWsSmem, st>>>(
         sel, ray_off + n_rays, t, rays_d, static_cast<const __half*>(h), static_cast<const __half*>(w_color_h), w_sel,
         rgb, static_cast<__half*>(hc1), static_cast<__half*>(hc2), image);
+    auto sem_kernel = n_classes == 40 ? heads_fwd_sem_kernel<40> : heads_fwd_sem_kernel<0>;
+    sem_kernel<<<heads_grid(k_max, kFwdSemCtas), 128, kFwdSemSmem, st>>>(
+        sel, ray_off + n_rays, t, static_cast<const __half*>(h), static_cast<const __half*>(w_sem_h),
+        static_cast<int>(n_classes), w_sel, static_cast<__half*>(logits), static_cast<__half*>(hs), semantics);
+    return check_launch("heads_fwd");
   } else {
     // The two kernels run CONCURRENTLY: the semantic kernel goes to a helper stream forked from / joined to `st` with
     // events (capturable), and each kernel's persistent grid is sized so that both fit an SM at once (2 colour + 3
