@@ -625,12 +625,14 @@ def run_ours(args):
             occupancy = {"error": repr(exc)[:300]}
 
     # ---------------------------------------------------------------- extra: config 4's 2^16-ray global batch, strong scaling
-    strong = None
+    strong, sweep = None, None
     if not args.no_extras:
-        try:
-            n_strong = 65536 // world
-            del engine
-            torch.cuda.empty_cache()
+        del engine
+        torch.cuda.empty_cache()
+
+        def strong_scaling(global_rays):
+            """one engine with global_rays / world rays per GPU: a few timed steps"""
+            n_strong = global_rays // world
             eng2 = TrainEngine(net, n_strong, num_steps=NUM_STEPS, upsample_steps=UPSAMPLE_STEPS,
                                one_m_to_scene_uom=uom, use_graph=not args.no_graph, exchange=args.exchange)
             b2 = make_batches(3, n_strong)
@@ -638,12 +640,21 @@ def run_ours(args):
                 eng2.train_step(*b2[s])
             k2 = max(3, args.steps // 4)
             ms2 = time_engine_steps(eng2, b2, 0, k2)
-            strong = {"global_batch": n_strong * world, "rays_per_gpu": n_strong, "steps": k2, "ms_per_step": ms2 / k2,
-                      "rays_per_s": n_strong * world * k2 / (ms2 * 1e-3), "scaling": "strong"}
             eng2.gather_masters()
             del eng2
+            torch.cuda.empty_cache()
+            return {"global_batch": n_strong * world, "rays_per_gpu": n_strong, "steps": k2, "ms_per_step": ms2 / k2,
+                    "rays_per_s": n_strong * world * k2 / (ms2 * 1e-3), "scaling": "strong"}
+
+        try:
+            strong = strong_scaling(65536)  # BASELINE.json configs[3]: ray batch 2^16 sharded over the GPUs
         except Exception as exc:  # noqa: BLE001 - an extra must never take the headline down
             strong = {"error": repr(exc)[:300]}
+        if world >= 2:  # BASELINE.json configs[4]: 2^18-ray batches, ray-sharded at 2 / 4 / 8 GPUs
+            try:
+                sweep = strong_scaling(262144)
+            except Exception as exc:  # noqa: BLE001
+                sweep = {"error": repr(exc)[:300]}
 
     clock_info = clocks.stop(t_wall0, t_wall1)
     if rank != 0:
@@ -738,7 +749,8 @@ def run_ours(args):
                            "api": "TrainEngine.load_batch(pinned host) + step() + loss readback"}},
         "gpu_launches": launches, "gpu_launches_per_step": by_name,
         "step_impl": "cuda-graph replay of %d kernels" % per_step_launches if not args.no_graph else "eager kernel chain",
-        "render": render_info, "trained": trained, "strong_scaling_2p16": strong, "config1": config1,
+        "render": render_info, "trained": trained, "strong_scaling_2p16": strong, "strong_scaling_2p18": sweep,
+        "config1": config1,
         "stand_in": stand_in, "occupancy_path": occupancy,
         "gradient_exchange": {"none": "single GPU", "nccl": "NCCL all-reduce + replicated Adam",
                               "peer": "ucsa_adam_exchange over symmetric memory (%s)" % (
