@@ -1,0 +1,59 @@
+"""Host-side logic that needs no GPU: workspace caching of the autograd path, the optimizer's argument checks, the
+label palette, owner slices of the flat parameter space."""
+import gc
+
+import numpy as np
+import pytest
+import torch
+
+from ucsa_neural_rendering_b200 import pipeline
+from ucsa_neural_rendering_b200.labels import default_palette
+from ucsa_neural_rendering_b200.optim import FusedAdam
+
+
+class _Net(torch.nn.Module):
+    pass
+
+
+def test_cached_workspace_is_reused_only_when_its_backward_is_done():
+    net = _Net()
+    ws1, tok1 = pipeline.cached_workspace(net, 8, 128, 128, 40, torch.device("cpu"), True)
+    assert tok1 is not None and ws1.enc is not None and ws1.tiled
+    out1 = ws1.image
+    # the first call's autograd node (token) is still alive: a second call must get its own workspace
+    ws2, tok2 = pipeline.cached_workspace(net, 8, 128, 128, 40, torch.device("cpu"), True)
+    assert ws2 is not ws1 and ws2.h.data_ptr() != ws1.h.data_ptr()
+    del tok1
+    gc.collect()
+    # released: the cached one is handed out again, with FRESH output tensors (callers keep the old ones)
+    ws3, tok3 = pipeline.cached_workspace(net, 8, 128, 128, 40, torch.device("cpu"), True)
+    assert ws3 is ws1 and ws3.image.data_ptr() != out1.data_ptr()
+    # inference workspaces (no token) are always reusable and carry no saved-activation buffers
+    wi, ti = pipeline.cached_workspace(net, 8, 128, 128, 40, torch.device("cpu"), False)
+    wi2, _ = pipeline.cached_workspace(net, 8, 128, 128, 40, torch.device("cpu"), False)
+    assert ti is None and wi is wi2 and wi.enc is None
+    # other shapes get other workspaces; the cache is bounded per network
+    for n in range(9, 9 + 2 * pipeline._WS_CACHE_MAX):
+        pipeline.cached_workspace(net, n, 16, 16, 40, torch.device("cpu"), False)
+    assert len(pipeline._WS_CACHE[net]) <= pipeline._WS_CACHE_MAX
+    del tok2, tok3
+
+
+def test_fused_adam_checks_its_arguments_and_refuses_cpu_parameters():
+    p = torch.nn.Parameter(torch.zeros(8))
+    with pytest.raises(ValueError):
+        FusedAdam([p], lr=-1.0)
+    with pytest.raises(ValueError):
+        FusedAdam([p], betas=(1.0, 0.99))
+    opt = FusedAdam([{"params": [p]}, {"params": [], "weight_decay": 1e-6}], lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    assert FusedAdam._step_supports_amp_scaling and not hasattr(opt, "grad_scale")  # GradScaler's protocol
+    assert opt.step() is None  # no gradients yet: nothing to do
+    p.grad = torch.ones(8)
+    with pytest.raises(Exception):
+        opt.step()  # CPU parameter: the optimizer has no CPU path
+
+
+def test_default_palette():
+    pal = default_palette(41)
+    assert pal.shape == (41, 3) and pal.dtype == np.uint8 and (pal[0] == 0).all()
+    assert len({tuple(c) for c in pal.tolist()}) == 41  # all labels distinguishable
