@@ -123,31 +123,30 @@ weights_bwd_kernel(const float* __restrict__ z_cat, const float* __restrict__ si
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t n = blockIdx.x * kWarpsPerCta + wib;
   if (n >= n_rays) return;
-  float* zs = sm + static_cast<size_t>(wib) * 5 * t;
+  // Three staged arrays per ray (z, sigma, dL/dw) + one transmittance carry per 32-sample chunk: 6 KB per ray at
+  // T = 512, so that all 4096 rays of a training batch are resident in ONE wave (five arrays -- with the weights and
+  // the transmittances staged as well -- were 1.4 waves).  The weights are recomputed (alpha * T, the very operations
+  // of weights_fwd, hence the same bits) and the transmittance of a chunk is re-scanned from its stored carry.
+  const uint32_t n_chunks = (t + 31) / 32;
+  float* zs = sm + static_cast<size_t>(wib) * (3 * t + n_chunks);
   float* sg = zs + t;
-  float* tr = sg + t;  // transmittance in front of each sample
-  float* gw = tr + t;  // dL/dw (0 where masked out)
-  float* ws = gw + t;  // the weights, staged so that no global load sits on the scan's dependency chain
+  float* gw = sg + t;            // dL/dw (0 where masked out)
+  float* chunk_carry = gw + t;   // transmittance in front of each chunk
   const uint64_t row = static_cast<uint64_t>(n) * t;
   stage_sorted(z_cat, sigma, order, row, t, lane, zs, sg);
-#pragma unroll 4
-  for (uint32_t s = lane; s < t; s += 32) ws[s] = w_sorted[row + s];
-  __syncwarp();
 
   float carry = 1.0f;
   int out = ray_off[n];
   for (uint32_t base = 0; base < t; base += 32) {
     const uint32_t s = base + lane;
     const bool valid = s < t;
-    float keep_f = 1.0f;
-    if (valid) keep_f = sample_terms(zs, sg, s, t, density_scale).keep;
-    const float trans = chunk_transmittance(keep_f, carry, lane);
-    const bool keep = valid && ws[s] > kMaskThreshold;
+    SampleTerms st{1.f, 0.f, 1.f, 0.f};
+    if (valid) st = sample_terms(zs, sg, s, t, density_scale);
+    if (lane == 0) chunk_carry[base >> 5] = carry;
+    const float trans = chunk_transmittance(valid ? st.keep : 1.0f, carry, lane);
+    const bool keep = valid && st.alpha * trans > kMaskThreshold;  // = the weight weights_fwd stored
     const unsigned ballot = __ballot_sync(kFullMask, keep);
-    if (valid) {
-      tr[s] = trans;
-      gw[s] = __int_as_float(keep ? out + __popc(ballot & ((1u << lane) - 1u)) : -1);  // compact row, for now
-    }
+    if (valid) gw[s] = __int_as_float(keep ? out + __popc(ballot & ((1u << lane) - 1u)) : -1);  // compact row, for now
     out += __popc(ballot);
   }
   __syncwarp();
@@ -158,17 +157,19 @@ weights_bwd_kernel(const float* __restrict__ z_cat, const float* __restrict__ si
   }
   __syncwarp();
   float suffix_carry = 0.f;
-  const uint32_t n_chunks = (t + 31) / 32;
   for (uint32_t c = n_chunks; c-- > 0;) {
     const uint32_t s = c * 32 + lane;
     const bool valid = s < t;
+    SampleTerms st{1.f, 0.f, 1.f, 0.f};
+    if (valid) st = sample_terms(zs, sg, s, t, density_scale);
+    float carry_c = chunk_carry[c];
+    const float trans = chunk_transmittance(valid ? st.keep : 1.0f, carry_c, lane);
     const float g = valid ? gw[s] : 0.f;
-    const float w = valid ? ws[s] : 0.f;
+    const float w = valid ? st.alpha * trans : 0.f;
     const float suffix = chunk_suffix(g * w, suffix_carry, lane);
     if (valid) {
-      const SampleTerms st = sample_terms(zs, sg, s, t, density_scale);
       const uint32_t slot = order != nullptr ? static_cast<uint32_t>(order[row + s]) : s;
-      d_sigma[row + slot] = sigma_grad(st, density_scale, g, tr[s], suffix);
+      d_sigma[row + slot] = sigma_grad(st, density_scale, g, trans, suffix);
     }
   }
 }
@@ -226,7 +227,7 @@ extern "C" int ucsa_weights_bwd(const float* z_cat, const float* sigma, const in
                                 uint32_t n_rays, uint32_t t, float density_scale, float* d_sigma, void* stream) {
   UCSA_REQUIRE(z_cat && sigma && w_sorted && ray_off && d_w_sel && d_sigma, "weights_bwd: null pointer");
   if (n_rays == 0) return UCSA_OK;
-  const size_t smem = static_cast<size_t>(kWarpsPerCta) * 5 * t * sizeof(float);
+  const size_t smem = static_cast<size_t>(kWarpsPerCta) * (3 * t + (t + 31) / 32) * sizeof(float);
   if (int rc = set_smem(reinterpret_cast<const void*>(weights_bwd_kernel), smem)) return rc;
   weights_bwd_kernel<<<ceil_div(n_rays, kWarpsPerCta), 32 * kWarpsPerCta, smem, as_stream(stream)>>>(
       z_cat, sigma, order, w_sorted, ray_off, d_w_sel, n_rays, t, density_scale, d_sigma);
