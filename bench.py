@@ -369,8 +369,7 @@ def run_ours(args):
 
     # per-kernel device time: the same steps once more, launched eagerly with CUDA events around the kernels
     timed = {"ucsa_density_fwd", "ucsa_density_bwd", "ucsa_heads_fwd", "ucsa_heads_bwd", "ucsa_adam_step",
-             "ucsa_adam_exchange", "ucsa_resample_merge", "ucsa_grad_check", "ucsa_weights_fwd", "ucsa_weights_bwd",
-             "ucsa_compact_masked"}
+             "ucsa_adam_exchange", "ucsa_resample_merge", "ucsa_grad_check", "ucsa_weights_compact", "ucsa_weights_bwd"}
     was_graph, engine.use_graph = engine.use_graph, False
     engine.train_step(*batches[0])
     torch.cuda.synchronize()

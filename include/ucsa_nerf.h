@@ -131,6 +131,17 @@ UCSA_API int ucsa_scan_counts(const int32_t* ray_count, uint32_t n_rays, int32_t
 UCSA_API int ucsa_compact_masked(const float* w_sorted, const float* z_cat, const int32_t* order, const int32_t* ray_off,
                         uint32_t n_rays, uint32_t t, int32_t* sel, float* w_sel, float* z_sel, void* stream);
 
+/* The three calls above as ONE launch (what the render pipeline uses): weights, masks and depth per ray, the global
+ * offsets by a decoupled look-back scan over the CTAs, and the compaction written from the weights still held in shared
+ * memory.  Same outputs bit for bit (w_sorted, depth, use_geo, ray_off [N+1], sel / w_sel / z_sel [K]).
+ * scratch: UCSA_WEIGHTS_SCRATCH_WORDS(n_rays) 32-bit words, 8-byte aligned, ZERO before the first call; the kernel
+ * leaves it zeroed, so one block serves every later call on the same stream (one block per concurrent stream). */
+#define UCSA_WEIGHTS_SCRATCH_WORDS(n_rays) (2u + 2u * (((n_rays) + 3u) / 4u))
+UCSA_API int ucsa_weights_compact(const float* z_cat, const float* sigma, const int32_t* order,
+                         const float* direction_norms, uint32_t n_rays, uint32_t t, float density_scale,
+                         float* w_sorted, float* depth, int32_t* ray_off, uint8_t* use_geo, int32_t* sel, float* w_sel,
+                         float* z_sel, uint32_t* scratch, void* stream);
+
 /* ---- a7/a12/a13 (+a14 fused). colour + semantic heads on the K masked-in rows (network_tcnn_semantics.py:147-207)
  * (two kernels: colour, then semantics) and, when image/semantics are non-null, the compositing of
  * renderer_semantics.py:279-285 fused into them:

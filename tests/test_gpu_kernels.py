@@ -32,6 +32,52 @@ def _rays(n, seed, outside=0):
     return o, d
 
 
+# ----------------------------------------------------------------------------------------------- a11
+@pytest.mark.parametrize("n,t,with_order", [(1, 7, False), (6, 33, True), (4096, 512, True), (70001, 64, True)],
+                         ids=["one-ray", "ragged", "config2", "more-ctas-than-resident"])
+def test_weights_compact_single_pass_equals_three_kernel_chain(ops, n, t, with_order):
+    """ucsa_weights_compact (weights + decoupled look-back scan + compaction in one launch) against the three
+    stand-alone kernels it replaces in the pipeline: every output bit for bit, twice in a row on the same scratch block
+    (the kernel re-arms it), and against torch for the scan itself."""
+    g = torch.Generator().manual_seed(n + t)
+    z = torch.sort(torch.rand(n, t, generator=g) * 5 + 0.1, dim=1).values
+    sigma = torch.rand(n, t, generator=g) ** 4 * 30
+    if n > 1:
+        sigma[n // 2] = 0  # a ray without any masked-in sample
+    order = None
+    if with_order:  # cat buffer in a scrambled slot order, `order` = sorted position -> slot
+        perm = torch.argsort(torch.rand(n, t, generator=g), dim=1)
+        z_cat, sig_cat = torch.empty_like(z), torch.empty_like(sigma)
+        z_cat.scatter_(1, perm, z)
+        sig_cat.scatter_(1, perm, sigma)
+        z, sigma, order = z_cat, sig_cat, perm.int().to(DEV)
+    z, sigma = z.to(DEV).contiguous(), sigma.to(DEV).contiguous()
+    dn = (1 + 0.3 * torch.rand(n, generator=g)).to(DEV)
+    f32, i32 = dict(dtype=torch.float32, device=DEV), dict(dtype=torch.int32, device=DEV)
+
+    def outputs():
+        return dict(w=torch.empty(n, t, **f32), depth=torch.empty(n, **f32), off=torch.empty(n + 1, **i32),
+                    use=torch.empty(n, t, dtype=torch.uint8, device=DEV), sel=torch.full((n * t,), -1, **i32),
+                    w_sel=torch.full((n * t,), -1.0, **f32), z_sel=torch.full((n * t,), -1.0, **f32))
+
+    a = outputs()
+    cnt = torch.empty(n, **i32)
+    ops.weights_fwd(z, sigma, order, dn, 1.0, a["w"], a["depth"], cnt, a["use"])
+    ops.scan_counts(cnt, a["off"])
+    ops.compact_masked(a["w"], z, order, a["off"], a["sel"], a["w_sel"], a["z_sel"])
+    assert torch.equal(a["off"][1:].long(), torch.cumsum(cnt.long(), 0)) and int(a["off"][0]) == 0
+    scratch = ops.weights_scratch(n, DEV)
+    for _ in range(2):
+        b = outputs()
+        ops.weights_compact(z, sigma, order, dn, 1.0, b["w"], b["depth"], b["off"], b["use"], b["sel"], b["w_sel"],
+                            b["z_sel"], scratch)
+        for key in a:
+            assert torch.equal(a[key], b[key]), key
+        assert int(scratch.abs().sum()) == 0  # re-armed
+    k = int(a["off"][-1])
+    assert 0 < k < n * t and (n == 1 or int(cnt[n // 2]) == 0)
+
+
 # ----------------------------------------------------------------------------------------------- a2
 def test_near_far_bit_exact(ops):
     o, d = _rays(5000, 1, outside=7)

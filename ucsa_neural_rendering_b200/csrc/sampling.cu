@@ -75,8 +75,9 @@ __global__ void sample_coarse_kernel(const float* __restrict__ nears, const floa
 
 // ---------------------------------------------------------------- a9/a10: renderer_semantics.py:182-222
 // One WARP per ray, several rays per CTA and no CTA-wide barrier; the cumulative product / sums are warp scans.
-// Shared memory per warp:
-// zc[Tc] sg[Tc] wt[Tc] cdf[Tc] zn[Tf] zs[Tf] bucket[Tf] member[Tf] (4-byte words), padded to 16 bytes.
+// Shared memory per warp: zc[Tc] sg[Tc] wt[Tc] (the cdf is formed in place over wt) zn[Tf] zs[Tf] (4-byte words) and
+// bucket[Tf] member[Tf] (16-bit: Tc, Tf <= 4096), padded to 16 bytes: 6 KB per ray at 256 + 256 samples, so that the
+// 28 rays an SM receives of a 4096-ray batch are resident at once (at 8 KB per ray the batch took 1.15 waves).
 __global__ void __launch_bounds__(256)
 resample_merge_kernel(const float* __restrict__ sigma, float* __restrict__ z_cat, const float* __restrict__ u,
                       uint64_t seed, const int32_t* __restrict__ step_dev, uint32_t ray_base, uint32_t tc, uint32_t tf,
@@ -89,18 +90,31 @@ resample_merge_kernel(const float* __restrict__ sigma, float* __restrict__ z_cat
   float* zc = sm;
   float* sg = zc + tc;
   float* wt = sg + tc;
-  float* cdf = wt + tc;
-  float* zn = cdf + tc;
+  float* cdf = wt;  // cdf[k] replaces wt[k] (same lane, same iteration)
+  float* zn = wt + tc;
   float* zs = zn + tf;
-  int* bucket = reinterpret_cast<int*>(zs + tf);  // coarse interval of every fine sample
-  int* member = bucket + tf;                      // fine samples grouped by bucket
+  uint16_t* bucket = reinterpret_cast<uint16_t*>(zs + tf);  // coarse interval of every fine sample
+  uint16_t* member = bucket + tf;                           // fine samples grouped by bucket
   const uint32_t t = tc + tf;
   const uint64_t row = static_cast<uint64_t>(n) * t;
   const int tid = threadIdx.x & 31, nt = 32;
 
-  for (uint32_t k = tid; k < tc; k += nt) {
-    zc[k] = z_cat[row + k];
-    sg[k] = sigma[row + k];
+  for (uint32_t k0 = tid; k0 < tc; k0 += 8 * nt) {  // eight chunks of loads in flight per lane
+    float zv[8], sv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t k = k0 + i * nt;
+      zv[i] = k < tc ? z_cat[row + k] : 0.f;
+      sv[i] = k < tc ? sigma[row + k] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t k = k0 + i * nt;
+      if (k < tc) {
+        zc[k] = zv[i];
+        sg[k] = sv[i];
+      }
+    }
   }
   __syncwarp();
   // coarse weights w_k = alpha_k * prod_{j<k} (1 - alpha_j + 1e-15) by a multiplicative warp scan over chunks of 32
@@ -173,7 +187,7 @@ resample_merge_kernel(const float* __restrict__ sigma, float* __restrict__ z_cat
       const uint32_t mid = (lo + hi) >> 1;
       if (zc[mid] <= v) lo = mid + 1; else hi = mid;
     }
-    bucket[j] = static_cast<int>(lo);
+    bucket[j] = static_cast<uint16_t>(lo);
     atomicAdd(&cnt[lo], 1);
   }
   __syncwarp();
@@ -195,7 +209,7 @@ resample_merge_kernel(const float* __restrict__ sigma, float* __restrict__ z_cat
     }
   }
   __syncwarp();
-  for (uint32_t j = tid; j < tf; j += nt) member[atomicAdd(&cnt[bucket[j]], 1)] = static_cast<int>(j);
+  for (uint32_t j = tid; j < tf; j += nt) member[atomicAdd(&cnt[bucket[j]], 1)] = static_cast<uint16_t>(j);
   __syncwarp();  // now cnt[b] = end of bucket b = start of bucket b + 1
   for (uint32_t j = tid; j < tf; j += nt) {
     const float v = zn[j];
@@ -270,9 +284,9 @@ extern "C" int ucsa_resample_merge(const float* sigma, float* z_cat, const float
   UCSA_REQUIRE(sigma && z_cat && order, "resample_merge: null pointer");
   UCSA_REQUIRE(tc >= 3 && tf >= 1 && tc <= 4096 && tf <= 4096, "resample_merge: need 3 <= Tc <= 4096, 1 <= Tf <= 4096");
   if (n_rays == 0) return UCSA_OK;
-  const uint32_t warp_floats = (4u * tc + 4u * tf + 3u) & ~3u;
+  const uint32_t warp_floats = (3u * tc + 3u * tf + 3u) & ~3u;
   const size_t warp_bytes = warp_floats * sizeof(float);
-  uint32_t warps = static_cast<uint32_t>((32u * 1024u) / warp_bytes);  // rays per CTA (one wave at 4096 rays)
+  uint32_t warps = static_cast<uint32_t>((24u * 1024u) / warp_bytes);  // rays per CTA: 4 at 256 + 256 samples
   warps = warps > 8 ? 8 : (warps < 1 ? 1 : warps);
   const size_t smem = warps * warp_bytes;
   if (smem > 48 * 1024)  // size depends on the call: set every time (per device, checked)

@@ -170,6 +170,25 @@ def weights_fwd(z_cat, sigma, order, direction_norms, density_scale, w_sorted, d
                                  _ptr(use_geo, torch.uint8), _stream()), "weights_fwd")
 
 
+def weights_scratch(n_rays, device):
+    """Zero-filled scratch block of ucsa_weights_compact (the kernel leaves it zeroed)."""
+    return torch.zeros(2 + 2 * ((n_rays + 3) // 4), dtype=torch.int32, device=device)
+
+
+def weights_compact(z_cat, sigma, order, direction_norms, density_scale, w_sorted, depth, ray_off, use_geo, sel, w_sel,
+                    z_sel, scratch):
+    """weights_fwd + scan_counts + compact_masked in one launch (decoupled look-back scan over the rays)."""
+    n, t = z_cat.shape
+    if scratch.numel() < 2 + 2 * ((n + 3) // 4):
+        raise ValueError("weights_compact: scratch block too small for this ray count")
+    check(lib().ucsa_weights_compact(_ptr(z_cat, torch.float32), _ptr(sigma, torch.float32), _ptr(order, torch.int32),
+                                     _ptr(direction_norms, torch.float32), n, t, float(density_scale),
+                                     _ptr(w_sorted, torch.float32), _ptr(depth, torch.float32),
+                                     _ptr(ray_off, torch.int32), _ptr(use_geo, torch.uint8), _ptr(sel, torch.int32),
+                                     _ptr(w_sel, torch.float32), _ptr(z_sel, torch.float32),
+                                     _ptr(scratch, torch.int32), _stream()), "weights_compact")
+
+
 def scan_counts(ray_count, ray_off):
     check(lib().ucsa_scan_counts(_ptr(ray_count, torch.int32), ray_count.shape[0], _ptr(ray_off, torch.int32),
                                  _stream()), "scan_counts")

@@ -37,7 +37,7 @@ class RenderWorkspace:
         self.h = torch.empty(n, t, 16, **f16)
         self.order = torch.empty(n, t, **i32) if tf > 0 else None
         self.w_sorted = torch.empty(n, t, **f32)
-        self.ray_count = torch.empty(n, **i32)
+        self.scan_scratch = ops.weights_scratch(n, device)
         self.use_geo = torch.empty(n, t, dtype=torch.uint8, device=device)
         self.ray_off = torch.empty(n + 1, **i32)
         self.sel = torch.empty(self.k_max, **i32)
@@ -118,10 +118,8 @@ def forward_chain(net, ws, rays_o, rays_d, dnorm, aabb, *, perturb, t_rand=None,
         ops.resample_merge(ws.sigma, ws.z_cat, ws.order, tc, tf, net.density_scale, u=u, seed=seed, ray_base=ray_base,
                            step_dev=step_dev)
         ops.density_fwd(grid, table_h, w_sig, net.bound, k0=tc, k1=t, **common)
-    ops.weights_fwd(ws.z_cat, ws.sigma, ws.order, dnorm, net.density_scale, ws.w_sorted, ws.depth, ws.ray_count,
-                    ws.use_geo)
-    ops.scan_counts(ws.ray_count, ws.ray_off)
-    ops.compact_masked(ws.w_sorted, ws.z_cat, ws.order, ws.ray_off, ws.sel, ws.w_sel, ws.z_sel)
+    ops.weights_compact(ws.z_cat, ws.sigma, ws.order, dnorm, net.density_scale, ws.w_sorted, ws.depth, ws.ray_off,
+                        ws.use_geo, ws.sel, ws.w_sel, ws.z_sel, ws.scan_scratch)
     ws.image.zero_()
     ws.semantics.zero_()
     ops.heads_fwd(ws.sel, ws.ray_off, n, t, ws.k_max, rays_d, ws.h, net.color_net.half_params(),
