@@ -92,6 +92,12 @@ def test_infer_staged_golden(golden_dir):
         out2 = net.render(_t(g["rays_o"]).to(DEV), _t(g["rays_d"]).to(DEV), **args)
     for k in out:
         torch.testing.assert_close(out2[k], out[k], rtol=1e-5, atol=1e-6)
+    # inference must not allocate (or write) the activations a backward pass would need: torch reports
+    # needs_input_grad = True under no_grad as well, the grad mode has to reach the fused node explicitly
+    from ucsa_neural_rendering_b200 import pipeline
+
+    cached = pipeline._WS_CACHE[net]
+    assert cached and all(not ws.need_grad and ws.enc is None and ws.hc1 is None for ws in cached.values())
 
 
 def test_fused_equals_generic_path_at_reference_sizes():

@@ -1097,17 +1097,20 @@ extern "C" int ucsa_heads_fwd(const int32_t* sel, const int32_t* ray_off, uint32
     // they take 0.275 ms instead of 0.316 ms one after the other (bench.py, config 2; (2,4) 0.279, (3,3) 0.283,
     // (2,2) 0.348).  UCSA_FWD_OVERLAP=0 restores the sequential launch; UCSA_FWD_COLOR_CTAS / UCSA_FWD_SEM_CTAS
     // override the grid sizes (bring-up knobs).
-    static int overlap = -1, color_ctas = 0, sem_ctas = 0;
+    // Without saved activations (inference) the colour kernel is latency-bound like the semantic one and wants a third
+    // CTA: full-frame rendering 50.6 ms per 640x480 view with (3,3) against 56.0 with (2,3) and 54.5 one after the
+    // other (scripts/render_probe.py).
+    static int overlap = -1, color_ctas_env = 0, sem_ctas = 0;
     if (overlap < 0) {
       std::lock_guard<std::mutex> lock(g_side_mutex);
       const char* e = getenv("UCSA_FWD_OVERLAP");
       const int ov = (e != nullptr && e[0] == '0') ? 0 : 1;
-      color_ctas = ov ? 2 : kFwdColorCtas;
       sem_ctas = ov ? 3 : kFwdSemCtas;
-      if (const char* c = getenv("UCSA_FWD_COLOR_CTAS")) color_ctas = atoi(c) >= 1 && atoi(c) <= 5 ? atoi(c) : color_ctas;
+      if (const char* c = getenv("UCSA_FWD_COLOR_CTAS")) color_ctas_env = atoi(c) >= 1 && atoi(c) <= 5 ? atoi(c) : 0;
       if (const char* c = getenv("UCSA_FWD_SEM_CTAS")) sem_ctas = atoi(c) >= 1 && atoi(c) <= 5 ? atoi(c) : sem_ctas;
       overlap = ov;
     }
+    const int color_ctas = color_ctas_env ? color_ctas_env : (!overlap ? kFwdColorCtas : (hc1 != nullptr ? 2 : 3));
     cudaStream_t st_sem = st;
     int dev = 0;
     if (overlap) {

@@ -377,7 +377,8 @@ class SemanticNeRFRenderer(nn.Module):
             # keyed by ray index) may ask for larger chunks when no graph is recorded (self.stage_chunk)
             stage_chunk = getattr(self, "stage_chunk", None)
             if stage_chunk and not torch.is_grad_enabled():
-                max_ray_batch = max(int(max_ray_batch), int(stage_chunk))
+                cap = max(int(max_ray_batch), int(stage_chunk))
+                max_ray_batch = -(-N // -(-N // cap)) if N > 0 else cap  # equal parts: one workspace shape, no ragged tail
             for b in range(B):
                 head = 0
                 while head < N:
