@@ -169,3 +169,47 @@ def test_oracle_reproduces_the_unmodified_lightning_step(golden_dir):
                                atol=1e-6)
     label_u8, _ = frontend.label_epilogue(full["semantics"][0].numpy(), full["image"][0].numpy())
     assert (label_u8.reshape(h, w).astype(np.int64) - 1 == g["nerf_semantics"][0]).mean() > 0.999
+
+
+def test_sh4_spec_is_the_published_real_spherical_harmonics():
+    """Row a7 has no tcnn build to pin against; what CAN be pinned independently is the mathematics: the 16 polynomials of
+    oracle/tcnn_spec.sh4_forward (network_tcnn_semantics.py:64-70: SphericalHarmonics, degree 4) must be the real
+    spherical harmonics of degree 0..3 in the order l^2 + l + m with the Condon-Shortley phase kept, evaluated here from
+    scipy's COMPLEX harmonics (sqrt(2) Re Y_l^m for m > 0, sqrt(2) Im Y_l^|m| for m < 0), not from polynomial constants."""
+    from scipy.special import sph_harm_y
+
+    rng = np.random.default_rng(0)
+    d = rng.normal(size=(2000, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    theta, phi = np.arccos(np.clip(d[:, 2], -1, 1)), np.arctan2(d[:, 1], d[:, 0])
+    cols = []
+    for l in range(4):
+        for m in range(-l, l + 1):
+            y = sph_harm_y(l, abs(m), theta, phi)
+            cols.append(y.real if m == 0 else np.sqrt(2) * (y.real if m > 0 else y.imag))
+    want = np.stack(cols, axis=1)
+    got = spec.sh4_forward(_t(((d + 1) / 2).astype(np.float32))).numpy()
+    # fp16 output: half an ulp of values up to ~0.75, plus the fp32 rounding of (d + 1) / 2 -> 2 x - 1
+    np.testing.assert_allclose(got, want, rtol=0, atol=2.6e-4)
+
+
+def test_mlp_spec_against_plain_half_precision_linear_layers():
+    """Row a6: tcnn_spec.mlp_forward (weights [out, in] per layer, fp32 accumulate, ReLU, fp16 between layers, constant-1
+    padding column) written a second time with torch.nn.functional.linear on float64 copies of the fp16 operands."""
+    g = torch.Generator().manual_seed(5)
+    dims, n_in, n_out = (32, 64, 64, 16), 31, 3
+    n_par = sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+    params = (torch.rand(n_par, generator=g) - 0.5) * 0.5
+    x = (torch.randn(257, n_in, generator=g)).half().float()
+    got = spec.mlp_forward(x, params, dims, n_in, n_out)
+    h = torch.cat([x, torch.ones(257, 1)], dim=1).double()
+    off = 0
+    for i, (fi, fo) in enumerate(zip(dims[:-1], dims[1:])):
+        w = params[off:off + fi * fo].half().double().view(fo, fi)
+        off += fi * fo
+        h = torch.nn.functional.linear(h, w)
+        if i < len(dims) - 2:
+            h = torch.relu(h)
+        h = h.float().half().double()
+    # the float64 product rounds once; the fp32 accumulation of the spec may land on the neighbouring fp16 value
+    np.testing.assert_allclose(got.numpy(), h[:, :n_out].float().numpy(), rtol=2e-3, atol=1e-4)

@@ -9,6 +9,7 @@ from __future__ import annotations
 import concurrent.futures as cf
 import hashlib
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -39,10 +40,32 @@ def _sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _stamp() -> str:
+_INCLUDE = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
+
+
+def _closure(path: str, seen: set) -> None:
+    """path and every file it includes with quotes (searched next to it, then in include/)."""
+    if path in seen:
+        return
+    seen.add(path)
+    with open(path, "r", errors="replace") as fh:
+        text = fh.read()
+    for name in _INCLUDE.findall(text):
+        for base in (os.path.dirname(path), INCLUDE_DIR):
+            cand = os.path.normpath(os.path.join(base, name))
+            if os.path.exists(cand):
+                _closure(cand, seen)
+                break
+
+
+def _source_stamp(src: str) -> str:
+    """Hash of the flags, the source and its include closure: an object is rebuilt only when one of those changed."""
     h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
-    inc = os.path.join(os.path.dirname(PKG_DIR), "include", "ucsa_nerf.h")
-    for path in [inc] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]:
+    deps: set = set()
+    _closure(os.path.join(CSRC, src), deps)
+    for path in sorted(deps):
+        h.update(path.encode())
         with open(path, "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()
@@ -50,17 +73,31 @@ def _stamp() -> str:
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
-    stamp_file = os.path.join(OBJ_DIR, "stamp")
-    stamp = _stamp()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp_file):
-        with open(stamp_file) as fh:
-            if fh.read().strip() == stamp:
+    sources = _sources()
+    stamps = {src: _source_stamp(src) for src in sources}
+
+    def stamp_path(src):
+        return os.path.join(OBJ_DIR, src[:-3] + ".stamp")
+
+    def fresh(src):
+        obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
+        if force or not os.path.exists(obj) or not os.path.exists(stamp_path(src)):
+            return False
+        with open(stamp_path(src)) as fh:
+            return fh.read().strip() == stamps[src]
+
+    stale = [src for src in sources if not fresh(src)]
+    lib_stamp_file = os.path.join(OBJ_DIR, "stamp")
+    lib_stamp = hashlib.sha256("".join(stamps[s] for s in sources).encode()).hexdigest()
+    if not stale and os.path.exists(LIB_PATH) and os.path.exists(lib_stamp_file):
+        with open(lib_stamp_file) as fh:
+            if fh.read().strip() == lib_stamp:
                 return LIB_PATH
     nvcc = _nvcc()
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE_DIR, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         res = subprocess.run(cmd, capture_output=True, text=True)
@@ -68,16 +105,19 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{res.stdout}\n{res.stderr}")
         if verbose:
             sys.stderr.write(res.stderr)
+        with open(stamp_path(src), "w") as fh:
+            fh.write(stamps[src])
         return obj
 
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
-        objs = list(pool.map(compile_one, _sources()))
+        list(pool.map(compile_one, stale))
+    objs = [os.path.join(OBJ_DIR, src[:-3] + ".o") for src in sources]
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs, "-lcudart"]
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
-    with open(stamp_file, "w") as fh:
-        fh.write(stamp)
+    with open(lib_stamp_file, "w") as fh:
+        fh.write(lib_stamp)
     return LIB_PATH
 
 
