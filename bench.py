@@ -605,6 +605,9 @@ def run_ours(args):
 
             ms_train = timed_ms(occ_train, 5)
             samples = int(occ_net.step_counter[(occ_net.local_step - 1) % 16, 0])
+            occ_net.fused_packed = False  # the module-by-module heads under autograd, for comparison
+            ms_train_modules = timed_ms(occ_train, 5)
+            occ_net.fused_packed = True
             occ_net.eval()
             with torch.no_grad():
                 vo, vd, vdn = scene.rays(0, torch.arange(scene.W * scene.H, device=dev))
@@ -615,9 +618,11 @@ def run_ours(args):
                          "occupied_fraction": float((occ_net.density_grid > min(0.01, occ_net.mean_density)).float().mean()),
                          "train_render_fwd_bwd_ms": ms_train, "train_rays": RAYS_PER_GPU, "train_samples": samples,
                          "train_rays_per_s": RAYS_PER_GPU / (ms_train * 1e-3),
+                         "train_render_fwd_bwd_ms_module_level_heads": ms_train_modules,
                          "infer_view_ms": ms_view, "infer_rays_per_s": scene.W * scene.H / (ms_view * 1e-3),
-                         "note": "module-level (eager) heads between the marching / compositing kernels; forward + "
-                                 "backward of the training render, no optimizer"}
+                         "note": "training render = march + fused heads node (density kernel + tensor-core heads "
+                                 "kernels each way) + ragged composite, forward + backward, no optimizer; "
+                                 "module_level_heads = the same with the nine module-level launches under autograd"}
             del occ_net
             torch.cuda.empty_cache()
         except Exception as exc:  # noqa: BLE001 - an extra must never take the headline down

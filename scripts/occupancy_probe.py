@@ -19,12 +19,26 @@ if __name__ == "__main__":
     g = torch.Generator(device=dev).manual_seed(1)
     pix = torch.randint(0, scene.W * scene.H, (4096,), device=dev, generator=g)
     o, d, dn = scene.rays(0, pix)
-    for it in range(2):
-        net.update_extra_state()
+    def train_render():
+        net.zero_grad(set_to_none=True)
         out = net.render(o[None], d[None], direction_norms=dn.view(1, -1, 1), staged=False, perturb=True, dt_gamma=1 / 128,
                          force_all_rays=True)
         (out["image"].sum() + out["semantics"].sum()).backward()
-    torch.cuda.synchronize()
+
+    for fused in (True, False):
+        net.fused_packed = fused
+        net.update_extra_state()
+        train_render()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            train_render()
+        e1.record()
+        torch.cuda.synchronize()
+        print("training render forward + backward,", "fused heads node" if fused else "module-level heads",
+              f"{e0.elapsed_time(e1) / 5:.3f} ms")
+    net.fused_packed = True
     print("samples", int(net.step_counter[(net.local_step - 1) % 16, 0]), "mean density", net.mean_density)
     net.eval()
     with torch.no_grad():

@@ -341,6 +341,73 @@ def test_run_cuda_end_to_end():
     torch.testing.assert_close(out2["semantics"], out["semantics"].detach(), rtol=5e-3, atol=5e-3)
 
 
+@pytest.mark.parametrize("m", [1000, 4096 + 128])
+def test_fused_packed_training_heads_match_the_module_level_forward(m):
+    """The training render of run_cuda evaluates the network on a packed stream of points.  forward_packed_train does it
+    as one fused autograd node (density kernel + tensor-core heads kernels each way, per-row gradients fed through the
+    fused compositing backward with unit weights); it must agree with the module-by-module forward(x, d) of
+    network_tcnn_semantics.py:102-128 -- outputs and all four parameter gradients."""
+    from ucsa_neural_rendering_b200.nerf import SemanticNeRFNetwork
+
+    net = SemanticNeRFNetwork(encoding="hashgrid", bound=4, cuda_ray=True, density_scale=1,
+                              num_semantic_classes=40).to(DEV).train()
+    with torch.no_grad():
+        net.encoder.params.uniform_(-0.5, 0.5)
+    g = torch.Generator().manual_seed(m)
+    x = ((torch.rand(m, 3, generator=g) - 0.5) * 7.9).to(DEV)
+    d = torch.nn.functional.normalize(torch.randn(m, 3, generator=g), dim=-1).to(DEV)
+    a, b, e = (torch.randn(m, generator=g).to(DEV), torch.randn(m, 3, generator=g).to(DEV),
+               torch.randn(m, 40, generator=g).to(DEV))
+    results = []
+    for fused in (False, True):
+        net.fused_packed = fused
+        net.zero_grad(set_to_none=True)
+        sigma, rgb, prob = net.forward_packed_train(x, d)
+        assert sigma.dtype == rgb.dtype == prob.dtype == torch.float32
+        ((sigma.clamp(max=50.0) * a).sum() + (rgb * b).sum() + (prob * e).sum()).backward()
+        results.append(([sigma.detach(), rgb.detach(), prob.detach()],
+                        [p.grad.detach().clone() for p in (net.encoder.params, net.sigma_net.params,
+                                                           net.color_net.params, net.semantics_net.params)]))
+    (out_m, grad_m), (out_f, grad_f) = results
+    # sigma = exp(h0) of an fp16 h0 with |h0| up to ~16: two fp16 ulps of h0 are 0.03 in log sigma
+    torch.testing.assert_close(out_f[0].log(), out_m[0].log(), rtol=0, atol=0.03, msg=lambda s: "log sigma: " + s)
+    for name, u, v in zip(("rgb", "prob"), out_f[1:], out_m[1:]):
+        torch.testing.assert_close(u, v, rtol=4e-3, atol=2e-3 * float(v.abs().max()), msg=lambda s, n=name: n + ": " + s)
+    for name, u, v in zip(("hash", "sigma_net", "color_net", "semantics_net"), grad_f, grad_m):
+        assert float(v.abs().max()) > 0, name
+        torch.testing.assert_close(u, v, rtol=3e-2, atol=1e-2 * float(v.abs().max()),
+                                   msg=lambda s, n=name: "grad " + n + ": " + s)
+
+
+def test_run_cuda_training_render_fused_against_module_level():
+    """The same training render (same grid, same marched samples: perturb off) through both forms of the heads."""
+    from ucsa_neural_rendering_b200.nerf import SemanticNeRFNetwork
+
+    net = SemanticNeRFNetwork(encoding="hashgrid", bound=4, cuda_ray=True, density_scale=1,
+                              num_semantic_classes=40).to(DEV).train()
+    with torch.no_grad():
+        net.encoder.params.uniform_(-0.5, 0.5)
+    net.update_extra_state()
+    n = 700
+    g = torch.Generator().manual_seed(9)
+    o = ((torch.rand(1, n, 3, generator=g) - 0.5)).to(DEV)
+    d = torch.nn.functional.normalize(torch.randn(1, n, 3, generator=g), dim=-1).to(DEV)
+    dn = (1 + 0.2 * torch.rand(1, n, 1, generator=g)).to(DEV)
+    got = []
+    for fused in (False, True):
+        net.fused_packed = fused
+        net.zero_grad(set_to_none=True)
+        out = net.render(o, d, direction_norms=dn, staged=False, perturb=False, dt_gamma=1 / 128, force_all_rays=True)
+        (out["image"].sum() + out["depth"].sum() + (out["semantics"] ** 2).sum()).backward()
+        got.append(({k: out[k].detach() for k in ("image", "depth", "semantics")},
+                    [p.grad.detach().clone() for p in net.parameters()]))
+    (out_m, grad_m), (out_f, grad_f) = got
+    for k in out_m:
+        torch.testing.assert_close(out_f[k], out_m[k], rtol=4e-3, atol=2e-3 * float(out_m[k].abs().max()))
+    for u, v in zip(grad_f, grad_m):
+        torch.testing.assert_close(u, v, rtol=3e-2, atol=1e-2 * float(v.abs().max()))
+
+
 def test_grid_refresh_kernel_chain_matches_eager_definition(ops):
     """Row a20 (defined by this repo after torch-ngp; the reference ships no update): the three-launch refresh of
     SemanticNeRFNetwork.update_extra_state against the eager definition in SemanticNeRFRenderer -- same cells, same

@@ -5,9 +5,9 @@ with perturb=True, the three losses, backward, Adam on both parameter groups.  H
 libucsa_nerf.so kernels on a static workspace -- no autograd engine, no eager tensor math, no host synchronisation:
 
     step counter += 1 -> zero gradients -> pipeline.forward_chain -> ucsa_nerf_loss -> pipeline.backward_chain
-    -> world == 1 : ucsa_grad_check -> ucsa_adam_step x 4
+    -> world == 1 : ucsa_grad_check -> ucsa_adam_step (ONE launch over the flat parameter space)
        world  > 1 : ucsa_grad_check -> barrier -> ucsa_adam_exchange -> barrier   (exchange = "peer", one NVLink domain)
-                    NCCL all-reduce of the flat gradients -> ucsa_grad_check -> ucsa_adam_step x 4   (exchange = "nccl")
+                    NCCL all-reduce of the flat gradients -> ucsa_grad_check -> ucsa_adam_step   (exchange = "nccl")
 
 ucsa_grad_check is GradScaler's overflow test (joint_train_lightning_net.py:46,509-513): the backward runs in fp16
 with a fixed loss scale, so an overflow shows up as inf / NaN in the flat gradient; such a step is skipped on every

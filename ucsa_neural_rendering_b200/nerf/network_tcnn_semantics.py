@@ -249,6 +249,76 @@ class _FusedRender(torch.autograd.Function):
         return g_table, g_sig, g_col, g_semw, None, None, None, None, None
 
 
+class _PackedHeadsFn(torch.autograd.Function):
+    """forward(x, d) of the network (network_tcnn_semantics.py:102-128) for a packed stream of points -- the training
+    render of the occupancy-grid path (run_cuda) -- as ONE autograd node: the fused density kernel and the two
+    tensor-core heads kernels each way instead of nine module-level launches with eager glue between them.
+
+    The heads kernels are the ones of the LIVE path; they take their per-row gradients through the fused compositing
+    backward, so the backward presents every point as a ray of its own with weight 1: dL/drgb_row = 1 * g_image[row],
+    dL/dlogits_row = soft-max backward of 1 * g_semantics[row] -- exactly the per-row gradients autograd hands us."""
+
+    @staticmethod
+    def forward(ctx, x, d, enc_params, sigma_params, color_params, sem_params, net, grad_enabled):
+        x = x.detach().float().contiguous()
+        d = d.detach().float().contiguous()
+        m = x.shape[0]
+        dev = x.device
+        c = net.num_semantic_classes
+        need = grad_enabled and any(ctx.needs_input_grad[2:6])
+        rows = ops.tile_rows(m)
+        f16 = dict(dtype=torch.float16, device=dev)
+        sigma = torch.empty(m, dtype=torch.float32, device=dev)
+        rgb = torch.empty(m, 3, dtype=torch.float32, device=dev)
+        h = torch.empty(m, 16, **f16)
+        logits = torch.empty(m, ops.MAX_CLASSES, **f16)
+        enc = torch.empty(rows, 32, **f16) if need else None
+        hid = torch.empty(rows, 64, **f16) if need else None
+        hc1, hc2, hs = (torch.empty(rows, 64, **f16) for _ in range(3)) if need else (None, None, None)
+        sel = torch.arange(m, dtype=torch.int32, device=dev)
+        # ray_off[n_rays] = K is all the heads kernels read of it: [0, m] serves the forward pass (one "ray" owning all
+        # rows, no compositing), the slot at index m the backward pass (m "rays" of one row each)
+        off = torch.zeros(m + 1, dtype=torch.int32, device=dev)
+        off[1].fill_(m)
+        off[m].fill_(m)
+        ops.density_fwd(net.encoder.grid, net.encoder.half_params(), net.sigma_net.half_params(), net.bound, xyz=x,
+                        sigma=sigma, h=h, enc=enc, hid=hid, tiled=need)
+        ops.heads_fwd(sel, off, 1, 1, m, d, h, net.color_net.half_params(), net.semantics_net.half_params(), c, rgb,
+                      logits, hc1=hc1, hc2=hc2, hs=hs)
+        prob = F.softmax(logits[:, :c].float(), dim=-1)
+        if need:
+            ctx.net = net
+            ctx.save_for_backward(x, d, h, enc, hid, rgb, hc1, hc2, hs, sel, off)
+        return sigma, rgb, prob
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_sigma, d_rgb, d_prob):
+        net = ctx.net
+        x, d, h, enc, hid, rgb, hc1, hc2, hs, sel, off = ctx.saved_tensors
+        m = x.shape[0]
+        dev = x.device
+        c = net.num_semantic_classes
+        f32 = dict(dtype=torch.float32, device=dev)
+        scale = net.loss_scale
+        n_table = net.encoder.params.numel()
+        sizes = (n_table, ops.SIGMA_PARAMS, ops.COLOR_PARAMS, ops.SEM_PARAMS)
+        flat = torch.zeros(sum(sizes), **f32)
+        g_table, g_sig, g_col, g_semw = torch.split(flat, sizes)
+        ones, zeros = torch.ones(m, **f32), torch.zeros(m, **f32)
+        d_rgb = torch.zeros(m, 3, **f32) if d_rgb is None else d_rgb.float().contiguous()
+        d_prob = torch.zeros(m, c, **f32) if d_prob is None else d_prob.float().contiguous()
+        dh = torch.zeros(m, 16, dtype=torch.float16, device=dev)
+        d_w = torch.empty(m, **f32)  # dL/dw of the unit weights: not used
+        ops.heads_bwd(sel, off, m, 1, m, d, h, net.color_net.half_params(), net.semantics_net.half_params(), c, rgb,
+                      hc1, hc2, hs, ones, zeros, d_rgb, zeros, d_prob, ones, scale, dh, d_w, g_col, g_semw)
+        ops.density_bwd(net.encoder.grid, net.sigma_net.half_params(), net.bound, xyz=x, h=h, enc=enc, hid=hid,
+                        d_sigma=None if d_sigma is None else d_sigma.float().contiguous(), dh=dh,
+                        use_geo=torch.ones(m, dtype=torch.uint8, device=dev), loss_scale=scale, grad_table=g_table,
+                        grad_w_sigma=g_sig, tiled=True)
+        return None, None, g_table, g_sig, g_col, g_semw, None, None
+
+
 class SemanticNeRFNetwork(SemanticNeRFRenderer):
 
     def __init__(self,
@@ -299,6 +369,7 @@ class SemanticNeRFNetwork(SemanticNeRFRenderer):
         # activations, so a part of 2^18 rays x 512 samples needs ~9 GB of scratch (a 640x480 view = two parts of
         # 153600 rays, 5.6 GB; 46.3 ms per view against 47.3 ms with 65536-ray parts).
         self.stage_chunk = 262144
+        self.fused_packed = True  # run_cuda's training render: heads as one fused autograd node (_PackedHeadsFn)
 
     # ------------------------------------------------------------------ module-level API of the reference
     def forward(self, x, d):
@@ -349,6 +420,16 @@ class SemanticNeRFNetwork(SemanticNeRFRenderer):
         ops.heads_fwd(st["sel"], st["off"], 1, 1, m, d, h, self.color_net.half_params(),
                       self.semantics_net.half_params(), c, rgb, logits)
         return sigma, rgb, (logits if want_logits else F.softmax(logits[:, :c].float(), dim=-1))
+
+    def forward_packed_train(self, x, d):
+        """forward(x, d) for a packed stream of points WITH autograd (the training render of run_cuda) as one fused node
+        (_PackedHeadsFn): -> sigma [M] f32, colour [M,3] f32, class probabilities [M,C] f32.  `fused_packed = False`
+        on the network restores the module-by-module forward."""
+        if x.shape[0] == 0 or not self.fused_packed:
+            sigma, color, sem = self(x, d)
+            return sigma, color.float(), sem
+        return _PackedHeadsFn.apply(x, d, self.encoder.params, self.sigma_net.params, self.color_net.params,
+                                    self.semantics_net.params, self, torch.is_grad_enabled())
 
     def color(self, x, d, mask=None, geo_feat=None, **kwargs):
         # masked evaluation, network_tcnn_semantics.py:147-178

@@ -262,7 +262,9 @@ class SemanticNeRFRenderer(nn.Module):
             xyzs, dirs, deltas, rays = raymarching.march_rays_train(
                 rays_o, rays_d, self.bound, self.density_grid, self.mean_density, nears, fars, counter, self.mean_count,
                 perturb, 128, force_all_rays, dt_gamma, bitfield=bits)
-            sigmas, rgbs, sems = self(xyzs, dirs)
+            # a subclass may offer the three heads on packed points as one fused autograd node
+            heads = getattr(self, "forward_packed_train", None) or self
+            sigmas, rgbs, sems = heads(xyzs, dirs)
             sigmas = self.density_scale * sigmas
             weights_sum, depth, image, semantics = raymarching.composite_rays_train_semantics(
                 sigmas, rgbs.float(), sems.float(), deltas, rays, c)
