@@ -219,11 +219,15 @@ UCSA_API int ucsa_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* r
                     const float* grid, const uint32_t* bitfield, float mean_density, const float* nears,
                     const float* fars, float* xyzs, float* dirs, float* deltas, uint32_t perturb, void* stream);
 /* rgb + depth as raymarching.cu:318-487; local_semantics [M,C] / semantics [N,C] optional (both null or both set):
- * the semantic kernels the reference declares (raymarching.h:12-13) but never implemented. */
+ * the semantic kernels the reference declares (raymarching.h:12-13) but never implemented.  Instead of the fp32
+ * probabilities the forward pass also takes the fp16 logits of the semantic head (logits_h [M, logits_ld], soft-max
+ * inside the kernel, as ucsa_composite_rays does); the backward pass hands out dL/d(probabilities) either way.
+ * deltas [M,2] must be 8-byte aligned. */
 UCSA_API int ucsa_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* local_semantics,
-                                      const float* deltas, const int32_t* rays, uint32_t M, uint32_t N,
-                                      uint32_t n_classes, float* weights_sum, float* depth, float* image,
-                                      float* semantics, void* stream);
+                                      const void* logits_h, uint32_t logits_ld, const float* deltas,
+                                      const int32_t* rays, uint32_t M, uint32_t N, uint32_t n_classes,
+                                      float* weights_sum, float* depth, float* image, float* semantics,
+                                      void* stream);
 UCSA_API int ucsa_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image,
                                        const float* grad_semantics, const float* sigmas, const float* rgbs,
                                        const float* deltas, const int32_t* rays, const float* weights_sum,

@@ -282,7 +282,8 @@ __device__ __forceinline__ float ragged_running(float v, float& carry, int lane)
 }
 
 __global__ void composite_train_fwd_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
-                                           const float* __restrict__ sem, const float* __restrict__ deltas,
+                                           const float* __restrict__ sem, const __half* __restrict__ logits,
+                                           uint32_t logits_ld, const float* __restrict__ deltas,
                                            const int32_t* __restrict__ rays, uint32_t M, uint32_t N, uint32_t C,
                                            float* __restrict__ weights_sum, float* __restrict__ depth,
                                            float* __restrict__ image, float* __restrict__ semantics) {
@@ -321,6 +322,24 @@ __global__ void composite_train_fwd_kernel(const float* __restrict__ sigmas, con
           const float wk = __shfl_sync(kFullMask, q.w, static_cast<int>(k));
           if (static_cast<uint32_t>(lane) < C) acc0 += wk * row[static_cast<uint64_t>(k) * C + lane];
           if (static_cast<uint32_t>(lane) + 32 < C) acc1 += wk * row[static_cast<uint64_t>(k) * C + lane + 32];
+        }
+      } else if (logits != nullptr) {
+        // class probabilities from the fp16 logits of the semantic head, soft-max across the lanes (as in
+        // composite_rays_kernel): the [M,C] fp32 probability tensor is never formed
+        const uint32_t cnt = num_steps - base < 32u ? num_steps - base : 32u;
+        const __half* row = logits + static_cast<uint64_t>(offset + base) * logits_ld;
+#pragma unroll 4
+        for (uint32_t k = 0; k < cnt; ++k) {
+          const float wk = __shfl_sync(kFullMask, q.w, static_cast<int>(k));
+          const __half* lg = row + static_cast<uint64_t>(k) * logits_ld;
+          const float l0 = static_cast<uint32_t>(lane) < C ? __half2float(lg[lane]) : -INFINITY;
+          const float l1 = static_cast<uint32_t>(lane) + 32 < C ? __half2float(lg[lane + 32]) : -INFINITY;
+          const float m = warp_max(fmaxf(l0, l1));
+          const float e0 = static_cast<uint32_t>(lane) < C ? __expf(l0 - m) : 0.f;
+          const float e1 = static_cast<uint32_t>(lane) + 32 < C ? __expf(l1 - m) : 0.f;
+          const float scale = wk / warp_sum(e0 + e1);
+          acc0 += scale * e0;
+          acc1 += scale * e1;
         }
       }
     }
@@ -679,16 +698,21 @@ extern "C" int ucsa_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t*
 }
 
 extern "C" int ucsa_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* local_semantics,
-                                                 const float* deltas, const int32_t* rays, uint32_t M, uint32_t N,
-                                                 uint32_t n_classes, float* weights_sum, float* depth, float* image,
-                                                 float* semantics, void* stream) {
+                                                 const void* logits_h, uint32_t logits_ld, const float* deltas,
+                                                 const int32_t* rays, uint32_t M, uint32_t N, uint32_t n_classes,
+                                                 float* weights_sum, float* depth, float* image, float* semantics,
+                                                 void* stream) {
   UCSA_REQUIRE(sigmas && rgbs && deltas && rays && weights_sum && depth && image, "composite_rays_train_forward: null pointer");
-  UCSA_REQUIRE((local_semantics == nullptr) == (semantics == nullptr), "composite_rays_train_forward: semantics in/out mismatch");
+  UCSA_REQUIRE(!(local_semantics && logits_h), "composite_rays_train_forward: give probabilities or logits, not both");
+  UCSA_REQUIRE((local_semantics == nullptr && logits_h == nullptr) == (semantics == nullptr),
+               "composite_rays_train_forward: semantics in/out mismatch");
+  UCSA_REQUIRE(logits_h == nullptr || logits_ld >= n_classes, "composite_rays_train_forward: logits row stride < classes");
   UCSA_REQUIRE(n_classes <= 64, "composite_rays_train_forward: at most 64 classes");
   UCSA_REQUIRE((reinterpret_cast<uintptr_t>(deltas) & 7u) == 0, "composite_rays_train_forward: deltas [M,2] must be 8-byte aligned");
   if (N == 0) return UCSA_OK;
   composite_train_fwd_kernel<<<ceil_div(static_cast<uint64_t>(N) * 32, 128), 128, 0, as_stream(stream)>>>(
-      sigmas, rgbs, local_semantics, deltas, rays, M, N, n_classes, weights_sum, depth, image, semantics);
+      sigmas, rgbs, local_semantics, static_cast<const __half*>(logits_h), logits_ld, deltas, rays, M, N, n_classes,
+      weights_sum, depth, image, semantics);
   return check_launch("composite_rays_train_forward");
 }
 

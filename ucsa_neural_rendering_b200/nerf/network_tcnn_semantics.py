@@ -249,74 +249,135 @@ class _FusedRender(torch.autograd.Function):
         return g_table, g_sig, g_col, g_semw, None, None, None, None, None
 
 
-class _PackedHeadsFn(torch.autograd.Function):
-    """forward(x, d) of the network (network_tcnn_semantics.py:102-128) for a packed stream of points -- the training
-    render of the occupancy-grid path (run_cuda) -- as ONE autograd node: the fused density kernel and the two
-    tensor-core heads kernels each way instead of nine module-level launches with eager glue between them.
+def _packed_heads_forward(net, x, d, need):
+    """density + both heads on a packed stream of points x, d [M,3] (f32, contiguous): the fused density kernel, then
+    the two tensor-core heads kernels on ALL points (identity row list, one direction per point).  `need`: keep the
+    activations the backward kernels read.  -> dict of sigma [M] f32, rgb [M,3] f32, logits [M,48] f16 + saved buffers."""
+    m = x.shape[0]
+    dev = x.device
+    rows = ops.tile_rows(m)
+    f16 = dict(dtype=torch.float16, device=dev)
+    st = {"sigma": torch.empty(m, dtype=torch.float32, device=dev), "rgb": torch.empty(m, 3, dtype=torch.float32, device=dev),
+          "h": torch.empty(m, 16, **f16), "logits": torch.empty(m, ops.MAX_CLASSES, **f16),
+          "enc": torch.empty(rows, 32, **f16) if need else None, "hid": torch.empty(rows, 64, **f16) if need else None,
+          "hc1": torch.empty(rows, 64, **f16) if need else None, "hc2": torch.empty(rows, 64, **f16) if need else None,
+          "hs": torch.empty(rows, 64, **f16) if need else None,
+          "sel": torch.arange(m, dtype=torch.int32, device=dev)}
+    # ray_off[n_rays] = K is all the heads kernels read of it: [0, m] serves the forward pass (one "ray" owning all
+    # rows, no compositing), the slot at index m the backward pass (m "rays" of one row each)
+    off = torch.zeros(m + 1, dtype=torch.int32, device=dev)
+    off[1].fill_(m)
+    off[m].fill_(m)
+    st["off"] = off
+    ops.density_fwd(net.encoder.grid, net.encoder.half_params(), net.sigma_net.half_params(), net.bound, xyz=x,
+                    sigma=st["sigma"], h=st["h"], enc=st["enc"], hid=st["hid"], tiled=need)
+    ops.heads_fwd(st["sel"], off, 1, 1, m, d, st["h"], net.color_net.half_params(), net.semantics_net.half_params(),
+                  net.num_semantic_classes, st["rgb"], st["logits"], hc1=st["hc1"], hc2=st["hc2"], hs=st["hs"])
+    return st
 
-    The heads kernels are the ones of the LIVE path; they take their per-row gradients through the fused compositing
-    backward, so the backward presents every point as a ray of its own with weight 1: dL/drgb_row = 1 * g_image[row],
-    dL/dlogits_row = soft-max backward of 1 * g_semantics[row] -- exactly the per-row gradients autograd hands us."""
+
+_PACKED_SAVED = ("h", "enc", "hid", "rgb", "hc1", "hc2", "hs", "sel", "off")
+
+
+def _packed_heads_backward(net, x, d, saved, d_sigma, d_rgb, d_prob):
+    """Backward of _packed_heads_forward from per-point gradients d_sigma [M], d_rgb [M,3], d_prob [M,C] (f32; d_prob is
+    the gradient of the soft-max OUTPUT).  The heads kernels are the ones of the LIVE path; they take their per-row
+    gradients through the fused compositing backward, so every point is presented as a ray of its own with weight 1:
+    dL/drgb_row = 1 * g_image[row], dL/dlogits_row = soft-max backward of 1 * g_semantics[row].
+    -> the four parameter gradients (views of one flat buffer)."""
+    h, enc, hid, rgb, hc1, hc2, hs, sel, off = saved
+    m = x.shape[0]
+    dev = x.device
+    c = net.num_semantic_classes
+    f32 = dict(dtype=torch.float32, device=dev)
+    scale = net.loss_scale
+    sizes = (net.encoder.params.numel(), ops.SIGMA_PARAMS, ops.COLOR_PARAMS, ops.SEM_PARAMS)
+    flat = torch.zeros(sum(sizes), **f32)
+    g_table, g_sig, g_col, g_semw = torch.split(flat, sizes)
+    ones, zeros = torch.ones(m, **f32), torch.zeros(m, **f32)
+    dh = torch.zeros(m, 16, dtype=torch.float16, device=dev)
+    d_w = torch.empty(m, **f32)  # dL/dw of the unit weights: not used
+    ops.heads_bwd(sel, off, m, 1, m, d, h, net.color_net.half_params(), net.semantics_net.half_params(), c, rgb,
+                  hc1, hc2, hs, ones, zeros, d_rgb, zeros, d_prob, ones, scale, dh, d_w, g_col, g_semw)
+    ops.density_bwd(net.encoder.grid, net.sigma_net.half_params(), net.bound, xyz=x, h=h, enc=enc, hid=hid,
+                    d_sigma=d_sigma, dh=dh, use_geo=torch.ones(m, dtype=torch.uint8, device=dev), loss_scale=scale,
+                    grad_table=g_table, grad_w_sigma=g_sig, tiled=True)
+    return g_table, g_sig, g_col, g_semw
+
+
+class _PackedHeadsFn(torch.autograd.Function):
+    """forward(x, d) of the network (network_tcnn_semantics.py:102-128) for a packed stream of points as ONE autograd
+    node: the fused density kernel and the two tensor-core heads kernels each way instead of nine module-level
+    launches with eager glue between them."""
 
     @staticmethod
     def forward(ctx, x, d, enc_params, sigma_params, color_params, sem_params, net, grad_enabled):
         x = x.detach().float().contiguous()
         d = d.detach().float().contiguous()
-        m = x.shape[0]
-        dev = x.device
-        c = net.num_semantic_classes
         need = grad_enabled and any(ctx.needs_input_grad[2:6])
-        rows = ops.tile_rows(m)
-        f16 = dict(dtype=torch.float16, device=dev)
-        sigma = torch.empty(m, dtype=torch.float32, device=dev)
-        rgb = torch.empty(m, 3, dtype=torch.float32, device=dev)
-        h = torch.empty(m, 16, **f16)
-        logits = torch.empty(m, ops.MAX_CLASSES, **f16)
-        enc = torch.empty(rows, 32, **f16) if need else None
-        hid = torch.empty(rows, 64, **f16) if need else None
-        hc1, hc2, hs = (torch.empty(rows, 64, **f16) for _ in range(3)) if need else (None, None, None)
-        sel = torch.arange(m, dtype=torch.int32, device=dev)
-        # ray_off[n_rays] = K is all the heads kernels read of it: [0, m] serves the forward pass (one "ray" owning all
-        # rows, no compositing), the slot at index m the backward pass (m "rays" of one row each)
-        off = torch.zeros(m + 1, dtype=torch.int32, device=dev)
-        off[1].fill_(m)
-        off[m].fill_(m)
-        ops.density_fwd(net.encoder.grid, net.encoder.half_params(), net.sigma_net.half_params(), net.bound, xyz=x,
-                        sigma=sigma, h=h, enc=enc, hid=hid, tiled=need)
-        ops.heads_fwd(sel, off, 1, 1, m, d, h, net.color_net.half_params(), net.semantics_net.half_params(), c, rgb,
-                      logits, hc1=hc1, hc2=hc2, hs=hs)
-        prob = F.softmax(logits[:, :c].float(), dim=-1)
+        st = _packed_heads_forward(net, x, d, need)
+        prob = F.softmax(st["logits"][:, :net.num_semantic_classes].float(), dim=-1)
         if need:
             ctx.net = net
-            ctx.save_for_backward(x, d, h, enc, hid, rgb, hc1, hc2, hs, sel, off)
-        return sigma, rgb, prob
+            ctx.save_for_backward(x, d, *(st[k] for k in _PACKED_SAVED))
+        return st["sigma"], st["rgb"], prob
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, d_sigma, d_rgb, d_prob):
-        net = ctx.net
-        x, d, h, enc, hid, rgb, hc1, hc2, hs, sel, off = ctx.saved_tensors
-        m = x.shape[0]
+        x, d, *saved = ctx.saved_tensors
+        grads = _packed_heads_backward(ctx.net, x, d, saved, d_sigma.float().contiguous(), d_rgb.float().contiguous(),
+                                       d_prob.float().contiguous())
+        return (None, None, *grads, None, None)
+
+
+class _PackedRenderFn(torch.autograd.Function):
+    """The training render of the occupancy-grid path (run_cuda) behind the march as ONE autograd node: heads on the
+    packed samples (_packed_heads_forward) and the ragged compositing of raymarching.cu:318-487 + the semantic channels,
+    which takes the fp16 logits directly (soft-max inside the kernel: no [M,C] fp32 probability tensor, no eager
+    soft-max).  Backward: ragged compositing backward -> per-sample gradients -> heads -> density.  Depth receives no
+    gradient, like in the reference (raymarching.py:209)."""
+
+    @staticmethod
+    def forward(ctx, enc_params, sigma_params, color_params, sem_params, xyzs, dirs, deltas, rays, net, grad_enabled):
+        x = xyzs.detach().float().contiguous()
+        d = dirs.detach().float().contiguous()
+        deltas = deltas.detach().float().contiguous()
+        rays = rays.contiguous()
+        n = rays.shape[0]
         dev = x.device
         c = net.num_semantic_classes
+        need = grad_enabled and any(ctx.needs_input_grad[:4])
+        st = _packed_heads_forward(net, x, d, need)
+        sig = st["sigma"] if net.density_scale == 1 else st["sigma"] * net.density_scale
         f32 = dict(dtype=torch.float32, device=dev)
-        scale = net.loss_scale
-        n_table = net.encoder.params.numel()
-        sizes = (n_table, ops.SIGMA_PARAMS, ops.COLOR_PARAMS, ops.SEM_PARAMS)
-        flat = torch.zeros(sum(sizes), **f32)
-        g_table, g_sig, g_col, g_semw = torch.split(flat, sizes)
-        ones, zeros = torch.ones(m, **f32), torch.zeros(m, **f32)
-        d_rgb = torch.zeros(m, 3, **f32) if d_rgb is None else d_rgb.float().contiguous()
-        d_prob = torch.zeros(m, c, **f32) if d_prob is None else d_prob.float().contiguous()
-        dh = torch.zeros(m, 16, dtype=torch.float16, device=dev)
-        d_w = torch.empty(m, **f32)  # dL/dw of the unit weights: not used
-        ops.heads_bwd(sel, off, m, 1, m, d, h, net.color_net.half_params(), net.semantics_net.half_params(), c, rgb,
-                      hc1, hc2, hs, ones, zeros, d_rgb, zeros, d_prob, ones, scale, dh, d_w, g_col, g_semw)
-        ops.density_bwd(net.encoder.grid, net.sigma_net.half_params(), net.bound, xyz=x, h=h, enc=enc, hid=hid,
-                        d_sigma=None if d_sigma is None else d_sigma.float().contiguous(), dh=dh,
-                        use_geo=torch.ones(m, dtype=torch.uint8, device=dev), loss_scale=scale, grad_table=g_table,
-                        grad_w_sigma=g_sig, tiled=True)
-        return None, None, g_table, g_sig, g_col, g_semw, None, None
+        ws, depth = torch.empty(n, **f32), torch.empty(n, **f32)
+        image, semantics = torch.empty(n, 3, **f32), torch.empty(n, c, **f32)
+        ops.composite_rays_train_forward(sig, st["rgb"], None, deltas, rays, c, ws, depth, image, semantics,
+                                         logits=st["logits"])
+        if need:
+            ctx.net = net
+            ctx.save_for_backward(x, d, deltas, rays, sig, ws, image, *(st[k] for k in _PACKED_SAVED))
+        ctx.mark_non_differentiable(depth)
+        return ws, depth, image, semantics
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_ws, g_depth, g_image, g_sem):
+        net = ctx.net
+        x, d, deltas, rays, sig, ws, image, *saved = ctx.saved_tensors
+        m = x.shape[0]
+        c = net.num_semantic_classes
+        f32 = dict(dtype=torch.float32, device=x.device)
+        # zero-filled: rows past the last sample (the stream is padded to whole tiles) and dropped rays stay 0
+        d_sigma, d_rgb, d_prob = torch.zeros(m, **f32), torch.zeros(m, 3, **f32), torch.zeros(m, c, **f32)
+        ops.composite_rays_train_backward(g_ws.float().contiguous(), g_image.float().contiguous(),
+                                          g_sem.float().contiguous(), sig, saved[3], deltas, rays, ws, image, c, d_sigma,
+                                          d_rgb, d_prob)
+        if net.density_scale != 1:
+            d_sigma = d_sigma * net.density_scale
+        grads = _packed_heads_backward(net, x, d, saved, d_sigma, d_rgb, d_prob)
+        return (*grads, None, None, None, None, None, None)
 
 
 class SemanticNeRFNetwork(SemanticNeRFRenderer):
@@ -430,6 +491,16 @@ class SemanticNeRFNetwork(SemanticNeRFRenderer):
             return sigma, color.float(), sem
         return _PackedHeadsFn.apply(x, d, self.encoder.params, self.sigma_net.params, self.color_net.params,
                                     self.semantics_net.params, self, torch.is_grad_enabled())
+
+    def render_packed_train(self, xyzs, dirs, deltas, rays):
+        """Heads + ragged compositing of a marched training batch (run_cuda) as one fused autograd node
+        (_PackedRenderFn) -> weights_sum [N], depth [N], image [N,3], semantics [N,C]; None when the fused form does
+        not apply (`fused_packed = False`, no samples): the caller then composes the pieces itself."""
+        if xyzs.shape[0] == 0 or not self.fused_packed:
+            return None
+        return _PackedRenderFn.apply(self.encoder.params, self.sigma_net.params, self.color_net.params,
+                                     self.semantics_net.params, xyzs, dirs, deltas, rays, self,
+                                     torch.is_grad_enabled())
 
     def color(self, x, d, mask=None, geo_feat=None, **kwargs):
         # masked evaluation, network_tcnn_semantics.py:147-178

@@ -262,12 +262,16 @@ class SemanticNeRFRenderer(nn.Module):
             xyzs, dirs, deltas, rays = raymarching.march_rays_train(
                 rays_o, rays_d, self.bound, self.density_grid, self.mean_density, nears, fars, counter, self.mean_count,
                 perturb, 128, force_all_rays, dt_gamma, bitfield=bits)
-            # a subclass may offer the three heads on packed points as one fused autograd node
-            heads = getattr(self, "forward_packed_train", None) or self
-            sigmas, rgbs, sems = heads(xyzs, dirs)
-            sigmas = self.density_scale * sigmas
-            weights_sum, depth, image, semantics = raymarching.composite_rays_train_semantics(
-                sigmas, rgbs.float(), sems.float(), deltas, rays, c)
+            # a subclass may offer heads + ragged compositing of the marched batch as one fused autograd node
+            fused = getattr(self, "render_packed_train", None)
+            fused = fused(xyzs, dirs, deltas, rays) if fused is not None else None
+            if fused is not None:
+                weights_sum, depth, image, semantics = fused
+            else:
+                sigmas, rgbs, sems = self(xyzs, dirs)
+                sigmas = self.density_scale * sigmas
+                weights_sum, depth, image, semantics = raymarching.composite_rays_train_semantics(
+                    sigmas, rgbs.float(), sems.float(), deltas, rays, c)
         else:
             dtype = torch.float32
             weights_sum = torch.zeros(n_rays, dtype=dtype, device=device)

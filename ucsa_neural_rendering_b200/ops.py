@@ -448,9 +448,12 @@ def march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_ga
 
 
 def composite_rays_train_forward(sigmas, rgbs, local_semantics, deltas, rays, n_classes, weights_sum, depth, image,
-                                 semantics):
+                                 semantics, logits=None):
+    """logits: fp16 [M, ld] of the semantic head instead of probabilities (soft-max inside the kernel)"""
     check(lib().ucsa_composite_rays_train_forward(_ptr(sigmas, torch.float32), _ptr(rgbs, torch.float32),
-                                                  _ptr(local_semantics, torch.float32), _ptr(deltas, torch.float32),
+                                                  _ptr(local_semantics, torch.float32), _ptr(logits, torch.float16),
+                                                  0 if logits is None else logits.shape[1],
+                                                  _ptr(deltas, torch.float32),
                                                   _ptr(rays, torch.int32), sigmas.shape[0], rays.shape[0], n_classes,
                                                   _ptr(weights_sum, torch.float32), _ptr(depth, torch.float32),
                                                   _ptr(image, torch.float32), _ptr(semantics, torch.float32),
