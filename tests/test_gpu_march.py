@@ -43,9 +43,10 @@ def make_scene(n_rays, seed, bound=4.0, cascades=3, h=128):
     return grid, o, d, aabb
 
 
+@pytest.mark.parametrize("staged", [True, False])  # one march + sample-parallel write | count march + write march
 @pytest.mark.parametrize("perturb", [0, 1])
 @pytest.mark.parametrize("use_bits", [False, True])
-def test_march_rays_train_bit_exact(ops, perturb, use_bits):
+def test_march_rays_train_bit_exact(ops, perturb, use_bits, staged):
     n = 700
     grid, o, d, aabb = make_scene(n, 3)
     mean_density = 0.008  # below 0.01: threshold = min(0.01, mean)
@@ -65,7 +66,7 @@ def test_march_rays_train_bit_exact(ops, perturb, use_bits):
         assert np.array_equal(bits.cpu().numpy().view(np.uint8), ref_bits), "occupancy bitfield must be bit-exact"
     counter = torch.zeros(2, dtype=torch.int32, device=DEV)
     xyz, dirs, deltas, rays = ops.march_rays_train(o.to(DEV), d.to(DEV), gd, bits, mean_density, 4.0, 1 / 128, g_near,
-                                                   g_far, m, counter, perturb)
+                                                   g_far, m, counter, perturb, staged=staged)
     assert np.array_equal(counter.cpu().numpy(), r_cnt)
     assert np.array_equal(rays.cpu().numpy(), r_rays), "ray (id, offset, count) triples must be bit-exact"
     total = int(r_cnt[0])
@@ -85,11 +86,13 @@ def test_march_rays_train_overflow_and_empty(ops):
     m = int(full[4][0]) // 2  # half of what is needed
     ref = raymarch.march_rays_train(o.numpy(), d.numpy(), grid.numpy(), 1.0, 4.0, 0.0, nears, fars, m, 0)
     counter = torch.zeros(2, dtype=torch.int32, device=DEV)
-    xyz, dirs, deltas, rays = ops.march_rays_train(o.to(DEV), d.to(DEV), grid.to(DEV), None, 1.0, 4.0, 0.0,
-                                                   torch.from_numpy(nears).to(DEV), torch.from_numpy(fars).to(DEV), m,
-                                                   counter, 0)
-    assert np.array_equal(rays.cpu().numpy(), ref[3]) and (ref[3][:4, 2] == 0).all()
-    assert np.array_equal(xyz.cpu().numpy(), ref[0]) and np.array_equal(deltas.cpu().numpy(), ref[2])
+    for staged in (True, False):
+        counter.zero_()
+        xyz, dirs, deltas, rays = ops.march_rays_train(o.to(DEV), d.to(DEV), grid.to(DEV), None, 1.0, 4.0, 0.0,
+                                                       torch.from_numpy(nears).to(DEV), torch.from_numpy(fars).to(DEV),
+                                                       m, counter, 0, staged=staged)
+        assert np.array_equal(rays.cpu().numpy(), ref[3]) and (ref[3][:4, 2] == 0).all()
+        assert np.array_equal(xyz.cpu().numpy(), ref[0]) and np.array_equal(deltas.cpu().numpy(), ref[2])
 
 
 def _ragged_inputs(seed, n=300, c=40):

@@ -118,17 +118,74 @@ __device__ __forceinline__ float train_t0(float near, uint32_t n, uint32_t pertu
   return t0;
 }
 
-// pass 1: number of occupied steps per ray
+// pass 1: number of occupied steps per ray.  The march is one dependent chain per ray (t += dt, the next probe
+// depends on it) and must stay one to remain bit-identical with the reference; what need not be repeated is the
+// chain itself: with a staging buffer (t_stage [n_rays, kMaxSteps]) this pass also records the parameter t of every
+// occupied step (a store off the dependent chain), and the samples are then written by a pass that is parallel over
+// the samples (march_write_staged_kernel) instead of marching every ray a second time.
 __global__ void march_count_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, March m,
                                    uint32_t n_rays, const float* __restrict__ nears, const float* __restrict__ fars,
-                                   uint32_t perturb, int32_t* __restrict__ counts) {
+                                   uint32_t perturb, int32_t* __restrict__ counts, float* __restrict__ t_stage) {
   const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n_rays) return;
   const Ray r = load_ray(rays_o, rays_d, n, fars[n]);
   float t = train_t0(nears[n], n, perturb), x, y, z, dt;
   uint32_t steps = 0;
-  while (t < r.far && steps < kMaxSteps) steps += m.probe(r, t, x, y, z, dt) ? 1u : 0u;
+  if (t_stage != nullptr) {
+    float* ts = t_stage + static_cast<uint64_t>(n) * kMaxSteps;
+    while (t < r.far && steps < kMaxSteps) {
+      const float t_probe = t;
+      if (m.probe(r, t, x, y, z, dt)) ts[steps++] = t_probe;
+    }
+  } else {
+    while (t < r.far && steps < kMaxSteps) steps += m.probe(r, t, x, y, z, dt) ? 1u : 0u;
+  }
   counts[n] = static_cast<int32_t>(steps);
+}
+
+// pass 2 with staged parameters: one warp per ray, lanes = consecutive samples.  Position, step size and the distance
+// to the previous sample are the expressions of March::probe / march_write_kernel evaluated at the recorded t.
+__global__ void march_write_staged_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, March m,
+                                          uint32_t n_rays, uint32_t max_points, const float* __restrict__ nears,
+                                          uint32_t perturb, const int32_t* __restrict__ counts,
+                                          const int32_t* __restrict__ offsets, const float* __restrict__ t_stage,
+                                          float* __restrict__ xyzs, float* __restrict__ dirs,
+                                          float* __restrict__ deltas, int32_t* __restrict__ rays) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= n_rays) return;
+  const uint32_t num_steps = static_cast<uint32_t>(counts[n]);
+  const uint32_t point_index = static_cast<uint32_t>(offsets[n]);
+  if (lane == 0) {
+    rays[n * 3] = static_cast<int32_t>(n);
+    rays[n * 3 + 1] = static_cast<int32_t>(point_index);
+    rays[n * 3 + 2] = static_cast<int32_t>(num_steps);
+  }
+  if (num_steps == 0 || point_index + num_steps >= max_points) return;
+  const Ray r = load_ray(rays_o, rays_d, n, 0.f);
+  const float* ts = t_stage + static_cast<uint64_t>(n) * kMaxSteps;
+  float last_carry = train_t0(nears[n], n, perturb);  // "last_t" in front of the ray's first sample
+  for (uint32_t base = 0; base < num_steps; base += 32) {
+    const uint32_t s = base + lane;
+    const bool valid = s < num_steps;
+    const float t = valid ? ts[s] : 0.f;
+    const float dt = clampf(t * m.dt_gamma, m.dt_min, m.dt_max);
+    const float t_after = t + dt;
+    float last_t = __shfl_up_sync(kFullMask, t_after, 1);
+    if (lane == 0) last_t = last_carry;
+    last_carry = __shfl_sync(kFullMask, t_after, 31);
+    if (valid) {
+      const uint64_t i = static_cast<uint64_t>(point_index) + s;
+      float* px = xyzs + 3 * i;
+      float* pd = dirs + 3 * i;
+      px[0] = clampf(r.ox + t * r.dx, -m.bound, m.bound);
+      px[1] = clampf(r.oy + t * r.dy, -m.bound, m.bound);
+      px[2] = clampf(r.oz + t * r.dz, -m.bound, m.bound);
+      pd[0] = r.dx, pd[1] = r.dy, pd[2] = r.dz;
+      deltas[2 * i] = dt;
+      deltas[2 * i + 1] = t_after - last_t;
+    }
+  }
 }
 
 // pass 2: write the samples of every ray at its scanned offset; rays[n] = (n, offset, count)
@@ -663,7 +720,8 @@ extern "C" int ucsa_march_rays_train(const float* rays_o, const float* rays_d, c
                                      const uint32_t* bitfield, float mean_density, float bound, float dt_gamma,
                                      uint32_t n_rays, uint32_t C, uint32_t H, uint32_t max_points, const float* nears,
                                      const float* fars, float* xyzs, float* dirs, float* deltas, int32_t* rays,
-                                     int32_t* counter, uint32_t perturb, int32_t* scratch, void* stream) {
+                                     int32_t* counter, uint32_t perturb, int32_t* scratch, float* t_stage,
+                                     void* stream) {
   UCSA_REQUIRE(rays_o && rays_d && nears && fars && xyzs && dirs && deltas && rays && counter && scratch,
                "march_rays_train: null pointer");
   March m;
@@ -672,11 +730,16 @@ extern "C" int ucsa_march_rays_train(const float* rays_o, const float* rays_d, c
   cudaStream_t st = as_stream(stream);
   int32_t* counts = scratch;            // [n_rays]
   int32_t* offsets = scratch + n_rays;  // [n_rays + 1]
-  march_count_kernel<<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, m, n_rays, nears, fars, perturb, counts);
+  march_count_kernel<<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, m, n_rays, nears, fars, perturb, counts,
+                                                            t_stage);
   march_scan_kernel<<<1, 1024, 0, st>>>(counts, n_rays, offsets);
   // the reference accumulates into `counter`; offsets start at its current value (0 for a fresh counter)
-  march_write_kernel<<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, m, n_rays, max_points, nears, fars, perturb,
-                                                            counts, offsets, 0, 0, xyzs, dirs, deltas, rays);
+  if (t_stage != nullptr)
+    march_write_staged_kernel<<<ceil_div(static_cast<uint64_t>(n_rays) * 32, 128), 128, 0, st>>>(
+        rays_o, rays_d, m, n_rays, max_points, nears, perturb, counts, offsets, t_stage, xyzs, dirs, deltas, rays);
+  else
+    march_write_kernel<<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, m, n_rays, max_points, nears, fars,
+                                                              perturb, counts, offsets, 0, 0, xyzs, dirs, deltas, rays);
   march_finish_kernel<<<1, 32, 0, st>>>(offsets, n_rays, counter);
   return check_launch("march_rays_train");
 }

@@ -413,8 +413,13 @@ def nerf_loss(image, depth, semantics, gt_rgb, labels, gt_depth, uom, w_sem, w_d
 
 
 # ---------------------------------------------------------------------------------------------- occupancy-grid path
+MARCH_STAGE_MAX_RAYS = 1 << 16  # staging = 4 KB per ray (256 MB at this size); larger batches march twice
+
+
 def march_rays_train(rays_o, rays_d, grid, bitfield, mean_density, bound, dt_gamma, nears, fars, max_points, counter,
-                     perturb):
+                     perturb, staged=True):
+    """staged: record the parameter of every occupied step in the counting pass and write the samples with a
+    sample-parallel pass (each ray is marched once instead of twice); same samples either way"""
     n = rays_o.shape[0]
     dev = rays_o.device
     c, h = grid.shape[0], grid.shape[1]
@@ -423,12 +428,13 @@ def march_rays_train(rays_o, rays_d, grid, bitfield, mean_density, bound, dt_gam
     deltas = torch.zeros(max_points, 2, dtype=torch.float32, device=dev)
     rays = torch.empty(n, 3, dtype=torch.int32, device=dev)
     scratch = torch.empty(2 * n + 1, dtype=torch.int32, device=dev)
+    t_stage = torch.empty(n * 1024, dtype=torch.float32, device=dev) if staged and 0 < n <= MARCH_STAGE_MAX_RAYS else None
     check(lib().ucsa_march_rays_train(_ptr(rays_o, torch.float32), _ptr(rays_d, torch.float32),
                                       _ptr(grid, torch.float32, "density_grid"), _ptr(bitfield, torch.int32, "bitfield"),
                                       float(mean_density), float(bound), float(dt_gamma), n, c, h, max_points,
                                       _ptr(nears, torch.float32), _ptr(fars, torch.float32), _ptr(xyzs), _ptr(dirs),
                                       _ptr(deltas), _ptr(rays), _ptr(counter, torch.int32, "counter"), int(perturb),
-                                      _ptr(scratch), _stream()), "march_rays_train")
+                                      _ptr(scratch), _ptr(t_stage), _stream()), "march_rays_train")
     return xyzs, dirs, deltas, rays
 
 
