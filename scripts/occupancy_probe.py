@@ -43,6 +43,18 @@ if __name__ == "__main__":
     net.eval()
     with torch.no_grad():
         vo, vd, vdn = scene.rays(0, torch.arange(scene.W * scene.H, device=dev))
-        out = net.render(vo[None], vd[None], direction_norms=vdn.view(1, -1, 1), staged=True, perturb=False, dt_gamma=1 / 128)
-    torch.cuda.synchronize()
+        ref = None
+        for steps in ((1, 8), (2, 8), (4, 8), (8, 8), (8, 16), (16, 16), (16, 32), (32, 32)):
+            net.wavefront_steps = steps
+            for rep in range(2):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = net.render(vo[None], vd[None], direction_norms=vdn.view(1, -1, 1), staged=True, perturb=False,
+                                 dt_gamma=1 / 128)
+                e1.record()
+                torch.cuda.synchronize()
+            if ref is None:
+                ref = out
+            diff = max(float((out[k] - ref[k]).abs().max()) for k in ("image", "depth", "semantics"))
+            print(f"inference view, steps per round {steps}: {e0.elapsed_time(e1):.1f} ms, max |diff| to (1, 8): {diff:.2e}")
     print("ok", float(out["image"].mean()))
