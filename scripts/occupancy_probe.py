@@ -40,6 +40,8 @@ if __name__ == "__main__":
               f"{e0.elapsed_time(e1) / 5:.3f} ms")
     net.fused_packed = True
     print("samples", int(net.step_counter[(net.local_step - 1) % 16, 0]), "mean density", net.mean_density)
+    if "--train-only" in sys.argv:
+        sys.exit(0)
     net.eval()
     with torch.no_grad():
         vo, vd, vdn = scene.rays(0, torch.arange(scene.W * scene.H, device=dev))

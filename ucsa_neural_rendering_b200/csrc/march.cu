@@ -314,6 +314,10 @@ __global__ void march_rays_kernel(uint32_t n_alive, uint32_t n_step, const int32
 // repeating the chain of the reference's single thread, took 0.24 + 0.20 ms for 1.6 M samples).  The class channels
 // keep lanes = classes: the weight of sample k is broadcast by shuffle and the [C] row is read / written coalesced.
 // Same terms as raymarching.cu:318-487, summed in scan order: equal to the sequential result within fp32 rounding.
+constexpr int kLogitsLd = UCSA_MAX_CLASSES;  // row stride of the semantic head's logits (heads kernels: [K,48] fp16)
+constexpr int kTileStride = kLogitsLd + 1;
+static_assert(kLogitsLd % 8 == 0, "logit rows are read as 16-byte vectors");
+
 struct RaggedChunk {
   float alpha, w, t_after;  // of this lane's sample (alpha = w = 0 past the end of the ray)
 };
@@ -352,6 +356,12 @@ __global__ void composite_train_fwd_kernel(const float* __restrict__ sigmas, con
   float r = 0, g = 0, b = 0, ws = 0, d = 0;  // per-lane partial sums
   float acc0 = 0.f, acc1 = 0.f;              // classes lane, lane + 32
   float t_carry = 1.0f, time_carry = 0.f;
+  // the warp's tile for the lanes = samples soft-max: rows of kLogitsLd halves, 16-byte aligned, at most kLogitsLd classes
+  __shared__ float tiles[4 * 32 * kTileStride];
+  float* tile = (logits != nullptr && logits_ld == kLogitsLd && C <= kLogitsLd &&
+                 (reinterpret_cast<uintptr_t>(logits) & 15u) == 0)
+                    ? tiles + (threadIdx.x >> 5) * 32 * kTileStride
+                    : nullptr;
   if (!empty) {
     for (uint32_t base = 0; base < num_steps; base += 32) {
       const uint32_t s = base + lane;
@@ -380,9 +390,46 @@ __global__ void composite_train_fwd_kernel(const float* __restrict__ sigmas, con
           if (static_cast<uint32_t>(lane) < C) acc0 += wk * row[static_cast<uint64_t>(k) * C + lane];
           if (static_cast<uint32_t>(lane) + 32 < C) acc1 += wk * row[static_cast<uint64_t>(k) * C + lane + 32];
         }
+      } else if (logits != nullptr && tile != nullptr) {
+        // class probabilities from the fp16 logits of the semantic head; the [M,C] fp32 probability tensor is never
+        // formed.  Soft-max with lanes = SAMPLES (a lane reads its own 96-byte row, one max / exp / sum chain per
+        // lane, no shuffles), exp values parked in the warp's shared-memory tile [32][49] (odd stride: conflict-free
+        // both ways), then lanes = classes add up the chunk's rows.  The soft-max across the lanes (below, kept for
+        // other row strides) costs two warp reductions per SAMPLE: ncu showed the kernel issue-bound with it (0.30 ms
+        // for 1.6 M samples at 8 % of the DRAM throughput).
+        const uint32_t cnt = num_steps - base < 32u ? num_steps - base : 32u;
+        float scale = 0.f;
+        if (valid) {
+          const uint4* lg = reinterpret_cast<const uint4*>(logits + static_cast<uint64_t>(i) * kLogitsLd);
+          uint4 v[kLogitsLd / 8];
+#pragma unroll
+          for (int j = 0; j < kLogitsLd / 8; ++j) v[j] = __ldg(lg + j);
+          const __half* hv = reinterpret_cast<const __half*>(v);
+          float m = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < kLogitsLd; ++c)
+            if (static_cast<uint32_t>(c) < C) m = fmaxf(m, __half2float(hv[c]));
+          float sum = 0.f;
+          float* mine = tile + lane * kTileStride;
+#pragma unroll
+          for (int c = 0; c < kLogitsLd; ++c) {
+            if (static_cast<uint32_t>(c) < C) {
+              const float e = __expf(__half2float(hv[c]) - m);
+              sum += e;
+              mine[c] = e;
+            }
+          }
+          scale = q.w / sum;
+        }
+        __syncwarp();
+        for (uint32_t k = 0; k < cnt; ++k) {
+          const float sk = __shfl_sync(kFullMask, scale, static_cast<int>(k));
+          if (static_cast<uint32_t>(lane) < C) acc0 += sk * tile[k * kTileStride + lane];
+          if (static_cast<uint32_t>(lane) + 32 < C) acc1 += sk * tile[k * kTileStride + lane + 32];
+        }
+        __syncwarp();
       } else if (logits != nullptr) {
-        // class probabilities from the fp16 logits of the semantic head, soft-max across the lanes (as in
-        // composite_rays_kernel): the [M,C] fp32 probability tensor is never formed
+        // (any row stride) soft-max across the lanes, as in composite_rays_kernel
         const uint32_t cnt = num_steps - base < 32u ? num_steps - base : 32u;
         const __half* row = logits + static_cast<uint64_t>(offset + base) * logits_ld;
 #pragma unroll 4
