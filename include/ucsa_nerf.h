@@ -208,10 +208,12 @@ UCSA_API int ucsa_composite_dense_bwd(const float* sigma, const float* z, const 
 /* ---- a16-a20. occupancy-grid path: replaces the bound kernels of raymarching.h:9-18 / bindings.cpp:5-18.
  * The occupancy test reads `bitfield` when non-null (ucsa_grid_packbits), else the float `grid` [C,H,H,H] exactly like
  * raymarching.cu:157,204-210 (density > min(0.01, mean_density)).  Sample offsets are handed out in ray order:
- * rays[n] = (n, offset, count); counter[0] += total samples, counter[1] += n_rays.  `scratch` is int32 [2*n_rays+1].
+ * rays[n] = (n, offset, count); counter[0] += total samples, counter[1] += n_rays.  `scratch` is int32
+ * [UCSA_MARCH_SCRATCH_INTS(n_rays)] (counts, offsets and the block sums of the two-level scan used above 4096 rays).
  * t_stage (optional, float [n_rays * 1024]): staging for the parameter t of every occupied step; with it every ray is
  * marched once and the samples are written by a sample-parallel pass, without it every ray is marched twice (count,
  * then write).  Same samples either way. */
+#define UCSA_MARCH_SCRATCH_INTS(n_rays) (2ull * (n_rays) + 2ull * (((n_rays) + 1023ull) / 1024ull) + 2ull)
 UCSA_API int ucsa_march_rays_train(const float* rays_o, const float* rays_d, const float* grid, const uint32_t* bitfield,
                           float mean_density, float bound, float dt_gamma, uint32_t n_rays, uint32_t C, uint32_t H,
                           uint32_t max_points, const float* nears, const float* fars, float* xyzs, float* dirs,

@@ -76,6 +76,25 @@ def test_march_rays_train_bit_exact(ops, perturb, use_bits, staged):
     assert np.array_equal(dirs[:total].cpu().numpy(), r_dir[:total])
 
 
+def test_march_rays_train_many_rays_two_level_scan(ops):
+    """above 4096 rays the per-ray offsets come from the two-level scan (block scans + scan of the block sums)"""
+    n = 9000  # nine 1024-ray blocks, the last one ragged
+    grid, o, d, aabb = make_scene(n, 11)
+    nears, fars = raymarch.near_far(o.numpy(), d.numpy(), aabb.numpy())
+    m = n * 1024
+    r_xyz, r_dir, r_del, r_rays, r_cnt = raymarch.march_rays_train(o.numpy(), d.numpy(), grid.numpy(), 0.008, 4.0,
+                                                                   1 / 128, nears, fars, m, 0)
+    counter = torch.zeros(2, dtype=torch.int32, device=DEV)
+    xyz, dirs, deltas, rays = ops.march_rays_train(o.to(DEV), d.to(DEV), grid.to(DEV), None, 0.008, 4.0, 1 / 128,
+                                                   torch.from_numpy(nears).to(DEV), torch.from_numpy(fars).to(DEV), m,
+                                                   counter, 0)
+    assert np.array_equal(counter.cpu().numpy(), r_cnt)
+    assert np.array_equal(rays.cpu().numpy(), r_rays), "ray (id, offset, count) triples must be bit-exact"
+    total = int(r_cnt[0])
+    assert np.array_equal(xyz[:total].cpu().numpy(), r_xyz[:total])
+    assert np.array_equal(deltas[:total].cpu().numpy(), r_del[:total])
+
+
 def test_march_rays_train_overflow_and_empty(ops):
     """rays past the M budget are dropped like the reference (offset + count >= M), empty rays have count 0"""
     n = 64

@@ -269,6 +269,38 @@ march_scan_kernel(const int32_t* __restrict__ counts, uint32_t n, int32_t* __res
   if (threadIdx.x == 0) offsets[n] = carry_s;
 }
 
+// Two-level form for many rays (the single CTA above walks the counts 1024 at a time: 256 dependent rounds at 2^18
+// rays): every CTA scans its own 1024 counts, the block totals go through march_scan_kernel, a third pass adds the
+// block offsets.
+__global__ void __launch_bounds__(1024)
+march_scan_block_kernel(const int32_t* __restrict__ counts, uint32_t n, int32_t* __restrict__ offsets,
+                        int32_t* __restrict__ block_sums) {
+  __shared__ int warp_total[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+  const int v = i < n ? counts[i] : 0;
+  const int incl = warp_iscan(v, lane);
+  if (lane == 31) warp_total[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    const int tot = warp_total[lane];
+    const int scan = warp_iscan(tot, lane);
+    warp_total[lane] = scan - tot;
+    if (lane == 31) block_sums[blockIdx.x] = scan;
+  }
+  __syncthreads();
+  if (i < n) offsets[i] = warp_total[wid] + incl - v;
+}
+
+__global__ void __launch_bounds__(1024)
+march_scan_add_kernel(int32_t* __restrict__ offsets, uint32_t n, const int32_t* __restrict__ block_offs) {
+  const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+  if (i < n) offsets[i] += block_offs[blockIdx.x];
+  if (i == 0) offsets[n] = block_offs[gridDim.x];
+}
+
+constexpr uint32_t kScanOneCtaRays = 4096;  // up to here the single CTA is the shortest path (6 us at 4096 rays)
+
 // ------------------------------------------------------------------ inference wavefront (raymarching.cu:528-634)
 __global__ void march_rays_kernel(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays_alive,
                                   const float* __restrict__ rays_t, const float* __restrict__ rays_o,
@@ -779,7 +811,16 @@ extern "C" int ucsa_march_rays_train(const float* rays_o, const float* rays_d, c
   int32_t* offsets = scratch + n_rays;  // [n_rays + 1]
   march_count_kernel<<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, m, n_rays, nears, fars, perturb, counts,
                                                             t_stage);
-  march_scan_kernel<<<1, 1024, 0, st>>>(counts, n_rays, offsets);
+  if (n_rays <= kScanOneCtaRays) {
+    march_scan_kernel<<<1, 1024, 0, st>>>(counts, n_rays, offsets);
+  } else {
+    const uint32_t n_blocks = ceil_div(n_rays, 1024u);
+    int32_t* block_sums = offsets + n_rays + 1;     // [n_blocks]
+    int32_t* block_offs = block_sums + n_blocks;    // [n_blocks + 1]
+    march_scan_block_kernel<<<n_blocks, 1024, 0, st>>>(counts, n_rays, offsets, block_sums);
+    march_scan_kernel<<<1, 1024, 0, st>>>(block_sums, n_blocks, block_offs);
+    march_scan_add_kernel<<<n_blocks, 1024, 0, st>>>(offsets, n_rays, block_offs);
+  }
   // the reference accumulates into `counter`; offsets start at its current value (0 for a fresh counter)
   if (t_stage != nullptr)
     march_write_staged_kernel<<<ceil_div(static_cast<uint64_t>(n_rays) * 32, 128), 128, 0, st>>>(

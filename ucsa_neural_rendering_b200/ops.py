@@ -427,7 +427,7 @@ def march_rays_train(rays_o, rays_d, grid, bitfield, mean_density, bound, dt_gam
     dirs = torch.zeros(max_points, 3, dtype=torch.float32, device=dev)
     deltas = torch.zeros(max_points, 2, dtype=torch.float32, device=dev)
     rays = torch.empty(n, 3, dtype=torch.int32, device=dev)
-    scratch = torch.empty(2 * n + 1, dtype=torch.int32, device=dev)
+    scratch = torch.empty(2 * n + 2 * ((n + 1023) // 1024) + 2, dtype=torch.int32, device=dev)  # UCSA_MARCH_SCRATCH_INTS
     t_stage = torch.empty(n * 1024, dtype=torch.float32, device=dev) if staged and 0 < n <= MARCH_STAGE_MAX_RAYS else None
     check(lib().ucsa_march_rays_train(_ptr(rays_o, torch.float32), _ptr(rays_d, torch.float32),
                                       _ptr(grid, torch.float32, "density_grid"), _ptr(bitfield, torch.int32, "bitfield"),
