@@ -1,6 +1,9 @@
 #!/usr/bin/env python
-"""The occupancy-grid path alone (rows a16-a20): grid refresh, one training render (forward + backward) and one
-inference view, for `ncu --metrics gpu__time_duration.sum` launch lists.  python scripts/occupancy_probe.py"""
+"""The occupancy-grid path alone (rows a16-a20): grid refresh, the training render (forward + backward) with the fused
+node and with the module-level heads, and one inference view for a sweep of wavefront schedules.  Also the target of
+`ncu --metrics gpu__time_duration.sum` launch lists (profiles/r2_occupancy_*.md).
+
+    python scripts/occupancy_probe.py [--train-only]"""
 import sys
 
 import torch
