@@ -57,3 +57,25 @@ def test_default_palette():
     pal = default_palette(41)
     assert pal.shape == (41, 3) and pal.dtype == np.uint8 and (pal[0] == 0).all()
     assert len({tuple(c) for c in pal.tolist()}) == 41  # all labels distinguishable
+
+
+def test_occupancy_path_knobs_and_refusals_without_a_gpu():
+    """cuda_ray=True facade on the host: the reference's buffers exist, the fused training render steps aside when it is
+    switched off or there is nothing to render (the caller then composes the module-level pieces like the reference's
+    run_cuda), and no packed-point operator accepts host tensors (there is no CPU fallback)."""
+    from ucsa_neural_rendering_b200 import _lib
+    from ucsa_neural_rendering_b200.nerf import SemanticNeRFNetwork
+
+    net = SemanticNeRFNetwork(encoding="hashgrid", bound=4, cuda_ray=True, density_scale=1, num_semantic_classes=40)
+    assert tuple(net.density_grid.shape) == (3, 128, 128, 128) and tuple(net.step_counter.shape) == (16, 2)
+    lo, hi = net.wavefront_steps
+    assert 1 <= lo <= hi
+    pts, rays = torch.zeros(5, 3), torch.zeros(1, 3, dtype=torch.int32)
+    assert net.render_packed_train(torch.zeros(0, 3), torch.zeros(0, 3), torch.zeros(0, 2), rays) is None
+    net.fused_packed = False
+    assert net.render_packed_train(pts, pts, torch.zeros(5, 2), rays) is None
+    net.fused_packed = True
+    for call in (lambda: net.render_packed_train(pts, pts, torch.zeros(5, 2), rays),
+                 lambda: net.forward_packed_train(pts, pts), lambda: net.forward_packed(pts, pts)):
+        with pytest.raises(_lib.UcsaError):
+            call()
