@@ -93,6 +93,15 @@ def test_host_side_argument_checks_run_before_any_launch(handle):
     rc = handle.ucsa_nerf_loss(one, one, one, one, None, one, one, 4, 40, 1.0, 0.04, 0.1, 1.0, one, one, one, one, None,
                                None)
     assert rc == -1 and b"null" in handle.ucsa_last_error_string()
+    # ragged training composite: probabilities or logits (not both), a logit row at least as wide as the class count,
+    # [M,2] step sizes read as 8-byte pairs
+    args = lambda sem, lg, ld, deltas: (one, one, sem, lg, ld, deltas, one, 64, 4, 40, one, one, one, one, None)  # noqa: E731
+    rc = handle.ucsa_composite_rays_train_forward(*args(one, one, 48, one))
+    assert rc == -1 and b"not both" in handle.ucsa_last_error_string()
+    rc = handle.ucsa_composite_rays_train_forward(*args(None, one, 32, one))
+    assert rc == -1 and b"row stride" in handle.ucsa_last_error_string()
+    rc = handle.ucsa_composite_rays_train_forward(*args(None, one, 48, ctypes.c_void_p(20)))
+    assert rc == -1 and b"8-byte aligned" in handle.ucsa_last_error_string()
 
 
 def test_tile_layout_helpers_and_launch_accounting():
