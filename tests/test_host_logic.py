@@ -79,3 +79,25 @@ def test_occupancy_path_knobs_and_refusals_without_a_gpu():
                  lambda: net.forward_packed_train(pts, pts), lambda: net.forward_packed(pts, pts)):
         with pytest.raises(_lib.UcsaError):
             call()
+
+
+def test_incremental_build_tracks_the_include_closure():
+    """An object is rebuilt when its source or anything it includes (transitively, with quotes) changes -- a stale
+    object behind an edited header would ship kernels that disagree about a layout."""
+    import os
+
+    from ucsa_neural_rendering_b200 import build
+
+    def closure(src):
+        deps = set()
+        build._closure(os.path.join(build.CSRC, src), deps)
+        return {os.path.basename(p) for p in deps}
+
+    header = "ucsa_nerf.h"
+    for src in build._sources():
+        assert {src, "common.cuh", header} <= closure(src), src
+    assert {"grid.cuh", "mlp_umma.cuh"} <= closure("density_tc.cu")
+    assert "mlp_umma.cuh" in closure("heads_tc.cu") and "grid.cuh" not in closure("march.cu")
+    assert "heads_tc.cu" not in closure("march.cu")
+    stamps = {src: build._source_stamp(src) for src in build._sources()}
+    assert len(set(stamps.values())) == len(stamps)
